@@ -1,0 +1,200 @@
+/*
+ * ssd_b200.h -- C ABI of the B200-native SSD anchor pipeline (libssd_b200.so).
+ *
+ * Drop-in boundary for the per-image anchor pipeline of georgymironov/single_shot_detection
+ * (paths below are relative to that repository).  The reference has no FFI of its own: the
+ * path is plain Python calling torch CPU ops.  Each entry point here replaces one of those
+ * Python functions; the Python classes in single_shot_detection_b200/ keep the reference's
+ * names and signatures and forward to these symbols (see INTEGRATION.md for the binding a
+ * maintainer of the reference would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing
+ *     synchronises and nothing allocates: scratch comes from a caller-provided workspace whose
+ *     size is returned by the matching *_workspace_bytes() query;
+ *   - every function returns an ssd_status; ssd_b200_last_error() gives the message of the
+ *     last failure on the calling thread;
+ *   - fp32 everywhere (the reference calls .float() on its inputs), int64 class ids where the
+ *     reference passes a LongTensor, uint8 masks (torch.bool storage);
+ *   - arithmetic that decides an index (IoU, thresholds, NMS overlap) is done with separately
+ *     rounded IEEE fp32 operations in the reference's operation order (no FMA contraction), so
+ *     matched indices and keep lists are bit exact on identical inputs.
+ */
+#ifndef SSD_B200_H_
+#define SSD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSD_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SSD_API __attribute__((visibility("default")))
+#else
+#define SSD_API
+#endif
+
+typedef enum {
+    SSD_OK = 0,
+    SSD_ERR_INVALID_ARGUMENT = 1,   /* null pointer, negative size, bad enum            */
+    SSD_ERR_MISALIGNED = 2,         /* a pointer violates the alignment stated below    */
+    SSD_ERR_WORKSPACE = 3,          /* workspace smaller than *_workspace_bytes()        */
+    SSD_ERR_UNSUPPORTED = 4,        /* shape outside the supported envelope (see docs)  */
+    SSD_ERR_CUDA = 5,               /* a CUDA runtime call failed                        */
+    SSD_ERR_NO_DEVICE = 6           /* no sm_100 device / kernel image not loadable      */
+} ssd_status;
+
+/* target row layout -- detection/target_assigner.py:7-14 */
+#define SSD_TARGET_COLS 6
+#define SSD_CLASS_COL 4
+#define SSD_SCORE_COL 5
+#define SSD_NEGATIVE_CLASS 0
+#define SSD_IGNORE_CLASS (-1)
+/* matcher sentinels -- detection/matcher.py:4-5 */
+#define SSD_NOT_MATCHED (-2)
+#define SSD_IGNORE (-1)
+
+SSD_API int ssd_b200_abi_version(void);
+SSD_API const char* ssd_b200_last_error(void);
+/* SSD_OK when the current device is compute capability 10.x and the sm_100a image loads. */
+SSD_API int ssd_b200_device_check(void);
+
+/* ------------------------------------------------------------------------------------------
+ * a2  bf/utils/box_utils.py:83-101  iou(a, b) -- pairwise IoU of corner boxes.
+ *     out[g*A + a] = inter / ((area_a[g] + area_b[a]) - inter), 0/0 -> NaN as in the reference.
+ * ---------------------------------------------------------------------------------------- */
+SSD_API int ssd_pairwise_iou(const float* a_corners, int num_a, const float* b_corners, int num_b,
+                     float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a3  detection/matcher.py:33-56  match_per_prediction(weights, matched, unmatched, force)
+ *     weights[G, A] row-major -> box_idx[A] int64 in {-2, -1, 0..G-1}.  Thresholds are the
+ *     fp32-rounded values (the reference compares in fp32).
+ * ---------------------------------------------------------------------------------------- */
+SSD_API int ssd_match_per_prediction(const float* weights, int num_gt, int num_anchors,
+                             float matched_threshold, float unmatched_threshold, int force_match,
+                             int64_t* box_idx_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a1+a2+a3+a4  detection/target_assigner.py:22-63  TargetAssigner.encode_ground_truth
+ *     One launch for the whole batch: to_corners(anchors) -> IoU -> per-anchor / per-GT argmax
+ *     -> forced match -> target rows.
+ *   anchors      [A,4]   (cx,cy,w,h) pixels, 16-byte aligned
+ *   gt_rows      [sum G_i, gt_cols] rows (x1,y1,x2,y2,class,score,...), gt_cols >= 6
+ *   gt_offsets   [B+1]   int32 row offsets into gt_rows (G_i = off[i+1]-off[i], 0 allowed)
+ *   max_gt       max_i G_i (host knows it when it packs the list); <= 4096
+ *   target_out   [B,A,6] fp32, 8-byte aligned
+ *   match_out    [B,A]   int32 matcher output per anchor, or NULL
+ *   stats_out    [B,4]   int32 {positives, ignored, positives with NaN box, G_i}, or NULL
+ * ---------------------------------------------------------------------------------------- */
+SSD_API int ssd_assign_targets(const float* anchors, const float* gt_rows, int gt_cols,
+                       const int32_t* gt_offsets, int max_gt, int batch, int num_anchors,
+                       float matched_threshold, float unmatched_threshold, int force_match,
+                       float* target_out, int32_t* match_out, int32_t* stats_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a1/a6/a7  box format + coding, bf/utils/box_utils.py:16-36 and detection/box_coder.py:13-57.
+ *     The in-place and out-of-place branches of the reference round differently; both orders
+ *     are provided.  src may equal dst.  Row strides are in floats (4 for packed boxes, 6 when
+ *     operating on the box columns of a target tensor view).  priors[A,4] are indexed by
+ *     row % A and may be NULL for the two format conversions.
+ * ---------------------------------------------------------------------------------------- */
+typedef enum {
+    SSD_BOX_TO_CORNERS = 0,               /* box_utils.py:23                                  */
+    SSD_BOX_TO_CENTROIDS = 1,             /* box_utils.py:36   ((max+min)/2, max-min)         */
+    SSD_BOX_TO_CENTROIDS_INPLACE = 2,     /* box_utils.py:33-34 (min+(max-min)/2)             */
+    SSD_BOX_ENCODE = 3,                   /* box_coder.py:32-34 log((wh+eps)/p_wh)            */
+    SSD_BOX_ENCODE_INPLACE = 4,           /* box_coder.py:22-29 log(wh/p_wh+eps)              */
+    SSD_BOX_DECODE = 5,                   /* box_coder.py:55-57                               */
+    SSD_BOX_DECODE_INPLACE = 6,           /* box_coder.py:47-52                               */
+    SSD_BOX_CENTROIDS_ENCODE_INPLACE = 7, /* 2 then 4 in one pass (multibox_loss.py:81-82)    */
+    SSD_BOX_DECODE_TO_CORNERS = 8         /* 5 then 0 in one pass (postprocessor.py:52-53)    */
+} ssd_box_op;
+
+SSD_API int ssd_box_transform(int op, const float* src, int64_t src_row_stride, float* dst,
+                      int64_t dst_row_stride, const float* priors, int64_t num_rows,
+                      int num_anchors, float xy_scale, float wh_scale, float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a5  detection/sampler.py:9-10  naive_sampler: mask = class != 0 && class != -1
+ * ---------------------------------------------------------------------------------------- */
+SSD_API int ssd_positive_mask(const int64_t* target_classes, int64_t count, uint8_t* mask_out,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a5  detection/sampler.py:12-25  hard_negative_mining
+ *   logits          [B,A,C] fp32, 16-byte aligned
+ *   target_classes  [B,A]   int64
+ *   loss_override   [B,A]   fp32 or NULL.  When given, it replaces -log_softmax(logits)[...,0]
+ *                   (stage-boundary parity: selection on identical fp32 inputs) and logits may
+ *                   be NULL.
+ *   ratio           negative_per_positive_ratio; ratio_is_integer says whether the reference
+ *                   would have computed n_pos*ratio in int64 (Python int) or fp32 (Python float)
+ *   mask_out        [B,A]   uint8 (torch.bool)
+ *   stats_out       [B,4]   int32 {positives, negatives, negatives selected, loss ties at cut}
+ *                   or NULL.  Ties at the cut are broken towards the lower anchor index.
+ * ---------------------------------------------------------------------------------------- */
+SSD_API size_t ssd_hard_negative_workspace_bytes(int batch, int num_anchors);
+SSD_API int ssd_hard_negative_mask(const float* logits, const int64_t* target_classes,
+                           const float* loss_override, int batch, int num_anchors, int num_cols,
+                           double ratio, int ratio_is_integer, double min_negatives,
+                           uint8_t* mask_out, int32_t* stats_out, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a7+a8+a9  detection/postprocessor.py:24-78  Postprocessor.postprocess, including
+ *           bf/utils/box_utils.py:165-194 nms (top-k + torchvision.ops.nms semantics).
+ * ---------------------------------------------------------------------------------------- */
+typedef enum { SSD_CONVERT_SOFTMAX = 0, SSD_CONVERT_SIGMOID = 1, SSD_CONVERT_IDENTITY = 2 } ssd_converter;
+typedef enum { SSD_BOXES_ENCODED = 0, SSD_BOXES_CORNERS = 1 } ssd_box_input;
+
+typedef struct {
+    int32_t batch;               /* B                                                        */
+    int32_t num_anchors;         /* A                                                        */
+    int32_t num_cols;            /* C score columns per anchor                               */
+    int32_t converter;           /* ssd_converter                                            */
+    int32_t first_fg_col;        /* columns below it are skipped; SOFTMAX: 1, SIGMOID: 0     */
+    int32_t box_input;           /* ssd_box_input: locs to decode, or ready corner boxes     */
+    float xy_scale, wh_scale;    /* BoxCoder scales                                          */
+    float score_threshold;       /* fp32-rounded; candidates need score > threshold          */
+    int32_t max_per_class;       /* K, 1..512                                                */
+    double overlap_threshold;    /* NMS IoU threshold, compared as (double)iou > threshold   */
+    int32_t max_total;           /* T; <= 0 means no final top-k                             */
+    int32_t det_capacity;        /* rows per image in dets_out; >= min(T or inf, Cf*K)       */
+} ssd_postprocess_params;
+
+SSD_API size_t ssd_postprocess_workspace_bytes(const ssd_postprocess_params* p);
+/*   scores     [B,A,C]  fp32, 16-byte aligned
+ *   boxes      [B,A,4]  fp32 locs (SSD_BOXES_ENCODED) or corner boxes (SSD_BOXES_CORNERS), 16-byte aligned
+ *   priors     [A,4]    fp32 (cx,cy,w,h); may be NULL with SSD_BOXES_CORNERS
+ *   dets_out   [B,det_capacity,6] fp32 rows (x1,y1,x2,y2,class,score); rows >= count are untouched
+ *   count_out  [B]      int32 rows written per image
+ *   anchor_out [B,det_capacity] int32 anchor index of each row, or NULL
+ *   status_out [4]      int32 {errors (always 0), (image,class) lists that took the exact
+ *                       column-rescan fallback, 0, 0} or NULL -- informational, results are exact
+ * Row order per image: > T rows -> descending score (ties: class-major position);
+ * otherwise class-major, descending score inside a class (ties: lower anchor first). */
+SSD_API int ssd_postprocess(const ssd_postprocess_params* p, const float* scores, const float* boxes,
+                    const float* priors, float* dets_out, int32_t* count_out, int32_t* anchor_out,
+                    int32_t* status_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a9  bf/utils/box_utils.py:165-194  nms(boxes, scores, overlap_threshold, score_threshold,
+ *     max_per_class) for one box set (hard NMS).  keep_out[i] = input row of the i-th kept box
+ *     (descending score).  keep_out holds min(n, max_per_class) entries (n when max_per_class<=0
+ *     is not supported: pass max_per_class in 1..512).
+ * ---------------------------------------------------------------------------------------- */
+SSD_API size_t ssd_nms_workspace_bytes(int num_boxes, int max_per_class);
+SSD_API int ssd_nms(const float* corner_boxes, const float* scores, int num_boxes, int max_per_class,
+            double overlap_threshold, int64_t* keep_out, int32_t* count_out, void* workspace,
+            size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSD_B200_H_ */

@@ -1,0 +1,63 @@
+"""Host-side plumbing: device copies of constant inputs and pinned staging buffers.
+
+The reference hands the pipeline CPU tensors every step (anchors are generated on the CPU,
+ground truth comes from the data loader).  Anchors are constant per input shape, so their device
+copy is cached (keyed on storage pointer, shape and version counter); ragged ground truth is
+packed into a reusable pinned buffer so that one async H2D copy moves a whole batch.
+"""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import torch
+
+_const_cache: Dict[Tuple, torch.Tensor] = {}
+_pinned: Dict[str, torch.Tensor] = {}
+_MAX_CONST = 16
+
+
+def device_copy(t: torch.Tensor, device: torch.device) -> torch.Tensor:
+    """fp32 contiguous copy of a (constant) tensor on ``device``; cached."""
+    if t.is_cuda and t.device == device and t.dtype == torch.float32 and t.is_contiguous():
+        return t
+    key = (t.data_ptr(), tuple(t.shape), t.dtype, t._version, str(device))
+    hit = _const_cache.get(key)
+    if hit is None:
+        if len(_const_cache) >= _MAX_CONST:
+            _const_cache.pop(next(iter(_const_cache)))
+        hit = t.detach().to(device=device, dtype=torch.float32).contiguous()
+        _const_cache[key] = hit
+    return hit
+
+
+_in_flight = {}
+
+
+def pinned_words(n: int) -> torch.Tensor:
+    """A pinned fp32 staging buffer of at least ``n`` words, reused between calls.  Waits for the
+    previous async copy out of it (see :func:`mark_in_flight`) before handing it back."""
+    ev = _in_flight.pop("words", None)
+    if ev is not None:
+        ev.synchronize()
+    buf = _pinned.get("words")
+    if buf is None or buf.numel() < n:
+        buf = torch.empty(max(n, 4096), dtype=torch.float32).pin_memory()
+        _pinned["words"] = buf
+    return buf
+
+
+def mark_in_flight(tag: str = "words") -> None:
+    """Record that an async H2D copy reading the pinned buffer was just enqueued."""
+    ev = torch.cuda.Event()
+    ev.record()
+    _in_flight[tag] = ev
+
+
+def pinned_buffer(tag: str, shape, dtype) -> torch.Tensor:
+    """A cached pinned buffer (cudaHostAlloc is far too slow to call per step)."""
+    key = f"{tag}:{tuple(shape)}:{dtype}"
+    buf = _pinned.get(key)
+    if buf is None:
+        buf = torch.empty(tuple(shape), dtype=dtype).pin_memory()
+        _pinned[key] = buf
+    return buf

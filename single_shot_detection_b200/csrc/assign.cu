@@ -1,0 +1,373 @@
+// Target assignment: detection/target_assigner.py:22-63 with detection/matcher.py:33-56 and
+// bf/utils/box_utils.py:16-23,38-101 fused into one launch for the whole batch.
+//
+// One thread-block CLUSTER per image.  The image's anchors are split across the CTAs of the
+// cluster; every thread owns one anchor at a time and walks the image's ground-truth boxes
+// (staged in shared memory):
+//   * IoU in the reference's operation order, every fp32 op rounded separately (no FMA):
+//       inter = clamp(min(x2)-max(x1),0) * clamp(min(y2)-max(y1),0)
+//       iou   = inter / ((area_gt + area_anchor) - inter)                 box_utils.py:93-101
+//   * per-anchor running max over GT (first maximum wins = lowest GT index, NaN sticks),
+//   * per-GT argmax over anchors: warp REDUX max on the ordered IoU key, ballot for the lowest
+//     lane, one shared-memory atomicMax on a 64-bit (key, ~anchor) word per warp that beats the
+//     current best; after a cluster barrier every CTA reads its peers' tables through
+//     distributed shared memory and reduces them -- no global atomics, no second launch.
+//   * thresholds in fp32, then the forced match of every GT to its best anchor, colliding GTs
+//     resolved towards the highest GT index (sequential index_put semantics)  matcher.py:49-54
+//   * target rows written as coalesced float2 stores                target_assigner.py:38-58
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace ssd {
+
+constexpr int kAssignThreads = 256;
+constexpr int kMaxGtPerImage = 4096;
+constexpr int kForcedPending = -3;
+
+struct AssignSmem {
+    // dynamic layout: float4 gbox[G]; float garea[G]; float2 gcs[G]; u64 best[G]; int match[chunk]
+};
+
+__device__ __forceinline__ float clamped_area(float x1, float y1, float x2, float y2) {
+    // (x2 - x1).clamp_(0) * (y2 - y1).clamp_(0)                      box_utils.py:46
+    const float w = fmaxf(fsub(x2, x1), 0.f);
+    const float h = fmaxf(fsub(y2, y1), 0.f);
+    return fmul(w, h);
+}
+
+__device__ __forceinline__ float iou_exact(float4 g, float garea, float4 a, float aarea) {
+    const float ix1 = fmaxf(g.x, a.x), iy1 = fmaxf(g.y, a.y);
+    const float ix2 = fminf(g.z, a.z), iy2 = fminf(g.w, a.w);
+    const float iw = fmaxf(fsub(ix2, ix1), 0.f);
+    const float ih = fmaxf(fsub(iy2, iy1), 0.f);
+    const float inter = fmul(iw, ih);
+    const float uni = fsub(fadd(garea, aarea), inter);
+    // 0 / positive is +0 exactly; everything else takes the IEEE divide (0/0 -> NaN as torch)
+    return (inter == 0.f && uni > 0.f) ? 0.f : fdiv(inter, uni);
+}
+
+__device__ __forceinline__ float4 corners_of(float4 c) {
+    // box_utils.py:23 -- w/2 is exact
+    const float hw = fmul(c.z, 0.5f), hh = fmul(c.w, 0.5f);
+    return make_float4(fsub(c.x, hw), fsub(c.y, hh), fadd(c.x, hw), fadd(c.y, hh));
+}
+
+__device__ __forceinline__ unsigned long long best_word(float iou, int anchor) {
+    uint32_t k = ordered_key(iou);
+    if (iou != iou) k = 0xFFFFFFFFu;                 // argmax treats NaN as the maximum
+    return ((unsigned long long)k << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)anchor);
+}
+
+__global__ void __launch_bounds__(kAssignThreads)
+assign_targets_kernel(const float4* __restrict__ anchors, const float* __restrict__ gt_rows, int gt_cols,
+                      const int32_t* __restrict__ gt_offsets, int A, int chunk, float matched_thr,
+                      float unmatched_thr, int force_match, float* __restrict__ target, int32_t* __restrict__ match_out,
+                      int32_t* __restrict__ stats) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int csize = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    const int img = blockIdx.x / csize;
+    const int g0 = gt_offsets[img];
+    const int G = gt_offsets[img + 1] - g0;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // carve (all CTAs of the cluster use the same carve so mapped addresses line up)
+    const int Gcap = G > 0 ? G : 1;
+    float4* gbox = reinterpret_cast<float4*>(smem_raw);
+    unsigned long long* best = reinterpret_cast<unsigned long long*>(gbox + Gcap);
+    float2* gcs = reinterpret_cast<float2*>(best + Gcap);
+    unsigned long long* merged = reinterpret_cast<unsigned long long*>(gcs + Gcap);
+    float* garea = reinterpret_cast<float*>(merged + Gcap);
+    int* match = reinterpret_cast<int*>(garea + Gcap);
+
+    const int a_begin = min(rank * chunk, A);
+    const int a_end = min(a_begin + chunk, A);
+    const int n_local = a_end - a_begin;
+
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        const float* row = gt_rows + (size_t)(g0 + g) * gt_cols;
+        const float4 bx = make_float4(row[0], row[1], row[2], row[3]);
+        gbox[g] = bx;
+        garea[g] = clamped_area(bx.x, bx.y, bx.z, bx.w);
+        gcs[g] = make_float2(row[SSD_CLASS_COL], row[SSD_SCORE_COL]);
+        best[g] = best_word(0.f, 0);      // an all-zero IoU row force-matches anchor 0
+    }
+    __syncthreads();
+
+    // ---- phase 1: per-anchor best GT, per-GT best anchor ----
+    if (G > 0) {
+        for (int base = 0; base < n_local; base += blockDim.x) {
+            const int la = base + threadIdx.x;
+            const bool valid = la < n_local;
+            const int a = a_begin + la;
+            float4 ab = make_float4(0.f, 0.f, 0.f, 0.f);
+            float aarea = 0.f;
+            if (valid) {
+                ab = corners_of(anchors[a]);
+                aarea = clamped_area(ab.x, ab.y, ab.z, ab.w);
+            }
+            float best_iou = -INFINITY;
+            int best_g = 0;
+            for (int g = 0; g < G; ++g) {
+                const float v = iou_exact(gbox[g], garea[g], ab, aarea);
+                // torch.max(dim=0): first maximum wins, NaN propagates and sticks
+                if (!(v <= best_iou) && !(best_iou != best_iou)) { best_iou = v; best_g = g; }
+                // per-GT argmax over anchors
+                uint32_t key = valid ? ordered_key(v) : 0u;
+                if (valid && v != v) key = 0xFFFFFFFFu;
+                const uint32_t wmax = __reduce_max_sync(FULL, key);
+                if (wmax > 0x80000000u) {               // somebody overlaps (key(+0) == 0x80000000)
+                    const unsigned bal = __ballot_sync(FULL, key == wmax);
+                    if (lane_id() == __ffs(bal) - 1) {
+                        const unsigned long long w = ((unsigned long long)key << 32) |
+                                                     (unsigned long long)(0xFFFFFFFFu - (uint32_t)a);
+                        if (w > best[g]) atomicMax(&best[g], w);
+                    }
+                }
+            }
+            if (valid) {
+                int m = best_g;
+                if (best_iou < unmatched_thr) m = SSD_NOT_MATCHED;              // matcher.py:49
+                else if (best_iou < matched_thr) m = SSD_IGNORE;                // matcher.py:50
+                match[la] = m;
+            }
+        }
+    } else {
+        for (int la = threadIdx.x; la < n_local; la += blockDim.x) match[la] = SSD_NOT_MATCHED;
+    }
+
+    // ---- merge the per-GT winners across the cluster through DSMEM ----
+    // Canonical DSMEM pattern: every CTA publishes its own table, cluster barrier, every CTA reads
+    // the peers' tables with remote loads and reduces locally.  (Remote atomics into one root
+    // table were observed NOT to be ordered by the cluster barrier on sm_100a.)
+    if (csize > 1 && G > 0 && force_match) {
+        __syncthreads();
+        cluster.sync();                                   // all local tables are final
+        for (int g = threadIdx.x; g < G; g += blockDim.x) {
+            unsigned long long m = best[g];
+            for (int r = 0; r < csize; ++r) {
+                if (r == rank) continue;
+                const unsigned long long* peer = cluster.map_shared_rank(best, r);
+                const unsigned long long v = peer[g];
+                m = v > m ? v : m;
+            }
+            merged[g] = m;
+        }
+        cluster.sync();                                   // nobody exits (or moves on) while peers still read
+        best = merged;
+    } else {
+        __syncthreads();
+    }
+
+    // ---- phase 2: forced matches (matcher.py:53-54), highest GT index wins a collision ----
+    if (force_match && G > 0) {
+        for (int g = threadIdx.x; g < G; g += blockDim.x) {
+            const int a = (int)(0xFFFFFFFFu - (uint32_t)(best[g] & 0xFFFFFFFFull));
+            if (a >= a_begin && a < a_end) match[a - a_begin] = kForcedPending;
+        }
+        __syncthreads();
+        for (int g = threadIdx.x; g < G; g += blockDim.x) {
+            const int a = (int)(0xFFFFFFFFu - (uint32_t)(best[g] & 0xFFFFFFFFull));
+            if (a >= a_begin && a < a_end) atomicMax(&match[a - a_begin], g);
+        }
+        __syncthreads();
+    }
+
+    // ---- phase 3: target rows, flat coalesced float2 stores over this CTA's [n_local, 6] slab ----
+    float2* out = reinterpret_cast<float2*>(target + ((size_t)img * A + a_begin) * SSD_TARGET_COLS);
+    int n_pos = 0, n_ign = 0, n_nan = 0;
+    for (int p = threadIdx.x; p < n_local * 3; p += blockDim.x) {
+        const int la = p / 3;
+        const int part = p - la * 3;
+        const int m = match[la];
+        float2 v;
+        if (m >= 0) {
+            const float4 bx = gbox[m];
+            const float2 cs = gcs[m];
+            v = part == 0 ? make_float2(bx.x, bx.y) : part == 1 ? make_float2(bx.z, bx.w) : cs;
+            if (part == 2) {
+                const bool pos = cs.x != (float)SSD_NEGATIVE_CLASS && cs.x != (float)SSD_IGNORE_CLASS;
+                n_pos += pos;
+                n_ign += cs.x == (float)SSD_IGNORE_CLASS;
+                n_nan += pos && (bx.x != bx.x || bx.y != bx.y || bx.z != bx.z || bx.w != bx.w);
+            }
+        } else if (m == SSD_IGNORE) {
+            v = part == 2 ? make_float2((float)SSD_IGNORE_CLASS, (float)SSD_IGNORE_CLASS) : make_float2(0.f, 0.f);
+            n_ign += part == 2;
+        } else {
+            v = part == 2 ? make_float2((float)SSD_NEGATIVE_CLASS, 1.f) : make_float2(0.f, 0.f);
+        }
+        out[p] = v;
+    }
+    if (match_out != nullptr) {
+        int32_t* mo = match_out + (size_t)img * A + a_begin;
+        for (int la = threadIdx.x; la < n_local; la += blockDim.x) mo[la] = match[la];
+    }
+    if (stats != nullptr) {
+        n_pos = __reduce_add_sync(FULL, n_pos);
+        n_ign = __reduce_add_sync(FULL, n_ign);
+        n_nan = __reduce_add_sync(FULL, n_nan);
+        if (lane_id() == 0) {
+            if (n_pos) atomicAdd(&stats[img * 4 + 0], n_pos);
+            if (n_ign) atomicAdd(&stats[img * 4 + 1], n_ign);
+            if (n_nan) atomicAdd(&stats[img * 4 + 2], n_nan);
+        }
+        if (rank == 0 && threadIdx.x == 0) stats[img * 4 + 3] = G;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// stand-alone pieces of the same path (API completeness: box_utils.iou, matcher.match_per_prediction)
+// ---------------------------------------------------------------------------------------------
+__global__ void pairwise_iou_kernel(const float4* __restrict__ a, int na, const float4* __restrict__ b, int nb,
+                                    float* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= nb) return;
+    const float4 ga = a[i], gb = b[j];
+    const float area_a = clamped_area(ga.x, ga.y, ga.z, ga.w);
+    const float area_b = clamped_area(gb.x, gb.y, gb.z, gb.w);
+    const float ix1 = fmaxf(ga.x, gb.x), iy1 = fmaxf(ga.y, gb.y);
+    const float ix2 = fminf(ga.z, gb.z), iy2 = fminf(ga.w, gb.w);
+    const float inter = fmul(fmaxf(fsub(ix2, ix1), 0.f), fmaxf(fsub(iy2, iy1), 0.f));
+    out[(size_t)i * nb + j] = fdiv(inter, fsub(fadd(area_a, area_b), inter));
+}
+
+// one CTA: weights[G, A] -> box_idx[A].  Columns are walked by threads (coalesced along A).
+__global__ void __launch_bounds__(1024)
+match_per_prediction_kernel(const float* __restrict__ w, int G, int A, float matched_thr, float unmatched_thr,
+                            int force_match, long long* __restrict__ box_idx, unsigned long long* __restrict__ best) {
+    // best[G] lives in global scratch (single CTA, so plain atomics + __syncthreads order it)
+    // generic weights (may be negative): start below every real key
+    for (int g = threadIdx.x; g < G; g += blockDim.x) best[g] = 0ull;
+    __syncthreads();
+    for (int base = 0; base < A; base += blockDim.x) {
+        const int a = base + threadIdx.x;
+        const bool valid = a < A;
+        float best_v = -INFINITY;
+        int best_g = 0;
+        for (int g = 0; g < G; ++g) {
+            const float v = valid ? w[(size_t)g * A + a] : 0.f;
+            if (valid && !(v <= best_v) && !(best_v != best_v)) { best_v = v; best_g = g; }
+            uint32_t key = valid ? ordered_key(v) : 0u;
+            if (valid && v != v) key = 0xFFFFFFFFu;
+            const uint32_t wmax = __reduce_max_sync(FULL, key);
+            const unsigned bal = __ballot_sync(FULL, key == wmax);
+            if (wmax != 0u && lane_id() == __ffs(bal) - 1) {
+                const unsigned long long word = ((unsigned long long)key << 32) |
+                                                (unsigned long long)(0xFFFFFFFFu - (uint32_t)a);
+                atomicMax(&best[g], word);
+            }
+        }
+        if (valid) {
+            long long m = best_g;
+            if (best_v < unmatched_thr) m = SSD_NOT_MATCHED;
+            else if (best_v < matched_thr) m = SSD_IGNORE;
+            box_idx[a] = m;
+        }
+    }
+    __syncthreads();
+    if (force_match && threadIdx.x == 0) {
+        // sequential, last writer wins -- G is small on this API path
+        for (int g = 0; g < G; ++g) {
+            const int a = (int)(0xFFFFFFFFu - (uint32_t)(best[g] & 0xFFFFFFFFull));
+            box_idx[a] = g;
+        }
+    }
+}
+
+static unsigned long long* g_match_scratch = nullptr;
+static int g_match_scratch_cap = 0;
+
+}  // namespace ssd
+
+using namespace ssd;
+
+extern "C" int ssd_pairwise_iou(const float* a_corners, int num_a, const float* b_corners, int num_b, float* out,
+                                void* stream) {
+    SSD_REQUIRE(num_a >= 0 && num_b >= 0, SSD_ERR_INVALID_ARGUMENT, "ssd_pairwise_iou: negative size");
+    if (num_a == 0 || num_b == 0) return SSD_OK;
+    SSD_REQUIRE(a_corners && b_corners && out, SSD_ERR_INVALID_ARGUMENT, "ssd_pairwise_iou: null pointer");
+    SSD_REQUIRE(aligned(a_corners, 16) && aligned(b_corners, 16), SSD_ERR_MISALIGNED,
+                "ssd_pairwise_iou: boxes must be 16-byte aligned");
+    SSD_REQUIRE(num_a <= 65535, SSD_ERR_UNSUPPORTED, "ssd_pairwise_iou: more than 65535 rows");
+    dim3 grid((num_b + 255) / 256, num_a);
+    pairwise_iou_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)a_corners, num_a,
+                                                                  (const float4*)b_corners, num_b, out);
+    SSD_CUDA(cudaGetLastError());
+    return SSD_OK;
+}
+
+extern "C" int ssd_match_per_prediction(const float* weights, int num_gt, int num_anchors, float matched_threshold,
+                                        float unmatched_threshold, int force_match, int64_t* box_idx_out,
+                                        void* stream) {
+    SSD_REQUIRE(num_gt >= 1 && num_anchors >= 1, SSD_ERR_INVALID_ARGUMENT,
+                "ssd_match_per_prediction: needs at least one box and one anchor");
+    SSD_REQUIRE(weights && box_idx_out, SSD_ERR_INVALID_ARGUMENT, "ssd_match_per_prediction: null pointer");
+    SSD_REQUIRE(num_gt <= kMaxGtPerImage, SSD_ERR_UNSUPPORTED, "ssd_match_per_prediction: more than %d boxes",
+                kMaxGtPerImage);
+    // small persistent scratch for the per-GT winners (API convenience path, not the batch path)
+    if (g_match_scratch_cap < kMaxGtPerImage) {
+        SSD_CUDA(cudaMalloc(&g_match_scratch, sizeof(unsigned long long) * kMaxGtPerImage));
+        g_match_scratch_cap = kMaxGtPerImage;
+    }
+    match_per_prediction_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(weights, num_gt, num_anchors, matched_threshold,
+                                                                       unmatched_threshold, force_match,
+                                                                       (long long*)box_idx_out, g_match_scratch);
+    SSD_CUDA(cudaGetLastError());
+    return SSD_OK;
+}
+
+extern "C" int ssd_assign_targets(const float* anchors, const float* gt_rows, int gt_cols, const int32_t* gt_offsets,
+                                  int max_gt, int batch, int num_anchors, float matched_threshold,
+                                  float unmatched_threshold, int force_match, float* target_out, int32_t* match_out,
+                                  int32_t* stats_out, void* stream) {
+    SSD_REQUIRE(batch >= 0 && num_anchors >= 0 && max_gt >= 0, SSD_ERR_INVALID_ARGUMENT,
+                "ssd_assign_targets: negative shape");
+    if (batch == 0 || num_anchors == 0) return SSD_OK;
+    SSD_REQUIRE(anchors && gt_offsets && target_out, SSD_ERR_INVALID_ARGUMENT, "ssd_assign_targets: null pointer");
+    SSD_REQUIRE(gt_rows || max_gt == 0, SSD_ERR_INVALID_ARGUMENT, "ssd_assign_targets: gt_rows is null");
+    SSD_REQUIRE(gt_cols >= 6, SSD_ERR_INVALID_ARGUMENT, "ssd_assign_targets: gt rows need >= 6 columns, got %d", gt_cols);
+    SSD_REQUIRE(matched_threshold >= unmatched_threshold, SSD_ERR_INVALID_ARGUMENT,
+                "ssd_assign_targets: matched_threshold < unmatched_threshold");
+    SSD_REQUIRE(max_gt <= kMaxGtPerImage, SSD_ERR_UNSUPPORTED, "ssd_assign_targets: more than %d boxes per image",
+                kMaxGtPerImage);
+    SSD_REQUIRE(aligned(anchors, 16), SSD_ERR_MISALIGNED, "ssd_assign_targets: anchors not 16-byte aligned");
+    SSD_REQUIRE(aligned(target_out, 8), SSD_ERR_MISALIGNED, "ssd_assign_targets: target not 8-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (stats_out) SSD_CUDA(cudaMemsetAsync(stats_out, 0, sizeof(int32_t) * 4 * batch, st));
+
+    // cluster size: enough CTAs to cover the GPU about twice, at most 8 (portable limit)
+    int cl = 1;
+    const int want = (2 * sm_count() + batch - 1) / batch;
+    while (cl < 8 && cl < want) cl <<= 1;
+    while (cl > 1 && (num_anchors + cl - 1) / cl < kAssignThreads) cl >>= 1;
+    const int chunk = (num_anchors + cl - 1) / cl;
+    const int gcap = max_gt > 0 ? max_gt : 1;
+    const size_t smem = (size_t)gcap * (sizeof(float4) + 2 * sizeof(unsigned long long) + sizeof(float2) + sizeof(float)) +
+                        (size_t)chunk * sizeof(int);
+    SSD_REQUIRE(smem <= 220 * 1024, SSD_ERR_UNSUPPORTED,
+                "ssd_assign_targets: %zu bytes of shared memory needed (anchors per CTA %d, boxes %d)", smem, chunk,
+                max_gt);
+    SSD_CUDA(cudaFuncSetAttribute(assign_targets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(batch * cl));
+    cfg.blockDim = dim3(kAssignThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SSD_CUDA(cudaLaunchKernelEx(&cfg, assign_targets_kernel, (const float4*)anchors, gt_rows, gt_cols, gt_offsets,
+                                num_anchors, chunk, matched_threshold, unmatched_threshold, force_match, target_out,
+                                match_out, stats_out));
+    return SSD_OK;
+}

@@ -1,0 +1,173 @@
+// Shared device/host helpers for the sm_100a anchor-pipeline kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/ssd_b200.h"
+
+namespace ssd {
+
+// ---------------------------------------------------------------------------------------------
+// host-side error plumbing
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define SSD_REQUIRE(cond, code, ...)            \
+    do {                                        \
+        if (!(cond)) {                          \
+            ::ssd::set_error(__VA_ARGS__);      \
+            return (code);                      \
+        }                                       \
+    } while (0)
+
+#define SSD_CUDA(call)                                              \
+    do {                                                            \
+        cudaError_t e__ = (call);                                   \
+        if (e__ != cudaSuccess) return ::ssd::cuda_fail(e__, #call); \
+    } while (0)
+
+inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+__host__ __device__ inline size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+int sm_count();
+
+// ---------------------------------------------------------------------------------------------
+// exact fp32 arithmetic: every op separately rounded (the file is also compiled with -fmad=false)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+
+// Monotone map float -> uint32 (a < b  <=>  key(a) < key(b) for non-NaN), NaN -> top.
+// Keys of real values lie in [0x007FFFFF (-inf), 0xFF800000 (+inf)].
+__device__ __forceinline__ uint32_t ordered_key(float v) {
+    uint32_t u = __float_as_uint(v);
+    if (v != v) return 0xFFFFFFFEu;
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_to_float(uint32_t k) {
+    uint32_t u = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+    return __uint_as_float(u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// warp helpers
+// ---------------------------------------------------------------------------------------------
+constexpr unsigned FULL = 0xFFFFFFFFu;
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+
+template <int WIDTH>
+__device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+    for (int o = WIDTH / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+template <int WIDTH>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = WIDTH / 2; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA bulk copy (cp.async.bulk, 1-D) + mbarrier: global -> shared staging for the logit streams
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// L2 eviction policies for the bulk copies
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+// bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                         uint64_t* bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// RowStream: a CTA walks a list of row tiles of a flat fp32 [rows, C] array.  Each tile is
+// fetched with one bulk copy of the 16-byte aligned superset of its bytes into a ring of
+// STAGES shared-memory buffers; `head` floats of slack precede the tile inside the buffer.
+// ---------------------------------------------------------------------------------------------
+struct TileDesc {
+    int64_t first_row;   // global row index (image * A + anchor)
+    int rows;            // rows in the tile (> 0)
+};
+
+template <int STAGES>
+struct RowStream {
+    float* buf[STAGES];
+    uint64_t* full;          // [STAGES] mbarriers
+    int stage_floats;
+
+    // Called by ONE thread.  Copies rows [first_row, first_row+rows) x C floats into stage s.
+    // total_floats = number of floats in the whole array (the copy never reads past it).
+    // Returns nothing; consumers call head_of() to find the first float of the tile.
+    __device__ __forceinline__ void issue(int s, const float* __restrict__ base, int64_t first_row, int rows,
+                                          int C, int64_t total_floats, uint64_t policy) {
+        const int64_t f0 = first_row * C;
+        const int64_t f1 = f0 + (int64_t)rows * C;
+        const int64_t fa = f0 & ~int64_t(3);
+        int64_t fe = (f1 + 3) & ~int64_t(3);
+        const int64_t n4 = total_floats & ~int64_t(3);
+        if (fe > n4) fe = n4 > fa ? n4 : fa;
+        const uint32_t bytes = (uint32_t)((fe - fa) * 4);
+        float* dst = buf[s];
+        // ragged tail of the very last tile of the array: at most 3 floats, plain loads
+        for (int64_t f = fe; f < f1; ++f) dst[f - fa] = __ldg(base + f);
+        if (bytes) {
+            mbar_expect_tx(&full[s], bytes);
+            bulk_g2s(dst, base + fa, bytes, &full[s], policy);
+        } else {
+            mbar_arrive(&full[s]);
+        }
+    }
+    __device__ __forceinline__ static int head_of(int64_t first_row, int C) {
+        return (int)((first_row * C) & 3);
+    }
+};
+
+}  // namespace ssd

@@ -1,0 +1,1029 @@
+// Post-processor: detection/postprocessor.py:24-78 (score conversion, decode, per-class
+// threshold -> top-k -> NMS, final top-k) with bf/utils/box_utils.py:165-194 (top-k + hard NMS,
+// torchvision.ops.nms semantics) -- batched over images x classes, five launches, no host sync.
+//
+// The reference walks B x (C-1) Python iterations, each gathering a score COLUMN out of the
+// class-fastest [B, A, C] layout.  Here the logits are only ever streamed row-major:
+//
+//  1. score_pass1   streams logits (TMA bulk -> smem ring).  Per row: max, sum exp (SOFTMAX) ->
+//                   rowstat[b,a] = (max, sum).  Per element a monotone "gate" value g (log-prob
+//                   for SOFTMAX, the raw value for SIGMOID / IDENTITY).  Each warp keeps the
+//                   running column maxima of the rows it sees and writes one vector per ROW BLOCK
+//                   (~32 rows): blockmax[b, blk, c].
+//  2. class_gate    one warp per (image, class): the K-th largest block maximum is a guaranteed
+//                   lower bound of the K-th largest score of that class (K different rows reach
+//                   it), and for i.i.d. scores only ~1.2 K elements exceed it.  gate[b,c] =
+//                   max(score-threshold gate, that bound - slack).
+//  3. score_pass2   streams the logits again (L2-resident for the SSD300-sized configs) with
+//                   rowstat, recomputes g bit-identically and appends (anchor, raw value) of the
+//                   few survivors g > gate[b,c] to a per-(image,class) candidate list.
+//  4. segment_nms   one CTA per (image, class): exact score for each candidate (same fp32 ops as
+//                   the reference: exp(x-max)/sum, 1/(1+exp(-x))), exact `score > threshold`,
+//                   sort by (score desc, anchor asc), keep K, decode + to_corners only those
+//                   boxes, IoU bit-matrix by warp ballot, sequential sweep -> kept rows.
+//  5. image_topk    one CTA per image: class-major concatenation, or -- when more than T rows
+//                   survive -- radix-select the T best and sort them descending.
+//
+// Exactness: steps 1-3 only PRUNE; every element whose exact score could rank in the top K of
+// its class passes the gate (the slack is orders of magnitude above the fp32 error of g).  The
+// exact scores, the exact threshold compare, the ordering and the NMS overlap test are evaluated
+// in step 4 with separately rounded fp32 ops in the reference's order; the NMS overlap compare
+// is float-vs-double as in torchvision's CPU kernel.
+#include <float.h>
+#include <math.h>
+
+#include "rowstream.cuh"
+
+namespace ssd {
+
+// ---------------------------------------------------------------------------------------------
+// plan: shapes, tiling and workspace layout (host)
+// ---------------------------------------------------------------------------------------------
+struct PostPlan {
+    int B, A, C, Cf, first_fg, K, T, det_cap, converter, box_input;
+    int warps;               // warps per streaming CTA
+    int tile_rows;           // rows per staged tile
+    int stage_floats;
+    size_t stream_smem;
+    int tiles_per_image;
+    int group_tiles;         // tiles whose rows form one row block per warp
+    int groups_per_image;
+    int num_items;           // B * groups_per_image (work items of the streaming kernels)
+    int split;               // row slots of a warp step kept as separate blocks (1..32/Q)
+    int nblk;                // row blocks per image = groups_per_image * warps * split
+    int cand_cap;            // candidate slots per (image, class)
+    // workspace offsets (bytes)
+    size_t off_rowstat, off_blockmax, off_gate, off_cand_count, off_cand, off_kept_count, off_kept, off_status,
+        off_anchor_tmp;
+    size_t total_bytes;
+};
+
+constexpr int kKeptCols = 6;          // x1,y1,x2,y2,score,anchor(bits)
+constexpr int kMaxPerClass = 512;
+constexpr int kNmsThreads = 128;
+constexpr int kTopkThreads = 512;
+
+template <int Q>
+static int rows_quantum() { return (kStreamThreads / 32) * (32 / Q); }
+
+static int quantum_for_cols(int C) {
+    int q = 0;
+#define SSD_Q(QQ, NN) q = rows_quantum<QQ>()
+    SSD_DISPATCH_ROW_SHAPE(C, SSD_Q);
+#undef SSD_Q
+    return q;
+}
+
+static int make_plan(const ssd_postprocess_params* p, PostPlan& pl) {
+    SSD_REQUIRE(p != nullptr, SSD_ERR_INVALID_ARGUMENT, "ssd_postprocess: null params");
+    SSD_REQUIRE(p->batch >= 0 && p->num_anchors >= 0, SSD_ERR_INVALID_ARGUMENT, "ssd_postprocess: negative shape");
+    SSD_REQUIRE(p->num_cols >= 1 && p->num_cols <= kMaxScoreCols, SSD_ERR_UNSUPPORTED,
+                "ssd_postprocess: num_cols %d outside 1..%d", p->num_cols, kMaxScoreCols);
+    SSD_REQUIRE(p->converter >= SSD_CONVERT_SOFTMAX && p->converter <= SSD_CONVERT_IDENTITY, SSD_ERR_INVALID_ARGUMENT,
+                "Wrong value for score_converter: %d", p->converter);
+    SSD_REQUIRE(p->first_fg_col >= 0 && p->first_fg_col < p->num_cols, SSD_ERR_INVALID_ARGUMENT,
+                "ssd_postprocess: first_fg_col %d outside the %d score columns", p->first_fg_col, p->num_cols);
+    SSD_REQUIRE(p->box_input == SSD_BOXES_ENCODED || p->box_input == SSD_BOXES_CORNERS, SSD_ERR_INVALID_ARGUMENT,
+                "ssd_postprocess: bad box_input %d", p->box_input);
+    SSD_REQUIRE(p->max_per_class >= 1 && p->max_per_class <= kMaxPerClass, SSD_ERR_UNSUPPORTED,
+                "ssd_postprocess: max_per_class %d outside 1..%d", p->max_per_class, kMaxPerClass);
+    pl.B = p->batch; pl.A = p->num_anchors; pl.C = p->num_cols; pl.first_fg = p->first_fg_col;
+    pl.Cf = pl.C - pl.first_fg; pl.K = p->max_per_class; pl.T = p->max_total; pl.det_cap = p->det_capacity;
+    pl.converter = p->converter; pl.box_input = p->box_input;
+    const long long all_rows = (long long)pl.Cf * pl.K;
+    const long long need = (pl.T > 0 && pl.T < all_rows) ? pl.T : all_rows;
+    SSD_REQUIRE(pl.det_cap >= need, SSD_ERR_INVALID_ARGUMENT,
+                "ssd_postprocess: det_capacity %d below the %lld rows an image can produce", pl.det_cap, need);
+    SSD_REQUIRE(all_rows <= 26000, SSD_ERR_UNSUPPORTED, "ssd_postprocess: classes*max_per_class = %lld > 26000", all_rows);
+
+    pl.warps = kStreamThreads / 32;
+    const int quantum = quantum_for_cols(pl.C);
+    int rows = (24 * 1024) / (pl.C * 4);
+    rows = rows / quantum * quantum;
+    if (rows > 32 * pl.warps) rows = 32 * pl.warps / quantum * quantum;
+    if (rows < quantum) rows = quantum;
+    pl.tile_rows = rows;
+    pl.stage_floats = (int)round_up((size_t)rows * pl.C + 8, 4);
+    pl.stream_smem = 128 + (size_t)kStreamStages * pl.stage_floats * 4;
+    const int A1 = pl.A > 0 ? pl.A : 1;
+    pl.tiles_per_image = (A1 + rows - 1) / rows;
+    // rows per block: ~32, smaller when the image has few anchors so that blocks >= ~2K exist
+    int want_rows = A1 / (2 * pl.K);
+    if (want_rows > 32) want_rows = 32;
+    const int rows_per_warp_tile = rows / pl.warps;
+    int gt = want_rows / rows_per_warp_tile;
+    if (gt < 1) gt = 1;
+    pl.group_tiles = gt;
+    pl.groups_per_image = (pl.tiles_per_image + gt - 1) / gt;
+    pl.num_items = pl.B * pl.groups_per_image;
+    // fewer rows per block than a warp sees in one tile: keep `split` row slots separate
+    int split = 1;
+    const int slots = quantum / pl.warps;                 // 32 / Q row slots per warp step
+    while (split < slots && rows_per_warp_tile * gt / split > (want_rows > 0 ? want_rows : 1)) split <<= 1;
+    pl.split = split;
+    pl.nblk = pl.groups_per_image * pl.warps * split;
+    int cap = 512;                        // power of two (the segment sort pads to one), >= 8K
+    while (cap < 8 * pl.K && cap < 4096) cap <<= 1;
+    pl.cand_cap = cap;
+
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += round_up(bytes, 256); return o; };
+    const size_t BA = (size_t)pl.B * A1;
+    pl.off_rowstat = take(BA * sizeof(float2));
+    pl.off_blockmax = take((size_t)pl.B * pl.nblk * pl.C * sizeof(float));
+    pl.off_gate = take((size_t)pl.B * pl.C * sizeof(float));
+    pl.off_cand_count = take((size_t)pl.B * pl.Cf * sizeof(int));
+    pl.off_cand = take((size_t)pl.B * pl.Cf * pl.cand_cap * sizeof(uint2));
+    pl.off_kept_count = take((size_t)pl.B * pl.Cf * sizeof(int));
+    pl.off_kept = take((size_t)pl.B * pl.Cf * pl.K * kKeptCols * sizeof(float));
+    pl.off_status = take(4 * sizeof(int));
+    pl.off_anchor_tmp = take((size_t)pl.B * (pl.det_cap > 0 ? pl.det_cap : 1) * sizeof(int));
+    pl.total_bytes = off;
+    return SSD_OK;
+}
+
+// device-side view of the tiling
+struct ScoreGrid {
+    int A, C, first_fg;
+    int tile_rows, stage_floats, tiles_per_image, group_tiles, groups_per_image, num_items, nblk, split;
+    int64_t total_floats;
+};
+
+// Enumerates the tiles of the work items a CTA owns: item = blockIdx.x + n*gridDim.x.
+struct TileCursor {
+    int item, tile, tile_end;
+    __device__ __forceinline__ void start(const ScoreGrid& g) {
+        item = blockIdx.x;
+        open(g);
+    }
+    __device__ __forceinline__ void open(const ScoreGrid& g) {
+        if (item < g.num_items) {
+            const int grp = item % g.groups_per_image;
+            tile = grp * g.group_tiles;
+            tile_end = min(tile + g.group_tiles, g.tiles_per_image);
+        }
+    }
+    __device__ __forceinline__ bool valid(const ScoreGrid& g) const { return item < g.num_items; }
+    __device__ __forceinline__ int image(const ScoreGrid& g) const { return item / g.groups_per_image; }
+    __device__ __forceinline__ int group(const ScoreGrid& g) const { return item % g.groups_per_image; }
+    __device__ __forceinline__ bool last_of_item() const { return tile + 1 == tile_end; }
+    __device__ __forceinline__ void next(const ScoreGrid& g) {
+        if (++tile == tile_end) {
+            item += gridDim.x;
+            open(g);
+        }
+    }
+    __device__ __forceinline__ int rows(const ScoreGrid& g) const { return min(g.tile_rows, g.A - tile * g.tile_rows); }
+    __device__ __forceinline__ int64_t first_row(const ScoreGrid& g) const {
+        return (int64_t)image(g) * g.A + (int64_t)tile * g.tile_rows;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// 1. score_pass1
+// ---------------------------------------------------------------------------------------------
+template <int Q, int NREG, int CONV>
+__global__ void __launch_bounds__(kStreamThreads)
+score_pass1_kernel(const float* __restrict__ scores, ScoreGrid g, float2* __restrict__ rowstat,
+                   float* __restrict__ blockmax) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    RowStream<kStreamStages> rs;
+    stream_setup(rs, smem, g.stage_floats);
+    const RowLanes<Q> ln;
+    const int warps = blockDim.x >> 5;
+    const int rows_per_warp = g.tile_rows / warps;
+    const uint64_t policy = policy_evict_last();       // pass 2 re-reads the same bytes
+
+    TileCursor prod, cons;
+    prod.start(g);
+    cons.start(g);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStreamStages && prod.valid(g); ++s) {
+            rs.issue(s, scores, prod.first_row(g), prod.rows(g), g.C, g.total_floats, policy);
+            prod.next(g);
+        }
+    }
+    float cmax[NREG];
+#pragma unroll
+    for (int i = 0; i < NREG; ++i) cmax[i] = -INFINITY;
+
+    for (int k = 0; cons.valid(g); ++k) {
+        const int s = k % kStreamStages;
+        const uint32_t parity = (k / kStreamStages) & 1;
+        const int64_t r0 = cons.first_row(g);
+        const int rows = cons.rows(g);
+        mbar_wait(&rs.full[s], parity);
+        const float* tile = rs.buf[s] + RowStream<kStreamStages>::head_of(r0, g.C);
+
+        const int wbase = warp_id() * rows_per_warp;
+        for (int step = 0; step < rows_per_warp; step += RowLanes<Q>::kRowsPerWarpStep) {
+            const int lr = wbase + step + ln.rl;
+            const bool valid = lr < rows;
+            if (__all_sync(FULL, !valid)) break;
+            float v[NREG];
+            load_row_slice<Q, NREG>(v, tile + (size_t)lr * g.C, ln.sub, g.C, valid, -INFINITY);
+            if (CONV == SSD_CONVERT_SOFTMAX) {
+                float m = v[0];
+#pragma unroll
+                for (int i = 1; i < NREG; ++i) m = fmaxf(m, v[i]);
+                m = group_max<Q>(m);
+                float sum = 0.f;
+#pragma unroll
+                for (int i = 0; i < NREG; ++i) {
+                    const int col = ln.sub + i * Q;
+                    if (col < g.C) sum = __fadd_rn(sum, expf(__fsub_rn(v[i], m)));
+                }
+                sum = group_sum<Q>(sum);
+                const float ls = logf(sum);
+                if (valid && ln.sub == 0) rowstat[r0 + lr] = make_float2(m, sum);
+#pragma unroll
+                for (int i = 0; i < NREG; ++i) {
+                    const int col = ln.sub + i * Q;
+                    const float gv = __fsub_rn(__fsub_rn(v[i], m), ls);
+                    if (valid && col < g.C && col >= g.first_fg) cmax[i] = fmaxf(cmax[i], gv);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < NREG; ++i) {
+                    const int col = ln.sub + i * Q;
+                    if (valid && col < g.C && col >= g.first_fg) cmax[i] = fmaxf(cmax[i], v[i]);
+                }
+            }
+        }
+        const bool flush = cons.last_of_item();
+        if (flush) {
+            // merge the row slots of the warp, then one vector per (block, warp)
+#pragma unroll
+            for (int i = 0; i < NREG; ++i) {
+                float x = cmax[i];
+#pragma unroll
+                for (int o = Q; o < 32; o <<= 1)
+                    if (o >= Q * g.split) x = fmaxf(x, __shfl_xor_sync(FULL, x, o));
+                cmax[i] = x;
+            }
+            if (ln.rl < g.split) {
+                float* dst = blockmax + ((size_t)cons.image(g) * g.nblk +
+                                         ((size_t)cons.group(g) * warps + warp_id()) * g.split + ln.rl) * g.C;
+#pragma unroll
+                for (int i = 0; i < NREG; ++i) {
+                    const int col = ln.sub + i * Q;
+                    if (col < g.C) dst[col] = cmax[i];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NREG; ++i) cmax[i] = -INFINITY;
+        }
+        cons.next(g);
+        __syncthreads();
+        if (threadIdx.x == 0 && prod.valid(g)) {
+            rs.issue(s, scores, prod.first_row(g), prod.rows(g), g.C, g.total_floats, policy);
+            prod.next(g);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2. class_gate: one warp per (image, column)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float next_below(float x) {
+    // largest float < x for finite x
+    if (x == 0.f) return -FLT_MIN * FLT_EPSILON;     // -denorm_min
+    uint32_t u = __float_as_uint(x);
+    u = (x > 0.f) ? u - 1 : u + 1;
+    return __uint_as_float(u);
+}
+
+__global__ void __launch_bounds__(256)
+class_gate_kernel(const float* __restrict__ blockmax, int B, int C, int first_fg, int nblk, int K, int converter,
+                  float score_thr, float* __restrict__ gate, int* __restrict__ cand_count, int* __restrict__ status) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (blockIdx.x == 0 && threadIdx.x < 4 && status != nullptr) status[threadIdx.x] = 0;
+    if (w >= B * C) return;
+    const int b = w / C, col = w % C;
+    const int lane = lane_id();
+    if (col < first_fg) {
+        if (lane == 0) gate[w] = INFINITY;
+        return;
+    }
+    // K-th largest block maximum of this column, by MSB-first bisection on ordered keys
+    const float* src = blockmax + (size_t)b * nblk * C + col;
+    float kth = -INFINITY;
+    if (nblk >= K) {
+        uint32_t prefix = 0;
+        int rem = K;
+        for (int bit = 31; bit >= 0; --bit) {
+            const uint32_t trial = prefix | (1u << bit);
+            int cnt = 0;
+            for (int i = lane; i < nblk; i += 32) {
+                const uint32_t key = ordered_key(src[(size_t)i * C]);
+                cnt += ((key >> bit) == (trial >> bit));
+            }
+            cnt = __reduce_add_sync(FULL, cnt);
+            if (cnt >= rem) prefix = trial; else rem -= cnt;
+        }
+        kth = key_to_float(prefix);
+    }
+    float g;
+    if (converter == SSD_CONVERT_SOFTMAX) {
+        // gate domain = log-probability; 1e-4 of slack is ~100x the fp32 error of the gate value
+        const float gthr = score_thr > 0.f ? logf(score_thr) - 1e-4f : -INFINITY;
+        g = fmaxf(gthr, kth - 1e-4f);
+    } else if (converter == SSD_CONVERT_SIGMOID) {
+        // gate domain = logit.  Slack of 1e-4 RELATIVE IN PROBABILITY, evaluated in double so that
+        // saturated scores (p == 1.0f for many logits) all stay candidates.
+        float gthr;
+        if (score_thr <= 0.f) gthr = -INFINITY;
+        else if (score_thr >= 1.f) gthr = INFINITY;
+        else {
+            const double t = (double)score_thr * (1.0 - 1e-4);
+            gthr = (float)(log(t / (1.0 - t))) - 1e-5f;
+        }
+        float gk = -INFINITY;
+        if (kth > -INFINITY) {
+            const double pk = 1.0 / (1.0 + exp(-(double)kth));
+            const double pt = pk * (1.0 - 1e-4);
+            const double x = log(pt / (1.0 - pt));
+            gk = (float)x - 1e-5f * (1.f + fabsf((float)x));
+            if (gk > kth) gk = kth - 1e-4f;
+        }
+        g = fmaxf(gthr, gk);
+    } else {
+        // probabilities given: exact.  Candidates need score > thr and, once K blocks reach kth,
+        // score >= kth.
+        g = score_thr;
+        if (kth > score_thr) g = next_below(kth);
+    }
+    if (lane == 0) {
+        gate[w] = g;
+        cand_count[b * (C - first_fg) + (col - first_fg)] = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3. score_pass2: emit candidates
+// ---------------------------------------------------------------------------------------------
+template <int Q, int NREG, int CONV>
+__global__ void __launch_bounds__(kStreamThreads)
+score_pass2_kernel(const float* __restrict__ scores, ScoreGrid g, const float2* __restrict__ rowstat,
+                   const float* __restrict__ gate, int* __restrict__ cand_count, uint2* __restrict__ cand, int cand_cap) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    RowStream<kStreamStages> rs;
+    stream_setup(rs, smem, g.stage_floats);
+    const RowLanes<Q> ln;
+    const int warps = blockDim.x >> 5;
+    const int rows_per_warp = g.tile_rows / warps;
+    const int Cf = g.C - g.first_fg;
+    const uint64_t policy = policy_evict_first();
+
+    TileCursor prod, cons;
+    prod.start(g);
+    cons.start(g);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStreamStages && prod.valid(g); ++s) {
+            rs.issue(s, scores, prod.first_row(g), prod.rows(g), g.C, g.total_floats, policy);
+            prod.next(g);
+        }
+    }
+    float gv[NREG];
+    int cur_image = -1;
+    for (int k = 0; cons.valid(g); ++k) {
+        const int s = k % kStreamStages;
+        const uint32_t parity = (k / kStreamStages) & 1;
+        const int64_t r0 = cons.first_row(g);
+        const int rows = cons.rows(g);
+        const int img = cons.image(g);
+        if (img != cur_image) {                 // per-lane slice of this image's gates
+            cur_image = img;
+#pragma unroll
+            for (int i = 0; i < NREG; ++i) {
+                const int col = ln.sub + i * Q;
+                gv[i] = (col < g.C) ? gate[(size_t)img * g.C + col] : INFINITY;
+            }
+        }
+        mbar_wait(&rs.full[s], parity);
+        const float* tile = rs.buf[s] + RowStream<kStreamStages>::head_of(r0, g.C);
+        const int a0 = cons.tile * g.tile_rows;
+
+        const int wbase = warp_id() * rows_per_warp;
+        for (int step = 0; step < rows_per_warp; step += RowLanes<Q>::kRowsPerWarpStep) {
+            const int lr = wbase + step + ln.rl;
+            const bool valid = lr < rows;
+            if (__all_sync(FULL, !valid)) break;
+            float v[NREG];
+            load_row_slice<Q, NREG>(v, tile + (size_t)lr * g.C, ln.sub, g.C, valid, -INFINITY);
+            float m = 0.f, ls = 0.f;
+            if (CONV == SSD_CONVERT_SOFTMAX) {
+                const float2 st = valid ? rowstat[r0 + lr] : make_float2(0.f, 1.f);
+                m = st.x;
+                ls = logf(st.y);
+            }
+#pragma unroll
+            for (int i = 0; i < NREG; ++i) {
+                float x = v[i];
+                if (CONV == SSD_CONVERT_SOFTMAX) x = __fsub_rn(__fsub_rn(x, m), ls);
+                if (valid && x > gv[i]) {
+                    const int col = ln.sub + i * Q;
+                    const int seg = img * Cf + (col - g.first_fg);
+                    const int slot = atomicAdd(&cand_count[seg], 1);
+                    if (slot < cand_cap)
+                        cand[(size_t)seg * cand_cap + slot] = make_uint2((uint32_t)(a0 + lr), __float_as_uint(v[i]));
+                }
+            }
+        }
+        cons.next(g);
+        __syncthreads();
+        if (threadIdx.x == 0 && prod.valid(g)) {
+            rs.issue(s, scores, prod.first_row(g), prod.rows(g), g.C, g.total_floats, policy);
+            prod.next(g);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// shared-memory bitonic sort of 64-bit keys, descending
+// ---------------------------------------------------------------------------------------------
+__device__ void bitonic_sort_desc(unsigned long long* keys, int n_pow2) {
+    for (int size = 2; size <= n_pow2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < (n_pow2 >> 1); t += blockDim.x) {
+                const int lo = 2 * t - (t & (stride - 1));
+                const int hi = lo + stride;
+                const bool desc = (lo & size) == 0;
+                const unsigned long long a = keys[lo], b = keys[hi];
+                if ((a < b) == desc) { keys[lo] = b; keys[hi] = a; }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// 4. segment_nms: one CTA per (image, foreground class)
+// ---------------------------------------------------------------------------------------------
+struct NmsArgs {
+    int A, C, Cf, first_fg, K, cand_cap, converter, box_input;
+    float score_thr, xy_scale, wh_scale;
+    double iou_thr;
+};
+
+__device__ __forceinline__ float exact_score(int converter, float x, float2 st) {
+    if (converter == SSD_CONVERT_SOFTMAX) return __fdiv_rn(expf(__fsub_rn(x, st.x)), st.y);   // exp(x-max)/sum
+    if (converter == SSD_CONVERT_SIGMOID) return __fdiv_rn(1.f, __fadd_rn(1.f, expf(-x)));     // 1/(1+exp(-x))
+    return x;
+}
+
+// Exact top-K of one score COLUMN, used when a candidate list overflowed (dense / heavily tied
+// scores).  Four strided sweeps over the column: three 11/11/10-bit histogram levels find the K-th
+// largest exact score key, the last sweep collects the winners (ties: lower anchor first).
+// Slow (strided 4-byte reads, exp + divide per element and sweep) but exact for any input.
+__device__ int exact_select_column(const NmsArgs& a, int img, int col, const float* __restrict__ scores,
+                                   const float2* __restrict__ rowstat, unsigned long long* keys_out,
+                                   uint32_t* hist, int* s_misc) {
+    const float* colp = scores + (size_t)img * a.A * a.C + col;
+    const float2* rs = rowstat + (size_t)img * a.A;
+    auto key_of = [&](int an) -> uint32_t {
+        float2 st = make_float2(0.f, 1.f);
+        if (a.converter == SSD_CONVERT_SOFTMAX) st = rs[an];
+        const float p = exact_score(a.converter, colp[(size_t)an * a.C], st);
+        return p > a.score_thr ? ordered_key(p) : 0u;
+    };
+    uint32_t prefix = 0u;
+    int rem = 0, k = 0;
+    for (int level = 0; level < 3; ++level) {
+        const int shift = level == 0 ? 21 : (level == 1 ? 10 : 0);
+        const int bins = level == 2 ? 1024 : 2048;
+        for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = 0u;
+        if (threadIdx.x == 0) s_misc[0] = 0;
+        __syncthreads();
+        int valid = 0;
+        for (int an = threadIdx.x; an < a.A; an += blockDim.x) {
+            const uint32_t key = key_of(an);
+            if (key == 0u) continue;
+            valid++;
+            const bool match = level == 0 || (level == 1 ? (key >> 21) == (prefix >> 21) : (key >> 10) == (prefix >> 10));
+            if (match) atomicAdd(&hist[(key >> shift) & (uint32_t)(bins - 1)], 1u);
+        }
+        if (level == 0) {
+            valid = __reduce_add_sync(FULL, valid);
+            if (lane_id() == 0 && valid) atomicAdd(&s_misc[0], valid);
+        }
+        __syncthreads();
+        if (level == 0) {
+            k = min(s_misc[0], a.K);
+            rem = k;
+            if (k == 0) return 0;
+        }
+        if (threadIdx.x == 0) {
+            int r = rem, b = bins - 1;
+            for (; b > 0; --b) {
+                if (r <= (int)hist[b]) break;
+                r -= (int)hist[b];
+            }
+            s_misc[1] = b;
+            s_misc[2] = r;
+            s_misc[3] = (int)hist[b];
+        }
+        __syncthreads();
+        prefix |= (uint32_t)s_misc[1] << shift;
+        rem = s_misc[2];
+        __syncthreads();
+    }
+    const uint32_t thr_key = prefix;
+    const int need_ties = rem;               // 1 <= need_ties <= number of keys == thr_key
+    // collection sweep, anchor order = (round, thread) so that ties go to the lower anchor
+    if (threadIdx.x == 0) { s_misc[0] = 0; s_misc[1] = 0; }     // [0] = slots used, [1] = ties seen so far
+    __syncthreads();
+    int* wcount = s_misc + 4;                                    // [nwarps]
+    const int nw = blockDim.x >> 5;
+    for (int base = 0; base < a.A; base += blockDim.x) {
+        const int an = base + threadIdx.x;
+        const uint32_t key = an < a.A ? key_of(an) : 0u;
+        const bool tie = key == thr_key && key != 0u;
+        const unsigned bal = __ballot_sync(FULL, tie);
+        if (lane_id() == 0) wcount[warp_id()] = __popc(bal);
+        __syncthreads();
+        int before = s_misc[1], total = 0;
+        for (int w = 0; w < nw; ++w) {
+            if (w < warp_id()) before += wcount[w];
+            total += wcount[w];
+        }
+        const int rank = before + __popc(bal & ((1u << lane_id()) - 1u));
+        if (key > thr_key || (tie && rank < need_ties)) {
+            const int slot = atomicAdd(&s_misc[0], 1);
+            keys_out[slot] = ((unsigned long long)key << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)an);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_misc[1] += total;
+        __syncthreads();
+    }
+    return k;
+}
+
+__global__ void __launch_bounds__(kNmsThreads)
+segment_nms_kernel(NmsArgs a, const float* __restrict__ scores, const float2* __restrict__ rowstat,
+                   const int* __restrict__ cand_count, const uint2* __restrict__ cand,
+                   const float4* __restrict__ boxes, const float4* __restrict__ priors, int* __restrict__ kept_count,
+                   float* __restrict__ kept, int* __restrict__ status) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint32_t s_hist[2048];
+    __shared__ int s_misc[4 + kNmsThreads / 32];
+    __shared__ int s_valid, s_nkeep;
+    const int seg = blockIdx.x;
+    const int img = seg / a.Cf;
+    int n_raw = cand_count[seg];
+    if (n_raw == 0) {
+        if (threadIdx.x == 0) kept_count[seg] = 0;
+        return;
+    }
+    // carve: keys[n2] u64 | box[K] float4 | area[K] | mask[K * words] | keep[K]
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem);
+    const bool overflow = n_raw > a.cand_cap;
+    int n2 = 32;
+    if (overflow) {
+        // the candidate list is incomplete: redo this (image, class) exactly from the score column
+        if (threadIdx.x == 0 && status != nullptr) atomicAdd(&status[1], 1);
+        n_raw = exact_select_column(a, img, a.first_fg + (seg - img * a.Cf), scores, rowstat, keys, s_hist, s_misc);
+        if (n_raw == 0) {
+            if (threadIdx.x == 0) kept_count[seg] = 0;
+            return;
+        }
+    }
+    while (n2 < n_raw) n2 <<= 1;
+    float4* sbox = reinterpret_cast<float4*>(keys + n2);
+    float* sarea = reinterpret_cast<float*>(sbox + a.K);
+    uint32_t* mask = reinterpret_cast<uint32_t*>(sarea + a.K);
+    if (threadIdx.x == 0) s_valid = overflow ? n_raw : 0;
+    __syncthreads();
+
+    int local_valid = 0;
+    for (int t = threadIdx.x; t < n2; t += blockDim.x) {
+        if (overflow) {
+            if (t >= n_raw) keys[t] = 0ull;
+            continue;
+        }
+        unsigned long long key = 0ull;
+        if (t < n_raw) {
+            const uint2 e = cand[(size_t)seg * a.cand_cap + t];
+            float2 st = make_float2(0.f, 1.f);
+            if (a.converter == SSD_CONVERT_SOFTMAX) st = rowstat[(size_t)img * a.A + e.x];
+            const float p = exact_score(a.converter, __uint_as_float(e.y), st);
+            if (p > a.score_thr) {                                   // postprocessor.py:62 (fp32 compare)
+                key = ((unsigned long long)ordered_key(p) << 32) | (unsigned long long)(0xFFFFFFFFu - e.x);
+                local_valid++;
+            }
+        }
+        keys[t] = key;
+    }
+    local_valid = __reduce_add_sync(FULL, local_valid);
+    if (lane_id() == 0 && local_valid) atomicAdd(&s_valid, local_valid);
+    bitonic_sort_desc(keys, n2);                 // (score desc, anchor asc); starts and ends with a barrier
+    const int n = min(s_valid, a.K);             // box_utils.py:186-188 top-k
+    if (n == 0) {
+        if (threadIdx.x == 0) kept_count[seg] = 0;
+        return;
+    }
+    const int words = (n + 31) >> 5;
+    int* keep = reinterpret_cast<int*>(mask + (size_t)a.K * ((a.K + 31) >> 5));
+
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const uint32_t anchor = 0xFFFFFFFFu - (uint32_t)(keys[t] & 0xFFFFFFFFull);
+        float4 bx = boxes[(size_t)img * a.A + anchor];
+        if (a.box_input == SSD_BOXES_ENCODED) {
+            const float4 p = priors[anchor];
+            // box_coder.py:55-57 then box_utils.py:23
+            const float cx = fadd(p.x, fdiv(fmul(p.z, bx.x), a.xy_scale));
+            const float cy = fadd(p.y, fdiv(fmul(p.w, bx.y), a.xy_scale));
+            const float w = fmul(p.z, expf(fdiv(bx.z, a.wh_scale)));
+            const float h = fmul(p.w, expf(fdiv(bx.w, a.wh_scale)));
+            const float hw = fmul(w, 0.5f), hh = fmul(h, 0.5f);
+            bx = make_float4(fsub(cx, hw), fsub(cy, hh), fadd(cx, hw), fadd(cy, hh));
+        }
+        sbox[t] = bx;
+        sarea[t] = fmul(fsub(bx.z, bx.x), fsub(bx.w, bx.y));          // torchvision: unclamped area
+    }
+    __syncthreads();
+
+    // IoU bit matrix: row i, word w covers boxes 32w..32w+31; only j > i matters
+    const int nwarps = blockDim.x >> 5;
+    for (int i = warp_id(); i < n; i += nwarps) {
+        const float4 bi = sbox[i];
+        const float ai = sarea[i];
+        for (int w = 0; w < words; ++w) {
+            uint32_t bits = 0u;
+            if (w >= (i >> 5)) {
+                const int j = (w << 5) + lane_id();
+                bool sup = false;
+                if (j > i && j < n) {
+                    const float4 bj = sbox[j];
+                    const float xx1 = fmaxf(bi.x, bj.x), yy1 = fmaxf(bi.y, bj.y);
+                    const float xx2 = fminf(bi.z, bj.z), yy2 = fminf(bi.w, bj.w);
+                    const float iw = fmaxf(0.f, fsub(xx2, xx1)), ih = fmaxf(0.f, fsub(yy2, yy1));
+                    const float inter = fmul(iw, ih);
+                    const float ovr = fdiv(inter, fsub(fadd(ai, sarea[j]), inter));
+                    sup = (double)ovr > a.iou_thr;                    // float-vs-double compare
+                }
+                bits = __ballot_sync(FULL, sup);
+            }
+            if (lane_id() == 0) mask[(size_t)i * words + w] = bits;
+        }
+    }
+    __syncthreads();
+
+    // greedy sweep in score order: lane l owns removed-word l
+    if (warp_id() == 0) {
+        uint32_t removed = 0u;
+        int nkeep = 0;
+        for (int i = 0; i < n; ++i) {
+            const uint32_t r = __shfl_sync(FULL, removed, i >> 5);
+            if (!((r >> (i & 31)) & 1u)) {
+                if (lane_id() < words) removed |= mask[(size_t)i * words + lane_id()];
+                if (lane_id() == 0) keep[nkeep] = i;
+                nkeep++;
+            }
+        }
+        if (lane_id() == 0) { s_nkeep = nkeep; kept_count[seg] = nkeep; }
+    }
+    __syncthreads();
+    const int nkeep = s_nkeep;
+    float* out = kept + (size_t)seg * a.K * kKeptCols;
+    for (int t = threadIdx.x; t < nkeep; t += blockDim.x) {
+        const int i = keep[t];
+        const unsigned long long key = keys[i];
+        const float4 bx = sbox[i];
+        float* o = out + (size_t)t * kKeptCols;
+        o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
+        o[4] = key_to_float((uint32_t)(key >> 32));
+        o[5] = __uint_as_float(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 5. image_topk: one CTA per image
+// ---------------------------------------------------------------------------------------------
+struct TopkShared {
+    int part[16][4];
+    int total[4];
+    unsigned long long wmin[16], wmax[16];
+    unsigned long long gmin, gmax;
+    int n_total, n_sel;
+};
+
+__device__ __forceinline__ void block_sum4_topk(TopkShared& sh, int (&c)[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[j] = __reduce_add_sync(FULL, c[j]);
+    if (lane_id() == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sh.part[warp_id()][j] = c[j];
+    }
+    __syncthreads();
+    if (warp_id() == 0) {
+        const int nw = blockDim.x >> 5;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int x = lane_id() < nw ? sh.part[lane_id()][j] : 0;
+            x = __reduce_add_sync(FULL, x);
+            if (lane_id() == 0) sh.total[j] = x;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[j] = sh.total[j];
+    __syncthreads();
+}
+
+__device__ __forceinline__ void write_det_row(float* dets, int* anchors, const float* kept, int K, int cls, int slot,
+                                              int out_row) {
+    const float* src = kept + ((size_t)cls * K + slot) * kKeptCols;
+    float* o = dets + (size_t)out_row * 6;
+    o[0] = src[0]; o[1] = src[1]; o[2] = src[2]; o[3] = src[3];
+    o[4] = (float)(cls + 1);                                           // postprocessor.py:66
+    o[5] = src[4];
+    if (anchors != nullptr) anchors[out_row] = (int)__float_as_uint(src[5]);
+}
+
+__global__ void __launch_bounds__(kTopkThreads)
+image_topk_kernel(int Cf, int K, int T, int det_cap, const int* __restrict__ kept_count, const float* __restrict__ kept,
+                  float* __restrict__ dets, int* __restrict__ det_count, int* __restrict__ det_anchor) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ TopkShared sh;
+    const int img = blockIdx.x;
+    int* offs = reinterpret_cast<int*>(smem);                              // [Cf + 1]
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem + round_up((size_t)(Cf + 1) * 4, 16));
+    const int* kc = kept_count + (size_t)img * Cf;
+    const float* kimg = kept + (size_t)img * Cf * K * kKeptCols;
+    float* dimg = dets + (size_t)img * det_cap * 6;
+    int* aimg = det_anchor ? det_anchor + (size_t)img * det_cap : nullptr;
+
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int c = 0; c < Cf; ++c) { offs[c] = acc; acc += kc[c]; }
+        offs[Cf] = acc;
+        sh.n_total = acc;
+        sh.n_sel = 0;
+    }
+    __syncthreads();
+    const int n = sh.n_total;
+
+    if (T <= 0 || n <= T) {
+        // class-major order, descending score inside a class            postprocessor.py:68-70
+        for (int c = warp_id(); c < Cf; c += (blockDim.x >> 5)) {
+            const int cnt = offs[c + 1] - offs[c];
+            for (int t = lane_id(); t < cnt; t += 32) write_det_row(dimg, aimg, kimg, K, c, t, offs[c] + t);
+        }
+        if (threadIdx.x == 0) det_count[img] = n;
+        return;
+    }
+
+    // keys = (score, ~position): unique, so exactly T of them are >= the T-th largest
+    for (int c = warp_id(); c < Cf; c += (blockDim.x >> 5)) {
+        const int cnt = offs[c + 1] - offs[c];
+        for (int t = lane_id(); t < cnt; t += 32) {
+            const float s = kimg[((size_t)c * K + t) * kKeptCols + 4];
+            const int pos = offs[c] + t;
+            keys[pos] = ((unsigned long long)ordered_key(s) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)pos);
+        }
+    }
+    __syncthreads();
+    unsigned long long lo = ~0ull, hi = 0ull;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { lo = min(lo, keys[i]); hi = max(hi, keys[i]); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(FULL, lo, o));
+        hi = max(hi, __shfl_xor_sync(FULL, hi, o));
+    }
+    if (lane_id() == 0) { sh.wmin[warp_id()] = lo; sh.wmax[warp_id()] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long l = ~0ull, h = 0ull;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) { l = min(l, sh.wmin[w]); h = max(h, sh.wmax[w]); }
+        sh.gmin = l; sh.gmax = h;
+    }
+    __syncthreads();
+    const unsigned long long diff = sh.gmin ^ sh.gmax;          // != 0: n > T >= 1 unique keys
+    const int hb = 63 - __clzll((long long)diff);
+    int shift = hb & ~1;
+    unsigned long long prefix = shift + 2 >= 64 ? 0ull : (sh.gmax >> (shift + 2)) << (shift + 2);
+    int rem = T;
+    unsigned long long thr_key = 0ull;       // select keys >= thr_key
+    for (; shift >= 0; shift -= 2) {
+        int d[4] = {0, 0, 0, 0};
+        const unsigned long long pre_hi = shift + 2 >= 64 ? 0ull : prefix >> (shift + 2);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const unsigned long long key = keys[i];
+            const unsigned long long khi = shift + 2 >= 64 ? 0ull : key >> (shift + 2);
+            if (khi == pre_hi) d[(int)((key >> shift) & 3ull)]++;
+        }
+        block_sum4_topk(sh, d);
+        int digit = 3;
+        for (; digit > 0; --digit) {
+            if (rem <= d[digit]) break;
+            rem -= d[digit];
+        }
+        prefix |= (unsigned long long)digit << shift;
+        thr_key = prefix;
+        if (rem == d[digit]) break;          // the whole bucket is needed: its lower edge is the cut
+    }
+    __syncthreads();
+    int t2 = 32;
+    while (t2 < T) t2 <<= 1;
+    unsigned long long* sel = keys + n;      // [t2]
+    for (int i = threadIdx.x; i < t2; i += blockDim.x) sel[i] = 0ull;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned long long key = keys[i];
+        if (key >= thr_key) {
+            const int slot = atomicAdd(&sh.n_sel, 1);
+            if (slot < t2) sel[slot] = key;
+        }
+    }
+    bitonic_sort_desc(sel, t2);
+    // sorted=True: descending score, ties by class-major position     postprocessor.py:72-74
+    for (int r = threadIdx.x; r < T; r += blockDim.x) {
+        const int pos = (int)(0xFFFFFFFFu - (uint32_t)(sel[r] & 0xFFFFFFFFull));
+        int c_lo = 0, c_hi = Cf;               // largest c with offs[c] <= pos
+        while (c_hi - c_lo > 1) {
+            const int mid = (c_lo + c_hi) >> 1;
+            if (offs[mid] <= pos) c_lo = mid; else c_hi = mid;
+        }
+        write_det_row(dimg, aimg, kimg, K, c_lo, pos - offs[c_lo], r);
+    }
+    if (threadIdx.x == 0) det_count[img] = T;
+}
+
+__global__ void widen_keep_kernel(const int* __restrict__ src, const int* __restrict__ count, long long* __restrict__ dst,
+                                  int cap) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cap && i < count[0]) dst[i] = src[i];
+}
+
+}  // namespace ssd
+
+using namespace ssd;
+
+extern "C" size_t ssd_postprocess_workspace_bytes(const ssd_postprocess_params* p) {
+    PostPlan pl;
+    if (make_plan(p, pl) != SSD_OK) return 0;
+    return pl.total_bytes;
+}
+
+static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, const float* scores,
+                           const float* boxes, const float* priors, float* dets_out, int32_t* count_out,
+                           int32_t* anchor_out, int32_t* status_out, unsigned char* ws, cudaStream_t st) {
+    float2* rowstat = (float2*)(ws + pl.off_rowstat);
+    float* blockmax = (float*)(ws + pl.off_blockmax);
+    float* gate = (float*)(ws + pl.off_gate);
+    int* cand_count = (int*)(ws + pl.off_cand_count);
+    uint2* cand = (uint2*)(ws + pl.off_cand);
+    int* kept_count = (int*)(ws + pl.off_kept_count);
+    float* kept = (float*)(ws + pl.off_kept);
+    int* status = (int*)(ws + pl.off_status);
+
+    ScoreGrid g;
+    g.A = pl.A; g.C = pl.C; g.first_fg = pl.first_fg; g.tile_rows = pl.tile_rows; g.stage_floats = pl.stage_floats;
+    g.tiles_per_image = pl.tiles_per_image; g.group_tiles = pl.group_tiles; g.groups_per_image = pl.groups_per_image;
+    g.num_items = pl.num_items; g.nblk = pl.nblk; g.split = pl.split; g.total_floats = (int64_t)pl.B * pl.A * pl.C;
+    int grid = 2 * sm_count();
+    if (grid > pl.num_items) grid = pl.num_items;
+
+#define SSD_LAUNCH_PASS1(QQ, NN)                                                                                      \
+    do {                                                                                                               \
+        auto launch = [&](auto kern) -> int {                                                                          \
+            SSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.stream_smem));    \
+            kern<<<grid, kStreamThreads, pl.stream_smem, st>>>(scores, g, rowstat, blockmax);                          \
+            return SSD_OK;                                                                                             \
+        };                                                                                                             \
+        int rc;                                                                                                        \
+        if (pl.converter == SSD_CONVERT_SOFTMAX) rc = launch(score_pass1_kernel<QQ, NN, SSD_CONVERT_SOFTMAX>);         \
+        else rc = launch(score_pass1_kernel<QQ, NN, SSD_CONVERT_IDENTITY>);                                            \
+        if (rc != SSD_OK) return rc;                                                                                   \
+    } while (0)
+    SSD_DISPATCH_ROW_SHAPE(pl.C, SSD_LAUNCH_PASS1);
+#undef SSD_LAUNCH_PASS1
+    SSD_CUDA(cudaGetLastError());
+
+    {
+        const int warps_needed = pl.B * pl.C;
+        const int blocks = (warps_needed * 32 + 255) / 256;
+        class_gate_kernel<<<blocks, 256, 0, st>>>(blockmax, pl.B, pl.C, pl.first_fg, pl.nblk, pl.K, pl.converter,
+                                                  p->score_threshold, gate, cand_count, status);
+        SSD_CUDA(cudaGetLastError());
+    }
+
+#define SSD_LAUNCH_PASS2(QQ, NN)                                                                                      \
+    do {                                                                                                               \
+        auto launch = [&](auto kern) -> int {                                                                          \
+            SSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.stream_smem));    \
+            kern<<<grid, kStreamThreads, pl.stream_smem, st>>>(scores, g, rowstat, gate, cand_count, cand, pl.cand_cap); \
+            return SSD_OK;                                                                                             \
+        };                                                                                                             \
+        int rc;                                                                                                        \
+        if (pl.converter == SSD_CONVERT_SOFTMAX) rc = launch(score_pass2_kernel<QQ, NN, SSD_CONVERT_SOFTMAX>);         \
+        else rc = launch(score_pass2_kernel<QQ, NN, SSD_CONVERT_IDENTITY>);                                            \
+        if (rc != SSD_OK) return rc;                                                                                   \
+    } while (0)
+    SSD_DISPATCH_ROW_SHAPE(pl.C, SSD_LAUNCH_PASS2);
+#undef SSD_LAUNCH_PASS2
+    SSD_CUDA(cudaGetLastError());
+
+    {
+        NmsArgs a;
+        a.A = pl.A; a.C = pl.C; a.Cf = pl.Cf; a.first_fg = pl.first_fg; a.K = pl.K; a.cand_cap = pl.cand_cap;
+        a.converter = pl.converter; a.box_input = pl.box_input; a.score_thr = p->score_threshold;
+        a.xy_scale = p->xy_scale; a.wh_scale = p->wh_scale; a.iou_thr = p->overlap_threshold;
+        const int kwords = (pl.K + 31) / 32;
+        const size_t key_slots = pl.cand_cap > kMaxPerClass ? pl.cand_cap : kMaxPerClass;
+        const size_t smem = key_slots * 8 + (size_t)pl.K * (16 + 4 + 4) + (size_t)pl.K * kwords * 4 + 64;
+        SSD_CUDA(cudaFuncSetAttribute(segment_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        segment_nms_kernel<<<pl.B * pl.Cf, kNmsThreads, smem, st>>>(a, scores, rowstat, cand_count, cand,
+                                                                     (const float4*)boxes, (const float4*)priors,
+                                                                     kept_count, kept, status);
+        SSD_CUDA(cudaGetLastError());
+    }
+    {
+        int t2 = 32;
+        while (t2 < pl.T) t2 <<= 1;
+        const size_t smem = round_up((size_t)(pl.Cf + 1) * 4, 16) + ((size_t)pl.Cf * pl.K + (pl.T > 0 ? t2 : 0)) * 8 + 64;
+        SSD_REQUIRE(smem <= 224 * 1024, SSD_ERR_UNSUPPORTED, "ssd_postprocess: final top-k needs %zu bytes of shared memory", smem);
+        SSD_CUDA(cudaFuncSetAttribute(image_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        image_topk_kernel<<<pl.B, kTopkThreads, smem, st>>>(pl.Cf, pl.K, pl.T, pl.det_cap, kept_count, kept, dets_out,
+                                                             count_out, anchor_out);
+        SSD_CUDA(cudaGetLastError());
+    }
+    if (status_out != nullptr)
+        SSD_CUDA(cudaMemcpyAsync(status_out, status, 4 * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    return SSD_OK;
+}
+
+extern "C" int ssd_postprocess(const ssd_postprocess_params* p, const float* scores, const float* boxes,
+                               const float* priors, float* dets_out, int32_t* count_out, int32_t* anchor_out,
+                               int32_t* status_out, void* workspace, size_t workspace_bytes, void* stream) {
+    PostPlan pl;
+    const int rc = make_plan(p, pl);
+    if (rc != SSD_OK) return rc;
+    if (pl.B == 0) return SSD_OK;
+    SSD_REQUIRE(count_out && dets_out, SSD_ERR_INVALID_ARGUMENT, "ssd_postprocess: null output pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pl.A == 0) {
+        SSD_CUDA(cudaMemsetAsync(count_out, 0, sizeof(int32_t) * pl.B, st));
+        if (status_out) SSD_CUDA(cudaMemsetAsync(status_out, 0, sizeof(int32_t) * 4, st));
+        return SSD_OK;
+    }
+    SSD_REQUIRE(scores && boxes && workspace, SSD_ERR_INVALID_ARGUMENT, "ssd_postprocess: null pointer");
+    SSD_REQUIRE(priors || pl.box_input == SSD_BOXES_CORNERS, SSD_ERR_INVALID_ARGUMENT,
+                "ssd_postprocess: priors are needed to decode locs");
+    SSD_REQUIRE(aligned(scores, 16) && aligned(boxes, 16) && (!priors || aligned(priors, 16)), SSD_ERR_MISALIGNED,
+                "ssd_postprocess: scores, boxes and priors must be 16-byte aligned");
+    SSD_REQUIRE(aligned(workspace, 256), SSD_ERR_MISALIGNED, "ssd_postprocess: workspace must be 256-byte aligned");
+    SSD_REQUIRE(workspace_bytes >= pl.total_bytes, SSD_ERR_WORKSPACE, "ssd_postprocess: workspace %zu < %zu bytes",
+                workspace_bytes, pl.total_bytes);
+    return run_postprocess(pl, p, scores, boxes, priors, dets_out, count_out, anchor_out, status_out,
+                           (unsigned char*)workspace, st);
+}
+
+// ---- box_utils.nms for one box set: the same machinery with B = 1, one score column ----
+static void nms_params(int num_boxes, int max_per_class, double thr, ssd_postprocess_params& p) {
+    memset(&p, 0, sizeof(p));
+    p.batch = 1; p.num_anchors = num_boxes; p.num_cols = 1; p.converter = SSD_CONVERT_IDENTITY; p.first_fg_col = 0;
+    p.box_input = SSD_BOXES_CORNERS; p.xy_scale = 1.f; p.wh_scale = 1.f; p.score_threshold = -INFINITY;
+    p.max_per_class = max_per_class; p.overlap_threshold = thr; p.max_total = 0; p.det_capacity = max_per_class;
+}
+
+extern "C" size_t ssd_nms_workspace_bytes(int num_boxes, int max_per_class) {
+    ssd_postprocess_params p;
+    nms_params(num_boxes, max_per_class, 0.5, p);
+    PostPlan pl;
+    if (make_plan(&p, pl) != SSD_OK) return 0;
+    return pl.total_bytes + round_up((size_t)max_per_class * 6 * sizeof(float), 256);
+}
+
+extern "C" int ssd_nms(const float* corner_boxes, const float* scores, int num_boxes, int max_per_class,
+                       double overlap_threshold, int64_t* keep_out, int32_t* count_out, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+    SSD_REQUIRE(num_boxes >= 0, SSD_ERR_INVALID_ARGUMENT, "ssd_nms: negative box count");
+    SSD_REQUIRE(count_out != nullptr, SSD_ERR_INVALID_ARGUMENT, "ssd_nms: null count_out");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (num_boxes == 0) {
+        SSD_CUDA(cudaMemsetAsync(count_out, 0, sizeof(int32_t), st));
+        return SSD_OK;
+    }
+    ssd_postprocess_params p;
+    nms_params(num_boxes, max_per_class, overlap_threshold, p);
+    PostPlan pl;
+    const int rc = make_plan(&p, pl);
+    if (rc != SSD_OK) return rc;
+    SSD_REQUIRE(corner_boxes && scores && keep_out && workspace, SSD_ERR_INVALID_ARGUMENT, "ssd_nms: null pointer");
+    SSD_REQUIRE(aligned(corner_boxes, 16) && aligned(scores, 16), SSD_ERR_MISALIGNED,
+                "ssd_nms: boxes and scores must be 16-byte aligned");
+    SSD_REQUIRE(aligned(workspace, 256), SSD_ERR_MISALIGNED, "ssd_nms: workspace must be 256-byte aligned");
+    SSD_REQUIRE(workspace_bytes >= ssd_nms_workspace_bytes(num_boxes, max_per_class), SSD_ERR_WORKSPACE,
+                "ssd_nms: workspace too small");
+    unsigned char* ws = (unsigned char*)workspace;
+    float* dets = (float*)(ws + pl.total_bytes);
+    int* anchors = (int*)(ws + pl.off_anchor_tmp);
+    const int rc2 = run_postprocess(pl, &p, scores, corner_boxes, nullptr, dets, count_out, anchors, nullptr, ws, st);
+    if (rc2 != SSD_OK) return rc2;
+    widen_keep_kernel<<<(max_per_class + 127) / 128, 128, 0, st>>>(anchors, count_out, (long long*)keep_out, max_per_class);
+    SSD_CUDA(cudaGetLastError());
+    return SSD_OK;
+}

@@ -1,0 +1,244 @@
+"""torch custom ops ``torch.ops.ssd_b200.*`` -- thin shims over the C ABI (include/ssd_b200.h).
+
+Each op is registered for the CUDA dispatch key only: calling it with CPU tensors raises (there is
+no CPU fallback).  An op takes the raw device pointers of its tensor arguments and the current
+CUDA stream and makes exactly one C-ABI call; no op synchronises.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _native as N
+
+_LIB = torch.library.Library("ssd_b200", "DEF")
+
+_LIB.define("pairwise_iou(Tensor a, Tensor b) -> Tensor")
+_LIB.define("match_per_prediction(Tensor weights, float matched_threshold, float unmatched_threshold, "
+            "bool force_match) -> Tensor")
+_LIB.define("assign_targets(Tensor anchors, Tensor gt_rows, Tensor gt_offsets, int max_gt, "
+            "float matched_threshold, float unmatched_threshold, bool force_match) -> (Tensor, Tensor, Tensor)")
+_LIB.define("box_transform(Tensor src, Tensor? priors, int op, float xy_scale, float wh_scale, float eps) -> Tensor")
+_LIB.define("box_transform_(Tensor(a!) boxes, Tensor? priors, int op, float xy_scale, float wh_scale, float eps) -> ()")
+_LIB.define("positive_mask(Tensor target_classes) -> Tensor")
+_LIB.define("hard_negative_mask(Tensor? logits, Tensor target_classes, Tensor? loss, float ratio, "
+            "bool ratio_is_integer, float min_negatives) -> (Tensor, Tensor)")
+_LIB.define("postprocess(Tensor scores, Tensor boxes, Tensor? priors, int converter, int first_fg_col, "
+            "int box_input, float xy_scale, float wh_scale, float score_threshold, int max_per_class, "
+            "float overlap_threshold, int max_total) -> (Tensor, Tensor, Tensor, Tensor)")
+_LIB.define("nms(Tensor boxes, Tensor scores, int max_per_class, float overlap_threshold) -> (Tensor, Tensor)")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+_workspaces: Dict[Tuple[int, str], torch.Tensor] = {}
+
+
+def workspace(nbytes: int, device: torch.device, tag: str = "default") -> torch.Tensor:
+    """A cached, 256-byte aligned scratch buffer on ``device`` (grown on demand, never shrunk)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    """fp32 + contiguous (the reference calls .float() on its inputs, postprocessor.py:39-40)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _rows_view(t: torch.Tensor) -> Optional[Tuple[int, int]]:
+    """(row_stride_in_floats, rows) if ``t[..., 4]`` is a uniformly strided set of 4-float rows."""
+    if t.dtype != torch.float32 or t.shape[-1] != 4 or t.stride(-1) != 1:
+        return None
+    if t.dim() == 1:
+        return 4, 1
+    rs = t.stride(-2)
+    expect = rs
+    for d in range(t.dim() - 2, -1, -1):
+        if t.shape[d] != 1 and t.stride(d) != expect:
+            return None
+        expect *= t.shape[d]
+    rows = 1
+    for d in range(t.dim() - 1):
+        rows *= t.shape[d]
+    if rs < 4 or rs % 2 or t.data_ptr() % 8:
+        return None
+    return rs, rows
+
+
+# ---------------------------------------------------------------------------------------------
+def _pairwise_iou(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    N.require_device()
+    a, b = _f32c(a), _f32c(b)
+    out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        N.check(N.lib().ssd_pairwise_iou(_ptr(a), a.shape[0], _ptr(b), b.shape[0], _ptr(out), _stream()))
+    return out
+
+
+def _match_per_prediction(weights: torch.Tensor, matched_threshold: float, unmatched_threshold: float,
+                          force_match: bool) -> torch.Tensor:
+    N.require_device()
+    w = _f32c(weights)
+    out = torch.empty((w.shape[1],), dtype=torch.int64, device=w.device)
+    with torch.cuda.device(w.device):
+        N.check(N.lib().ssd_match_per_prediction(_ptr(w), w.shape[0], w.shape[1], matched_threshold,
+                                                 unmatched_threshold, int(force_match), _ptr(out), _stream()))
+    return out
+
+
+def _assign_targets(anchors: torch.Tensor, gt_rows: torch.Tensor, gt_offsets: torch.Tensor, max_gt: int,
+                    matched_threshold: float, unmatched_threshold: float, force_match: bool):
+    N.require_device()
+    batch = gt_offsets.numel() - 1
+    num_anchors = anchors.shape[0]
+    dev = anchors.device
+    target = torch.empty((batch, num_anchors, 6), dtype=torch.float32, device=dev)
+    match = torch.empty((batch, num_anchors), dtype=torch.int32, device=dev)
+    stats = torch.empty((batch, 4), dtype=torch.int32, device=dev)
+    gt_cols = gt_rows.shape[1] if gt_rows.dim() == 2 else 6
+    with torch.cuda.device(dev):
+        N.check(N.lib().ssd_assign_targets(_ptr(anchors), _ptr(gt_rows) if gt_rows.numel() else None, gt_cols,
+                                           _ptr(gt_offsets), max_gt, batch, num_anchors, matched_threshold,
+                                           unmatched_threshold, int(force_match), _ptr(target), _ptr(match),
+                                           _ptr(stats), _stream()))
+    return target, match, stats
+
+
+def _box_call(op: int, src: torch.Tensor, src_stride: int, dst: torch.Tensor, dst_stride: int,
+              priors: Optional[torch.Tensor], rows: int, xy: float, wh: float, eps: float) -> None:
+    num_anchors = priors.shape[0] if priors is not None else 1
+    with torch.cuda.device(src.device):
+        N.check(N.lib().ssd_box_transform(op, _ptr(src), src_stride, _ptr(dst), dst_stride, _ptr(priors), rows,
+                                          num_anchors, xy, wh, eps, _stream()))
+
+
+def _box_transform(src: torch.Tensor, priors: Optional[torch.Tensor], op: int, xy_scale: float, wh_scale: float,
+                   eps: float) -> torch.Tensor:
+    N.require_device()
+    view = _rows_view(src)
+    if view is None:
+        src = _f32c(src)
+        view = (4, src.numel() // 4)
+    out = torch.empty(src.shape, dtype=torch.float32, device=src.device)
+    _box_call(op, src, view[0], out, 4, priors, view[1], xy_scale, wh_scale, eps)
+    return out
+
+
+def _box_transform_(boxes: torch.Tensor, priors: Optional[torch.Tensor], op: int, xy_scale: float, wh_scale: float,
+                    eps: float) -> None:
+    N.require_device()
+    view = _rows_view(boxes)
+    if view is None:                      # exotic strides: round-trip through a packed copy
+        tmp = boxes.float().contiguous()
+        _box_call(op, tmp, 4, tmp, 4, priors, tmp.numel() // 4, xy_scale, wh_scale, eps)
+        boxes.copy_(tmp)
+        return
+    _box_call(op, boxes, view[0], boxes, view[0], priors, view[1], xy_scale, wh_scale, eps)
+
+
+def _positive_mask(target_classes: torch.Tensor) -> torch.Tensor:
+    N.require_device()
+    cls = target_classes if target_classes.dtype == torch.int64 else target_classes.long()
+    cls = cls if cls.is_contiguous() else cls.contiguous()
+    out = torch.empty(cls.shape, dtype=torch.bool, device=cls.device)
+    with torch.cuda.device(cls.device):
+        N.check(N.lib().ssd_positive_mask(_ptr(cls), cls.numel(), _ptr(out), _stream()))
+    return out
+
+
+def _hard_negative_mask(logits: Optional[torch.Tensor], target_classes: torch.Tensor, loss: Optional[torch.Tensor],
+                        ratio: float, ratio_is_integer: bool, min_negatives: float):
+    N.require_device()
+    cls = target_classes if target_classes.dtype == torch.int64 else target_classes.long()
+    cls = cls if cls.is_contiguous() else cls.contiguous()
+    batch, num_anchors = cls.shape
+    dev = cls.device
+    num_cols = 0
+    if logits is not None:
+        logits = _f32c(logits.detach())
+        num_cols = logits.numel() // max(batch * num_anchors, 1)
+    if loss is not None:
+        loss = _f32c(loss.detach())
+    mask = torch.empty((batch, num_anchors), dtype=torch.bool, device=dev)
+    stats = torch.empty((batch, 4), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        nbytes = N.lib().ssd_hard_negative_workspace_bytes(batch, num_anchors)
+        ws = workspace(nbytes, dev, "mining")
+        N.check(N.lib().ssd_hard_negative_mask(_ptr(logits), _ptr(cls), _ptr(loss), batch, num_anchors, num_cols,
+                                               float(ratio), int(ratio_is_integer), float(min_negatives), _ptr(mask),
+                                               _ptr(stats), _ptr(ws), ws.numel(), _stream()))
+    return mask, stats
+
+
+def det_capacity(num_fg: int, max_per_class: int, max_total: int) -> int:
+    rows = num_fg * max_per_class
+    return min(rows, max_total) if max_total > 0 else rows
+
+
+def _postprocess(scores: torch.Tensor, boxes: torch.Tensor, priors: Optional[torch.Tensor], converter: int,
+                 first_fg_col: int, box_input: int, xy_scale: float, wh_scale: float, score_threshold: float,
+                 max_per_class: int, overlap_threshold: float, max_total: int):
+    N.require_device()
+    scores = _f32c(scores.detach())
+    boxes = _f32c(boxes.detach())
+    batch = scores.shape[0]
+    num_anchors = boxes.numel() // max(4 * batch, 1)
+    num_cols = scores.numel() // max(batch * num_anchors, 1)
+    dev = scores.device
+    p = N.PostprocessParams()
+    p.batch, p.num_anchors, p.num_cols = batch, num_anchors, num_cols
+    p.converter, p.first_fg_col, p.box_input = converter, first_fg_col, box_input
+    p.xy_scale, p.wh_scale, p.score_threshold = xy_scale, wh_scale, score_threshold
+    p.max_per_class, p.overlap_threshold, p.max_total = max_per_class, overlap_threshold, max_total
+    cap = det_capacity(num_cols - first_fg_col, max_per_class, max_total)
+    p.det_capacity = cap
+    dets = torch.empty((batch, cap, 6), dtype=torch.float32, device=dev)
+    counts = torch.empty((batch,), dtype=torch.int32, device=dev)
+    anchors = torch.empty((batch, cap), dtype=torch.int32, device=dev)
+    status = torch.empty((4,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        nbytes = N.lib().ssd_postprocess_workspace_bytes(ctypes.byref(p))
+        if nbytes == 0:
+            N.check(N.lib().ssd_postprocess(ctypes.byref(p), None, None, None, None, None, None, None, None, 0, None))
+        ws = workspace(nbytes, dev, "postprocess")
+        N.check(N.lib().ssd_postprocess(ctypes.byref(p), _ptr(scores), _ptr(boxes), _ptr(priors), _ptr(dets),
+                                        _ptr(counts), _ptr(anchors), _ptr(status), _ptr(ws), ws.numel(), _stream()))
+    return dets, counts, anchors, status
+
+
+def _nms(boxes: torch.Tensor, scores: torch.Tensor, max_per_class: int, overlap_threshold: float):
+    N.require_device()
+    boxes, scores = _f32c(boxes), _f32c(scores)
+    n = scores.numel()
+    dev = boxes.device
+    keep = torch.empty((max_per_class,), dtype=torch.int64, device=dev)
+    count = torch.zeros((1,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        nbytes = N.lib().ssd_nms_workspace_bytes(n, max_per_class)
+        ws = workspace(max(nbytes, 256), dev, "nms")
+        N.check(N.lib().ssd_nms(_ptr(boxes), _ptr(scores), n, max_per_class, overlap_threshold, _ptr(keep),
+                                _ptr(count), _ptr(ws), ws.numel(), _stream()))
+    return keep, count
+
+
+for _name, _fn in [("pairwise_iou", _pairwise_iou), ("match_per_prediction", _match_per_prediction),
+                   ("assign_targets", _assign_targets), ("box_transform", _box_transform),
+                   ("box_transform_", _box_transform_), ("positive_mask", _positive_mask),
+                   ("hard_negative_mask", _hard_negative_mask), ("postprocess", _postprocess), ("nms", _nms)]:
+    _LIB.impl(_name, _fn, "CUDA")
+
+OPS = torch.ops.ssd_b200

@@ -1,0 +1,40 @@
+"""Samplers -- same interface as the reference's ``detection/sampler.py``.
+
+``detection/init.py:90-92`` looks a sampler up by name and filters its config through
+``sampler.__code__.co_varnames``, so these stay plain Python functions with the reference's
+parameter names.
+"""
+import math
+
+from .ops import OPS
+from .target_assigner import NEGATIVE_CLASS, IGNORE_CLASS  # noqa: F401  (re-exported like the reference)
+
+
+def naive_sampler(predictions, target_classes):
+    return OPS.positive_mask(target_classes)
+
+
+def hard_negative_mining(predictions, target_classes, negative_per_positive_ratio, min_negative_per_image):
+    """3:1 online hard-negative mining, detection/sampler.py:12-25.
+
+    predictions [B, A, C] logits, target_classes [B, A] int64 -> bool [B, A].  Loss values that tie
+    exactly across the cut go to the lower anchor index (the reference's unstable argsort leaves
+    that case implementation defined).
+    """
+    ratio_is_integer = isinstance(negative_per_positive_ratio, int) and not isinstance(negative_per_positive_ratio, bool)
+    mask, stats = OPS.hard_negative_mask(predictions, target_classes, None, float(negative_per_positive_ratio),
+                                         ratio_is_integer, float(min_negative_per_image))
+    hard_negative_mining.last_stats = stats
+    return mask
+
+
+hard_negative_mining.last_stats = None
+
+
+def hard_negative_mining_from_loss(loss, target_classes, negative_per_positive_ratio, min_negative_per_image):
+    """Selection half only: ``loss`` [B, A] replaces -log_softmax(predictions)[..., 0].  Used to check
+    the selection bit-exactly on identical fp32 inputs."""
+    ratio_is_integer = isinstance(negative_per_positive_ratio, int)
+    mask, _ = OPS.hard_negative_mask(None, target_classes, loss, float(negative_per_positive_ratio),
+                                     ratio_is_integer, float(min_negative_per_image))
+    return mask

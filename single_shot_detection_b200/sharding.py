@@ -1,0 +1,70 @@
+"""Multi-GPU: shard the batch by image, one exchange at the end.
+
+Every stage of the path is per-image independent and the anchors are a replicated constant, so
+rank r simply runs the pipeline on images [r*B/W, (r+1)*B/W).  The only collective is a final
+all-gather of the padded detections, their counts and the matched-target statistics, packed into
+ONE buffer per rank (<= 4.8 KB per image) so that a single ``all_gather_into_tensor`` over
+NCCL / NVLink moves everything.  The reference has no equivalent (its eval is replicated on every
+rank, bf/builders/data_builder.py:58); the invariant is gathered result == single-GPU result.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def image_shard(batch: int, rank: int, world: int) -> Tuple[int, int]:
+    """[lo, hi) of the images rank ``rank`` owns; shards differ by at most one image."""
+    base, extra = divmod(batch, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_capacity(batch: int, world: int) -> int:
+    return (batch + world - 1) // world
+
+
+def pack_shard(dets: torch.Tensor, counts: torch.Tensor, stats: torch.Tensor, capacity: int) -> torch.Tensor:
+    """[capacity, T*6 + 1 + 4] fp32 words: detections, then count and stats bit-cast from int32.
+    Rows beyond the local image count have count = -1."""
+    n, t = dets.shape[0], dets.shape[1]
+    words = t * 6 + 5
+    buf = torch.zeros((capacity, words), dtype=torch.float32, device=dets.device)
+    ints = buf.view(torch.int32)
+    ints[:, t * 6] = -1
+    if n:
+        buf[:n, : t * 6] = dets.reshape(n, t * 6)
+        ints[:n, t * 6] = counts.to(torch.int32)
+        ints[:n, t * 6 + 1:] = stats.to(torch.int32)
+    return buf
+
+
+def unpack_gathered(gathered: torch.Tensor, batch: int, world: int, max_rows: int):
+    """Inverse of pack_shard over the concatenation of all ranks' buffers."""
+    capacity = gathered.shape[0] // world
+    ints = gathered.view(torch.int32)
+    keep = []
+    for r in range(world):
+        lo, hi = image_shard(batch, r, world)
+        keep.extend(range(r * capacity, r * capacity + (hi - lo)))
+    idx = torch.tensor(keep, dtype=torch.long, device=gathered.device)
+    rows = gathered.index_select(0, idx)
+    irows = ints.index_select(0, idx)
+    dets = rows[:, : max_rows * 6].reshape(batch, max_rows, 6)
+    counts = irows[:, max_rows * 6].contiguous()
+    stats = irows[:, max_rows * 6 + 1:].contiguous()
+    return dets, counts, stats
+
+
+def all_gather_detections(dets: torch.Tensor, counts: torch.Tensor, stats: torch.Tensor, batch: int,
+                          group: Optional[dist.ProcessGroup] = None):
+    """dets [B_local, T, 6], counts [B_local], stats [B_local, 4] -> the same for the whole batch,
+    identical on every rank.  One collective."""
+    world = dist.get_world_size(group)
+    capacity = shard_capacity(batch, world)
+    mine = pack_shard(dets, counts, stats, capacity)
+    out = torch.empty((world * capacity, mine.shape[1]), dtype=mine.dtype, device=mine.device)
+    dist.all_gather_into_tensor(out, mine, group=group)
+    return unpack_gathered(out, batch, world, dets.shape[1])

@@ -1,0 +1,502 @@
+"""GPU parity: the CUDA path (through torch.ops.ssd_b200.* -> C ABI) against the CPU oracle and
+against the golden fixtures the reference itself produced.
+
+Bars (BASELINE.json north_star): matched indices, mining selections and NMS keep lists bit
+exact on identical fp32 stage inputs; encoded / decoded boxes and scores within 1e-5 relative.
+"""
+import numpy as np
+import pytest
+import torch
+
+import golden_io as gio
+from oracle import anchor_pipeline_oracle as ora
+from single_shot_detection_b200 import workloads as wl
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-5          # tolerance of the floating-point stages (north_star: 1e-5 relative)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda", 0)
+
+
+@pytest.fixture(scope="module", params=gio.PIPELINE_CASES)
+def case(request):
+    return gio.PipelineCase(request.param)
+
+
+def _modules():
+    from single_shot_detection_b200 import box_coder, box_utils, matcher, postprocessor, sampler, target_assigner
+    return target_assigner, matcher, box_coder, sampler, postprocessor, box_utils
+
+
+# ----------------------------------------------------------------------------------------------
+# target assignment (a1-a4)
+# ----------------------------------------------------------------------------------------------
+def test_assign_targets_bit_exact_vs_golden(case, dev):
+    ta, *_ = _modules()
+    assigner = ta.TargetAssigner(case.matched, case.unmatched, nan_check="sync")
+    target = assigner.encode_ground_truth(case.gt, case.anchors)
+    assert target.is_cuda and target.shape == (case.B, case.A, 6)
+    match = assigner.last_match.cpu().long()
+    bad = (match != case.match_idx).nonzero()
+    assert bad.numel() == 0, f"matched indices differ at {bad[:8].tolist()}"
+    assert torch.equal(target.cpu(), case.target)
+    stats = assigner.last_stats.cpu()
+    cls = case.target[..., 4]
+    assert stats[:, 0].tolist() == ((cls != 0) & (cls != -1)).sum(1).tolist()
+    assert stats[:, 1].tolist() == (cls == -1).sum(1).tolist()
+    assert stats[:, 3].tolist() == [g.shape[0] for g in case.gt]
+
+
+def test_assign_targets_random_vs_oracle(dev):
+    ta, *_ = _modules()
+    gen = torch.Generator().manual_seed(7)
+    for name, batch, thr in [("tiny_voc_b3", 5, (0.5, 0.5)), ("ssd_mb2_coco_b64", 9, (0.5, 0.4)),
+                             ("retina500_coco_b32", 3, (0.5, 0.4)), ("ssd300_voc_8108_b8", 40, (0.6, 0.3))]:
+        w = wl.WORKLOADS[name]
+        anchors = wl.build_anchors(w)
+        gt = wl.make_ground_truth(batch, w.img, w.num_fg, w.max_gt, gen, mixup=0.4 if batch % 2 else None)
+        gt[batch // 2] = torch.zeros((0, 6))
+        assigner = ta.TargetAssigner(*thr)
+        target = assigner.encode_ground_truth(gt, anchors)
+        ref, ref_match = ora.assign_targets(gt, anchors, *thr, return_match=True)
+        assert torch.equal(assigner.last_match.cpu().long(), torch.stack(ref_match)), name
+        assert torch.equal(target.cpu(), ref), name
+
+
+def test_assign_many_boxes_and_collisions(dev):
+    """G larger than a warp, duplicated boxes (ties) and GTs that all force the same anchor."""
+    ta, *_ = _modules()
+    w = wl.WORKLOADS["tiny_voc_b3"]
+    anchors = wl.build_anchors(w)
+    gen = torch.Generator().manual_seed(11)
+    base = wl.make_ground_truth(1, w.img, w.num_fg, 5, gen)[0]
+    many = torch.cat([base] * 40, dim=0)                      # 40 copies -> exact IoU ties
+    tiny = torch.tensor([[1., 1., 1.5, 1.5, 2., 1.], [1., 1., 1.25, 1.5, 3., 1.], [1., 1., 1.5, 1.25, 4., 1.]])
+    gt = [many, tiny, torch.cat([tiny, base])]
+    assigner = ta.TargetAssigner(0.5, 0.2)
+    target = assigner.encode_ground_truth(gt, anchors)
+    ref, ref_match = ora.assign_targets(gt, anchors, 0.5, 0.2, return_match=True)
+    assert torch.equal(assigner.last_match.cpu().long(), torch.stack(ref_match))
+    assert torch.equal(target.cpu(), ref)
+
+
+def test_assign_nan_assert(dev):
+    ta, *_ = _modules()
+    w = wl.WORKLOADS["tiny_voc_b3"]
+    anchors = wl.build_anchors(w)
+    gt = [torch.tensor([[float("nan"), 2., 30., 30., 1., 1.]])]
+    with pytest.raises(AssertionError):
+        ta.TargetAssigner(0.5, 0.5, nan_check="sync").encode_ground_truth(gt, anchors)
+    with pytest.raises(AssertionError):
+        ta.TargetAssigner(0.3, 0.5).encode_ground_truth([torch.zeros((0, 6))], anchors)
+
+
+def test_iou_and_matcher_api(case, dev):
+    _, matcher, _, _, _, box_utils = _modules()
+    if case.gt[0].shape[0] == 0:
+        pytest.skip("empty image")
+    corners = box_utils.to_corners(case.anchors.to(dev))
+    assert torch.equal(corners.cpu(), ora.corners_from_centroids(case.anchors))
+    iou = box_utils.iou(case.gt[0][:, :4].contiguous().to(dev), corners)
+    ref = ora.pairwise_iou(case.gt[0][:, :4], ora.corners_from_centroids(case.anchors))
+    assert torch.equal(iou.cpu(), ref)
+    idx = matcher.match_per_prediction(iou, case.matched, case.unmatched)
+    assert idx.dtype == torch.int64
+    assert torch.equal(idx.cpu(), case.match_idx[0])
+    assert matcher.NOT_MATCHED == -2 and matcher.IGNORE == -1
+
+
+# ----------------------------------------------------------------------------------------------
+# box coding (a6, a7)
+# ----------------------------------------------------------------------------------------------
+def _close(a, b):
+    torch.testing.assert_close(a, b, rtol=REL, atol=1e-6, equal_nan=True)
+
+
+def test_box_coder_all_orders(case, dev):
+    _, _, bc, _, _, box_utils = _modules()
+    w = case.w
+    coder = bc.BoxCoder(w.xy_scale, w.wh_scale, w.eps)
+    # the loss route: in place on the strided view target[..., 0:4]          multibox_loss.py:81-82
+    t = case.target.to(dev)
+    tl = t[..., 0:4]
+    assert box_utils.to_centroids(tl, inplace=True) is None
+    ref_t = case.target.clone()
+    ref_tl = ref_t[..., 0:4]
+    ora.centroids_from_corners(ref_tl, inplace=True)
+    assert torch.equal(tl.cpu(), ref_tl)
+    assert coder.encode_box(tl, case.anchors, inplace=True) is tl
+    _close(tl.cpu(), case.enc_inplace)
+    assert torch.equal(tl.cpu()[..., :2], case.enc_inplace[..., :2])            # xy: no transcendental
+    assert torch.equal(t.cpu()[..., 4:], case.target[..., 4:])                   # class/score untouched
+    # fused single pass, same rounding
+    t2 = case.target.to(dev)
+    coder.encode_corners_(t2[..., 0:4], case.anchors)
+    assert torch.equal(t2, t)
+    # out-of-place orders
+    cen = box_utils.to_centroids(case.target[..., 0:4].to(dev))
+    ref_cen = ora.centroids_from_corners(case.target[..., 0:4])
+    assert torch.equal(cen.cpu(), ref_cen)
+    enc = coder.encode_box(cen, case.anchors)
+    _close(enc.cpu(), ora.encode_boxes(ref_cen, case.anchors, w.xy_scale, w.wh_scale, w.eps))
+    locs = case.locs.view(case.B, case.A, 4)
+    dec = coder.decode_box(locs.to(dev), case.anchors)
+    ref_dec = ora.decode_boxes(locs, case.anchors, w.xy_scale, w.wh_scale)
+    _close(dec.cpu(), ref_dec)
+    assert torch.equal(dec.cpu()[..., :2], ref_dec[..., :2])
+    dec_in = locs.to(dev).clone()
+    coder.decode_box(dec_in, case.anchors, inplace=torch.tensor(1))
+    _close(dec_in.cpu(), ora.decode_boxes(locs.clone(), case.anchors, w.xy_scale, w.wh_scale, inplace=True))
+    if case.full:
+        _close(dec.cpu(), case.t("decoded"))
+        _close(enc.cpu(), case.t("enc_oop"))
+
+
+# ----------------------------------------------------------------------------------------------
+# samplers (a5)
+# ----------------------------------------------------------------------------------------------
+def test_naive_sampler(case, dev):
+    _, _, _, sampler, _, _ = _modules()
+    cls = case.target[..., 4].long().to(dev)
+    mask = sampler.naive_sampler(None, cls)
+    assert mask.dtype == torch.bool and torch.equal(mask.cpu(), case.naive_mask)
+
+
+def test_hard_negative_selection_bit_exact_on_identical_loss(case, dev):
+    """Stage boundary: feed the oracle's own fp32 criterion, demand the identical selection."""
+    _, _, _, sampler, _, _ = _modules()
+    w = case.w
+    cls = case.target[..., 4].long()
+    loss = ora.background_loss(case.scores.view(case.B, case.A, case.C))
+    ref = ora.mine_hard_negatives(None, cls, w.ratio, w.min_neg, canonical=True, loss=loss)
+    mask = sampler.hard_negative_mining_from_loss(loss.to(dev), cls.to(dev), w.ratio, w.min_neg)
+    assert torch.equal(mask.cpu(), ref)
+    tied = ora.mining_boundary_tie(loss, cls, w.ratio, w.min_neg)
+    for i in range(case.B):                      # and it is the reference's own answer when unique
+        if not tied[i]:
+            assert torch.equal(mask[i].cpu(), case.hnm_mask[i])
+
+
+def test_hard_negative_mining_end_to_end(case, dev):
+    _, _, _, sampler, _, _ = _modules()
+    w = case.w
+    cls = case.target[..., 4].long().to(dev)
+    logits = case.scores.view(case.B, case.A, case.C).to(dev)
+    mask = sampler.hard_negative_mining(logits, cls, w.ratio, w.min_neg)
+    stats = sampler.hard_negative_mining.last_stats.cpu()
+    # counts are exact; the set may differ only through ulp-level differences of log_softmax
+    assert mask.sum(1).tolist() == case.hnm_mask.sum(1).tolist()
+    mism = int((mask.cpu() != case.hnm_mask).sum())
+    assert mism <= 2 * case.B, f"{mism} anchors differ from the reference selection"
+    cls_cpu = cls.cpu()
+    assert stats[:, 0].tolist() == ((cls_cpu != 0) & (cls_cpu != -1)).sum(1).tolist()
+    assert stats[:, 1].tolist() == (cls_cpu == 0).sum(1).tolist()
+
+
+@pytest.mark.parametrize("ratio,min_neg", [(3, 5), (3.0, 5), (2.5, 0), (1, 100000), (0, 0), (7, 1)])
+def test_hard_negative_ratio_variants_and_ties(dev, ratio, min_neg):
+    """Quantised losses force ties across the cut; the kernel's rule is lower anchor first."""
+    _, _, _, sampler, _, _ = _modules()
+    gen = torch.Generator().manual_seed(3)
+    b, a = 4, 3000
+    cls = torch.zeros((b, a), dtype=torch.long)
+    cls[torch.rand((b, a), generator=gen) < 0.02] = 3
+    cls[torch.rand((b, a), generator=gen) < 0.05] = -1
+    cls[3] = 0                                                          # no positives at all
+    loss = (torch.rand((b, a), generator=gen) * 8).round() / 8          # heavy ties
+    loss[2] = 1.0                                                       # all equal
+    ref = ora.mine_hard_negatives(None, cls, ratio, min_neg, canonical=True, loss=loss)
+    mask = sampler.hard_negative_mining_from_loss(loss.to(dev), cls.to(dev), ratio, min_neg)
+    assert torch.equal(mask.cpu(), ref)
+
+
+def test_hard_negative_large_anchor_counts(dev):
+    """A > 12288 (shared-memory keys) and A > 56000 (global keys) paths of the selection kernel."""
+    _, _, _, sampler, _, _ = _modules()
+    gen = torch.Generator().manual_seed(5)
+    for a in (20000, 70000):
+        cls = torch.zeros((2, a), dtype=torch.long)
+        cls[torch.rand((2, a), generator=gen) < 0.01] = 1
+        logits = torch.randn((2, a, 5), generator=gen)
+        loss = ora.background_loss(logits)
+        ref = ora.mine_hard_negatives(None, cls, 3, 5, canonical=True, loss=loss)
+        mask = sampler.hard_negative_mining_from_loss(loss.to(dev), cls.to(dev), 3, 5)
+        assert torch.equal(mask.cpu(), ref), a
+        full = sampler.hard_negative_mining(logits.to(dev), cls.to(dev), 3, 5)
+        assert int((full.cpu() != ref).sum()) <= 4, a
+
+
+def test_mining_loss_matches_log_softmax(dev):
+    """The streamed criterion itself, read back through the keys: relative 1e-5."""
+    _, _, _, sampler, _, _ = _modules()
+    gen = torch.Generator().manual_seed(9)
+    for c in (2, 6, 21, 32, 64, 81, 91, 200, 300):
+        a = 777
+        logits = torch.randn((2, a, c), generator=gen) * 3
+        cls = torch.zeros((2, a), dtype=torch.long)
+        # with ratio huge every negative is selected; with one positive and ratio 1, exactly the
+        # single largest loss is selected -> its argmax must match the oracle's
+        cls[:, 0] = 1
+        mask = sampler.hard_negative_mining(logits.to(dev), cls.to(dev), 1, 0).cpu()
+        loss = ora.background_loss(logits)
+        loss[:, 0] = -1
+        for i in range(2):
+            picked = mask[i].nonzero().view(-1).tolist()
+            assert len(picked) == 2 and picked[0] == 0
+            best = float(loss[i].max())
+            assert abs(float(loss[i, picked[1]]) - best) <= REL * abs(best), (c, i)
+
+
+# ----------------------------------------------------------------------------------------------
+# post-processor (a7-a9)
+# ----------------------------------------------------------------------------------------------
+def _postprocessor(case, max_total):
+    _, _, bc, _, pp, _ = _modules()
+    w = case.w
+    coder = bc.BoxCoder(w.xy_scale, w.wh_scale, w.eps)
+    return pp.Postprocessor(coder, w.score_threshold,
+                            {"max_per_class": w.max_per_class, "overlap_threshold": w.overlap_threshold},
+                            score_converter=w.converter, max_total=max_total)
+
+
+def _dets_close(m, r, img):
+    """Scores within 1e-5 relative.  Corner coordinates are differences of decoded centre/size
+    values that are each within 1e-5 relative, so their ABSOLUTE error scales with the image
+    size: atol = 2e-5 * img."""
+    return (m.shape == r.shape and torch.equal(m[:, 4], r[:, 4])
+            and torch.allclose(m[:, 5], r[:, 5], rtol=REL, atol=1e-7)
+            and torch.allclose(m[:, :4], r[:, :4], rtol=REL, atol=2e-5 * img))
+
+
+def _compare_dets(mine, ref, img):
+    assert len(mine) == len(ref)
+    for i, (m, r) in enumerate(zip(mine, ref)):
+        m = m.cpu()
+        assert m.shape == r.shape, (i, m.shape, r.shape)
+        assert torch.equal(m[:, 4], r[:, 4]), f"image {i}: class column differs"
+        torch.testing.assert_close(m[:, 5], r[:, 5], rtol=REL, atol=1e-7)
+        torch.testing.assert_close(m[:, :4], r[:, :4], rtol=REL, atol=2e-5 * img)
+
+
+@pytest.mark.parametrize("max_total", ["cfg", None])
+def test_postprocess_vs_reference_golden(case, dev, max_total):
+    w = case.w
+    mt = w.max_total if max_total == "cfg" else None
+    ref = case.dets if max_total == "cfg" else case.dets_all
+    post = _postprocessor(case, mt)
+    dets = post.postprocess((case.scores.to(dev), case.locs.to(dev)), case.anchors)
+    assert post.last_status[0] == 0
+    if mt is not None:
+        # final top-k: equal scores may be ordered differently by the reference's topk
+        for m, r in zip(dets, ref):
+            assert m.shape == r.shape
+            torch.testing.assert_close(m.cpu()[:, 5], r[:, 5], rtol=REL, atol=1e-6)
+        dets = [d.cpu()[torch.argsort(d.cpu()[:, 5], descending=True, stable=True)] for d in dets]
+        same = all(_dets_close(d, r, w.img) for d, r in zip(dets, ref))
+        if not same:
+            for d, r in zip(dets, ref):
+                assert len(torch.unique(r[:, 5])) < r.shape[0], "rows differ without a score tie"
+        return
+    _compare_dets(dets, ref, w.img)
+
+
+def test_postprocess_stage_exact_keep_lists(case, dev):
+    """Identical fp32 stage inputs (the oracle's probabilities and decoded corners) -> the kept
+    anchors per class, their order and every output bit must match."""
+    from single_shot_detection_b200 import _native as N
+    from single_shot_detection_b200.ops import OPS
+    w = case.w
+    logits = case.scores.view(case.B, case.A, case.C)
+    probs = torch.softmax(logits, -1) if w.converter == "SOFTMAX" else torch.sigmoid(logits)
+    first_fg = 1 if w.converter == "SOFTMAX" else 0
+    fg = probs[..., first_fg:]
+    corners = ora.corners_from_centroids(ora.decode_boxes(case.locs.view(case.B, case.A, 4), case.anchors,
+                                                          w.xy_scale, w.wh_scale))
+    assert not bool(ora.class_topk_boundary_tie(fg, w.score_threshold, w.max_per_class).any())
+    ref, ref_keep = ora.detections_from_scores(fg, corners, w.score_threshold, w.overlap_threshold,
+                                               w.max_per_class, None, canonical=True, return_keep=True)
+    dets, counts, anchors, status = OPS.postprocess(probs.contiguous().to(dev), corners.contiguous().to(dev), None,
+                                                    N.CONVERT_IDENTITY, first_fg, N.BOXES_CORNERS, 1.0, 1.0,
+                                                    float(w.score_threshold), w.max_per_class,
+                                                    float(w.overlap_threshold), 0)
+    assert status.tolist()[0] == 0
+    counts = counts.tolist()
+    for i in range(case.B):
+        assert counts[i] == ref[i].shape[0], i
+        assert torch.equal(dets[i, :counts[i]].cpu(), ref[i]), i
+        assert anchors[i, :counts[i]].cpu().tolist() == torch.cat(ref_keep[i]).tolist(), i
+    # with the final top-k: descending score, ties by class-major position
+    ref_t = ora.detections_from_scores(fg, corners, w.score_threshold, w.overlap_threshold, w.max_per_class,
+                                       w.max_total, canonical=True)
+    dets, counts, anchors, status = OPS.postprocess(probs.contiguous().to(dev), corners.contiguous().to(dev), None,
+                                                    N.CONVERT_IDENTITY, first_fg, N.BOXES_CORNERS, 1.0, 1.0,
+                                                    float(w.score_threshold), w.max_per_class,
+                                                    float(w.overlap_threshold), w.max_total)
+    for i in range(case.B):
+        assert torch.equal(dets[i, :counts[i]].cpu(), ref_t[i]), i
+
+
+def test_postprocess_sparse_and_empty_classes(dev):
+    """Realistic score sparsity: most classes have no candidate, some have fewer than K."""
+    from single_shot_detection_b200 import _native as N
+    from single_shot_detection_b200.ops import OPS
+    gen = torch.Generator().manual_seed(21)
+    b, a, c = 3, 2268, 21
+    probs = torch.rand((b, a, c), generator=gen) * 0.009
+    hot = torch.rand((b, a, c), generator=gen) < 0.002
+    probs[hot] = torch.rand((int(hot.sum()),), generator=gen)
+    probs[1] = 0.0                                                     # an image with no detection
+    cxy = torch.rand((b, a, 2), generator=gen) * 300
+    wh = torch.rand((b, a, 2), generator=gen) * 80 + 2
+    corners = torch.cat([cxy - wh / 2, cxy + wh / 2], dim=-1)
+    ref, ref_keep = ora.detections_from_scores(probs[..., 1:], corners, 0.01, 0.45, 100, 200, canonical=True,
+                                               return_keep=True)
+    dets, counts, anchors, status = OPS.postprocess(probs.to(dev), corners.to(dev), None, N.CONVERT_IDENTITY, 1,
+                                                    N.BOXES_CORNERS, 1.0, 1.0, 0.01, 100, 0.45, 200)
+    assert status.tolist()[0] == 0
+    for i in range(b):
+        assert int(counts[i]) == ref[i].shape[0]
+        assert torch.equal(dets[i, :int(counts[i])].cpu(), ref[i])
+
+
+def test_postprocess_score_ties_and_duplicates(dev):
+    """Exact score ties inside a class (lower anchor first) and identical boxes (suppressed)."""
+    from single_shot_detection_b200 import _native as N
+    from single_shot_detection_b200.ops import OPS
+    gen = torch.Generator().manual_seed(22)
+    b, a, c = 2, 1500, 3
+    probs = (torch.rand((b, a, c), generator=gen) * 64).round() / 64          # 65 distinct values
+    cxy = (torch.rand((b, a, 2), generator=gen) * 20).round() * 10
+    wh = (torch.rand((b, a, 2), generator=gen) * 4).round() * 8 + 8
+    corners = torch.cat([cxy - wh / 2, cxy + wh / 2], dim=-1)
+    ref = ora.detections_from_scores(probs, corners, 0.3, 0.5, 50, None, canonical=True)
+    dets, counts, anchors, status = OPS.postprocess(probs.to(dev), corners.to(dev), None, N.CONVERT_IDENTITY, 0,
+                                                    N.BOXES_CORNERS, 1.0, 1.0, 0.3, 50, 0.5, 0)
+    for i in range(b):
+        assert int(counts[i]) == ref[i].shape[0]
+        assert torch.equal(dets[i, :int(counts[i])].cpu(), ref[i])
+
+
+def test_postprocess_overflow_fallback_is_exact(dev):
+    """Dense / fully tied scores overflow the candidate lists; the column-rescan fallback must
+    still give the canonical answer (ties -> lower anchor) for every converter."""
+    from single_shot_detection_b200 import _native as N
+    from single_shot_detection_b200.ops import OPS
+    gen = torch.Generator().manual_seed(31)
+    b, a, c = 2, 5000, 4
+    cxy = torch.rand((b, a, 2), generator=gen) * 300
+    wh = torch.rand((b, a, 2), generator=gen) * 30 + 2
+    corners = torch.cat([cxy - wh / 2, cxy + wh / 2], dim=-1)
+    probs = torch.full((b, a, c), 0.5)
+    probs[0, :, 1] = (torch.rand((a,), generator=gen) * 4).round() / 8 + 0.25       # 5 distinct values
+    probs[1, :, 2] = torch.linspace(0.02, 0.9, a)                                    # sorted ascending
+    probs[1, :, 3] = torch.linspace(0.9, 0.02, a)                                    # sorted descending
+    ref = ora.detections_from_scores(probs, corners, 0.01, 0.45, 100, 200, canonical=True)
+    dets, counts, anchors, status = OPS.postprocess(probs.to(dev), corners.to(dev), None, N.CONVERT_IDENTITY, 0,
+                                                    N.BOXES_CORNERS, 1.0, 1.0, 0.01, 100, 0.45, 200)
+    st = status.tolist()
+    assert st[0] == 0 and st[1] > 0, st           # the fallback really ran
+    for i in range(b):
+        assert int(counts[i]) == ref[i].shape[0]
+        assert torch.equal(dets[i, :int(counts[i])].cpu(), ref[i])
+    # saturated logits: sigmoid == 1.0f for many anchors, softmax one-hot
+    logits = torch.full((1, a, c), -20.0)
+    logits[0, ::3, 1] = 30.0
+    logits[0, 1::3, 2] = 25.0 + torch.rand((len(range(1, a, 3)),), generator=gen)
+    for conv, name, first in ((N.CONVERT_SIGMOID, "SIGMOID", 0), (N.CONVERT_SOFTMAX, "SOFTMAX", 1)):
+        fg = ora.convert_scores(logits, name)
+        ref = ora.detections_from_scores(fg, corners[:1], 0.01, 0.45, 100, 200, canonical=True)
+        dets, counts, anchors, status = OPS.postprocess(logits.to(dev), corners[:1].contiguous().to(dev), None, conv,
+                                                        first, N.BOXES_CORNERS, 1.0, 1.0, 0.01, 100, 0.45, 200)
+        n = int(counts[0])
+        assert n == ref[0].shape[0], name
+        torch.testing.assert_close(dets[0, :n].cpu(), ref[0], rtol=REL, atol=1e-6)
+
+
+def test_nms_api_vs_torchvision_golden(dev):
+    _, _, _, _, _, box_utils = _modules()
+    z = gio.load("nms.npz")
+    for i in range(int(z["num_cases"])):
+        bx, sc = torch.from_numpy(z[f"boxes_{i}"]), torch.from_numpy(z[f"scores_{i}"])
+        if bx.shape[0] > 512:
+            continue
+        (bk, sk), keep = box_utils.nms(bx.to(dev), sc.to(dev), float(z[f"thr_{i}"]), 0.01, None)
+        assert keep.cpu().tolist() == z[f"keep_{i}"].tolist(), i
+    for i in range(int(z["num_topk_cases"])):
+        bx, sc = torch.from_numpy(z[f"topk_boxes_{i}"]), torch.from_numpy(z[f"topk_scores_{i}"])
+        (bk, sk), keep = box_utils.nms(bx.to(dev), sc.to(dev), 0.45, 0.01, int(z[f"topk_k_{i}"]))
+        assert torch.equal(bk.cpu(), torch.from_numpy(z[f"topk_kept_boxes_{i}"])), i
+        assert torch.equal(sk.cpu(), torch.from_numpy(z[f"topk_kept_scores_{i}"])), i
+
+
+def test_postprocessor_interface(dev):
+    _, _, bc, _, pp, _ = _modules()
+    coder = bc.BoxCoder(10.0, 5.0)
+    with pytest.raises(ValueError):
+        pp.Postprocessor(coder, 0.01, {"max_per_class": 100, "overlap_threshold": 0.45}, score_converter="TANH")
+    post = pp.Postprocessor(coder, 0.01, {"max_per_class": 100, "overlap_threshold": 0.45}, max_total=200)
+    assert post.box_coder is coder and post.score_threshold == 0.01 and post.max_total == 200
+    with pytest.raises(TypeError):
+        post.postprocess((torch.zeros(1, 40), torch.zeros(1, 16)), torch.ones(4, 4))
+
+
+# ----------------------------------------------------------------------------------------------
+# whole timed region, BASELINE-sized shapes: properties that do not need the (slow) oracle
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,batch", [("ssd300_voc_b32", 32), ("ssd512_coco_b32", 4), ("retina500_coco_b32", 2)])
+def test_full_size_properties(dev, name, batch):
+    from single_shot_detection_b200.pipeline import AnchorPipeline
+    w = wl.WORKLOADS[name]
+    anchors, gt, scores, locs = wl.make_inputs(w, seed=23, batch=batch)
+    pipe = AnchorPipeline(w.cfg())
+    target, mask, dets = pipe.step(gt, anchors, scores, locs)
+    a = anchors.shape[0]
+    match = pipe.target_assigner.last_match.cpu()
+    cls = target[..., 4].cpu()
+    # every ground-truth box owns at least one anchor unless a later box took its only one
+    for i, g in enumerate(gt):
+        owned = set(match[i][match[i] >= 0].tolist())
+        assert len(owned) >= 1 and max(owned) < g.shape[0]
+    # mining: positives always sampled, ignored never, count = pos + min(max(3*pos,5), neg)
+    m = mask.cpu()
+    pos = (cls != 0) & (cls != -1)
+    assert bool((m & pos).eq(pos).all()) and not bool((m & (cls == -1)).any())
+    if w.sampler == "hard_negative_mining":
+        n_pos, n_neg = pos.sum(1), (cls == 0).sum(1)
+        want = n_pos + torch.minimum(torch.clamp(n_pos * w.ratio, min=w.min_neg), n_neg)
+        assert m.sum(1).tolist() == want.tolist()
+    else:
+        assert torch.equal(m, pos)
+    # detections: at most T rows, scores above threshold, sorted descending when the top-k hit,
+    # classes in range, boxes well formed, and idempotent (same call, same bits)
+    dets2 = pipe.postprocessor.postprocess((scores.to(dev), locs.to(dev)), anchors)
+    for d, d2 in zip(dets, dets2):
+        d = d.cpu()
+        assert torch.equal(d, d2.cpu())
+        assert d.shape[0] <= w.max_total and d.shape[1] == 6
+        assert bool((d[:, 5] > w.score_threshold).all())
+        if d.shape[0] == w.max_total:
+            assert bool((d[1:, 5] <= d[:-1, 5]).all())
+        assert bool(((d[:, 4] >= 1) & (d[:, 4] <= w.num_fg)).all())
+        assert bool((d[:, 2] >= d[:, 0]).all()) and bool((d[:, 3] >= d[:, 1]).all())
+
+
+def test_full_size_ssd300_b8_vs_oracle(dev):
+    """BASELINE configs[0] at full size against the oracle (a few seconds of CPU)."""
+    from single_shot_detection_b200.pipeline import AnchorPipeline
+    w = wl.WORKLOADS["ssd300_voc_b8"]
+    anchors, gt, scores, locs = wl.make_inputs(w, seed=23)
+    pipe = AnchorPipeline(w.cfg())
+    target, mask, dets = pipe.step(gt, anchors, scores, locs)
+    ref_target, ref_mask, ref_dets = ora.run_step(gt, anchors, scores, locs, w.cfg(), canonical=True,
+                                                   use_torchvision=False)
+    pos = ora.positives_mask(target[..., 4].cpu().long())
+    assert torch.equal(target[..., 4:].cpu(), ref_target[..., 4:])
+    torch.testing.assert_close(target[..., :4].cpu()[pos], ref_target[..., :4][pos], rtol=REL, atol=1e-6)
+    assert int((mask.cpu() != ref_mask).sum()) <= 8
+    _compare_dets(dets, ref_dets, w.img)
