@@ -61,6 +61,8 @@ typedef enum {
 
 SSD_API int ssd_b200_abi_version(void);
 SSD_API const char* ssd_b200_last_error(void);
+/* kernels this library has launched so far in this process (bench.py reports it as gpu_launches) */
+SSD_API unsigned long long ssd_b200_launch_count(void);
 /* SSD_OK when the current device is compute capability 10.x and the sm_100a image loads. */
 SSD_API int ssd_b200_device_check(void);
 
@@ -140,6 +142,11 @@ SSD_API int ssd_positive_mask(const int64_t* target_classes, int64_t count, uint
  *                   or NULL.  Ties at the cut are broken towards the lower anchor index.
  * ---------------------------------------------------------------------------------------- */
 SSD_API size_t ssd_hard_negative_workspace_bytes(int batch, int num_anchors);
+/* First half only: the streamed mining criterion folded with the class id into one sortable
+ * uint32 key per anchor (0 = ignored, 0xFFFFFFFF = positive, else ordered(-log_softmax[0])).
+ * This is the HBM-bound kernel of the sampler; exported so it can be timed / profiled alone. */
+SSD_API int ssd_mining_keys(const float* logits, const int64_t* target_classes, int batch, int num_anchors,
+                    int num_cols, uint32_t* keys_out, void* stream);
 SSD_API int ssd_hard_negative_mask(const float* logits, const int64_t* target_classes,
                            const float* loss_override, int batch, int num_anchors, int num_cols,
                            double ratio, int ratio_is_integer, double min_negatives,

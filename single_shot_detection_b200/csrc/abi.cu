@@ -19,6 +19,9 @@ int cuda_fail(cudaError_t e, const char* what) {
     return SSD_ERR_CUDA;
 }
 
+static unsigned long long g_launches = 0;
+void count_launch(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+
 int sm_count() {
     static int cached[64] = {0};
     int dev = 0;
@@ -36,6 +39,8 @@ __global__ void probe_kernel(int* out) { *out = 100; }
 }  // namespace ssd
 
 extern "C" int ssd_b200_abi_version(void) { return SSD_B200_ABI_VERSION; }
+
+extern "C" unsigned long long ssd_b200_launch_count(void) { return __atomic_load_n(&ssd::g_launches, __ATOMIC_RELAXED); }
 
 extern "C" const char* ssd_b200_last_error(void) { return ssd::g_error; }
 

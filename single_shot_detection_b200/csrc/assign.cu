@@ -298,6 +298,7 @@ extern "C" int ssd_pairwise_iou(const float* a_corners, int num_a, const float* 
     pairwise_iou_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)a_corners, num_a,
                                                                   (const float4*)b_corners, num_b, out);
     SSD_CUDA(cudaGetLastError());
+    count_launch();
     return SSD_OK;
 }
 
@@ -318,6 +319,7 @@ extern "C" int ssd_match_per_prediction(const float* weights, int num_gt, int nu
                                                                        unmatched_threshold, force_match,
                                                                        (long long*)box_idx_out, g_match_scratch);
     SSD_CUDA(cudaGetLastError());
+    count_launch();
     return SSD_OK;
 }
 
@@ -369,5 +371,6 @@ extern "C" int ssd_assign_targets(const float* anchors, const float* gt_rows, in
     SSD_CUDA(cudaLaunchKernelEx(&cfg, assign_targets_kernel, (const float4*)anchors, gt_rows, gt_cols, gt_offsets,
                                 num_anchors, chunk, matched_threshold, unmatched_threshold, force_match, target_out,
                                 match_out, stats_out));
+    count_launch();
     return SSD_OK;
 }

@@ -90,6 +90,7 @@ static int launch_box(bool vec4, const float* src, int64_t ss, float* dst, int64
     else
         box_transform_kernel<OP, false><<<blocks, 256, 0, st>>>(src, ss, dst, ds, (const float4*)priors, rows, A, xy, wh, eps);
     SSD_CUDA(cudaGetLastError());
+    count_launch();
     return SSD_OK;
 }
 

@@ -33,6 +33,7 @@ int cuda_fail(cudaError_t e, const char* what);
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 __host__ __device__ inline size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 int sm_count();
+void count_launch(int n = 1);      // bumps the library-wide kernel launch counter (ssd_b200_launch_count)
 
 // ---------------------------------------------------------------------------------------------
 // exact fp32 arithmetic: every op separately rounded (the file is also compiled with -fmad=false)

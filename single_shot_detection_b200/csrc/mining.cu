@@ -328,7 +328,41 @@ extern "C" int ssd_positive_mask(const int64_t* target_classes, int64_t count, u
     positive_mask_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
         (const long long*)target_classes, mask_out, count);
     SSD_CUDA(cudaGetLastError());
+    count_launch();
     return SSD_OK;
+}
+
+static int launch_mining_keys(const float* logits, const int64_t* target_classes, int64_t total_rows, int num_cols,
+                              uint32_t* keys, cudaStream_t st) {
+    SSD_REQUIRE(num_cols >= 1 && num_cols <= kMaxScoreCols, SSD_ERR_UNSUPPORTED,
+                "mining: num_cols %d outside 1..%d", num_cols, kMaxScoreCols);
+    SSD_REQUIRE(aligned(logits, 16), SSD_ERR_MISALIGNED, "mining: logits not 16-byte aligned");
+    const StreamShape shp = make_stream_shape(num_cols, 32);
+    const int num_tiles = (int)((total_rows + shp.tile_rows - 1) / shp.tile_rows);
+    int grid = 2 * sm_count();
+    if (grid > num_tiles) grid = num_tiles;
+#define SSD_LAUNCH_MINING(QQ, NN)                                                                                   \
+    do {                                                                                                             \
+        auto kern = mining_loss_kernel<QQ, NN>;                                                                      \
+        SSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shp.smem_bytes));      \
+        kern<<<grid, kStreamThreads, shp.smem_bytes, st>>>(logits, (const long long*)target_classes, keys,          \
+                                                            total_rows, num_cols, shp.tile_rows, shp.stage_floats,   \
+                                                            num_tiles);                                              \
+    } while (0)
+    SSD_DISPATCH_ROW_SHAPE(num_cols, SSD_LAUNCH_MINING);
+#undef SSD_LAUNCH_MINING
+    SSD_CUDA(cudaGetLastError());
+    count_launch();
+    return SSD_OK;
+}
+
+extern "C" int ssd_mining_keys(const float* logits, const int64_t* target_classes, int batch, int num_anchors,
+                               int num_cols, uint32_t* keys_out, void* stream) {
+    SSD_REQUIRE(batch >= 0 && num_anchors >= 0, SSD_ERR_INVALID_ARGUMENT, "ssd_mining_keys: negative shape");
+    if (batch == 0 || num_anchors == 0) return SSD_OK;
+    SSD_REQUIRE(logits && target_classes && keys_out, SSD_ERR_INVALID_ARGUMENT, "ssd_mining_keys: null pointer");
+    return launch_mining_keys(logits, target_classes, (int64_t)batch * num_anchors, num_cols, keys_out,
+                              (cudaStream_t)stream);
 }
 
 extern "C" size_t ssd_hard_negative_workspace_bytes(int batch, int num_anchors) {
@@ -356,25 +390,10 @@ extern "C" int ssd_hard_negative_mask(const float* logits, const int64_t* target
         mining_keys_from_loss_kernel<<<(unsigned)((total_rows + threads - 1) / threads), threads, 0, st>>>(
             loss_override, (const long long*)target_classes, keys, total_rows);
         SSD_CUDA(cudaGetLastError());
+    count_launch();
     } else {
-        SSD_REQUIRE(num_cols >= 1 && num_cols <= kMaxScoreCols, SSD_ERR_UNSUPPORTED,
-                    "ssd_hard_negative_mask: num_cols %d outside 1..%d", num_cols, kMaxScoreCols);
-        SSD_REQUIRE(aligned(logits, 16), SSD_ERR_MISALIGNED, "ssd_hard_negative_mask: logits not 16-byte aligned");
-        const StreamShape shp = make_stream_shape(num_cols, 32);
-        const int num_tiles = (int)((total_rows + shp.tile_rows - 1) / shp.tile_rows);
-        int grid = 2 * sm_count();
-        if (grid > num_tiles) grid = num_tiles;
-#define SSD_LAUNCH_MINING(QQ, NN)                                                                                   \
-    do {                                                                                                             \
-        auto kern = mining_loss_kernel<QQ, NN>;                                                                      \
-        SSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shp.smem_bytes));      \
-        kern<<<grid, kStreamThreads, shp.smem_bytes, st>>>(logits, (const long long*)target_classes, keys,          \
-                                                            total_rows, num_cols, shp.tile_rows, shp.stage_floats,   \
-                                                            num_tiles);                                              \
-    } while (0)
-        SSD_DISPATCH_ROW_SHAPE(num_cols, SSD_LAUNCH_MINING);
-#undef SSD_LAUNCH_MINING
-        SSD_CUDA(cudaGetLastError());
+        const int rc = launch_mining_keys(logits, target_classes, total_rows, num_cols, keys, st);
+        if (rc != SSD_OK) return rc;
     }
 
     if (num_anchors <= 12 * kSelThreads) {
@@ -390,5 +409,6 @@ extern "C" int ssd_hard_negative_mask(const float* logits, const int64_t* target
                                               mask_out, stats_out);
     }
     SSD_CUDA(cudaGetLastError());
+    count_launch();
     return SSD_OK;
 }

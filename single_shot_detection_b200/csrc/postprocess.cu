@@ -901,6 +901,7 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
     SSD_DISPATCH_ROW_SHAPE(pl.C, SSD_LAUNCH_PASS1);
 #undef SSD_LAUNCH_PASS1
     SSD_CUDA(cudaGetLastError());
+    count_launch();
 
     {
         const int warps_needed = pl.B * pl.C;
@@ -908,6 +909,7 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
         class_gate_kernel<<<blocks, 256, 0, st>>>(blockmax, pl.B, pl.C, pl.first_fg, pl.nblk, pl.K, pl.converter,
                                                   p->score_threshold, gate, cand_count, status);
         SSD_CUDA(cudaGetLastError());
+    count_launch();
     }
 
 #define SSD_LAUNCH_PASS2(QQ, NN)                                                                                      \
@@ -925,6 +927,7 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
     SSD_DISPATCH_ROW_SHAPE(pl.C, SSD_LAUNCH_PASS2);
 #undef SSD_LAUNCH_PASS2
     SSD_CUDA(cudaGetLastError());
+    count_launch();
 
     {
         NmsArgs a;
@@ -939,6 +942,7 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
                                                                      (const float4*)boxes, (const float4*)priors,
                                                                      kept_count, kept, status);
         SSD_CUDA(cudaGetLastError());
+    count_launch();
     }
     {
         int t2 = 32;
@@ -949,6 +953,7 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
         image_topk_kernel<<<pl.B, kTopkThreads, smem, st>>>(pl.Cf, pl.K, pl.T, pl.det_cap, kept_count, kept, dets_out,
                                                              count_out, anchor_out);
         SSD_CUDA(cudaGetLastError());
+    count_launch();
     }
     if (status_out != nullptr)
         SSD_CUDA(cudaMemcpyAsync(status_out, status, 4 * sizeof(int), cudaMemcpyDeviceToDevice, st));
@@ -1025,5 +1030,6 @@ extern "C" int ssd_nms(const float* corner_boxes, const float* scores, int num_b
     if (rc2 != SSD_OK) return rc2;
     widen_keep_kernel<<<(max_per_class + 127) / 128, 128, 0, st>>>(anchors, count_out, (long long*)keep_out, max_per_class);
     SSD_CUDA(cudaGetLastError());
+    count_launch();
     return SSD_OK;
 }

@@ -16,7 +16,7 @@ a CUDA graph (launch-bound configs: ~10 kernels of a few microseconds each).
 from __future__ import annotations
 
 import functools
-from typing import Dict, Optional
+from typing import Dict, NamedTuple, Optional
 
 import torch
 
@@ -24,6 +24,17 @@ from . import _devcache, box_utils, sampler as _sampler
 from .box_coder import BoxCoder
 from .postprocessor import Postprocessor
 from .target_assigner import CLASS_INDEX, LOC_INDEX_END, LOC_INDEX_START, PackedGroundTruth, TargetAssigner, pack_ground_truth
+
+
+class StepOutput(NamedTuple):
+    target: torch.Tensor          # [B, A, 6], box columns encoded in place
+    mask: torch.Tensor            # [B, A] bool sampler output
+    dets: torch.Tensor            # [B, T, 6] padded detections
+    counts: torch.Tensor          # [B] int32 rows used in dets
+    det_anchors: torch.Tensor     # [B, T] int32 anchor of every detection row
+    status: torch.Tensor          # [4] int32 (see ssd_postprocess)
+    stats: torch.Tensor           # [B, 4] int32 positives, hard negatives, ignored, detections
+    shard: Optional[torch.Tensor]  # packed exchange buffer, when requested
 
 
 class AnchorPipeline:
@@ -71,25 +82,35 @@ class AnchorPipeline:
         return mask
 
     # -- device-resident, sync-free -------------------------------------------------------------
-    def step_device(self, packed: PackedGroundTruth, anchors_dev, scores_dev, locs_dev):
+    def step_device(self, packed: PackedGroundTruth, anchors_dev, scores_dev, locs_dev,
+                    shard_capacity: Optional[int] = None) -> "StepOutput":
+        """``shard_capacity``: also pack (dets, counts, stats) into the one-buffer layout
+        ``sharding.all_gather_detections`` exchanges (so the packing is part of the graph)."""
         target = self.target_assigner.encode_packed(packed, anchors_dev)
         mask = self._sample_and_encode(target, anchors_dev, scores_dev)
         dets, counts, det_anchors, status = self.postprocessor.postprocess_padded((scores_dev, locs_dev), anchors_dev)
-        return target, mask, dets, counts, det_anchors, status
+        mining = _sampler.hard_negative_mining.last_stats if self.cfg["sampler"] == "hard_negative_mining" else None
+        stats = matched_stats(self.target_assigner.last_stats, mining, counts)
+        shard = None
+        if shard_capacity is not None:
+            from . import sharding
+            shard = sharding.pack_shard(dets, counts, stats, shard_capacity)
+        return StepOutput(target, mask, dets, counts, det_anchors, status, stats, shard)
 
-    def capture(self, packed: PackedGroundTruth, anchors_dev, scores_dev, locs_dev, warmup: int = 2):
+    def capture(self, packed: PackedGroundTruth, anchors_dev, scores_dev, locs_dev, warmup: int = 2,
+                shard_capacity: Optional[int] = None) -> "StepOutput":
         """Record ``step_device`` on these (static) buffers into a CUDA graph; returns the outputs
         the replays will keep overwriting."""
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                out = self.step_device(packed, anchors_dev, scores_dev, locs_dev)
+                out = self.step_device(packed, anchors_dev, scores_dev, locs_dev, shard_capacity)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            out = self.step_device(packed, anchors_dev, scores_dev, locs_dev)
+            out = self.step_device(packed, anchors_dev, scores_dev, locs_dev, shard_capacity)
         self._graph = graph
         return out
 

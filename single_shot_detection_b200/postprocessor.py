@@ -60,6 +60,7 @@ class Postprocessor(object):
             processed: list(:len Batch) of torch.tensor(:shape [Boxes_i, 6] ~ {[0-3] - box, [4] - class, [5] - score})
         """
         dets, counts, anchors, status = self.postprocess_padded(prediction, priors)
+        self.last_padded = (dets, counts, anchors, status)
         host = _devcache.pinned_buffer("post_counts", (counts.numel() + 4,), torch.int32)
         host[: counts.numel()].copy_(counts, non_blocking=True)
         host[counts.numel():].copy_(status, non_blocking=True)

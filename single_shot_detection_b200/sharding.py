@@ -45,6 +45,9 @@ def unpack_gathered(gathered: torch.Tensor, batch: int, world: int, max_rows: in
     """Inverse of pack_shard over the concatenation of all ranks' buffers."""
     capacity = gathered.shape[0] // world
     ints = gathered.view(torch.int32)
+    if batch == world * capacity:                       # even shards: pure views, no kernel
+        dets = gathered[:, : max_rows * 6].reshape(batch, max_rows, 6)
+        return dets, ints[:, max_rows * 6], ints[:, max_rows * 6 + 1:]
     keep = []
     for r in range(world):
         lo, hi = image_shard(batch, r, world)
@@ -65,6 +68,13 @@ def all_gather_detections(dets: torch.Tensor, counts: torch.Tensor, stats: torch
     world = dist.get_world_size(group)
     capacity = shard_capacity(batch, world)
     mine = pack_shard(dets, counts, stats, capacity)
+    return all_gather_packed(mine, batch, dets.shape[1], group)
+
+
+def all_gather_packed(mine: torch.Tensor, batch: int, max_rows: int, group: Optional[dist.ProcessGroup] = None):
+    """The collective alone, for a shard already packed by :func:`pack_shard` (e.g. inside a CUDA graph)."""
+    world = dist.get_world_size(group)
+    capacity = mine.shape[0]
     out = torch.empty((world * capacity, mine.shape[1]), dtype=mine.dtype, device=mine.device)
     dist.all_gather_into_tensor(out, mine, group=group)
-    return unpack_gathered(out, batch, world, dets.shape[1])
+    return unpack_gathered(out, batch, world, max_rows)

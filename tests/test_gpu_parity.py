@@ -296,7 +296,7 @@ def test_postprocess_vs_reference_golden(case, dev, max_total):
         for m, r in zip(dets, ref):
             assert m.shape == r.shape
             torch.testing.assert_close(m.cpu()[:, 5], r[:, 5], rtol=REL, atol=1e-6)
-        dets = [d.cpu()[torch.argsort(d.cpu()[:, 5], descending=True, stable=True)] for d in dets]
+        dets = [d.cpu() for d in dets]           # same row order as the reference: sorted only if n > T
         same = all(_dets_close(d, r, w.img) for d, r in zip(dets, ref))
         if not same:
             for d, r in zip(dets, ref):
