@@ -1,0 +1,233 @@
+// Row-tile streaming skeleton shared by the logit-streaming kernels (hard-negative mining loss,
+// post-processor score passes).
+//
+// Layout recap: logits are [rows, C] fp32 with the class index fastest (detection/detector.py:50-66
+// emits [B, A*C]).  The CTA is warp specialised:
+//   * one PRODUCER warp walks the CTA's tile list and, per tile, issues cp.async.bulk (TMA, 1-D)
+//     copies -- the tile's logits plus an optional 8-byte-per-row side array (class ids or the
+//     (max, sum) row statistics) -- into a STAGES-deep shared-memory ring; completion is tracked
+//     by the stage's `full` mbarrier (expect_tx), reuse by its `empty` mbarrier;
+//   * kConsumerWarps CONSUMER warps wait on `full`, reduce rows out of shared memory and arrive
+//     on `empty`.  No block-wide barrier in the steady state.
+// A row is owned by Q adjacent lanes (lane `sub` holds columns sub, sub+Q, ... in NREG registers),
+// so one warp covers 32/Q rows per step and every value is read from shared memory exactly once.
+// Copies are made of the 16-byte aligned superset of the wanted bytes (TMA needs 16-byte aligned
+// addresses and sizes; rows are 4*C bytes, so tile starts are only 4-byte aligned in general).
+#pragma once
+
+#include "common.cuh"
+
+namespace ssd {
+
+constexpr int kConsumerWarps = 8;
+constexpr int kStreamThreads = (kConsumerWarps + 1) * 32;
+constexpr int kStreamStages = 4;
+constexpr int kMaxScoreCols = 1024;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+// exp / log for the STREAMED reductions (row sums, gate values): one MUFU each.  Relative error
+// ~3e-7 on a softmax denominator; the exact per-candidate scores use expf / IEEE divide.
+__device__ __forceinline__ float fast_exp(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(__fmul_rn(x, kLog2e)));
+    return y;
+}
+__device__ __forceinline__ float fast_log(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return __fmul_rn(y, kLn2);
+}
+
+// Tiling of a [B images x A rows x C cols] array.  The mining kernel views its flat [B*A, C]
+// input as one image.  Work item = `group_tiles` consecutive tiles of one image; items are dealt
+// round-robin to CTAs.
+struct ScoreGrid {
+    int A, C, first_fg;
+    int tile_rows, tiles_per_image, group_tiles, groups_per_image, num_items;
+    int stage_bytes;          // bytes per ring stage (logit tile + side array, 16-byte multiples)
+    int side_offset;          // byte offset of the side array inside a stage
+    int nblk, split;          // post-processor block-max bookkeeping (unused by mining)
+    int64_t total_floats;     // B*A*C
+    int64_t total_rows;       // B*A
+};
+
+struct TileCursor {
+    int item, tile, tile_end;
+    __device__ __forceinline__ void start(const ScoreGrid& g) {
+        item = blockIdx.x;
+        open(g);
+    }
+    __device__ __forceinline__ void open(const ScoreGrid& g) {
+        if (item < g.num_items) {
+            const int grp = item % g.groups_per_image;
+            tile = grp * g.group_tiles;
+            tile_end = min(tile + g.group_tiles, g.tiles_per_image);
+        }
+    }
+    __device__ __forceinline__ bool valid(const ScoreGrid& g) const { return item < g.num_items; }
+    __device__ __forceinline__ int image(const ScoreGrid& g) const { return item / g.groups_per_image; }
+    __device__ __forceinline__ int group(const ScoreGrid& g) const { return item % g.groups_per_image; }
+    __device__ __forceinline__ bool last_of_item() const { return tile + 1 == tile_end; }
+    __device__ __forceinline__ void next(const ScoreGrid& g) {
+        if (++tile == tile_end) {
+            item += gridDim.x;
+            open(g);
+        }
+    }
+    __device__ __forceinline__ int rows(const ScoreGrid& g) const { return min(g.tile_rows, g.A - tile * g.tile_rows); }
+    __device__ __forceinline__ int64_t first_row(const ScoreGrid& g) const {
+        return (int64_t)image(g) * g.A + (int64_t)tile * g.tile_rows;
+    }
+};
+
+// shared memory: [0,64) full barriers, [64,128) empty barriers, then the stages
+__device__ __forceinline__ uint64_t* full_bar(unsigned char* smem, int s) { return reinterpret_cast<uint64_t*>(smem) + s; }
+__device__ __forceinline__ uint64_t* empty_bar(unsigned char* smem, int s) { return reinterpret_cast<uint64_t*>(smem + 64) + s; }
+__device__ __forceinline__ unsigned char* stage_ptr(unsigned char* smem, const ScoreGrid& g, int s) {
+    return smem + 128 + (size_t)s * g.stage_bytes;
+}
+__device__ __forceinline__ int tile_head(int64_t first_row, int C) { return (int)((first_row * C) & 3); }
+__device__ __forceinline__ int side_head(int64_t first_row) { return (int)(first_row & 1); }
+
+__device__ __forceinline__ void stream_init(unsigned char* smem) {
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kStreamStages; ++s) {
+            mbar_init(full_bar(smem, s), 1);
+            mbar_init(empty_bar(smem, s), kConsumerWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+}
+
+// Producer side: called by ONE lane.  Copies the tile [first_row, first_row+rows) x C floats (and
+// rows 8-byte side elements when `side` != nullptr) into stage `dst`.
+__device__ __forceinline__ void produce_tile(unsigned char* dst, uint64_t* full, const ScoreGrid& g,
+                                             const float* __restrict__ base, const unsigned long long* __restrict__ side,
+                                             int64_t first_row, int rows, uint64_t policy) {
+    const int64_t f0 = first_row * g.C;
+    const int64_t f1 = f0 + (int64_t)rows * g.C;
+    const int64_t fa = f0 & ~int64_t(3);
+    int64_t fe = (f1 + 3) & ~int64_t(3);
+    const int64_t n4 = g.total_floats & ~int64_t(3);
+    if (fe > n4) fe = n4 > fa ? n4 : fa;
+    const uint32_t bytes = (uint32_t)((fe - fa) * 4);
+    float* tdst = reinterpret_cast<float*>(dst);
+    for (int64_t f = fe; f < f1; ++f) tdst[f - fa] = __ldg(base + f);          // <= 3 floats, array tail only
+    uint32_t sbytes = 0;
+    int64_t sa = 0;
+    unsigned long long* sdst = reinterpret_cast<unsigned long long*>(dst + g.side_offset);
+    if (side != nullptr) {
+        const int64_t r1 = first_row + rows;
+        sa = first_row & ~int64_t(1);
+        int64_t se = (r1 + 1) & ~int64_t(1);
+        const int64_t n2 = g.total_rows & ~int64_t(1);
+        if (se > n2) se = n2 > sa ? n2 : sa;
+        sbytes = (uint32_t)((se - sa) * 8);
+        for (int64_t r = se; r < r1; ++r) sdst[r - sa] = __ldg(side + r);      // <= 1 element, array tail only
+    }
+    if (bytes + sbytes) {
+        mbar_expect_tx(full, bytes + sbytes);
+        if (bytes) bulk_g2s(tdst, base + fa, bytes, full, policy);
+        if (sbytes) bulk_g2s(sdst, side + sa, sbytes, full, policy);
+    } else {
+        mbar_arrive(full);
+    }
+}
+
+// The producer warp's whole life: stream every tile of this CTA through the ring.
+__device__ __forceinline__ void producer_loop(unsigned char* smem, const ScoreGrid& g, const float* __restrict__ base,
+                                              const unsigned long long* __restrict__ side, uint64_t policy) {
+    if (lane_id() != 0) return;
+    TileCursor cur;
+    cur.start(g);
+    for (int k = 0; cur.valid(g); ++k, cur.next(g)) {
+        const int s = k % kStreamStages;
+        if (k >= kStreamStages) mbar_wait(empty_bar(smem, s), ((k / kStreamStages) - 1) & 1);
+        produce_tile(stage_ptr(smem, g, s), full_bar(smem, s), g, base, side, cur.first_row(g), cur.rows(g), policy);
+    }
+}
+
+// Lane geometry of the Q-lanes-per-row mapping.
+template <int Q>
+struct RowLanes {
+    int sub;       // column phase of this lane
+    int rl;        // row slot of this lane inside the warp step
+    static constexpr int kRowsPerWarpStep = 32 / Q;
+    __device__ __forceinline__ RowLanes() : sub(lane_id() % Q), rl(lane_id() / Q) {}
+};
+
+// Load the NREG register slice of one row from a staged tile; out-of-range slots get -inf
+// (exp(-inf - m) == 0 and max(-inf, x) == x, so no further predication is needed).
+template <int Q, int NREG>
+__device__ __forceinline__ void load_row_slice(float (&v)[NREG], const float* row, int sub, int C, bool row_valid) {
+#pragma unroll
+    for (int i = 0; i < NREG; ++i) {
+        const int col = sub + i * Q;
+        v[i] = (row_valid && col < C) ? row[col] : -INFINITY;
+    }
+}
+
+// row max and sum of exp(x - max) over the Q lanes that own the row
+template <int Q, int NREG>
+__device__ __forceinline__ void row_max_sum(const float (&v)[NREG], float& m, float& sum) {
+    m = v[0];
+#pragma unroll
+    for (int i = 1; i < NREG; ++i) m = fmaxf(m, v[i]);
+    m = group_max<Q>(m);
+    sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NREG; ++i) sum = __fadd_rn(sum, fast_exp(__fsub_rn(v[i], m)));
+    sum = group_sum<Q>(sum);
+}
+
+// Dispatch table C -> (Q, NREG).  NREG*Q >= C.
+#define SSD_DISPATCH_ROW_SHAPE(C, CALL)                      \
+    do {                                                     \
+        if ((C) <= 8) { CALL(1, 8); }                        \
+        else if ((C) <= 24) { CALL(4, 6); }                  \
+        else if ((C) <= 32) { CALL(4, 8); }                  \
+        else if ((C) <= 64) { CALL(8, 8); }                  \
+        else if ((C) <= 88) { CALL(8, 11); }                 \
+        else if ((C) <= 128) { CALL(8, 16); }                \
+        else if ((C) <= 256) { CALL(32, 8); }                \
+        else { CALL(32, 32); }                               \
+    } while (0)
+
+inline int lanes_per_row(int C) {
+    int q = 0;
+#define SSD_Q_(QQ, NN) q = QQ
+    SSD_DISPATCH_ROW_SHAPE(C, SSD_Q_);
+#undef SSD_Q_
+    return q;
+}
+
+// Host: tile geometry.  tile_rows is a multiple of the rows all consumer warps cover in one step.
+inline void plan_tiles(ScoreGrid& g, int images, int A, int C, bool with_side, int target_tile_bytes = 12 * 1024) {
+    const int quantum = kConsumerWarps * (32 / lanes_per_row(C));
+    int rows = target_tile_bytes / (C * 4);
+    rows = rows / quantum * quantum;
+    if (rows > 4 * quantum) rows = 4 * quantum;
+    if (rows < quantum) rows = quantum;
+    g.A = A; g.C = C;
+    g.tile_rows = rows;
+    g.tiles_per_image = (A + rows - 1) / rows;
+    g.group_tiles = 1;
+    g.groups_per_image = g.tiles_per_image;
+    g.num_items = images * g.groups_per_image;
+    const size_t tile_bytes = round_up((size_t)rows * C * 4 + 32, 16);
+    g.side_offset = (int)tile_bytes;
+    g.stage_bytes = (int)(tile_bytes + (with_side ? round_up((size_t)rows * 8 + 32, 16) : 0));
+    g.total_floats = (int64_t)images * A * C;
+    g.total_rows = (int64_t)images * A;
+    g.first_fg = 0; g.nblk = 0; g.split = 1;
+}
+inline size_t stream_smem_bytes(const ScoreGrid& g) { return 128 + (size_t)kStreamStages * g.stage_bytes; }
+inline int stream_grid(const ScoreGrid& g) {
+    int grid = 4 * sm_count();
+    return grid < g.num_items ? grid : g.num_items;
+}
+
+}  // namespace ssd

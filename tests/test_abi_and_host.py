@@ -1,0 +1,108 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/ssd_b200.h declares,
+the ctypes binding mirrors the header, the product package has no route into oracle/, and the
+reference-shaped Python surface keeps the reference's names.  No kernel is launched here."""
+import ast
+import ctypes
+import inspect
+import os
+import re
+
+import pytest
+
+from single_shot_detection_b200 import _native as N
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "single_shot_detection_b200")
+
+
+def _header_symbols():
+    text = open(N.HEADER_PATH).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"SSD_API\s+[\w\s\*]+?\b(ssd_\w+)\s*\(", text)))
+
+
+def test_header_declares_the_bound_symbols():
+    assert _header_symbols() == N.exported_symbols()
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    assert os.path.exists(N.LIB_PATH), "libssd_b200.so missing: run __graft_entry__.build()"
+    handle = ctypes.CDLL(N.LIB_PATH)
+    for name in _header_symbols():
+        assert hasattr(handle, name), f"{name} is declared in ssd_b200.h but not exported"
+    handle.ssd_b200_abi_version.restype = ctypes.c_int
+    assert handle.ssd_b200_abi_version() == 1
+    # only the declared entry points are visible (the kernels and helpers are hidden)
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", N.LIB_PATH], capture_output=True, text=True).stdout
+    exported = sorted(ln.split()[-1] for ln in out.splitlines() if " T " in ln and "ssd_" in ln.split()[-1])
+    assert exported == _header_symbols()
+
+
+def test_postprocess_params_struct_matches_header_layout():
+    # int32 x6, float x3, int32, double, int32 x2 -> the double sits at offset 40 on every LP64 ABI
+    assert N.PostprocessParams.overlap_threshold.offset == 40
+    assert ctypes.sizeof(N.PostprocessParams) == 56
+
+
+def test_argument_validation_without_a_device():
+    """Entry points validate their arguments before touching CUDA, so these run without a GPU."""
+    lib = N.lib()
+    assert lib.ssd_box_transform(99, None, 4, None, 4, None, 1, 1, 1.0, 1.0, 0.0, None) == 1
+    assert b"bad op" in lib.ssd_b200_last_error()
+    assert lib.ssd_assign_targets(None, None, 6, None, 0, -1, 10, 0.5, 0.5, 1, None, None, None, None) == 1
+    assert lib.ssd_hard_negative_mask(None, None, None, 1, 8, 3, 3.0, 1, 5.0, None, None, None, 0, None) == 1
+    p = N.PostprocessParams()
+    p.batch, p.num_anchors, p.num_cols, p.converter = 1, 8, 3, 7
+    assert lib.ssd_postprocess_workspace_bytes(ctypes.byref(p)) == 0
+    assert b"score_converter" in lib.ssd_b200_last_error()
+    # empty work is a no-op, not an error
+    assert lib.ssd_positive_mask(None, 0, None, None) == 0
+
+
+def test_product_package_never_imports_the_oracle():
+    for fn in os.listdir(PKG):
+        if not fn.endswith(".py"):
+            continue
+        tree = ast.parse(open(os.path.join(PKG, fn)).read())
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""]
+            assert not any(n.split(".")[0] == "oracle" for n in names), f"{fn} imports the oracle"
+
+
+def test_reference_surface_names_and_signatures():
+    from single_shot_detection_b200 import box_coder, box_utils, matcher, postprocessor, sampler, target_assigner
+    # detection/target_assigner.py:7-14
+    assert (target_assigner.LOC_INDEX_START, target_assigner.LOC_INDEX_END, target_assigner.CLASS_INDEX,
+            target_assigner.SCORE_INDEX, target_assigner.TARGET_SIZE) == (0, 4, 4, 5, 6)
+    assert (target_assigner.NEGATIVE_CLASS, target_assigner.IGNORE_CLASS) == (0, -1)
+    assert (matcher.NOT_MATCHED, matcher.IGNORE) == (-2, -1)
+    # detection/init.py:90-92 filters the sampler config through __code__.co_varnames
+    names = sampler.hard_negative_mining.__code__.co_varnames
+    assert "negative_per_positive_ratio" in names and "min_negative_per_image" in names
+    assert list(inspect.signature(sampler.naive_sampler).parameters) == ["predictions", "target_classes"]
+    assert list(inspect.signature(target_assigner.TargetAssigner.encode_ground_truth).parameters) == \
+        ["self", "ground_truth", "anchors"]
+    assert list(inspect.signature(box_coder.BoxCoder.__init__).parameters)[:4] == ["self", "xy_scale", "wh_scale", "eps"]
+    assert list(inspect.signature(box_coder.BoxCoder.encode_box).parameters) == ["self", "boxes", "priors", "inplace"]
+    assert list(inspect.signature(box_coder.BoxCoder.decode_box).parameters) == ["self", "boxes", "priors", "inplace"]
+    assert list(inspect.signature(postprocessor.Postprocessor.__init__).parameters) == \
+        ["self", "box_coder", "score_threshold", "nms", "score_converter", "max_total"]
+    assert list(inspect.signature(box_utils.nms).parameters) == \
+        ["boxes", "scores", "overlap_threshold", "score_threshold", "max_per_class", "soft", "sigma"]
+    with pytest.raises(ValueError):                       # detection/postprocessor.py:22
+        postprocessor.Postprocessor(box_coder.BoxCoder(10, 5), .01, {"max_per_class": 100, "overlap_threshold": .45},
+                                    score_converter="TANH")
+
+
+def test_cpu_tensors_are_rejected_not_silently_computed():
+    import torch
+    from single_shot_detection_b200 import box_utils
+    with pytest.raises(TypeError):
+        box_utils.to_corners(torch.zeros(3, 4))
+    with pytest.raises(TypeError):
+        box_utils.iou(torch.zeros(3, 4), torch.zeros(2, 4))
