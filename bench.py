@@ -223,7 +223,7 @@ def run_ours(args):
         pipes[k].replay()
         if world > 1:       # the one exchange step of the path: detections + counts + stats, one collective
             return sharding.all_gather_packed(outs[k].shard, B * world, w.max_total)
-        return outs[k].dets, outs[k].counts, outs[k].stats
+        return outs[k].dets, outs[k].counts, outs[k].assign_stats
 
     def barrier():
         if world > 1:
@@ -335,8 +335,11 @@ def roofline_probe(w, dev_sets, anchors_dev, pipe, B, A, C, nsets, iters: int = 
     cls = [torch.zeros((B, A), dtype=torch.int64, device=dev) for _ in range(nsets)]
     lib = N.lib()
 
+    ws = torch.empty((lib.ssd_hard_negative_workspace_bytes(B, A),), dtype=torch.uint8, device=dev)
+
     def launch(k):
-        N.check(lib.ssd_mining_keys(dev_sets[k][1].data_ptr(), cls[k].data_ptr(), B, A, C, keys.data_ptr(), stream))
+        N.check(lib.ssd_mining_keys(dev_sets[k][1].data_ptr(), cls[k].data_ptr(), B, A, C, keys.data_ptr(),
+                                    ws.data_ptr(), ws.numel(), stream))
 
     for i in range(5):
         launch(i % nsets)

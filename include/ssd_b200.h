@@ -65,6 +65,11 @@ SSD_API const char* ssd_b200_last_error(void);
 SSD_API unsigned long long ssd_b200_launch_count(void);
 /* SSD_OK when the current device is compute capability 10.x and the sm_100a image loads. */
 SSD_API int ssd_b200_device_check(void);
+/* Diagnostics: when enabled, every kernel launch of this library is bracketed by CUDA events on
+ * its stream (do not enable while capturing a CUDA graph).  The report synchronises the device and
+ * writes "label:mean_us:count,..." into buf; returns the number of characters written. */
+SSD_API void ssd_b200_timing_enable(int on);
+SSD_API size_t ssd_b200_timing_report(char* buf, size_t capacity);
 
 /* ------------------------------------------------------------------------------------------
  * a2  bf/utils/box_utils.py:83-101  iou(a, b) -- pairwise IoU of corner boxes.
@@ -131,7 +136,7 @@ SSD_API int ssd_positive_mask(const int64_t* target_classes, int64_t count, uint
 /* ------------------------------------------------------------------------------------------
  * a5  detection/sampler.py:12-25  hard_negative_mining
  *   logits          [B,A,C] fp32, 16-byte aligned
- *   target_classes  [B,A]   int64
+ *   target_classes  [B,A]   int64, 16-byte aligned
  *   loss_override   [B,A]   fp32 or NULL.  When given, it replaces -log_softmax(logits)[...,0]
  *                   (stage-boundary parity: selection on identical fp32 inputs) and logits may
  *                   be NULL.
@@ -143,10 +148,11 @@ SSD_API int ssd_positive_mask(const int64_t* target_classes, int64_t count, uint
  * ---------------------------------------------------------------------------------------- */
 SSD_API size_t ssd_hard_negative_workspace_bytes(int batch, int num_anchors);
 /* First half only: the streamed mining criterion folded with the class id into one sortable
- * uint32 key per anchor (0 = ignored, 0xFFFFFFFF = positive, else ordered(-log_softmax[0])).
+ * uint32 key per anchor (0 = ignored, 0xFFFFFFFF = positive, else ordered(-log_softmax[0])), plus
+ * the per-image loss histograms the selection reads (kept inside the workspace, same size query).
  * This is the HBM-bound kernel of the sampler; exported so it can be timed / profiled alone. */
 SSD_API int ssd_mining_keys(const float* logits, const int64_t* target_classes, int batch, int num_anchors,
-                    int num_cols, uint32_t* keys_out, void* stream);
+                    int num_cols, uint32_t* keys_out, void* workspace, size_t workspace_bytes, void* stream);
 SSD_API int ssd_hard_negative_mask(const float* logits, const int64_t* target_classes,
                            const float* loss_override, int batch, int num_anchors, int num_cols,
                            double ratio, int ratio_is_integer, double min_negatives,

@@ -46,6 +46,8 @@ _SIGNATURES = {
     "ssd_b200_abi_version": (c_int, []),
     "ssd_b200_last_error": (c_char_p, []),
     "ssd_b200_device_check": (c_int, []),
+    "ssd_b200_timing_enable": (None, [c_int]),
+    "ssd_b200_timing_report": (c_size_t, [ctypes.c_char_p, c_size_t]),
     "ssd_pairwise_iou": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "ssd_match_per_prediction": (c_int, [c_void_p, c_int, c_int, c_float, c_float, c_int, c_void_p, c_void_p]),
     "ssd_assign_targets": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_float, c_int,
@@ -54,7 +56,7 @@ _SIGNATURES = {
                                   c_float, c_float, c_void_p]),
     "ssd_positive_mask": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "ssd_b200_launch_count": (ctypes.c_ulonglong, []),
-    "ssd_mining_keys": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "ssd_mining_keys": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ssd_hard_negative_workspace_bytes": (c_size_t, [c_int, c_int]),
     "ssd_hard_negative_mask": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_int, c_double,
                                        c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -36,6 +36,29 @@ int sm_count() {
 
 __global__ void probe_kernel(int* out) { *out = 100; }
 
+// ---- optional per-launch timing (diagnostics; off by default, not capturable into a graph) ----
+constexpr int kTimingSlots = 8192;
+static bool g_timing = false;
+static int g_timing_used = 0;
+static cudaEvent_t g_ev[kTimingSlots][2];
+static const char* g_label[kTimingSlots];
+static bool g_ev_ready = false;
+
+int timing_begin(const char* label, cudaStream_t st) {
+    if (!g_timing || g_timing_used >= kTimingSlots) return -1;
+    if (!g_ev_ready) {
+        for (int i = 0; i < kTimingSlots; ++i) { cudaEventCreate(&g_ev[i][0]); cudaEventCreate(&g_ev[i][1]); }
+        g_ev_ready = true;
+    }
+    const int i = g_timing_used++;
+    g_label[i] = label;
+    cudaEventRecord(g_ev[i][0], st);
+    return i;
+}
+void timing_end(int slot, cudaStream_t st) {
+    if (slot >= 0) cudaEventRecord(g_ev[slot][1], st);
+}
+
 }  // namespace ssd
 
 extern "C" int ssd_b200_abi_version(void) { return SSD_B200_ABI_VERSION; }
@@ -64,4 +87,32 @@ extern "C" int ssd_b200_device_check(void) {
         return SSD_ERR_NO_DEVICE;
     }
     return SSD_OK;
+}
+
+extern "C" void ssd_b200_timing_enable(int on) {
+    ssd::g_timing = on != 0;
+    ssd::g_timing_used = 0;
+}
+
+extern "C" size_t ssd_b200_timing_report(char* buf, size_t capacity) {
+    using namespace ssd;
+    cudaDeviceSynchronize();
+    struct Acc { const char* label; double us; int n; };
+    Acc acc[64];
+    int na = 0;
+    for (int i = 0; i < g_timing_used; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, g_ev[i][0], g_ev[i][1]) != cudaSuccess) continue;
+        int j = 0;
+        for (; j < na; ++j) if (acc[j].label == g_label[i] || strcmp(acc[j].label, g_label[i]) == 0) break;
+        if (j == na) { if (na == 64) continue; acc[na++] = {g_label[i], 0.0, 0}; }
+        acc[j].us += 1e3 * ms;
+        acc[j].n += 1;
+    }
+    size_t off = 0;
+    for (int j = 0; j < na && buf && off + 96 < capacity; ++j)
+        off += (size_t)snprintf(buf + off, capacity - off, "%s%s:%.2f:%d", j ? "," : "", acc[j].label, acc[j].us / acc[j].n, acc[j].n);
+    if (buf && capacity) buf[off < capacity ? off : capacity - 1] = 0;
+    g_timing_used = 0;
+    return off;
 }

@@ -368,6 +368,7 @@ extern "C" int ssd_assign_targets(const float* anchors, const float* gt_rows, in
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    LaunchTimer lt_("assign", st);
     SSD_CUDA(cudaLaunchKernelEx(&cfg, assign_targets_kernel, (const float4*)anchors, gt_rows, gt_cols, gt_offsets,
                                 num_anchors, chunk, matched_threshold, unmatched_threshold, force_match, target_out,
                                 match_out, stats_out));

@@ -85,6 +85,7 @@ template <int OP>
 static int launch_box(bool vec4, const float* src, int64_t ss, float* dst, int64_t ds, const float* priors,
                       int64_t rows, int A, float xy, float wh, float eps, cudaStream_t st) {
     const unsigned blocks = (unsigned)((rows + 255) / 256);
+    LaunchTimer lt_("box", st);
     if (vec4)
         box_transform_kernel<OP, true><<<blocks, 256, 0, st>>>(src, ss, dst, ds, (const float4*)priors, rows, A, xy, wh, eps);
     else

@@ -34,6 +34,15 @@ inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_
 __host__ __device__ inline size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 int sm_count();
 void count_launch(int n = 1);      // bumps the library-wide kernel launch counter (ssd_b200_launch_count)
+// diagnostics: per-launch CUDA-event timing when enabled through ssd_b200_timing_enable()
+int timing_begin(const char* label, cudaStream_t st);
+void timing_end(int slot, cudaStream_t st);
+struct LaunchTimer {
+    int slot;
+    cudaStream_t st;
+    LaunchTimer(const char* label, cudaStream_t s) : slot(timing_begin(label, s)), st(s) {}
+    ~LaunchTimer() { timing_end(slot, st); }
+};
 
 // ---------------------------------------------------------------------------------------------
 // exact fp32 arithmetic: every op separately rounded (the file is also compiled with -fmad=false)
@@ -127,48 +136,5 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
         ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
 }
-
-// ---------------------------------------------------------------------------------------------
-// RowStream: a CTA walks a list of row tiles of a flat fp32 [rows, C] array.  Each tile is
-// fetched with one bulk copy of the 16-byte aligned superset of its bytes into a ring of
-// STAGES shared-memory buffers; `head` floats of slack precede the tile inside the buffer.
-// ---------------------------------------------------------------------------------------------
-struct TileDesc {
-    int64_t first_row;   // global row index (image * A + anchor)
-    int rows;            // rows in the tile (> 0)
-};
-
-template <int STAGES>
-struct RowStream {
-    float* buf[STAGES];
-    uint64_t* full;          // [STAGES] mbarriers
-    int stage_floats;
-
-    // Called by ONE thread.  Copies rows [first_row, first_row+rows) x C floats into stage s.
-    // total_floats = number of floats in the whole array (the copy never reads past it).
-    // Returns nothing; consumers call head_of() to find the first float of the tile.
-    __device__ __forceinline__ void issue(int s, const float* __restrict__ base, int64_t first_row, int rows,
-                                          int C, int64_t total_floats, uint64_t policy) {
-        const int64_t f0 = first_row * C;
-        const int64_t f1 = f0 + (int64_t)rows * C;
-        const int64_t fa = f0 & ~int64_t(3);
-        int64_t fe = (f1 + 3) & ~int64_t(3);
-        const int64_t n4 = total_floats & ~int64_t(3);
-        if (fe > n4) fe = n4 > fa ? n4 : fa;
-        const uint32_t bytes = (uint32_t)((fe - fa) * 4);
-        float* dst = buf[s];
-        // ragged tail of the very last tile of the array: at most 3 floats, plain loads
-        for (int64_t f = fe; f < f1; ++f) dst[f - fa] = __ldg(base + f);
-        if (bytes) {
-            mbar_expect_tx(&full[s], bytes);
-            bulk_g2s(dst, base + fa, bytes, &full[s], policy);
-        } else {
-            mbar_arrive(&full[s]);
-        }
-    }
-    __device__ __forceinline__ static int head_of(int64_t first_row, int C) {
-        return (int)((first_row * C) & 3);
-    }
-};
 
 }  // namespace ssd

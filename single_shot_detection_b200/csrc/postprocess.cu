@@ -41,16 +41,8 @@ namespace ssd {
 // ---------------------------------------------------------------------------------------------
 struct PostPlan {
     int B, A, C, Cf, first_fg, K, T, det_cap, converter, box_input;
-    int warps;               // warps per streaming CTA
-    int tile_rows;           // rows per staged tile
-    int stage_floats;
-    size_t stream_smem;
-    int tiles_per_image;
-    int group_tiles;         // tiles whose rows form one row block per warp
-    int groups_per_image;
-    int num_items;           // B * groups_per_image (work items of the streaming kernels)
-    int split;               // row slots of a warp step kept as separate blocks (1..32/Q)
-    int nblk;                // row blocks per image = groups_per_image * warps * split
+    ScoreGrid g;             // tiling of the streaming kernels (shared by both passes)
+    int nblk;                // row blocks per image
     int cand_cap;            // candidate slots per (image, class)
     // workspace offsets (bytes)
     size_t off_rowstat, off_blockmax, off_gate, off_cand_count, off_cand, off_kept_count, off_kept, off_status,
@@ -62,17 +54,6 @@ constexpr int kKeptCols = 6;          // x1,y1,x2,y2,score,anchor(bits)
 constexpr int kMaxPerClass = 512;
 constexpr int kNmsThreads = 128;
 constexpr int kTopkThreads = 512;
-
-template <int Q>
-static int rows_quantum() { return (kStreamThreads / 32) * (32 / Q); }
-
-static int quantum_for_cols(int C) {
-    int q = 0;
-#define SSD_Q(QQ, NN) q = rows_quantum<QQ>()
-    SSD_DISPATCH_ROW_SHAPE(C, SSD_Q);
-#undef SSD_Q
-    return q;
-}
 
 static int make_plan(const ssd_postprocess_params* p, PostPlan& pl) {
     SSD_REQUIRE(p != nullptr, SSD_ERR_INVALID_ARGUMENT, "ssd_postprocess: null params");
@@ -96,39 +77,33 @@ static int make_plan(const ssd_postprocess_params* p, PostPlan& pl) {
                 "ssd_postprocess: det_capacity %d below the %lld rows an image can produce", pl.det_cap, need);
     SSD_REQUIRE(all_rows <= 26000, SSD_ERR_UNSUPPORTED, "ssd_postprocess: classes*max_per_class = %lld > 26000", all_rows);
 
-    pl.warps = kStreamThreads / 32;
-    const int quantum = quantum_for_cols(pl.C);
-    int rows = (24 * 1024) / (pl.C * 4);
-    rows = rows / quantum * quantum;
-    if (rows > 32 * pl.warps) rows = 32 * pl.warps / quantum * quantum;
-    if (rows < quantum) rows = quantum;
-    pl.tile_rows = rows;
-    pl.stage_floats = (int)round_up((size_t)rows * pl.C + 8, 4);
-    pl.stream_smem = 128 + (size_t)kStreamStages * pl.stage_floats * 4;
     const int A1 = pl.A > 0 ? pl.A : 1;
-    pl.tiles_per_image = (A1 + rows - 1) / rows;
-    // rows per block: ~32, smaller when the image has few anchors so that blocks >= ~2K exist
+    ScoreGrid& g = pl.g;
+    plan_tiles(g, pl.B, A1, pl.C, pl.converter == SSD_CONVERT_SOFTMAX);
+    g.first_fg = pl.first_fg;
+    // rows per block: ~32, smaller when the image has few anchors so that >= ~2K blocks exist
     int want_rows = A1 / (2 * pl.K);
     if (want_rows > 32) want_rows = 32;
-    const int rows_per_warp_tile = rows / pl.warps;
+    const int rows_per_warp_tile = g.tile_rows / kConsumerWarps;
     int gt = want_rows / rows_per_warp_tile;
     if (gt < 1) gt = 1;
-    pl.group_tiles = gt;
-    pl.groups_per_image = (pl.tiles_per_image + gt - 1) / gt;
-    pl.num_items = pl.B * pl.groups_per_image;
+    g.group_tiles = gt;
+    g.groups_per_image = (g.tiles_per_image + gt - 1) / gt;
+    g.num_items = pl.B * g.groups_per_image;
     // fewer rows per block than a warp sees in one tile: keep `split` row slots separate
     int split = 1;
-    const int slots = quantum / pl.warps;                 // 32 / Q row slots per warp step
+    const int slots = 32 / lanes_per_row(pl.C);           // row slots per warp step
     while (split < slots && rows_per_warp_tile * gt / split > (want_rows > 0 ? want_rows : 1)) split <<= 1;
-    pl.split = split;
-    pl.nblk = pl.groups_per_image * pl.warps * split;
+    g.split = split;
+    g.nblk = g.groups_per_image * kConsumerWarps * split;
+    pl.nblk = g.nblk;
     int cap = 512;                        // power of two (the segment sort pads to one), >= 8K
     while (cap < 8 * pl.K && cap < 4096) cap <<= 1;
     pl.cand_cap = cap;
 
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += round_up(bytes, 256); return o; };
-    const size_t BA = (size_t)pl.B * A1;
+    const size_t BA = (size_t)pl.B * A1 + 2;
     pl.off_rowstat = take(BA * sizeof(float2));
     pl.off_blockmax = take((size_t)pl.B * pl.nblk * pl.C * sizeof(float));
     pl.off_gate = take((size_t)pl.B * pl.C * sizeof(float));
@@ -142,117 +117,55 @@ static int make_plan(const ssd_postprocess_params* p, PostPlan& pl) {
     return SSD_OK;
 }
 
-// device-side view of the tiling
-struct ScoreGrid {
-    int A, C, first_fg;
-    int tile_rows, stage_floats, tiles_per_image, group_tiles, groups_per_image, num_items, nblk, split;
-    int64_t total_floats;
-};
-
-// Enumerates the tiles of the work items a CTA owns: item = blockIdx.x + n*gridDim.x.
-struct TileCursor {
-    int item, tile, tile_end;
-    __device__ __forceinline__ void start(const ScoreGrid& g) {
-        item = blockIdx.x;
-        open(g);
-    }
-    __device__ __forceinline__ void open(const ScoreGrid& g) {
-        if (item < g.num_items) {
-            const int grp = item % g.groups_per_image;
-            tile = grp * g.group_tiles;
-            tile_end = min(tile + g.group_tiles, g.tiles_per_image);
-        }
-    }
-    __device__ __forceinline__ bool valid(const ScoreGrid& g) const { return item < g.num_items; }
-    __device__ __forceinline__ int image(const ScoreGrid& g) const { return item / g.groups_per_image; }
-    __device__ __forceinline__ int group(const ScoreGrid& g) const { return item % g.groups_per_image; }
-    __device__ __forceinline__ bool last_of_item() const { return tile + 1 == tile_end; }
-    __device__ __forceinline__ void next(const ScoreGrid& g) {
-        if (++tile == tile_end) {
-            item += gridDim.x;
-            open(g);
-        }
-    }
-    __device__ __forceinline__ int rows(const ScoreGrid& g) const { return min(g.tile_rows, g.A - tile * g.tile_rows); }
-    __device__ __forceinline__ int64_t first_row(const ScoreGrid& g) const {
-        return (int64_t)image(g) * g.A + (int64_t)tile * g.tile_rows;
-    }
-};
-
 // ---------------------------------------------------------------------------------------------
-// 1. score_pass1
+// 1. score_pass1: row statistics + per-block column maxima of the gate value
+//    SOFTMAX: gate value of an element = its log-probability  x - (max + log(sum));
+//    SIGMOID / IDENTITY: the raw value (both converters are monotone per element).
 // ---------------------------------------------------------------------------------------------
 template <int Q, int NREG, int CONV>
 __global__ void __launch_bounds__(kStreamThreads)
 score_pass1_kernel(const float* __restrict__ scores, ScoreGrid g, float2* __restrict__ rowstat,
                    float* __restrict__ blockmax) {
     extern __shared__ __align__(128) unsigned char smem[];
-    RowStream<kStreamStages> rs;
-    stream_setup(rs, smem, g.stage_floats);
-    const RowLanes<Q> ln;
-    const int warps = blockDim.x >> 5;
-    const int rows_per_warp = g.tile_rows / warps;
-    const uint64_t policy = policy_evict_last();       // pass 2 re-reads the same bytes
-
-    TileCursor prod, cons;
-    prod.start(g);
-    cons.start(g);
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kStreamStages && prod.valid(g); ++s) {
-            rs.issue(s, scores, prod.first_row(g), prod.rows(g), g.C, g.total_floats, policy);
-            prod.next(g);
-        }
+    stream_init(smem);
+    if (warp_id() == kConsumerWarps) {
+        producer_loop(smem, g, scores, nullptr, policy_evict_last());      // pass 2 re-reads the same bytes
+        return;
     }
+    const RowLanes<Q> ln;
+    const int rows_per_warp = g.tile_rows / kConsumerWarps;
     float cmax[NREG];
 #pragma unroll
     for (int i = 0; i < NREG; ++i) cmax[i] = -INFINITY;
 
-    for (int k = 0; cons.valid(g); ++k) {
-        const int s = k % kStreamStages;
-        const uint32_t parity = (k / kStreamStages) & 1;
-        const int64_t r0 = cons.first_row(g);
-        const int rows = cons.rows(g);
-        mbar_wait(&rs.full[s], parity);
-        const float* tile = rs.buf[s] + RowStream<kStreamStages>::head_of(r0, g.C);
-
+    TileCursor cur;
+    cur.start(g);
+    for (int k = 0; cur.valid(g); ++k) {
+        const int64_t r0 = cur.first_row(g);
+        const int rows = cur.rows(g);
+        const StagedTile tile = consumer_acquire(smem, g, k, r0);
         const int wbase = warp_id() * rows_per_warp;
+#pragma unroll 2
         for (int step = 0; step < rows_per_warp; step += RowLanes<Q>::kRowsPerWarpStep) {
             const int lr = wbase + step + ln.rl;
             const bool valid = lr < rows;
-            if (__all_sync(FULL, !valid)) break;
             float v[NREG];
-            load_row_slice<Q, NREG>(v, tile + (size_t)lr * g.C, ln.sub, g.C, valid, -INFINITY);
+            load_row_slice<Q, NREG>(v, tile.logits + (size_t)lr * g.C, ln.sub, g.C, valid);
             if (CONV == SSD_CONVERT_SOFTMAX) {
-                float m = v[0];
-#pragma unroll
-                for (int i = 1; i < NREG; ++i) m = fmaxf(m, v[i]);
-                m = group_max<Q>(m);
-                float sum = 0.f;
-#pragma unroll
-                for (int i = 0; i < NREG; ++i) {
-                    const int col = ln.sub + i * Q;
-                    if (col < g.C) sum = __fadd_rn(sum, expf(__fsub_rn(v[i], m)));
-                }
-                sum = group_sum<Q>(sum);
-                const float ls = logf(sum);
+                float m, sum;
+                row_max_sum<Q, NREG>(v, valid, m, sum);
                 if (valid && ln.sub == 0) rowstat[r0 + lr] = make_float2(m, sum);
+                const float t = __fadd_rn(m, logf(sum));
 #pragma unroll
-                for (int i = 0; i < NREG; ++i) {
-                    const int col = ln.sub + i * Q;
-                    const float gv = __fsub_rn(__fsub_rn(v[i], m), ls);
-                    if (valid && col < g.C && col >= g.first_fg) cmax[i] = fmaxf(cmax[i], gv);
-                }
+                for (int i = 0; i < NREG; ++i) cmax[i] = fmaxf(cmax[i], __fsub_rn(v[i], t));   // -inf slots stay -inf
             } else {
 #pragma unroll
-                for (int i = 0; i < NREG; ++i) {
-                    const int col = ln.sub + i * Q;
-                    if (valid && col < g.C && col >= g.first_fg) cmax[i] = fmaxf(cmax[i], v[i]);
-                }
+                for (int i = 0; i < NREG; ++i) cmax[i] = fmaxf(cmax[i], v[i]);
             }
         }
-        const bool flush = cons.last_of_item();
-        if (flush) {
-            // merge the row slots of the warp, then one vector per (block, warp)
+        consumer_release(smem, k);
+        if (cur.last_of_item()) {
+            // merge the row slots of the warp down to `split` blocks, then one vector per block
 #pragma unroll
             for (int i = 0; i < NREG; ++i) {
                 float x = cmax[i];
@@ -262,8 +175,8 @@ score_pass1_kernel(const float* __restrict__ scores, ScoreGrid g, float2* __rest
                 cmax[i] = x;
             }
             if (ln.rl < g.split) {
-                float* dst = blockmax + ((size_t)cons.image(g) * g.nblk +
-                                         ((size_t)cons.group(g) * warps + warp_id()) * g.split + ln.rl) * g.C;
+                float* dst = blockmax + ((size_t)cur.image(g) * g.nblk +
+                                         ((size_t)cur.group(g) * kConsumerWarps + warp_id()) * g.split + ln.rl) * g.C;
 #pragma unroll
                 for (int i = 0; i < NREG; ++i) {
                     const int col = ln.sub + i * Q;
@@ -273,17 +186,13 @@ score_pass1_kernel(const float* __restrict__ scores, ScoreGrid g, float2* __rest
 #pragma unroll
             for (int i = 0; i < NREG; ++i) cmax[i] = -INFINITY;
         }
-        cons.next(g);
-        __syncthreads();
-        if (threadIdx.x == 0 && prod.valid(g)) {
-            rs.issue(s, scores, prod.first_row(g), prod.rows(g), g.C, g.total_floats, policy);
-            prod.next(g);
-        }
+        cur.next(g);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// 2. class_gate: one warp per (image, column)
+// 2. class_gate: one CTA per image, one warp per score column at a time.  The K-th largest block
+//    maximum of a column is a guaranteed lower bound of the K-th largest score of that class.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float next_below(float x) {
     // largest float < x for finite x
@@ -293,42 +202,13 @@ __device__ __forceinline__ float next_below(float x) {
     return __uint_as_float(u);
 }
 
-__global__ void __launch_bounds__(256)
-class_gate_kernel(const float* __restrict__ blockmax, int B, int C, int first_fg, int nblk, int K, int converter,
-                  float score_thr, float* __restrict__ gate, int* __restrict__ cand_count, int* __restrict__ status) {
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (blockIdx.x == 0 && threadIdx.x < 4 && status != nullptr) status[threadIdx.x] = 0;
-    if (w >= B * C) return;
-    const int b = w / C, col = w % C;
-    const int lane = lane_id();
-    if (col < first_fg) {
-        if (lane == 0) gate[w] = INFINITY;
-        return;
-    }
-    // K-th largest block maximum of this column, by MSB-first bisection on ordered keys
-    const float* src = blockmax + (size_t)b * nblk * C + col;
-    float kth = -INFINITY;
-    if (nblk >= K) {
-        uint32_t prefix = 0;
-        int rem = K;
-        for (int bit = 31; bit >= 0; --bit) {
-            const uint32_t trial = prefix | (1u << bit);
-            int cnt = 0;
-            for (int i = lane; i < nblk; i += 32) {
-                const uint32_t key = ordered_key(src[(size_t)i * C]);
-                cnt += ((key >> bit) == (trial >> bit));
-            }
-            cnt = __reduce_add_sync(FULL, cnt);
-            if (cnt >= rem) prefix = trial; else rem -= cnt;
-        }
-        kth = key_to_float(prefix);
-    }
-    float g;
+__device__ __forceinline__ float gate_from_kth(int converter, float score_thr, float kth) {
     if (converter == SSD_CONVERT_SOFTMAX) {
         // gate domain = log-probability; 1e-4 of slack is ~100x the fp32 error of the gate value
         const float gthr = score_thr > 0.f ? logf(score_thr) - 1e-4f : -INFINITY;
-        g = fmaxf(gthr, kth - 1e-4f);
-    } else if (converter == SSD_CONVERT_SIGMOID) {
+        return fmaxf(gthr, kth - 1e-4f);
+    }
+    if (converter == SSD_CONVERT_SIGMOID) {
         // gate domain = logit.  Slack of 1e-4 RELATIVE IN PROBABILITY, evaluated in double so that
         // saturated scores (p == 1.0f for many logits) all stay candidates.
         float gthr;
@@ -346,52 +226,110 @@ class_gate_kernel(const float* __restrict__ blockmax, int B, int C, int first_fg
             gk = (float)x - 1e-5f * (1.f + fabsf((float)x));
             if (gk > kth) gk = kth - 1e-4f;
         }
-        g = fmaxf(gthr, gk);
-    } else {
-        // probabilities given: exact.  Candidates need score > thr and, once K blocks reach kth,
-        // score >= kth.
-        g = score_thr;
-        if (kth > score_thr) g = next_below(kth);
+        return fmaxf(gthr, gk);
+    }
+    // probabilities given: exact.  Candidates need score > thr and, once K blocks reach kth, score >= kth.
+    float g = score_thr;
+    if (kth > score_thr) g = next_below(kth);
+    return g;
+}
+
+constexpr int kGateCols = 8;                 // score columns per CTA, one warp each
+constexpr int kGateThreads = kGateCols * 32;
+constexpr int kGateKeysPerLane = 16;         // (merged) blocks per lane held in registers
+constexpr int kGateBits = 20;                // resolved MSBs of the K-th largest key; the rest rounds DOWN
+
+// Any lower bound of the K-th largest block maximum is a valid gate, so (a) adjacent blocks are
+// merged on load until at most 32*kGateKeysPerLane remain (a coarser partition of the rows is still
+// a partition) and (b) the bisection stops after kGateBits bits and leaves the low bits zero
+// (a slightly smaller key).  Both only let a few more candidates through.
+__global__ void __launch_bounds__(kGateThreads)
+class_gate_kernel(const float* __restrict__ blockmax, int C, int first_fg, int nblk, int K, int converter,
+                  float score_thr, float* __restrict__ gate, int* __restrict__ cand_count, int* __restrict__ status) {
+    extern __shared__ __align__(16) uint32_t skey[];          // [merged blocks][kGateCols + 1]
+    const int b = blockIdx.y;
+    const int c0 = blockIdx.x * kGateCols;
+    const int lane = lane_id();
+    if (b == 0 && blockIdx.x == 0 && threadIdx.x < 4 && status != nullptr) status[threadIdx.x] = 0;
+    const int merge = (nblk + 32 * kGateKeysPerLane - 1) / (32 * kGateKeysPerLane);
+    const int nm = (nblk + merge - 1) / merge;                 // merged blocks, <= 512
+    const float* src = blockmax + (size_t)b * nblk * C;
+    // coalesced load: 8 consecutive columns of one block row per 8 threads
+    for (int t = threadIdx.x; t < nm * kGateCols; t += kGateThreads) {
+        const int mb = t / kGateCols, cc = t % kGateCols;
+        float v = -INFINITY;
+        if (c0 + cc < C) {
+            const int lo = mb * merge, hi = min(lo + merge, nblk);
+            for (int i = lo; i < hi; ++i) {
+                const float x = src[(size_t)i * C + c0 + cc];
+                v = (x != x || x > v) ? x : v;                  // NaN (sorts on top) sticks
+                if (x != x) break;
+            }
+        }
+        skey[mb * (kGateCols + 1) + cc] = ordered_key(v);
+    }
+    __syncthreads();
+    const int col = c0 + warp_id();
+    if (col >= C) return;
+    if (col < first_fg) {
+        if (lane == 0) gate[b * C + col] = INFINITY;
+        return;
+    }
+    float kth = -INFINITY;
+    if (nm >= K) {
+        uint32_t key[kGateKeysPerLane];
+#pragma unroll
+        for (int j = 0; j < kGateKeysPerLane; ++j) {
+            const int i = lane + 32 * j;
+            key[j] = i < nm ? skey[i * (kGateCols + 1) + warp_id()] : 0u;      // 0 < every real key
+        }
+        // largest T (on the resolved bits) with count(key >= T) >= K
+        uint32_t T = 0u;
+        for (int bit = 31; bit > 31 - kGateBits; --bit) {
+            const uint32_t trial = T | (1u << bit);
+            int cnt = 0;
+#pragma unroll
+            for (int j = 0; j < kGateKeysPerLane; ++j) cnt += key[j] >= trial;
+            cnt = __reduce_add_sync(FULL, cnt);
+            if (cnt >= K) T = trial;
+        }
+        // T == 0 only if fewer than K keys have any resolved bit set; key 0x007FFFFF is -inf
+        kth = T < 0x00800000u ? -INFINITY : key_to_float(T);
+        if (kth != kth) kth = -INFINITY;
     }
     if (lane == 0) {
-        gate[w] = g;
+        gate[b * C + col] = gate_from_kth(converter, score_thr, kth);
         cand_count[b * (C - first_fg) + (col - first_fg)] = 0;
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// 3. score_pass2: emit candidates
+// 3. score_pass2: emit candidates (gate value above the class gate)
 // ---------------------------------------------------------------------------------------------
 template <int Q, int NREG, int CONV>
 __global__ void __launch_bounds__(kStreamThreads)
 score_pass2_kernel(const float* __restrict__ scores, ScoreGrid g, const float2* __restrict__ rowstat,
                    const float* __restrict__ gate, int* __restrict__ cand_count, uint2* __restrict__ cand, int cand_cap) {
     extern __shared__ __align__(128) unsigned char smem[];
-    RowStream<kStreamStages> rs;
-    stream_setup(rs, smem, g.stage_floats);
-    const RowLanes<Q> ln;
-    const int warps = blockDim.x >> 5;
-    const int rows_per_warp = g.tile_rows / warps;
-    const int Cf = g.C - g.first_fg;
-    const uint64_t policy = policy_evict_first();
-
-    TileCursor prod, cons;
-    prod.start(g);
-    cons.start(g);
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kStreamStages && prod.valid(g); ++s) {
-            rs.issue(s, scores, prod.first_row(g), prod.rows(g), g.C, g.total_floats, policy);
-            prod.next(g);
-        }
+    stream_init(smem);
+    if (warp_id() == kConsumerWarps) {
+        producer_loop(smem, g, scores,
+                      CONV == SSD_CONVERT_SOFTMAX ? reinterpret_cast<const unsigned long long*>(rowstat) : nullptr,
+                      policy_evict_first());
+        return;
     }
+    const RowLanes<Q> ln;
+    const int rows_per_warp = g.tile_rows / kConsumerWarps;
+    const int Cf = g.C - g.first_fg;
+
     float gv[NREG];
     int cur_image = -1;
-    for (int k = 0; cons.valid(g); ++k) {
-        const int s = k % kStreamStages;
-        const uint32_t parity = (k / kStreamStages) & 1;
-        const int64_t r0 = cons.first_row(g);
-        const int rows = cons.rows(g);
-        const int img = cons.image(g);
+    TileCursor cur;
+    cur.start(g);
+    for (int k = 0; cur.valid(g); ++k, cur.next(g)) {
+        const int64_t r0 = cur.first_row(g);
+        const int rows = cur.rows(g);
+        const int img = cur.image(g);
         if (img != cur_image) {                 // per-lane slice of this image's gates
             cur_image = img;
 #pragma unroll
@@ -400,42 +338,43 @@ score_pass2_kernel(const float* __restrict__ scores, ScoreGrid g, const float2* 
                 gv[i] = (col < g.C) ? gate[(size_t)img * g.C + col] : INFINITY;
             }
         }
-        mbar_wait(&rs.full[s], parity);
-        const float* tile = rs.buf[s] + RowStream<kStreamStages>::head_of(r0, g.C);
-        const int a0 = cons.tile * g.tile_rows;
-
+        const StagedTile tile = consumer_acquire(smem, g, k, r0);
+        const int a0 = cur.tile * g.tile_rows;
         const int wbase = warp_id() * rows_per_warp;
         for (int step = 0; step < rows_per_warp; step += RowLanes<Q>::kRowsPerWarpStep) {
             const int lr = wbase + step + ln.rl;
             const bool valid = lr < rows;
-            if (__all_sync(FULL, !valid)) break;
             float v[NREG];
-            load_row_slice<Q, NREG>(v, tile + (size_t)lr * g.C, ln.sub, g.C, valid, -INFINITY);
-            float m = 0.f, ls = 0.f;
+            load_row_slice<Q, NREG>(v, tile.logits + (size_t)lr * g.C, ln.sub, g.C, valid);
+            float t = 0.f;
             if (CONV == SSD_CONVERT_SOFTMAX) {
-                const float2 st = valid ? rowstat[r0 + lr] : make_float2(0.f, 1.f);
-                m = st.x;
-                ls = logf(st.y);
+                float2 st = make_float2(0.f, 1.f);
+                if (valid) st = reinterpret_cast<const float2*>(tile.side)[lr];
+                t = __fadd_rn(st.x, logf(st.y));            // bit-identical to pass 1
             }
+            // survivors: all slot reservations of the step are issued before the first one is used
+            int slot[NREG];
+            unsigned hit = 0u;
 #pragma unroll
             for (int i = 0; i < NREG; ++i) {
-                float x = v[i];
-                if (CONV == SSD_CONVERT_SOFTMAX) x = __fsub_rn(__fsub_rn(x, m), ls);
-                if (valid && x > gv[i]) {
-                    const int col = ln.sub + i * Q;
-                    const int seg = img * Cf + (col - g.first_fg);
-                    const int slot = atomicAdd(&cand_count[seg], 1);
-                    if (slot < cand_cap)
-                        cand[(size_t)seg * cand_cap + slot] = make_uint2((uint32_t)(a0 + lr), __float_as_uint(v[i]));
+                const float x = CONV == SSD_CONVERT_SOFTMAX ? __fsub_rn(v[i], t) : v[i];
+                slot[i] = 0;
+                if (x > gv[i]) {                            // -inf padding and gv = +inf never pass
+                    hit |= 1u << i;
+                    slot[i] = atomicAdd(&cand_count[img * Cf + (ln.sub + i * Q - g.first_fg)], 1);
+                }
+            }
+            if (hit) {
+#pragma unroll
+                for (int i = 0; i < NREG; ++i) {
+                    if (((hit >> i) & 1u) && slot[i] < cand_cap) {
+                        const int seg = img * Cf + (ln.sub + i * Q - g.first_fg);
+                        cand[(size_t)seg * cand_cap + slot[i]] = make_uint2((uint32_t)(a0 + lr), __float_as_uint(v[i]));
+                    }
                 }
             }
         }
-        cons.next(g);
-        __syncthreads();
-        if (threadIdx.x == 0 && prod.valid(g)) {
-            rs.issue(s, scores, prod.first_row(g), prod.rows(g), g.C, g.total_floats, policy);
-            prod.next(g);
-        }
+        consumer_release(smem, k);
     }
 }
 
@@ -660,7 +599,9 @@ segment_nms_kernel(NmsArgs a, const float* __restrict__ scores, const float2* __
                     const float xx2 = fminf(bi.z, bj.z), yy2 = fminf(bi.w, bj.w);
                     const float iw = fmaxf(0.f, fsub(xx2, xx1)), ih = fmaxf(0.f, fsub(yy2, yy1));
                     const float inter = fmul(iw, ih);
-                    const float ovr = fdiv(inter, fsub(fadd(ai, sarea[j]), inter));
+                    const float uni = fsub(fadd(ai, sarea[j]), inter);
+                    // disjoint boxes (the common case): 0 / positive is exactly +0, no divide needed
+                    const float ovr = (inter == 0.f && uni > 0.f) ? 0.f : fdiv(inter, uni);
                     sup = (double)ovr > a.iou_thr;                    // float-vs-double compare
                 }
                 bits = __ballot_sync(FULL, sup);
@@ -879,18 +820,16 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
     float* kept = (float*)(ws + pl.off_kept);
     int* status = (int*)(ws + pl.off_status);
 
-    ScoreGrid g;
-    g.A = pl.A; g.C = pl.C; g.first_fg = pl.first_fg; g.tile_rows = pl.tile_rows; g.stage_floats = pl.stage_floats;
-    g.tiles_per_image = pl.tiles_per_image; g.group_tiles = pl.group_tiles; g.groups_per_image = pl.groups_per_image;
-    g.num_items = pl.num_items; g.nblk = pl.nblk; g.split = pl.split; g.total_floats = (int64_t)pl.B * pl.A * pl.C;
-    int grid = 2 * sm_count();
-    if (grid > pl.num_items) grid = pl.num_items;
+    const ScoreGrid& g = pl.g;
+    const int grid = stream_grid(g);
+    const size_t stream_smem = stream_smem_bytes(g);
 
 #define SSD_LAUNCH_PASS1(QQ, NN)                                                                                      \
     do {                                                                                                               \
         auto launch = [&](auto kern) -> int {                                                                          \
-            SSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.stream_smem));    \
-            kern<<<grid, kStreamThreads, pl.stream_smem, st>>>(scores, g, rowstat, blockmax);                          \
+            SSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem));    \
+            LaunchTimer lt_("pass1", st);                                                            \
+            kern<<<grid, kStreamThreads, stream_smem, st>>>(scores, g, rowstat, blockmax);                          \
             return SSD_OK;                                                                                             \
         };                                                                                                             \
         int rc;                                                                                                        \
@@ -904,10 +843,13 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
     count_launch();
 
     {
-        const int warps_needed = pl.B * pl.C;
-        const int blocks = (warps_needed * 32 + 255) / 256;
-        class_gate_kernel<<<blocks, 256, 0, st>>>(blockmax, pl.B, pl.C, pl.first_fg, pl.nblk, pl.K, pl.converter,
-                                                  p->score_threshold, gate, cand_count, status);
+        LaunchTimer lt_("gate", st);
+        const int merge = (pl.nblk + 32 * kGateKeysPerLane - 1) / (32 * kGateKeysPerLane);
+        const int nm = (pl.nblk + merge - 1) / merge;
+        const size_t gsmem = (size_t)nm * (kGateCols + 1) * sizeof(uint32_t);
+        dim3 ggrid((pl.C + kGateCols - 1) / kGateCols, pl.B);
+        class_gate_kernel<<<ggrid, kGateThreads, gsmem, st>>>(blockmax, pl.C, pl.first_fg, pl.nblk, pl.K, pl.converter,
+                                                               p->score_threshold, gate, cand_count, status);
         SSD_CUDA(cudaGetLastError());
     count_launch();
     }
@@ -915,8 +857,9 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
 #define SSD_LAUNCH_PASS2(QQ, NN)                                                                                      \
     do {                                                                                                               \
         auto launch = [&](auto kern) -> int {                                                                          \
-            SSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.stream_smem));    \
-            kern<<<grid, kStreamThreads, pl.stream_smem, st>>>(scores, g, rowstat, gate, cand_count, cand, pl.cand_cap); \
+            SSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem));    \
+            LaunchTimer lt_("pass2", st);                                                            \
+            kern<<<grid, kStreamThreads, stream_smem, st>>>(scores, g, rowstat, gate, cand_count, cand, pl.cand_cap); \
             return SSD_OK;                                                                                             \
         };                                                                                                             \
         int rc;                                                                                                        \
@@ -938,6 +881,7 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
         const size_t key_slots = pl.cand_cap > kMaxPerClass ? pl.cand_cap : kMaxPerClass;
         const size_t smem = key_slots * 8 + (size_t)pl.K * (16 + 4 + 4) + (size_t)pl.K * kwords * 4 + 64;
         SSD_CUDA(cudaFuncSetAttribute(segment_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LaunchTimer lt_("nms", st);
         segment_nms_kernel<<<pl.B * pl.Cf, kNmsThreads, smem, st>>>(a, scores, rowstat, cand_count, cand,
                                                                      (const float4*)boxes, (const float4*)priors,
                                                                      kept_count, kept, status);
@@ -950,6 +894,7 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
         const size_t smem = round_up((size_t)(pl.Cf + 1) * 4, 16) + ((size_t)pl.Cf * pl.K + (pl.T > 0 ? t2 : 0)) * 8 + 64;
         SSD_REQUIRE(smem <= 224 * 1024, SSD_ERR_UNSUPPORTED, "ssd_postprocess: final top-k needs %zu bytes of shared memory", smem);
         SSD_CUDA(cudaFuncSetAttribute(image_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LaunchTimer lt_("topk", st);
         image_topk_kernel<<<pl.B, kTopkThreads, smem, st>>>(pl.Cf, pl.K, pl.T, pl.det_cap, kept_count, kept, dets_out,
                                                              count_out, anchor_out);
         SSD_CUDA(cudaGetLastError());

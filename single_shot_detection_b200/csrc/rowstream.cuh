@@ -1,52 +1,166 @@
 // Row-tile streaming skeleton shared by the logit-streaming kernels (hard-negative mining loss,
 // post-processor score passes).
 //
-// Layout recap: logits are [rows, C] fp32 with the class index fastest (detection/detector.py:50-66
-// emits [B, A*C]).  A CTA takes tiles of `tile_rows` consecutive rows, fetches each tile with ONE
-// cp.async.bulk (TMA, 1-D) into a STAGES-deep shared-memory ring guarded by mbarriers, and its
-// warps reduce rows out of shared memory.  A row is owned by Q adjacent lanes (lane `sub` holds
-// columns sub, sub+Q, ... in NREG registers), so one warp covers 32/Q rows per step and every
-// value is read from shared memory exactly once.
+// Layout recap: logits are [B, A, C] fp32 with the class index fastest (detection/detector.py:50-66
+// emits [B, A*C]).  The CTA is warp specialised:
+//   * one PRODUCER warp walks the CTA's tile list and, per tile, issues cp.async.bulk (TMA, 1-D)
+//     copies -- the tile's logits plus an optional 8-byte-per-row side array (class ids or the
+//     (max, sum) row statistics) -- into a STAGES-deep shared-memory ring; completion is tracked
+//     by the stage's `full` mbarrier (expect_tx), reuse by its `empty` mbarrier;
+//   * kConsumerWarps CONSUMER warps wait on `full`, reduce rows out of shared memory and arrive
+//     on `empty`.  No block-wide barrier in the steady state.
+// A row is owned by Q adjacent lanes (lane `sub` holds columns sub, sub+Q, ... in NREG registers),
+// so one warp covers 32/Q rows per step and every value is read from shared memory exactly once.
+// Copies are made of the 16-byte aligned superset of the wanted bytes (TMA needs 16-byte aligned
+// addresses and sizes; rows are 4*C bytes, so tile starts are only 4-byte aligned in general).
 #pragma once
 
 #include "common.cuh"
 
 namespace ssd {
 
-constexpr int kStreamThreads = 256;
-constexpr int kStreamStages = 3;
+constexpr int kConsumerWarps = 8;
+constexpr int kStreamThreads = (kConsumerWarps + 1) * 32;
+constexpr int kStreamStages = 4;
+constexpr int kMaxScoreCols = 1024;
+constexpr float kLog2e = 1.4426950408889634f;
 
-struct StreamShape {
-    int tile_rows;       // rows per tile
-    int stage_floats;    // floats per stage buffer (tile_rows*C + 8, rounded to 4)
-    size_t smem_bytes;   // dynamic shared memory for the ring + barriers
-};
-
-// tile_rows is a multiple of `row_quantum` (so that tiles hold whole 32-row blocks etc.)
-inline StreamShape make_stream_shape(int C, int row_quantum, int target_tile_bytes = 24 * 1024) {
-    StreamShape s;
-    int rows = target_tile_bytes / (C * 4);
-    rows = rows / row_quantum * row_quantum;
-    if (rows < row_quantum) rows = row_quantum;
-    s.tile_rows = rows;
-    s.stage_floats = (int)round_up((size_t)rows * C + 8, 4);
-    s.smem_bytes = 128 + (size_t)kStreamStages * s.stage_floats * 4;
-    return s;
+// exp(d) for the STREAMED row sums, d = x - max already rounded as the reference rounds it: one
+// FMUL + one MUFU.  Relative error <= 2^-22 per term, exp(0) == 1 exactly (rows whose scores tie in
+// the reference keep tying); the exact per-candidate scores use expf / IEEE divide.
+__device__ __forceinline__ float fast_exp(float d) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(__fmul_rn(d, kLog2e)));
+    return y;
 }
 
-// Carves dynamic shared memory and initialises the barriers.  Must be called by all threads.
-template <int STAGES>
-__device__ __forceinline__ void stream_setup(RowStream<STAGES>& rs, unsigned char* smem, int stage_floats) {
-    rs.full = reinterpret_cast<uint64_t*>(smem);
-    rs.stage_floats = stage_floats;
-#pragma unroll
-    for (int s = 0; s < STAGES; ++s) rs.buf[s] = reinterpret_cast<float*>(smem + 128) + (size_t)s * stage_floats;
+// Tiling of a [B images x A rows x C cols] array.  Work item = `group_tiles` consecutive tiles of
+// one image; items are dealt round-robin to CTAs.  Tiles never cross an image boundary.
+struct ScoreGrid {
+    int A, C, first_fg;
+    int tile_rows, tiles_per_image, group_tiles, groups_per_image, num_items;
+    int stage_bytes;          // bytes per ring stage (logit tile + side array, 16-byte multiples)
+    int side_offset;          // byte offset of the side array inside a stage
+    int nblk, split;          // post-processor block-max bookkeeping (unused by mining)
+    int64_t total_floats;     // B*A*C
+    int64_t total_rows;       // B*A
+};
+
+struct TileCursor {
+    int item, tile, tile_end;
+    __device__ __forceinline__ void start(const ScoreGrid& g) {
+        item = blockIdx.x;
+        open(g);
+    }
+    __device__ __forceinline__ void open(const ScoreGrid& g) {
+        if (item < g.num_items) {
+            const int grp = item % g.groups_per_image;
+            tile = grp * g.group_tiles;
+            tile_end = min(tile + g.group_tiles, g.tiles_per_image);
+        }
+    }
+    __device__ __forceinline__ bool valid(const ScoreGrid& g) const { return item < g.num_items; }
+    __device__ __forceinline__ int image(const ScoreGrid& g) const { return item / g.groups_per_image; }
+    __device__ __forceinline__ int group(const ScoreGrid& g) const { return item % g.groups_per_image; }
+    __device__ __forceinline__ bool last_of_item() const { return tile + 1 == tile_end; }
+    __device__ __forceinline__ void next(const ScoreGrid& g) {
+        if (++tile == tile_end) {
+            item += gridDim.x;
+            open(g);
+        }
+    }
+    __device__ __forceinline__ int rows(const ScoreGrid& g) const { return min(g.tile_rows, g.A - tile * g.tile_rows); }
+    __device__ __forceinline__ int64_t first_row(const ScoreGrid& g) const {
+        return (int64_t)image(g) * g.A + (int64_t)tile * g.tile_rows;
+    }
+};
+
+// shared memory: [0,64) full barriers, [64,128) empty barriers, then the stages
+__device__ __forceinline__ uint64_t* full_bar(unsigned char* smem, int s) { return reinterpret_cast<uint64_t*>(smem) + s; }
+__device__ __forceinline__ uint64_t* empty_bar(unsigned char* smem, int s) { return reinterpret_cast<uint64_t*>(smem + 64) + s; }
+__device__ __forceinline__ unsigned char* stage_ptr(unsigned char* smem, const ScoreGrid& g, int s) {
+    return smem + 128 + (size_t)s * g.stage_bytes;
+}
+__device__ __forceinline__ int tile_head(int64_t first_row, int C) { return (int)((first_row * C) & 3); }
+__device__ __forceinline__ int side_head(int64_t first_row) { return (int)(first_row & 1); }
+
+__device__ __forceinline__ void stream_init(unsigned char* smem) {
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) mbar_init(&rs.full[s], 1);
+        for (int s = 0; s < kStreamStages; ++s) {
+            mbar_init(full_bar(smem, s), 1);
+            mbar_init(empty_bar(smem, s), kConsumerWarps);
+        }
         mbar_fence_init();
     }
     __syncthreads();
+}
+
+// Producer side: called by ONE lane.  Copies the tile [first_row, first_row+rows) x C floats (and
+// rows 8-byte side elements when `side` != nullptr) into stage `dst`.
+__device__ __forceinline__ void produce_tile(unsigned char* dst, uint64_t* full, const ScoreGrid& g,
+                                             const float* __restrict__ base, const unsigned long long* __restrict__ side,
+                                             int64_t first_row, int rows, uint64_t policy) {
+    const int64_t f0 = first_row * g.C;
+    const int64_t f1 = f0 + (int64_t)rows * g.C;
+    const int64_t fa = f0 & ~int64_t(3);
+    int64_t fe = (f1 + 3) & ~int64_t(3);
+    const int64_t n4 = g.total_floats & ~int64_t(3);
+    if (fe > n4) fe = n4 > fa ? n4 : fa;
+    const uint32_t bytes = (uint32_t)((fe - fa) * 4);
+    float* tdst = reinterpret_cast<float*>(dst);
+    for (int64_t f = fe; f < f1; ++f) tdst[f - fa] = __ldg(base + f);          // <= 3 floats, array tail only
+    uint32_t sbytes = 0;
+    int64_t sa = 0;
+    unsigned long long* sdst = reinterpret_cast<unsigned long long*>(dst + g.side_offset);
+    if (side != nullptr) {
+        const int64_t r1 = first_row + rows;
+        sa = first_row & ~int64_t(1);
+        int64_t se = (r1 + 1) & ~int64_t(1);
+        const int64_t n2 = g.total_rows & ~int64_t(1);
+        if (se > n2) se = n2 > sa ? n2 : sa;
+        sbytes = (uint32_t)((se - sa) * 8);
+        for (int64_t r = se; r < r1; ++r) sdst[r - sa] = __ldg(side + r);      // <= 1 element, array tail only
+    }
+    if (bytes + sbytes) {
+        mbar_expect_tx(full, bytes + sbytes);
+        if (bytes) bulk_g2s(tdst, base + fa, bytes, full, policy);
+        if (sbytes) bulk_g2s(sdst, side + sa, sbytes, full, policy);
+    } else {
+        mbar_arrive(full);
+    }
+}
+
+// The producer warp's whole life: stream every tile of this CTA through the ring.
+__device__ __forceinline__ void producer_loop(unsigned char* smem, const ScoreGrid& g, const float* __restrict__ base,
+                                              const unsigned long long* __restrict__ side, uint64_t policy) {
+    if (lane_id() != 0) return;
+    TileCursor cur;
+    cur.start(g);
+    for (int k = 0; cur.valid(g); ++k, cur.next(g)) {
+        const int s = k % kStreamStages;
+        if (k >= kStreamStages) mbar_wait(empty_bar(smem, s), ((k / kStreamStages) - 1) & 1);
+        produce_tile(stage_ptr(smem, g, s), full_bar(smem, s), g, base, side, cur.first_row(g), cur.rows(g), policy);
+    }
+}
+
+// Consumer side of the ring: wait for tile k, hand out its pointers, release it.
+struct StagedTile {
+    const float* logits;                 // first float of the tile's first row
+    const unsigned long long* side;      // first side element of the tile (8 bytes per row)
+};
+__device__ __forceinline__ StagedTile consumer_acquire(unsigned char* smem, const ScoreGrid& g, int k, int64_t first_row) {
+    const int s = k % kStreamStages;
+    mbar_wait(full_bar(smem, s), (k / kStreamStages) & 1);
+    unsigned char* st = stage_ptr(smem, g, s);
+    StagedTile t;
+    t.logits = reinterpret_cast<const float*>(st) + tile_head(first_row, g.C);
+    t.side = reinterpret_cast<const unsigned long long*>(st + g.side_offset) + side_head(first_row);
+    return t;
+}
+__device__ __forceinline__ void consumer_release(unsigned char* smem, int k) {
+    __syncwarp();
+    if (lane_id() == 0) mbar_arrive(empty_bar(smem, k % kStreamStages));
 }
 
 // Lane geometry of the Q-lanes-per-row mapping.
@@ -58,15 +172,29 @@ struct RowLanes {
     __device__ __forceinline__ RowLanes() : sub(lane_id() % Q), rl(lane_id() / Q) {}
 };
 
-// Load the NREG register slice of one row from a staged tile; out-of-range slots get `fill`.
+// Load the NREG register slice of one row from a staged tile; out-of-range slots get -inf
+// (exp(-inf - m) == 0 and max(-inf, x) == x, so no further predication is needed).
 template <int Q, int NREG>
-__device__ __forceinline__ void load_row_slice(float (&v)[NREG], const float* __restrict__ row, int sub, int C,
-                                               bool row_valid, float fill) {
+__device__ __forceinline__ void load_row_slice(float (&v)[NREG], const float* row, int sub, int C, bool row_valid) {
 #pragma unroll
     for (int i = 0; i < NREG; ++i) {
         const int col = sub + i * Q;
-        v[i] = (row_valid && col < C) ? row[col] : fill;
+        v[i] = (row_valid && col < C) ? row[col] : -INFINITY;
     }
+}
+
+// row max and sum of exp(x - max) over the Q lanes that own the row (invalid rows: m = 0, sum = 0)
+template <int Q, int NREG>
+__device__ __forceinline__ void row_max_sum(const float (&v)[NREG], bool row_valid, float& m, float& sum) {
+    m = v[0];
+#pragma unroll
+    for (int i = 1; i < NREG; ++i) m = fmaxf(m, v[i]);
+    m = group_max<Q>(m);
+    if (!row_valid) m = 0.f;
+    sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NREG; ++i) sum = __fadd_rn(sum, fast_exp(__fsub_rn(v[i], m)));
+    sum = group_sum<Q>(sum);
 }
 
 // Dispatch table C -> (Q, NREG).  NREG*Q >= C.
@@ -82,6 +210,42 @@ __device__ __forceinline__ void load_row_slice(float (&v)[NREG], const float* __
         else { CALL(32, 32); }                               \
     } while (0)
 
-constexpr int kMaxScoreCols = 1024;
+inline int lanes_per_row(int C) {
+    int q = 0;
+#define SSD_Q_(QQ, NN) q = QQ
+    SSD_DISPATCH_ROW_SHAPE(C, SSD_Q_);
+#undef SSD_Q_
+    return q;
+}
+
+// Host: tile geometry.  tile_rows is a multiple of the rows all consumer warps cover in one step.
+inline void plan_tiles(ScoreGrid& g, int images, int A, int C, bool with_side, int target_tile_bytes = 12 * 1024) {
+    const int quantum = kConsumerWarps * (32 / lanes_per_row(C));
+    int rows = target_tile_bytes / (C * 4);
+    rows = rows / quantum * quantum;
+    if (rows > 4 * quantum) rows = 4 * quantum;
+    if (rows < quantum) rows = quantum;
+    g.A = A; g.C = C;
+    g.tile_rows = rows;
+    g.tiles_per_image = (A + rows - 1) / rows;
+    g.group_tiles = 1;
+    g.groups_per_image = g.tiles_per_image;
+    g.num_items = images * g.groups_per_image;
+    const size_t tile_bytes = round_up((size_t)rows * C * 4 + 32, 16);
+    g.side_offset = (int)tile_bytes;
+    g.stage_bytes = (int)(tile_bytes + (with_side ? round_up((size_t)rows * 8 + 32, 16) : 0));
+    g.total_floats = (int64_t)images * A * C;
+    g.total_rows = (int64_t)images * A;
+    g.first_fg = 0; g.nblk = 0; g.split = 1;
+}
+inline size_t stream_smem_bytes(const ScoreGrid& g) { return 128 + (size_t)kStreamStages * g.stage_bytes; }
+inline int stream_grid(const ScoreGrid& g) {
+    // resident CTAs per SM by shared memory (227 KB usable), at most 4; grid = a whole number of waves
+    int per_sm = (int)((size_t)(220 * 1024) / (stream_smem_bytes(g) + 1024));
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+    int grid = per_sm * sm_count();
+    return grid < g.num_items ? grid : g.num_items;
+}
 
 }  // namespace ssd

@@ -165,6 +165,8 @@ def _hard_negative_mask(logits: Optional[torch.Tensor], target_classes: torch.Te
     N.require_device()
     cls = target_classes if target_classes.dtype == torch.int64 else target_classes.long()
     cls = cls if cls.is_contiguous() else cls.contiguous()
+    if cls.data_ptr() % 16:                      # the class ids ride the TMA ring: 16-byte aligned
+        cls = cls.clone()
     batch, num_anchors = cls.shape
     dev = cls.device
     num_cols = 0

@@ -33,8 +33,10 @@ class StepOutput(NamedTuple):
     counts: torch.Tensor          # [B] int32 rows used in dets
     det_anchors: torch.Tensor     # [B, T] int32 anchor of every detection row
     status: torch.Tensor          # [4] int32 (see ssd_postprocess)
-    stats: torch.Tensor           # [B, 4] int32 positives, hard negatives, ignored, detections
+    stats: Optional[torch.Tensor]  # [B, 4] int32 positives, hard negatives, ignored, detections (with shard)
     shard: Optional[torch.Tensor]  # packed exchange buffer, when requested
+    assign_stats: Optional[torch.Tensor] = None   # [B, 4] int32 positives, ignored, NaN boxes, G (ssd_assign_targets)
+    mining_stats: Optional[torch.Tensor] = None   # [B, 4] int32 positives, negatives, selected, ties (ssd_hard_negative_mask)
 
 
 class AnchorPipeline:
@@ -56,6 +58,7 @@ class AnchorPipeline:
             score_converter=cfg["converter"], max_total=cfg["max_total"])
         self.fuse_encode = False       # True: one pass for to_centroids+encode (same rounding)
         self._graph = None
+        self._side = None
 
     # -- the reference-facing call -------------------------------------------------------------
     def step(self, ground_truth, anchors, scores, locs):
@@ -85,17 +88,32 @@ class AnchorPipeline:
     def step_device(self, packed: PackedGroundTruth, anchors_dev, scores_dev, locs_dev,
                     shard_capacity: Optional[int] = None) -> "StepOutput":
         """``shard_capacity``: also pack (dets, counts, stats) into the one-buffer layout
-        ``sharding.all_gather_detections`` exchanges (so the packing is part of the graph)."""
-        target = self.target_assigner.encode_packed(packed, anchors_dev)
-        mask = self._sample_and_encode(target, anchors_dev, scores_dev)
+        ``sharding.all_gather_detections`` exchanges (so the packing is part of the graph).
+
+        The train-side chain (assign -> sampler -> encode) and the post-processor are independent,
+        so they are enqueued on two streams (fork / join with events; capturable into one graph
+        with two parallel branches)."""
+        main = torch.cuda.current_stream()
+        side = self._side_stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            target = self.target_assigner.encode_packed(packed, anchors_dev)
+            mask = self._sample_and_encode(target, anchors_dev, scores_dev)
         dets, counts, det_anchors, status = self.postprocessor.postprocess_padded((scores_dev, locs_dev), anchors_dev)
+        main.wait_stream(side)
         mining = _sampler.hard_negative_mining.last_stats if self.cfg["sampler"] == "hard_negative_mining" else None
-        stats = matched_stats(self.target_assigner.last_stats, mining, counts)
-        shard = None
+        stats, shard = None, None
         if shard_capacity is not None:
             from . import sharding
+            stats = matched_stats(self.target_assigner.last_stats, mining, counts)
             shard = sharding.pack_shard(dets, counts, stats, shard_capacity)
-        return StepOutput(target, mask, dets, counts, det_anchors, status, stats, shard)
+        return StepOutput(target, mask, dets, counts, det_anchors, status, stats, shard,
+                          self.target_assigner.last_stats, mining)
+
+    def _side_stream(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        return self._side
 
     def capture(self, packed: PackedGroundTruth, anchors_dev, scores_dev, locs_dev, warmup: int = 2,
                 shard_capacity: Optional[int] = None) -> "StepOutput":
