@@ -499,6 +499,8 @@ __device__ int exact_select_column(const NmsArgs& a, int img, int col, const flo
     return k;
 }
 
+constexpr int kRankSortMax = 256;     // candidate lists up to this size are sorted by ranking
+
 __global__ void __launch_bounds__(kNmsThreads)
 segment_nms_kernel(NmsArgs a, const float* __restrict__ scores, const float2* __restrict__ rowstat,
                    const int* __restrict__ cand_count, const uint2* __restrict__ cand,
@@ -510,15 +512,24 @@ segment_nms_kernel(NmsArgs a, const float* __restrict__ scores, const float2* __
     __shared__ int s_valid, s_nkeep;
     const int seg = blockIdx.x;
     const int img = seg / a.Cf;
+    const int lane = lane_id();
     int n_raw = cand_count[seg];
     if (n_raw == 0) {
         if (threadIdx.x == 0) kept_count[seg] = 0;
         return;
     }
-    // carve: keys[n2] u64 | box[K] float4 | area[K] | mask[K * words] | keep[K]
+    // carve: keys[key_slots] u64 | sorted[K] u64 | box[K] float4 | area[K] | mask[K * kwords] | keep[K]
+    const int key_slots = a.cand_cap > kMaxPerClass ? a.cand_cap : kMaxPerClass;
+    const int kwords = (a.K + 31) >> 5;
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem);
+    unsigned long long* sorted = keys + key_slots;
+    float4* sbox = reinterpret_cast<float4*>(sorted + ((a.K + 1) & ~1));          // 16-byte aligned
+    float* sarea = reinterpret_cast<float*>(sbox + a.K);
+    uint32_t* mask = reinterpret_cast<uint32_t*>(sarea + a.K);
+    int* keep = reinterpret_cast<int*>(mask + (size_t)a.K * kwords);
+
     const bool overflow = n_raw > a.cand_cap;
-    int n2 = 32;
+    if (threadIdx.x == 0) s_valid = 0;
     if (overflow) {
         // the candidate list is incomplete: redo this (image, class) exactly from the score column
         if (threadIdx.x == 0 && status != nullptr) atomicAdd(&status[1], 1);
@@ -527,46 +538,69 @@ segment_nms_kernel(NmsArgs a, const float* __restrict__ scores, const float2* __
             if (threadIdx.x == 0) kept_count[seg] = 0;
             return;
         }
+        if (threadIdx.x == 0) s_valid = n_raw;
     }
-    while (n2 < n_raw) n2 <<= 1;
-    float4* sbox = reinterpret_cast<float4*>(keys + n2);
-    float* sarea = reinterpret_cast<float*>(sbox + a.K);
-    uint32_t* mask = reinterpret_cast<uint32_t*>(sarea + a.K);
-    if (threadIdx.x == 0) s_valid = overflow ? n_raw : 0;
     __syncthreads();
 
-    int local_valid = 0;
-    for (int t = threadIdx.x; t < n2; t += blockDim.x) {
-        if (overflow) {
-            if (t >= n_raw) keys[t] = 0ull;
-            continue;
-        }
-        unsigned long long key = 0ull;
-        if (t < n_raw) {
-            const uint2 e = cand[(size_t)seg * a.cand_cap + t];
-            float2 st = make_float2(0.f, 1.f);
-            if (a.converter == SSD_CONVERT_SOFTMAX) st = rowstat[(size_t)img * a.A + e.x];
-            const float p = exact_score(a.converter, __uint_as_float(e.y), st);
-            if (p > a.score_thr) {                                   // postprocessor.py:62 (fp32 compare)
-                key = ((unsigned long long)ordered_key(p) << 32) | (unsigned long long)(0xFFFFFFFFu - e.x);
-                local_valid++;
+    // ---- exact scores: key = (ordered score, ~anchor), 0 = below the threshold ----
+    const bool by_rank = n_raw <= kRankSortMax;
+    int n2 = 32;
+    while (n2 < n_raw) n2 <<= 1;
+    const int fill = by_rank ? ((n_raw + 1) & ~1) : n2;
+    if (!overflow) {
+        int local_valid = 0;
+        for (int t = threadIdx.x; t < fill; t += blockDim.x) {
+            unsigned long long key = 0ull;
+            if (t < n_raw) {
+                const uint2 e = cand[(size_t)seg * a.cand_cap + t];
+                float2 st = make_float2(0.f, 1.f);
+                if (a.converter == SSD_CONVERT_SOFTMAX) st = rowstat[(size_t)img * a.A + e.x];
+                const float p = exact_score(a.converter, __uint_as_float(e.y), st);
+                if (p > a.score_thr) {                                   // postprocessor.py:62 (fp32 compare)
+                    key = ((unsigned long long)ordered_key(p) << 32) | (unsigned long long)(0xFFFFFFFFu - e.x);
+                    local_valid++;
+                }
             }
+            keys[t] = key;
         }
-        keys[t] = key;
+        local_valid = __reduce_add_sync(FULL, local_valid);
+        if (lane == 0 && local_valid) atomicAdd(&s_valid, local_valid);
+    } else {
+        for (int t = n_raw + threadIdx.x; t < fill; t += blockDim.x) keys[t] = 0ull;
     }
-    local_valid = __reduce_add_sync(FULL, local_valid);
-    if (lane_id() == 0 && local_valid) atomicAdd(&s_valid, local_valid);
-    bitonic_sort_desc(keys, n2);                 // (score desc, anchor asc); starts and ends with a barrier
+    __syncthreads();
     const int n = min(s_valid, a.K);             // box_utils.py:186-188 top-k
     if (n == 0) {
         if (threadIdx.x == 0) kept_count[seg] = 0;
         return;
     }
-    const int words = (n + 31) >> 5;
-    int* keep = reinterpret_cast<int*>(mask + (size_t)a.K * ((a.K + 31) >> 5));
 
+    // ---- order: (score desc, anchor asc) ----
+    if (by_rank) {
+        // keys are unique, so the rank of a key is the number of larger keys; no barrier in the loop
+        const ulonglong2* k2 = reinterpret_cast<const ulonglong2*>(keys);
+        for (int t = threadIdx.x; t < n_raw; t += blockDim.x) {
+            const unsigned long long me = keys[t];
+            if (me == 0ull) continue;
+            int rank = 0;
+#pragma unroll 4
+            for (int j = 0; j < (fill >> 1); ++j) {
+                const ulonglong2 o = k2[j];
+                rank += (o.x > me) + (o.y > me);
+            }
+            if (rank < n) sorted[rank] = me;
+        }
+        __syncthreads();
+    } else {
+        bitonic_sort_desc(keys, n2);                 // starts and ends with a barrier
+        for (int t = threadIdx.x; t < n; t += blockDim.x) sorted[t] = keys[t];
+        __syncthreads();
+    }
+    const int words = (n + 31) >> 5;
+
+    // ---- boxes of the n best: decode + to_corners only these ----
     for (int t = threadIdx.x; t < n; t += blockDim.x) {
-        const uint32_t anchor = 0xFFFFFFFFu - (uint32_t)(keys[t] & 0xFFFFFFFFull);
+        const uint32_t anchor = 0xFFFFFFFFu - (uint32_t)(sorted[t] & 0xFFFFFFFFull);
         float4 bx = boxes[(size_t)img * a.A + anchor];
         if (a.box_input == SSD_BOXES_ENCODED) {
             const float4 p = priors[anchor];
@@ -583,54 +617,66 @@ segment_nms_kernel(NmsArgs a, const float* __restrict__ scores, const float2* __
     }
     __syncthreads();
 
-    // IoU bit matrix: row i, word w covers boxes 32w..32w+31; only j > i matters
+    // ---- IoU bit matrix: row i, word w covers boxes 32w..32w+31; only j > i matters ----
     const int nwarps = blockDim.x >> 5;
     for (int i = warp_id(); i < n; i += nwarps) {
         const float4 bi = sbox[i];
         const float ai = sarea[i];
-        for (int w = 0; w < words; ++w) {
-            uint32_t bits = 0u;
-            if (w >= (i >> 5)) {
-                const int j = (w << 5) + lane_id();
-                bool sup = false;
-                if (j > i && j < n) {
-                    const float4 bj = sbox[j];
-                    const float xx1 = fmaxf(bi.x, bj.x), yy1 = fmaxf(bi.y, bj.y);
-                    const float xx2 = fminf(bi.z, bj.z), yy2 = fminf(bi.w, bj.w);
-                    const float iw = fmaxf(0.f, fsub(xx2, xx1)), ih = fmaxf(0.f, fsub(yy2, yy1));
-                    const float inter = fmul(iw, ih);
-                    const float uni = fsub(fadd(ai, sarea[j]), inter);
-                    // disjoint boxes (the common case): 0 / positive is exactly +0, no divide needed
-                    const float ovr = (inter == 0.f && uni > 0.f) ? 0.f : fdiv(inter, uni);
-                    sup = (double)ovr > a.iou_thr;                    // float-vs-double compare
-                }
-                bits = __ballot_sync(FULL, sup);
+        for (int w = i >> 5; w < words; ++w) {
+            const int j = (w << 5) + lane;
+            bool sup = false;
+            if (j > i && j < n) {
+                const float4 bj = sbox[j];
+                const float iw = fmaxf(0.f, fsub(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)));
+                const float ih = fmaxf(0.f, fsub(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)));
+                const float inter = fmul(iw, ih);
+                const float uni = fsub(fadd(ai, sarea[j]), inter);
+                // disjoint boxes (the common case): 0 / positive is exactly +0, no divide needed
+                const float ovr = (inter == 0.f && uni > 0.f) ? 0.f : fdiv(inter, uni);
+                sup = (double)ovr > a.iou_thr;                        // float-vs-double compare
             }
-            if (lane_id() == 0) mask[(size_t)i * words + w] = bits;
+            const uint32_t bits = __ballot_sync(FULL, sup);
+            if (lane == 0) mask[(size_t)i * words + w] = bits;
         }
     }
     __syncthreads();
 
-    // greedy sweep in score order: lane l owns removed-word l
+    // ---- greedy sweep in score order (warp 0).  Lane l owns word l of the suppressed set; rows are
+    //      resolved 32 at a time: the chunk's diagonal words are exchanged up front, the sequential
+    //      part is a register-only chain, the kept rows' mask words are pre-loaded. ----
     if (warp_id() == 0) {
         uint32_t removed = 0u;
         int nkeep = 0;
-        for (int i = 0; i < n; ++i) {
-            const uint32_t r = __shfl_sync(FULL, removed, i >> 5);
-            if (!((r >> (i & 31)) & 1u)) {
-                if (lane_id() < words) removed |= mask[(size_t)i * words + lane_id()];
-                if (lane_id() == 0) keep[nkeep] = i;
-                nkeep++;
+        for (int c = 0; c < words; ++c) {
+            const int r0 = c << 5;
+            const int rows_c = min(32, n - r0);
+            uint32_t later[32];                       // mask[r0 + l][lane] for the words after this chunk
+#pragma unroll
+            for (int l = 0; l < 32; ++l)
+                later[l] = (l < rows_c && lane > c && lane < words) ? mask[(size_t)(r0 + l) * words + lane] : 0u;
+            const uint32_t diag = lane < rows_c ? mask[(size_t)(r0 + lane) * words + c] : 0u;
+            uint32_t cur = __shfl_sync(FULL, removed, c);
+            if (rows_c < 32) cur |= ~0u << rows_c;
+            uint32_t kbits = 0u;
+#pragma unroll
+            for (int l = 0; l < 32; ++l) {
+                const uint32_t d = __shfl_sync(FULL, diag, l);
+                if (!((cur >> l) & 1u)) { cur |= d; kbits |= 1u << l; }
             }
+#pragma unroll
+            for (int l = 0; l < 32; ++l)
+                if ((kbits >> l) & 1u) removed |= later[l];
+            if ((kbits >> lane) & 1u) keep[nkeep + __popc(kbits & ((1u << lane) - 1u))] = r0 + lane;
+            nkeep += __popc(kbits);
         }
-        if (lane_id() == 0) { s_nkeep = nkeep; kept_count[seg] = nkeep; }
+        if (lane == 0) { s_nkeep = nkeep; kept_count[seg] = nkeep; }
     }
     __syncthreads();
     const int nkeep = s_nkeep;
     float* out = kept + (size_t)seg * a.K * kKeptCols;
     for (int t = threadIdx.x; t < nkeep; t += blockDim.x) {
         const int i = keep[t];
-        const unsigned long long key = keys[i];
+        const unsigned long long key = sorted[i];
         const float4 bx = sbox[i];
         float* o = out + (size_t)t * kKeptCols;
         o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
@@ -642,37 +688,6 @@ segment_nms_kernel(NmsArgs a, const float* __restrict__ scores, const float2* __
 // ---------------------------------------------------------------------------------------------
 // 5. image_topk: one CTA per image
 // ---------------------------------------------------------------------------------------------
-struct TopkShared {
-    int part[16][4];
-    int total[4];
-    unsigned long long wmin[16], wmax[16];
-    unsigned long long gmin, gmax;
-    int n_total, n_sel;
-};
-
-__device__ __forceinline__ void block_sum4_topk(TopkShared& sh, int (&c)[4]) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) c[j] = __reduce_add_sync(FULL, c[j]);
-    if (lane_id() == 0) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) sh.part[warp_id()][j] = c[j];
-    }
-    __syncthreads();
-    if (warp_id() == 0) {
-        const int nw = blockDim.x >> 5;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int x = lane_id() < nw ? sh.part[lane_id()][j] : 0;
-            x = __reduce_add_sync(FULL, x);
-            if (lane_id() == 0) sh.total[j] = x;
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < 4; ++j) c[j] = sh.total[j];
-    __syncthreads();
-}
-
 __device__ __forceinline__ void write_det_row(float* dets, int* anchors, const float* kept, int K, int cls, int slot,
                                               int out_row) {
     const float* src = kept + ((size_t)cls * K + slot) * kKeptCols;
@@ -683,100 +698,116 @@ __device__ __forceinline__ void write_det_row(float* dets, int* anchors, const f
     if (anchors != nullptr) anchors[out_row] = (int)__float_as_uint(src[5]);
 }
 
+struct TopkShared {
+    int wsum[kTopkThreads / 32];
+    int cnt[4];
+    int n_total, n_sel, n_tie;
+};
+
 __global__ void __launch_bounds__(kTopkThreads)
 image_topk_kernel(int Cf, int K, int T, int det_cap, const int* __restrict__ kept_count, const float* __restrict__ kept,
                   float* __restrict__ dets, int* __restrict__ det_count, int* __restrict__ det_anchor) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ TopkShared sh;
     const int img = blockIdx.x;
+    const int lane = lane_id();
+    const int nwarps = blockDim.x >> 5;
     int* offs = reinterpret_cast<int*>(smem);                              // [Cf + 1]
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem + round_up((size_t)(Cf + 1) * 4, 16));
+    uint32_t* skey = reinterpret_cast<uint32_t*>(smem + round_up((size_t)(Cf + 1) * 4, 16));   // [Cf*K] score keys
     const int* kc = kept_count + (size_t)img * Cf;
     const float* kimg = kept + (size_t)img * Cf * K * kKeptCols;
     float* dimg = dets + (size_t)img * det_cap * 6;
     int* aimg = det_anchor ? det_anchor + (size_t)img * det_cap : nullptr;
 
-    if (threadIdx.x == 0) {
-        int acc = 0;
-        for (int c = 0; c < Cf; ++c) { offs[c] = acc; acc += kc[c]; }
-        offs[Cf] = acc;
-        sh.n_total = acc;
-        sh.n_sel = 0;
+    // exclusive scan of the per-class counts (warp 0, 32 classes per round)
+    if (warp_id() == 0) {
+        int base = 0;
+        for (int c0 = 0; c0 < Cf; c0 += 32) {
+            const int c = c0 + lane;
+            const int v = c < Cf ? kc[c] : 0;
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (c < Cf) offs[c] = base + incl - v;
+            base += __shfl_sync(FULL, incl, 31);
+        }
+        if (lane == 0) { offs[Cf] = base; sh.n_total = base; sh.n_sel = 0; sh.n_tie = 0; sh.cnt[0] = sh.cnt[1] = sh.cnt[2] = sh.cnt[3] = 0; }
     }
     __syncthreads();
     const int n = sh.n_total;
 
     if (T <= 0 || n <= T) {
         // class-major order, descending score inside a class            postprocessor.py:68-70
-        for (int c = warp_id(); c < Cf; c += (blockDim.x >> 5)) {
+        for (int c = warp_id(); c < Cf; c += nwarps) {
             const int cnt = offs[c + 1] - offs[c];
-            for (int t = lane_id(); t < cnt; t += 32) write_det_row(dimg, aimg, kimg, K, c, t, offs[c] + t);
+            for (int t = lane; t < cnt; t += 32) write_det_row(dimg, aimg, kimg, K, c, t, offs[c] + t);
         }
         if (threadIdx.x == 0) det_count[img] = n;
         return;
     }
 
-    // keys = (score, ~position): unique, so exactly T of them are >= the T-th largest
-    for (int c = warp_id(); c < Cf; c += (blockDim.x >> 5)) {
+    // score keys in class-major position order
+    for (int c = warp_id(); c < Cf; c += nwarps) {
         const int cnt = offs[c + 1] - offs[c];
-        for (int t = lane_id(); t < cnt; t += 32) {
-            const float s = kimg[((size_t)c * K + t) * kKeptCols + 4];
-            const int pos = offs[c] + t;
-            keys[pos] = ((unsigned long long)ordered_key(s) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)pos);
-        }
+        for (int t = lane; t < cnt; t += 32) skey[offs[c] + t] = ordered_key(kimg[((size_t)c * K + t) * kKeptCols + 4]);
     }
     __syncthreads();
-    unsigned long long lo = ~0ull, hi = 0ull;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) { lo = min(lo, keys[i]); hi = max(hi, keys[i]); }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        lo = min(lo, __shfl_xor_sync(FULL, lo, o));
-        hi = max(hi, __shfl_xor_sync(FULL, hi, o));
+
+    // S = the T-th largest score key: the largest S with count(key >= S) >= T.  One barrier per bit;
+    // the counters rotate over four slots (slot p+2 is cleared while slot p is in use).
+    uint32_t S = 0u;
+    for (int bit = 31, pass = 0; bit >= 0; --bit, ++pass) {
+        const uint32_t trial = S | (1u << bit);
+        int c = 0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) c += skey[i] >= trial;
+        c = __reduce_add_sync(FULL, c);
+        if (lane == 0 && c) atomicAdd(&sh.cnt[pass & 3], c);
+        if (threadIdx.x == 0) sh.cnt[(pass + 2) & 3] = 0;
+        __syncthreads();
+        if (sh.cnt[pass & 3] >= T) S = trial;
     }
-    if (lane_id() == 0) { sh.wmin[warp_id()] = lo; sh.wmax[warp_id()] = hi; }
+    // rows with key > S all make it; ties on S go to the lowest class-major positions  postprocessor.py:72-74
+    int gt = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) gt += skey[i] > S;
+    gt = __reduce_add_sync(FULL, gt);
+    __syncthreads();                                   // every thread is done reading cnt[]
+    if (threadIdx.x == 0) sh.cnt[0] = 0;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long l = ~0ull, h = 0ull;
-        for (int w = 0; w < (blockDim.x >> 5); ++w) { l = min(l, sh.wmin[w]); h = max(h, sh.wmax[w]); }
-        sh.gmin = l; sh.gmax = h;
-    }
+    if (lane == 0 && gt) atomicAdd(&sh.cnt[0], gt);
     __syncthreads();
-    const unsigned long long diff = sh.gmin ^ sh.gmax;          // != 0: n > T >= 1 unique keys
-    const int hb = 63 - __clzll((long long)diff);
-    int shift = hb & ~1;
-    unsigned long long prefix = shift + 2 >= 64 ? 0ull : (sh.gmax >> (shift + 2)) << (shift + 2);
-    int rem = T;
-    unsigned long long thr_key = 0ull;       // select keys >= thr_key
-    for (; shift >= 0; shift -= 2) {
-        int d[4] = {0, 0, 0, 0};
-        const unsigned long long pre_hi = shift + 2 >= 64 ? 0ull : prefix >> (shift + 2);
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const unsigned long long key = keys[i];
-            const unsigned long long khi = shift + 2 >= 64 ? 0ull : key >> (shift + 2);
-            if (khi == pre_hi) d[(int)((key >> shift) & 3ull)]++;
-        }
-        block_sum4_topk(sh, d);
-        int digit = 3;
-        for (; digit > 0; --digit) {
-            if (rem <= d[digit]) break;
-            rem -= d[digit];
-        }
-        prefix |= (unsigned long long)digit << shift;
-        thr_key = prefix;
-        if (rem == d[digit]) break;          // the whole bucket is needed: its lower edge is the cut
-    }
-    __syncthreads();
+    const int need_ties = T - sh.cnt[0];               // >= 1
+
     int t2 = 32;
     while (t2 < T) t2 <<= 1;
-    unsigned long long* sel = keys + n;      // [t2]
+    unsigned long long* sel = reinterpret_cast<unsigned long long*>(
+        smem + round_up((size_t)(Cf + 1) * 4, 16) + round_up((size_t)Cf * K * 4, 16));   // [t2]
     for (int i = threadIdx.x; i < t2; i += blockDim.x) sel[i] = 0ull;
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const unsigned long long key = keys[i];
-        if (key >= thr_key) {
-            const int slot = atomicAdd(&sh.n_sel, 1);
-            if (slot < t2) sel[slot] = key;
+    // ordered pass (position order) so that ties are taken from the front
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const uint32_t key = i < n ? skey[i] : 0u;
+        const bool tie = i < n && key == S;
+        const unsigned bal = __ballot_sync(FULL, tie);
+        if (lane == 0) sh.wsum[warp_id()] = __popc(bal);
+        __syncthreads();
+        int before = sh.n_tie, total = 0;
+        for (int w = 0; w < nwarps; ++w) {
+            const int x = sh.wsum[w];
+            if (w < warp_id()) before += x;
+            total += x;
         }
+        const int trank = before + __popc(bal & ((1u << lane) - 1u));
+        if (i < n && (key > S || (tie && trank < need_ties))) {
+            const int slot = atomicAdd(&sh.n_sel, 1);
+            sel[slot] = ((unsigned long long)key << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)i);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) sh.n_tie += total;
+        __syncthreads();
     }
     bitonic_sort_desc(sel, t2);
     // sorted=True: descending score, ties by class-major position     postprocessor.py:72-74
@@ -879,7 +910,7 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
         a.xy_scale = p->xy_scale; a.wh_scale = p->wh_scale; a.iou_thr = p->overlap_threshold;
         const int kwords = (pl.K + 31) / 32;
         const size_t key_slots = pl.cand_cap > kMaxPerClass ? pl.cand_cap : kMaxPerClass;
-        const size_t smem = key_slots * 8 + (size_t)pl.K * (16 + 4 + 4) + (size_t)pl.K * kwords * 4 + 64;
+        const size_t smem = key_slots * 8 + (size_t)(pl.K + 1) * (8 + 16 + 4 + 4) + (size_t)pl.K * kwords * 4 + 64;
         SSD_CUDA(cudaFuncSetAttribute(segment_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         LaunchTimer lt_("nms", st);
         segment_nms_kernel<<<pl.B * pl.Cf, kNmsThreads, smem, st>>>(a, scores, rowstat, cand_count, cand,
@@ -891,7 +922,8 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
     {
         int t2 = 32;
         while (t2 < pl.T) t2 <<= 1;
-        const size_t smem = round_up((size_t)(pl.Cf + 1) * 4, 16) + ((size_t)pl.Cf * pl.K + (pl.T > 0 ? t2 : 0)) * 8 + 64;
+        const size_t smem = round_up((size_t)(pl.Cf + 1) * 4, 16) + round_up((size_t)pl.Cf * pl.K * 4, 16) +
+                            (size_t)(pl.T > 0 ? t2 : 0) * 8 + 64;
         SSD_REQUIRE(smem <= 224 * 1024, SSD_ERR_UNSUPPORTED, "ssd_postprocess: final top-k needs %zu bytes of shared memory", smem);
         SSD_CUDA(cudaFuncSetAttribute(image_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         LaunchTimer lt_("topk", st);
