@@ -225,21 +225,32 @@ mining_select_kernel(const uint32_t* __restrict__ keys, const int* __restrict__ 
     const bool rank_bin = partial && need < in_bin;   // otherwise the whole boundary bin is taken
     const bool in_smem = in_bin <= kBoundaryCap;
 
-    // ---- one pass over the keys ----
-    for (int a = tid; a < A; a += kSelThreads) {
-        const uint32_t key = gk[a];
-        uint8_t sel;
-        if (key == kKeyPositive) sel = 1;
-        else if (key == kKeyIgnored) sel = 0;
-        else {
-            const int bin = key_bin(key);
-            sel = bin > cut_bin || (bin == cut_bin && !rank_bin);
-            if (rank_bin && bin == cut_bin && in_smem) {
-                const int slot = atomicAdd(&sh.n_cand, 1);
-                sh.cand[slot] = ((unsigned long long)key << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)a);
-            }
+    // ---- one pass over the keys (four loads in flight per thread) ----
+    for (int a0 = tid; a0 < A; a0 += 4 * kSelThreads) {
+        uint32_t kk[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int a = a0 + u * kSelThreads;
+            kk[u] = a < A ? gk[a] : kKeyIgnored;
         }
-        gm[a] = sel;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int a = a0 + u * kSelThreads;
+            if (a >= A) break;
+            const uint32_t key = kk[u];
+            uint8_t sel;
+            if (key == kKeyPositive) sel = 1;
+            else if (key == kKeyIgnored) sel = 0;
+            else {
+                const int bin = key_bin(key);
+                sel = bin > cut_bin || (bin == cut_bin && !rank_bin);
+                if (rank_bin && bin == cut_bin && in_smem) {
+                    const int slot = atomicAdd(&sh.n_cand, 1);
+                    sh.cand[slot] = ((unsigned long long)key << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)a);
+                }
+            }
+            gm[a] = sel;
+        }
     }
     int num_ties = 0;
     if (rank_bin) {

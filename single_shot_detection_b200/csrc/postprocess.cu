@@ -46,11 +46,21 @@ struct PostPlan {
     int cand_cap;            // candidate slots per (image, class)
     // workspace offsets (bytes)
     size_t off_rowstat, off_blockmax, off_gate, off_cand_count, off_cand, off_kept_count, off_kept, off_status,
-        off_anchor_tmp;
+        off_anchor_tmp, off_score_hist;
     size_t total_bytes;
 };
 
 constexpr int kKeptCols = 6;          // x1,y1,x2,y2,score,anchor(bits)
+constexpr int kScoreBins = 4096;      // per-image histogram of the kept scores (final top-k)
+constexpr int kTopkBoundaryCap = 1024;
+
+// Monotone (non-decreasing) map of a kept score to a histogram bin; probabilities spread over the
+// whole range, anything else is clamped (the boundary bin is ranked exactly, so only speed depends
+// on the spread).
+__device__ __forceinline__ int score_bin(float v) {
+    const float s = fminf(fmaxf(__fmul_rn(v, (float)(kScoreBins - 2)), 0.f), (float)(kScoreBins - 2));
+    return 1 + (int)s;                 // 1 .. kScoreBins-1 (NaN never reaches here: it fails score > thr)
+}
 constexpr int kMaxPerClass = 512;
 constexpr int kNmsThreads = 128;
 constexpr int kTopkThreads = 512;
@@ -113,6 +123,7 @@ static int make_plan(const ssd_postprocess_params* p, PostPlan& pl) {
     pl.off_kept = take((size_t)pl.B * pl.Cf * pl.K * kKeptCols * sizeof(float));
     pl.off_status = take(4 * sizeof(int));
     pl.off_anchor_tmp = take((size_t)pl.B * (pl.det_cap > 0 ? pl.det_cap : 1) * sizeof(int));
+    pl.off_score_hist = take((size_t)pl.B * kScoreBins * sizeof(int));
     pl.total_bytes = off;
     return SSD_OK;
 }
@@ -245,7 +256,8 @@ constexpr int kGateBits = 20;                // resolved MSBs of the K-th larges
 // (a slightly smaller key).  Both only let a few more candidates through.
 __global__ void __launch_bounds__(kGateThreads)
 class_gate_kernel(const float* __restrict__ blockmax, int C, int first_fg, int nblk, int K, int converter,
-                  float score_thr, float* __restrict__ gate, int* __restrict__ cand_count, int* __restrict__ status) {
+                  float score_thr, float* __restrict__ gate, int* __restrict__ cand_count, int* __restrict__ status,
+                  int* __restrict__ score_hist, int hist_words) {
     extern __shared__ __align__(16) uint32_t skey[];          // [merged blocks][kGateCols + 1]
     const int b = blockIdx.y;
     const int c0 = blockIdx.x * kGateCols;
@@ -254,19 +266,43 @@ class_gate_kernel(const float* __restrict__ blockmax, int C, int first_fg, int n
     const int merge = (nblk + 32 * kGateKeysPerLane - 1) / (32 * kGateKeysPerLane);
     const int nm = (nblk + merge - 1) / merge;                 // merged blocks, <= 512
     const float* src = blockmax + (size_t)b * nblk * C;
-    // coalesced load: 8 consecutive columns of one block row per 8 threads
-    for (int t = threadIdx.x; t < nm * kGateCols; t += kGateThreads) {
-        const int mb = t / kGateCols, cc = t % kGateCols;
-        float v = -INFINITY;
-        if (c0 + cc < C) {
-            const int lo = mb * merge, hi = min(lo + merge, nblk);
-            for (int i = lo; i < hi; ++i) {
-                const float x = src[(size_t)i * C + c0 + cc];
-                v = (x != x || x > v) ? x : v;                  // NaN (sorts on top) sticks
-                if (x != x) break;
+    // zero the per-image score histograms for the NMS kernel (grid-stride over the whole array)
+    {
+        const int nthreads = gridDim.x * gridDim.y * kGateThreads;
+        const int gtid = (blockIdx.y * gridDim.x + blockIdx.x) * kGateThreads + threadIdx.x;
+        for (int i = gtid; i < hist_words; i += nthreads) score_hist[i] = 0;
+    }
+    // coalesced load: 8 consecutive columns of one block row per 8 threads, four rows in flight
+    if (merge == 1) {
+        const int total = nm * kGateCols;
+        for (int t0 = threadIdx.x; t0 < total; t0 += 4 * kGateThreads) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int t = t0 + u * kGateThreads;
+                const int mb = t / kGateCols, cc = t % kGateCols;
+                v[u] = (t < total && c0 + cc < C) ? src[(size_t)mb * C + c0 + cc] : -INFINITY;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int t = t0 + u * kGateThreads;
+                if (t < total) skey[(t / kGateCols) * (kGateCols + 1) + t % kGateCols] = ordered_key(v[u]);
             }
         }
-        skey[mb * (kGateCols + 1) + cc] = ordered_key(v);
+    } else {
+        for (int t = threadIdx.x; t < nm * kGateCols; t += kGateThreads) {
+            const int mb = t / kGateCols, cc = t % kGateCols;
+            float v = -INFINITY;
+            if (c0 + cc < C) {
+                const int lo = mb * merge, hi = min(lo + merge, nblk);
+                for (int i = lo; i < hi; ++i) {
+                    const float x = src[(size_t)i * C + c0 + cc];
+                    v = (x != x || x > v) ? x : v;                  // NaN (sorts on top) sticks
+                    if (x != x) break;
+                }
+            }
+            skey[mb * (kGateCols + 1) + cc] = ordered_key(v);
+        }
     }
     __syncthreads();
     const int col = c0 + warp_id();
@@ -505,7 +541,7 @@ __global__ void __launch_bounds__(kNmsThreads)
 segment_nms_kernel(NmsArgs a, const float* __restrict__ scores, const float2* __restrict__ rowstat,
                    const int* __restrict__ cand_count, const uint2* __restrict__ cand,
                    const float4* __restrict__ boxes, const float4* __restrict__ priors, int* __restrict__ kept_count,
-                   float* __restrict__ kept, int* __restrict__ status) {
+                   float* __restrict__ kept, int* __restrict__ status, int* __restrict__ score_hist) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint32_t s_hist[2048];
     __shared__ int s_misc[4 + kNmsThreads / 32];
@@ -680,8 +716,10 @@ segment_nms_kernel(NmsArgs a, const float* __restrict__ scores, const float2* __
         const float4 bx = sbox[i];
         float* o = out + (size_t)t * kKeptCols;
         o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
-        o[4] = key_to_float((uint32_t)(key >> 32));
+        const float score = key_to_float((uint32_t)(key >> 32));
+        o[4] = score;
         o[5] = __uint_as_float(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
+        atomicAdd(score_hist + (size_t)img * kScoreBins + score_bin(score), 1);
     }
 }
 
@@ -700,25 +738,44 @@ __device__ __forceinline__ void write_det_row(float* dets, int* anchors, const f
 
 struct TopkShared {
     int wsum[kTopkThreads / 32];
+    int warp_tot[kTopkThreads / 32];
     int cnt[4];
-    int n_total, n_sel, n_tie;
+    int n_total, n_sel, n_tie, n_cand, cut_bin, above, in_bin;
 };
 
+// Final top-k (postprocessor.py:70-74): the T best of the image's kept rows, descending score,
+// ties by class-major position.  The NMS kernel has already histogrammed the kept scores, so the
+// cut is found with one suffix scan; rows above the cut bin are taken, the cut bin is ranked
+// exactly.  A cut bin too crowded to rank (scores tied en masse) falls back to a bit-wise bisection.
 __global__ void __launch_bounds__(kTopkThreads)
 image_topk_kernel(int Cf, int K, int T, int det_cap, const int* __restrict__ kept_count, const float* __restrict__ kept,
-                  float* __restrict__ dets, int* __restrict__ det_count, int* __restrict__ det_anchor) {
+                  const int* __restrict__ score_hist, float* __restrict__ dets, int* __restrict__ det_count,
+                  int* __restrict__ det_anchor) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ TopkShared sh;
     const int img = blockIdx.x;
     const int lane = lane_id();
-    const int nwarps = blockDim.x >> 5;
+    const int tid = threadIdx.x;
+    constexpr int nwarps = kTopkThreads / 32;
+    int t2 = 32;
+    while (t2 < T) t2 <<= 1;
     int* offs = reinterpret_cast<int*>(smem);                              // [Cf + 1]
-    uint32_t* skey = reinterpret_cast<uint32_t*>(smem + round_up((size_t)(Cf + 1) * 4, 16));   // [Cf*K] score keys
+    unsigned long long* sel = reinterpret_cast<unsigned long long*>(smem + round_up((size_t)(Cf + 1) * 4, 16));   // [t2]
+    unsigned long long* cand = sel + t2;                                   // [kTopkBoundaryCap] (later: sorted)
+    uint32_t* skey = reinterpret_cast<uint32_t*>(cand + kTopkBoundaryCap); // [Cf*K] fallback only
     const int* kc = kept_count + (size_t)img * Cf;
     const float* kimg = kept + (size_t)img * Cf * K * kKeptCols;
     float* dimg = dets + (size_t)img * det_cap * 6;
     int* aimg = det_anchor ? det_anchor + (size_t)img * det_cap : nullptr;
 
+    // the histogram loads go out first (8 bins per thread, higher bins = larger scores)
+    static_assert(kScoreBins == 8 * kTopkThreads, "eight bins per thread");
+    int hb[8];
+    if (T > 0) {
+        const int4* h4 = reinterpret_cast<const int4*>(score_hist + (size_t)img * kScoreBins) + 2 * tid;
+        const int4 lo = h4[0], hi = h4[1];
+        hb[0] = lo.x; hb[1] = lo.y; hb[2] = lo.z; hb[3] = lo.w; hb[4] = hi.x; hb[5] = hi.y; hb[6] = hi.z; hb[7] = hi.w;
+    }
     // exclusive scan of the per-class counts (warp 0, 32 classes per round)
     if (warp_id() == 0) {
         int base = 0;
@@ -734,7 +791,11 @@ image_topk_kernel(int Cf, int K, int T, int det_cap, const int* __restrict__ kep
             if (c < Cf) offs[c] = base + incl - v;
             base += __shfl_sync(FULL, incl, 31);
         }
-        if (lane == 0) { offs[Cf] = base; sh.n_total = base; sh.n_sel = 0; sh.n_tie = 0; sh.cnt[0] = sh.cnt[1] = sh.cnt[2] = sh.cnt[3] = 0; }
+        if (lane == 0) {
+            offs[Cf] = base;
+            sh.n_total = base; sh.n_sel = 0; sh.n_tie = 0; sh.n_cand = 0; sh.cut_bin = -1; sh.above = 0; sh.in_bin = 0;
+            sh.cnt[0] = sh.cnt[1] = sh.cnt[2] = sh.cnt[3] = 0;
+        }
     }
     __syncthreads();
     const int n = sh.n_total;
@@ -745,74 +806,134 @@ image_topk_kernel(int Cf, int K, int T, int det_cap, const int* __restrict__ kep
             const int cnt = offs[c + 1] - offs[c];
             for (int t = lane; t < cnt; t += 32) write_det_row(dimg, aimg, kimg, K, c, t, offs[c] + t);
         }
-        if (threadIdx.x == 0) det_count[img] = n;
+        if (tid == 0) det_count[img] = n;
         return;
     }
 
-    // score keys in class-major position order
-    for (int c = warp_id(); c < Cf; c += nwarps) {
-        const int cnt = offs[c + 1] - offs[c];
-        for (int t = lane; t < cnt; t += 32) skey[offs[c] + t] = ordered_key(kimg[((size_t)c * K + t) * kKeptCols + 4]);
-    }
-    __syncthreads();
-
-    // S = the T-th largest score key: the largest S with count(key >= S) >= T.  One barrier per bit;
-    // the counters rotate over four slots (slot p+2 is cleared while slot p is in use).
-    uint32_t S = 0u;
-    for (int bit = 31, pass = 0; bit >= 0; --bit, ++pass) {
-        const uint32_t trial = S | (1u << bit);
-        int c = 0;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) c += skey[i] >= trial;
-        c = __reduce_add_sync(FULL, c);
-        if (lane == 0 && c) atomicAdd(&sh.cnt[pass & 3], c);
-        if (threadIdx.x == 0) sh.cnt[(pass + 2) & 3] = 0;
-        __syncthreads();
-        if (sh.cnt[pass & 3] >= T) S = trial;
-    }
-    // rows with key > S all make it; ties on S go to the lowest class-major positions  postprocessor.py:72-74
-    int gt = 0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) gt += skey[i] > S;
-    gt = __reduce_add_sync(FULL, gt);
-    __syncthreads();                                   // every thread is done reading cnt[]
-    if (threadIdx.x == 0) sh.cnt[0] = 0;
-    __syncthreads();
-    if (lane == 0 && gt) atomicAdd(&sh.cnt[0], gt);
-    __syncthreads();
-    const int need_ties = T - sh.cnt[0];               // >= 1
-
-    int t2 = 32;
-    while (t2 < T) t2 <<= 1;
-    unsigned long long* sel = reinterpret_cast<unsigned long long*>(
-        smem + round_up((size_t)(Cf + 1) * 4, 16) + round_up((size_t)Cf * K * 4, 16));   // [t2]
-    for (int i = threadIdx.x; i < t2; i += blockDim.x) sel[i] = 0ull;
-    __syncthreads();
-    // ordered pass (position order) so that ties are taken from the front
-    for (int base = 0; base < n; base += blockDim.x) {
-        const int i = base + threadIdx.x;
-        const uint32_t key = i < n ? skey[i] : 0u;
-        const bool tie = i < n && key == S;
-        const unsigned bal = __ballot_sync(FULL, tie);
-        if (lane == 0) sh.wsum[warp_id()] = __popc(bal);
-        __syncthreads();
-        int before = sh.n_tie, total = 0;
-        for (int w = 0; w < nwarps; ++w) {
-            const int x = sh.wsum[w];
-            if (w < warp_id()) before += x;
-            total += x;
+    // ---- cut bin: above(bin) < T <= above(bin) + hist[bin] ----
+    {
+        int own = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) own += hb[j];
+        int incl = own;                                   // suffix sum inside the warp (towards higher lanes)
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_down_sync(FULL, incl, o);
+            if (lane + o < 32) incl += t;
         }
-        const int trank = before + __popc(bal & ((1u << lane) - 1u));
-        if (i < n && (key > S || (tie && trank < need_ties))) {
-            const int slot = atomicAdd(&sh.n_sel, 1);
-            sel[slot] = ((unsigned long long)key << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)i);
+        if (lane == 0) sh.warp_tot[warp_id()] = incl;
+        __syncthreads();
+        const int wt = lane < nwarps ? sh.warp_tot[lane] : 0;
+        const int higher = __reduce_add_sync(FULL, lane > warp_id() ? wt : 0);
+        int above = higher + incl - own;
+        if (above < T && above + own >= T) {
+#pragma unroll
+            for (int j = 7; j >= 0; --j) {
+                if (above < T && above + hb[j] >= T) { sh.cut_bin = 8 * tid + j; sh.above = above; sh.in_bin = hb[j]; }
+                above += hb[j];
+            }
         }
         __syncthreads();
-        if (threadIdx.x == 0) sh.n_tie += total;
-        __syncthreads();
     }
-    bitonic_sort_desc(sel, t2);
-    // sorted=True: descending score, ties by class-major position     postprocessor.py:72-74
-    for (int r = threadIdx.x; r < T; r += blockDim.x) {
-        const int pos = (int)(0xFFFFFFFFu - (uint32_t)(sel[r] & 0xFFFFFFFFull));
+    const int cut_bin = sh.cut_bin, in_bin = sh.in_bin;
+    const int need = T - sh.above;                        // rows wanted from the cut bin, 1..in_bin
+
+    if (in_bin <= kTopkBoundaryCap) {
+        // one pass over the kept rows: composite = (score key, ~class-major position)
+        for (int c = warp_id(); c < Cf; c += nwarps) {
+            const int cnt = offs[c + 1] - offs[c];
+            for (int t = lane; t < cnt; t += 32) {
+                const float sc = kimg[((size_t)c * K + t) * kKeptCols + 4];
+                const int bin = score_bin(sc);
+                if (bin >= cut_bin) {
+                    const unsigned long long comp = ((unsigned long long)ordered_key(sc) << 32) |
+                                                    (unsigned long long)(0xFFFFFFFFu - (uint32_t)(offs[c] + t));
+                    if (bin > cut_bin || need == in_bin) sel[atomicAdd(&sh.n_sel, 1)] = comp;
+                    else cand[atomicAdd(&sh.n_cand, 1)] = comp;
+                }
+            }
+        }
+        __syncthreads();
+        if (need < in_bin) {
+            const int nc = sh.n_cand;
+            for (int i = tid; i < nc; i += kTopkThreads) {
+                const unsigned long long me = cand[i];
+                int rank = 0;
+                for (int j = 0; j < nc; ++j) rank += cand[j] > me;
+                if (rank < need) sel[atomicAdd(&sh.n_sel, 1)] = me;
+            }
+            __syncthreads();
+        }
+    } else {
+        // crowded cut bin: S = the T-th largest score key by bit-wise bisection over all rows.  One
+        // barrier per bit; the counters rotate over four slots (slot p+2 is cleared while p is in use).
+        for (int c = warp_id(); c < Cf; c += nwarps) {
+            const int cnt = offs[c + 1] - offs[c];
+            for (int t = lane; t < cnt; t += 32) skey[offs[c] + t] = ordered_key(kimg[((size_t)c * K + t) * kKeptCols + 4]);
+        }
+        __syncthreads();
+        uint32_t S = 0u;
+        for (int bit = 31, pass = 0; bit >= 0; --bit, ++pass) {
+            const uint32_t trial = S | (1u << bit);
+            int c = 0;
+            for (int i = tid; i < n; i += kTopkThreads) c += skey[i] >= trial;
+            c = __reduce_add_sync(FULL, c);
+            if (lane == 0 && c) atomicAdd(&sh.cnt[pass & 3], c);
+            if (tid == 0) sh.cnt[(pass + 2) & 3] = 0;
+            __syncthreads();
+            if (sh.cnt[pass & 3] >= T) S = trial;
+        }
+        int gt = 0;
+        for (int i = tid; i < n; i += kTopkThreads) gt += skey[i] > S;
+        gt = __reduce_add_sync(FULL, gt);
+        __syncthreads();                                   // every thread is done reading cnt[]
+        if (tid == 0) sh.cnt[0] = 0;
+        __syncthreads();
+        if (lane == 0 && gt) atomicAdd(&sh.cnt[0], gt);
+        __syncthreads();
+        const int need_ties = T - sh.cnt[0];               // >= 1
+        // ordered pass (position order) so that ties are taken from the front
+        for (int base = 0; base < n; base += kTopkThreads) {
+            const int i = base + tid;
+            const uint32_t key = i < n ? skey[i] : 0u;
+            const bool tie = i < n && key == S;
+            const unsigned bal = __ballot_sync(FULL, tie);
+            if (lane == 0) sh.wsum[warp_id()] = __popc(bal);
+            __syncthreads();
+            int before = sh.n_tie, total = 0;
+            for (int w = 0; w < nwarps; ++w) {
+                const int x = sh.wsum[w];
+                if (w < warp_id()) before += x;
+                total += x;
+            }
+            const int trank = before + __popc(bal & ((1u << lane) - 1u));
+            if (i < n && (key > S || (tie && trank < need_ties)))
+                sel[atomicAdd(&sh.n_sel, 1)] = ((unsigned long long)key << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)i);
+            __syncthreads();
+            if (tid == 0) sh.n_tie += total;
+            __syncthreads();
+        }
+    }
+
+    // ---- order the T selected rows: descending score, ties by class-major position ----
+    const unsigned long long* ordered;
+    if (T <= kTopkBoundaryCap) {
+        unsigned long long* sorted = cand;                 // the candidates are no longer needed
+        for (int r = tid; r < T; r += kTopkThreads) {
+            const unsigned long long me = sel[r];
+            int rank = 0;
+            for (int j = 0; j < T; ++j) rank += sel[j] > me;
+            sorted[rank] = me;
+        }
+        ordered = sorted;
+        __syncthreads();
+    } else {
+        for (int i = T + tid; i < t2; i += kTopkThreads) sel[i] = 0ull;
+        bitonic_sort_desc(sel, t2);
+        ordered = sel;
+    }
+    for (int r = tid; r < T; r += kTopkThreads) {
+        const int pos = (int)(0xFFFFFFFFu - (uint32_t)(ordered[r] & 0xFFFFFFFFull));
         int c_lo = 0, c_hi = Cf;               // largest c with offs[c] <= pos
         while (c_hi - c_lo > 1) {
             const int mid = (c_lo + c_hi) >> 1;
@@ -820,7 +941,7 @@ image_topk_kernel(int Cf, int K, int T, int det_cap, const int* __restrict__ kep
         }
         write_det_row(dimg, aimg, kimg, K, c_lo, pos - offs[c_lo], r);
     }
-    if (threadIdx.x == 0) det_count[img] = T;
+    if (tid == 0) det_count[img] = T;
 }
 
 __global__ void widen_keep_kernel(const int* __restrict__ src, const int* __restrict__ count, long long* __restrict__ dst,
@@ -850,6 +971,7 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
     int* kept_count = (int*)(ws + pl.off_kept_count);
     float* kept = (float*)(ws + pl.off_kept);
     int* status = (int*)(ws + pl.off_status);
+    int* score_hist = (int*)(ws + pl.off_score_hist);
 
     const ScoreGrid& g = pl.g;
     const int grid = stream_grid(g);
@@ -880,7 +1002,8 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
         const size_t gsmem = (size_t)nm * (kGateCols + 1) * sizeof(uint32_t);
         dim3 ggrid((pl.C + kGateCols - 1) / kGateCols, pl.B);
         class_gate_kernel<<<ggrid, kGateThreads, gsmem, st>>>(blockmax, pl.C, pl.first_fg, pl.nblk, pl.K, pl.converter,
-                                                               p->score_threshold, gate, cand_count, status);
+                                                               p->score_threshold, gate, cand_count, status,
+                                                               score_hist, pl.B * kScoreBins);
         SSD_CUDA(cudaGetLastError());
     count_launch();
     }
@@ -915,19 +1038,19 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
         LaunchTimer lt_("nms", st);
         segment_nms_kernel<<<pl.B * pl.Cf, kNmsThreads, smem, st>>>(a, scores, rowstat, cand_count, cand,
                                                                      (const float4*)boxes, (const float4*)priors,
-                                                                     kept_count, kept, status);
+                                                                     kept_count, kept, status, score_hist);
         SSD_CUDA(cudaGetLastError());
     count_launch();
     }
     {
         int t2 = 32;
         while (t2 < pl.T) t2 <<= 1;
-        const size_t smem = round_up((size_t)(pl.Cf + 1) * 4, 16) + round_up((size_t)pl.Cf * pl.K * 4, 16) +
-                            (size_t)(pl.T > 0 ? t2 : 0) * 8 + 64;
+        const size_t smem = round_up((size_t)(pl.Cf + 1) * 4, 16) + (size_t)(pl.T > 0 ? t2 : 0) * 8 +
+                            (size_t)kTopkBoundaryCap * 8 + round_up((size_t)pl.Cf * pl.K * 4, 16) + 64;
         SSD_REQUIRE(smem <= 224 * 1024, SSD_ERR_UNSUPPORTED, "ssd_postprocess: final top-k needs %zu bytes of shared memory", smem);
         SSD_CUDA(cudaFuncSetAttribute(image_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         LaunchTimer lt_("topk", st);
-        image_topk_kernel<<<pl.B, kTopkThreads, smem, st>>>(pl.Cf, pl.K, pl.T, pl.det_cap, kept_count, kept, dets_out,
+        image_topk_kernel<<<pl.B, kTopkThreads, smem, st>>>(pl.Cf, pl.K, pl.T, pl.det_cap, kept_count, kept, score_hist, dets_out,
                                                              count_out, anchor_out);
         SSD_CUDA(cudaGetLastError());
     count_launch();
