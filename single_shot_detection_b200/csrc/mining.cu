@@ -53,7 +53,7 @@ __device__ __forceinline__ void publish_key(uint32_t key, float loss, uint32_t* 
     (void)loss;
 }
 
-template <int Q, int NREG>
+template <int Q, int NREG, int CMIN>
 __global__ void __launch_bounds__(kStreamThreads)
 mining_loss_kernel(const float* __restrict__ logits, const long long* __restrict__ cls, uint32_t* __restrict__ keys,
                    int* __restrict__ hist, ScoreGrid g) {
@@ -64,6 +64,7 @@ mining_loss_kernel(const float* __restrict__ logits, const long long* __restrict
         return;
     }
     const RowLanes<Q> ln;
+    const RowShape<Q, NREG, CMIN> shape(ln.sub, g.C);
     const int rows_per_warp = g.tile_rows / kConsumerWarps;
     TileCursor cur;
     cur.start(g);
@@ -76,14 +77,13 @@ mining_loss_kernel(const float* __restrict__ logits, const long long* __restrict
 #pragma unroll 2
         for (int step = 0; step < rows_per_warp; step += RowLanes<Q>::kRowsPerWarpStep) {
             const int lr = wbase + step + ln.rl;
-            const bool valid = lr < rows;
             float v[NREG];
-            load_row_slice<Q, NREG>(v, tile.logits + (size_t)lr * g.C, ln.sub, g.C, valid);
+            shape.load(v, tile.logits + (size_t)lr * g.C, ln.sub);
             float m, sum;
-            row_max_sum<Q, NREG>(v, valid, m, sum);
-            if (valid && ln.sub == 0) {
+            row_max_sum<Q, NREG>(v, m, sum);
+            if (lr < rows && ln.sub == 0) {
                 // v[0] of lane sub == 0 is column 0
-                const float loss = __fsub_rn(__fadd_rn(m, logf(sum)), v[0]);
+                const float loss = __fsub_rn(__fadd_rn(m, fast_log(sum)), v[0]);
                 const long long c = (long long)tile.side[lr];
                 publish_key(mining_key(loss, c), loss, keys, r0 + lr, hist_img);
             }
@@ -354,9 +354,9 @@ static int launch_mining_keys(const float* logits, const int64_t* target_classes
     plan_tiles(g, batch, num_anchors, num_cols, true);
     const int grid = stream_grid(g);
     const size_t smem = stream_smem_bytes(g);
-#define SSD_LAUNCH_MINING(QQ, NN)                                                                                   \
+#define SSD_LAUNCH_MINING(QQ, NN, CM)                                                                                   \
     do {                                                                                                             \
-        auto kern = mining_loss_kernel<QQ, NN>;                                                                      \
+        auto kern = mining_loss_kernel<QQ, NN, CM>;                                                                    \
         SSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
         LaunchTimer lt_("mining_loss", st);                                                            \
         kern<<<grid, kStreamThreads, smem, st>>>(logits, (const long long*)target_classes, keys, hist, g);           \

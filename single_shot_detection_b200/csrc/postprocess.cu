@@ -42,6 +42,7 @@ namespace ssd {
 struct PostPlan {
     int B, A, C, Cf, first_fg, K, T, det_cap, converter, box_input;
     ScoreGrid g;             // tiling of the streaming kernels (shared by both passes)
+    int grid;                // CTAs of the streaming kernels
     int nblk;                // row blocks per image
     int cand_cap;            // candidate slots per (image, class)
     // workspace offsets (bytes)
@@ -53,6 +54,8 @@ struct PostPlan {
 constexpr int kKeptCols = 6;          // x1,y1,x2,y2,score,anchor(bits)
 constexpr int kScoreBins = 4096;      // per-image histogram of the kept scores (final top-k)
 constexpr int kTopkBoundaryCap = 1024;
+constexpr int kQueueCap = 96;         // pass-2 survivor queue: entries per warp
+constexpr size_t kQueueBytes = (size_t)kConsumerWarps * kQueueCap * 3 * sizeof(uint32_t);
 
 // Monotone (non-decreasing) map of a kept score to a histogram bin; probabilities spread over the
 // whole range, anything else is clamped (the boundary bin is ranked exactly, so only speed depends
@@ -107,6 +110,7 @@ static int make_plan(const ssd_postprocess_params* p, PostPlan& pl) {
     g.split = split;
     g.nblk = g.groups_per_image * kConsumerWarps * split;
     pl.nblk = g.nblk;
+    pl.grid = stream_grid(g, kQueueBytes);
     int cap = 512;                        // power of two (the segment sort pads to one), >= 8K
     while (cap < 8 * pl.K && cap < 4096) cap <<= 1;
     pl.cand_cap = cap;
@@ -133,7 +137,7 @@ static int make_plan(const ssd_postprocess_params* p, PostPlan& pl) {
 //    SOFTMAX: gate value of an element = its log-probability  x - (max + log(sum));
 //    SIGMOID / IDENTITY: the raw value (both converters are monotone per element).
 // ---------------------------------------------------------------------------------------------
-template <int Q, int NREG, int CONV>
+template <int Q, int NREG, int CMIN, int CONV>
 __global__ void __launch_bounds__(kStreamThreads)
 score_pass1_kernel(const float* __restrict__ scores, ScoreGrid g, float2* __restrict__ rowstat,
                    float* __restrict__ blockmax) {
@@ -144,6 +148,7 @@ score_pass1_kernel(const float* __restrict__ scores, ScoreGrid g, float2* __rest
         return;
     }
     const RowLanes<Q> ln;
+    const RowShape<Q, NREG, CMIN> shape(ln.sub, g.C);
     const int rows_per_warp = g.tile_rows / kConsumerWarps;
     float cmax[NREG];
 #pragma unroll
@@ -161,17 +166,19 @@ score_pass1_kernel(const float* __restrict__ scores, ScoreGrid g, float2* __rest
             const int lr = wbase + step + ln.rl;
             const bool valid = lr < rows;
             float v[NREG];
-            load_row_slice<Q, NREG>(v, tile.logits + (size_t)lr * g.C, ln.sub, g.C, valid);
+            shape.load(v, tile.logits + (size_t)lr * g.C, ln.sub);
             if (CONV == SSD_CONVERT_SOFTMAX) {
                 float m, sum;
-                row_max_sum<Q, NREG>(v, valid, m, sum);
+                row_max_sum<Q, NREG>(v, m, sum);
                 if (valid && ln.sub == 0) rowstat[r0 + lr] = make_float2(m, sum);
-                const float t = __fadd_rn(m, logf(sum));
+                // rows past the end of a partial tile: t = +inf turns every gate value into -inf / NaN,
+                // both of which fmaxf drops
+                const float t = valid ? __fadd_rn(m, fast_log(sum)) : INFINITY;
 #pragma unroll
-                for (int i = 0; i < NREG; ++i) cmax[i] = fmaxf(cmax[i], __fsub_rn(v[i], t));   // -inf slots stay -inf
+                for (int i = 0; i < NREG; ++i) cmax[i] = fmaxf(cmax[i], __fsub_rn(v[i], t));
             } else {
 #pragma unroll
-                for (int i = 0; i < NREG; ++i) cmax[i] = fmaxf(cmax[i], v[i]);
+                for (int i = 0; i < NREG; ++i) cmax[i] = fmaxf(cmax[i], valid ? v[i] : -INFINITY);
             }
         }
         consumer_release(smem, k);
@@ -342,7 +349,28 @@ class_gate_kernel(const float* __restrict__ blockmax, int C, int first_fg, int n
 // ---------------------------------------------------------------------------------------------
 // 3. score_pass2: emit candidates (gate value above the class gate)
 // ---------------------------------------------------------------------------------------------
-template <int Q, int NREG, int CONV>
+// Survivors are parked in a per-warp shared-memory queue and appended to the per-(image, class)
+// candidate lists in batches: one returning global atomic per entry, 32 in flight per warp, instead
+// of a round trip in the middle of every row step.
+
+struct CandQueue {
+    uint32_t* seg;      // [kQueueCap] segment = image * Cf + foreground column
+    uint32_t* anchor;   // [kQueueCap]
+    uint32_t* val;      // [kQueueCap] raw score bits
+    int n;              // warp-uniform fill
+    __device__ __forceinline__ void flush(int* __restrict__ cand_count, uint2* __restrict__ cand, int cand_cap) {
+        __syncwarp();
+        for (int e = lane_id(); e < n; e += 32) {
+            const uint32_t sg = seg[e];
+            const int slot = atomicAdd(&cand_count[sg], 1);
+            if (slot < cand_cap) cand[(size_t)sg * cand_cap + slot] = make_uint2(anchor[e], val[e]);
+        }
+        __syncwarp();
+        n = 0;
+    }
+};
+
+template <int Q, int NREG, int CMIN, int CONV>
 __global__ void __launch_bounds__(kStreamThreads)
 score_pass2_kernel(const float* __restrict__ scores, ScoreGrid g, const float2* __restrict__ rowstat,
                    const float* __restrict__ gate, int* __restrict__ cand_count, uint2* __restrict__ cand, int cand_cap) {
@@ -355,8 +383,15 @@ score_pass2_kernel(const float* __restrict__ scores, ScoreGrid g, const float2* 
         return;
     }
     const RowLanes<Q> ln;
+    const RowShape<Q, NREG, CMIN> shape(ln.sub, g.C);
     const int rows_per_warp = g.tile_rows / kConsumerWarps;
     const int Cf = g.C - g.first_fg;
+    CandQueue q;
+    {
+        uint32_t* base = reinterpret_cast<uint32_t*>(smem + stream_smem_bytes_dev(g)) + warp_id() * kQueueCap * 3;
+        q.seg = base; q.anchor = base + kQueueCap; q.val = base + 2 * kQueueCap; q.n = 0;
+    }
+    const unsigned lt_mask = (1u << lane_id()) - 1u;
 
     float gv[NREG];
     int cur_image = -1;
@@ -381,37 +416,42 @@ score_pass2_kernel(const float* __restrict__ scores, ScoreGrid g, const float2* 
             const int lr = wbase + step + ln.rl;
             const bool valid = lr < rows;
             float v[NREG];
-            load_row_slice<Q, NREG>(v, tile.logits + (size_t)lr * g.C, ln.sub, g.C, valid);
+            shape.load(v, tile.logits + (size_t)lr * g.C, ln.sub);
             float t = 0.f;
             if (CONV == SSD_CONVERT_SOFTMAX) {
-                float2 st = make_float2(0.f, 1.f);
-                if (valid) st = reinterpret_cast<const float2*>(tile.side)[lr];
-                t = __fadd_rn(st.x, logf(st.y));            // bit-identical to pass 1
+                const float2 st = reinterpret_cast<const float2*>(tile.side)[lr];
+                t = __fadd_rn(st.x, fast_log(st.y));            // bit-identical to pass 1
             }
-            // survivors: all slot reservations of the step are issued before the first one is used
-            int slot[NREG];
             unsigned hit = 0u;
 #pragma unroll
             for (int i = 0; i < NREG; ++i) {
                 const float x = CONV == SSD_CONVERT_SOFTMAX ? __fsub_rn(v[i], t) : v[i];
-                slot[i] = 0;
-                if (x > gv[i]) {                            // -inf padding and gv = +inf never pass
-                    hit |= 1u << i;
-                    slot[i] = atomicAdd(&cand_count[img * Cf + (ln.sub + i * Q - g.first_fg)], 1);
-                }
+                hit |= (x > gv[i]) ? (1u << i) : 0u;            // -inf padding and gv = +inf never pass
             }
-            if (hit) {
+            if (!valid) hit = 0u;
+            // park the survivors: every round each lane with a pending hit adds one entry
+            unsigned bal = __ballot_sync(FULL, hit != 0u);
+            while (bal) {
+                const int add = __popc(bal);
+                if (q.n + add > kQueueCap) q.flush(cand_count, cand, cand_cap);
+                if (hit) {
+                    const int i = __ffs(hit) - 1;
+                    hit &= hit - 1;
+                    float x = v[0];
 #pragma unroll
-                for (int i = 0; i < NREG; ++i) {
-                    if (((hit >> i) & 1u) && slot[i] < cand_cap) {
-                        const int seg = img * Cf + (ln.sub + i * Q - g.first_fg);
-                        cand[(size_t)seg * cand_cap + slot[i]] = make_uint2((uint32_t)(a0 + lr), __float_as_uint(v[i]));
-                    }
+                    for (int j = 1; j < NREG; ++j) x = (i == j) ? v[j] : x;
+                    const int pos = q.n + __popc(bal & lt_mask);
+                    q.seg[pos] = (uint32_t)(img * Cf + (ln.sub + i * Q - g.first_fg));
+                    q.anchor[pos] = (uint32_t)(a0 + lr);
+                    q.val[pos] = __float_as_uint(x);
                 }
+                q.n += add;
+                bal = __ballot_sync(FULL, hit != 0u);
             }
         }
         consumer_release(smem, k);
     }
+    q.flush(cand_count, cand, cand_cap);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -440,7 +480,28 @@ struct NmsArgs {
     int A, C, Cf, first_fg, K, cand_cap, converter, box_input;
     float score_thr, xy_scale, wh_scale;
     double iou_thr;
+    // exact division-free form of `(double)RN32(inter / uni) > iou_thr` (see nms_threshold_split)
+    double iou_mid;
+    int iou_even, exact_mul;
 };
+
+// torchvision compares the fp32 quotient with the double threshold.  Let T32 be the smallest float
+// whose value exceeds the threshold and P32 its predecessor: the quotient rounds to >= T32 exactly
+// when the real quotient lies above the midpoint M of P32 and T32 (or on it, when T32's mantissa is
+// even -- round to nearest even).  M has 25 significant bits, so M * uni is exact in double.
+static void nms_threshold_split(double thr, NmsArgs& a) {
+    a.iou_thr = thr;
+    a.exact_mul = 0; a.iou_mid = 0.0; a.iou_even = 0;
+    if (!(thr > 1e-30 && thr < 1e30)) return;
+    const float f0 = (float)thr;
+    const float t32 = ((double)f0 > thr) ? f0 : nextafterf(f0, INFINITY);
+    const float p32 = nextafterf(t32, -INFINITY);
+    uint32_t bits;
+    memcpy(&bits, &t32, sizeof(bits));
+    a.iou_mid = ((double)p32 + (double)t32) * 0.5;
+    a.iou_even = (bits & 1u) == 0u;
+    a.exact_mul = 1;
+}
 
 __device__ __forceinline__ float exact_score(int converter, float x, float2 st) {
     if (converter == SSD_CONVERT_SOFTMAX) return __fdiv_rn(expf(__fsub_rn(x, st.x)), st.y);   // exp(x-max)/sum
@@ -653,26 +714,39 @@ segment_nms_kernel(NmsArgs a, const float* __restrict__ scores, const float2* __
     }
     __syncthreads();
 
-    // ---- IoU bit matrix: row i, word w covers boxes 32w..32w+31; only j > i matters ----
-    const int nwarps = blockDim.x >> 5;
-    for (int i = warp_id(); i < n; i += nwarps) {
-        const float4 bi = sbox[i];
-        const float ai = sarea[i];
-        for (int w = i >> 5; w < words; ++w) {
-            const int j = (w << 5) + lane;
-            bool sup = false;
-            if (j > i && j < n) {
-                const float4 bj = sbox[j];
-                const float iw = fmaxf(0.f, fsub(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)));
-                const float ih = fmaxf(0.f, fsub(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)));
-                const float inter = fmul(iw, ih);
-                const float uni = fsub(fadd(ai, sarea[j]), inter);
-                // disjoint boxes (the common case): 0 / positive is exactly +0, no divide needed
-                const float ovr = (inter == 0.f && uni > 0.f) ? 0.f : fdiv(inter, uni);
-                sup = (double)ovr > a.iou_thr;                        // float-vs-double compare
+    // ---- IoU bit matrix: bit j of row i set <=> box i suppresses box j (j > i).  The n(n-1)/2 pairs
+    //      are dealt out flat over the CTA so every lane has work; suppressing pairs are rare and are
+    //      recorded with a shared-memory atomicOr. ----
+    for (int t = threadIdx.x; t < n * words; t += blockDim.x) mask[t] = 0u;
+    __syncthreads();
+    {
+        int i = 0, off = threadIdx.x;                 // pair (i, i + 1 + off)
+        for (;;) {
+            while (i < n - 1 && off >= n - 1 - i) { off -= n - 1 - i; ++i; }
+            if (i >= n - 1) break;
+            const int j = i + 1 + off;
+            const float4 bi = sbox[i], bj = sbox[j];
+            const float iw = fmaxf(0.f, fsub(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)));
+            const float ih = fmaxf(0.f, fsub(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)));
+            const float inter = fmul(iw, ih);
+            if (inter != 0.f) {                       // disjoint boxes: IoU is +0 (or 0/0, never > thr)
+                const float uni = fsub(fadd(sarea[i], sarea[j]), inter);
+                bool sup;
+                if (a.exact_mul && inter > 0.f && uni > 0.f) {
+                    // RN(inter / uni) >= T32  <=>  inter > M * uni, or == with T32 even; the product of a
+                    // 25-bit and a 24-bit significand is exact in double (see nms_threshold_split)
+                    const double lhs = (double)inter, rhs = a.iou_mid * (double)uni;
+                    sup = lhs > rhs || (lhs == rhs && a.iou_even);
+                } else {
+                    sup = (double)fdiv(inter, uni) > a.iou_thr;           // float-vs-double compare
+                }
+                if (sup) atomicOr(&mask[(size_t)i * words + (j >> 5)], 1u << (j & 31));
+            } else if (a.iou_thr < 0.0) {
+                // a negative threshold suppresses disjoint boxes too (0 > thr); uni > 0 assumed as in torchvision's 0/uni
+                const float uni = fsub(fadd(sarea[i], sarea[j]), inter);
+                if ((double)fdiv(inter, uni) > a.iou_thr) atomicOr(&mask[(size_t)i * words + (j >> 5)], 1u << (j & 31));
             }
-            const uint32_t bits = __ballot_sync(FULL, sup);
-            if (lane == 0) mask[(size_t)i * words + w] = bits;
+            off += blockDim.x;
         }
     }
     __syncthreads();
@@ -974,10 +1048,11 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
     int* score_hist = (int*)(ws + pl.off_score_hist);
 
     const ScoreGrid& g = pl.g;
-    const int grid = stream_grid(g);
+    const int grid = pl.grid;
     const size_t stream_smem = stream_smem_bytes(g);
+    const size_t pass2_smem = stream_smem + kQueueBytes;
 
-#define SSD_LAUNCH_PASS1(QQ, NN)                                                                                      \
+#define SSD_LAUNCH_PASS1(QQ, NN, CM)                                                                                     \
     do {                                                                                                               \
         auto launch = [&](auto kern) -> int {                                                                          \
             SSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem));    \
@@ -986,8 +1061,8 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
             return SSD_OK;                                                                                             \
         };                                                                                                             \
         int rc;                                                                                                        \
-        if (pl.converter == SSD_CONVERT_SOFTMAX) rc = launch(score_pass1_kernel<QQ, NN, SSD_CONVERT_SOFTMAX>);         \
-        else rc = launch(score_pass1_kernel<QQ, NN, SSD_CONVERT_IDENTITY>);                                            \
+        if (pl.converter == SSD_CONVERT_SOFTMAX) rc = launch(score_pass1_kernel<QQ, NN, CM, SSD_CONVERT_SOFTMAX>);         \
+        else rc = launch(score_pass1_kernel<QQ, NN, CM, SSD_CONVERT_IDENTITY>);                                            \
         if (rc != SSD_OK) return rc;                                                                                   \
     } while (0)
     SSD_DISPATCH_ROW_SHAPE(pl.C, SSD_LAUNCH_PASS1);
@@ -1008,17 +1083,17 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
     count_launch();
     }
 
-#define SSD_LAUNCH_PASS2(QQ, NN)                                                                                      \
+#define SSD_LAUNCH_PASS2(QQ, NN, CM)                                                                                     \
     do {                                                                                                               \
         auto launch = [&](auto kern) -> int {                                                                          \
-            SSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem));    \
+            SSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass2_smem));    \
             LaunchTimer lt_("pass2", st);                                                            \
-            kern<<<grid, kStreamThreads, stream_smem, st>>>(scores, g, rowstat, gate, cand_count, cand, pl.cand_cap); \
+            kern<<<grid, kStreamThreads, pass2_smem, st>>>(scores, g, rowstat, gate, cand_count, cand, pl.cand_cap); \
             return SSD_OK;                                                                                             \
         };                                                                                                             \
         int rc;                                                                                                        \
-        if (pl.converter == SSD_CONVERT_SOFTMAX) rc = launch(score_pass2_kernel<QQ, NN, SSD_CONVERT_SOFTMAX>);         \
-        else rc = launch(score_pass2_kernel<QQ, NN, SSD_CONVERT_IDENTITY>);                                            \
+        if (pl.converter == SSD_CONVERT_SOFTMAX) rc = launch(score_pass2_kernel<QQ, NN, CM, SSD_CONVERT_SOFTMAX>);         \
+        else rc = launch(score_pass2_kernel<QQ, NN, CM, SSD_CONVERT_IDENTITY>);                                            \
         if (rc != SSD_OK) return rc;                                                                                   \
     } while (0)
     SSD_DISPATCH_ROW_SHAPE(pl.C, SSD_LAUNCH_PASS2);
@@ -1030,7 +1105,8 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
         NmsArgs a;
         a.A = pl.A; a.C = pl.C; a.Cf = pl.Cf; a.first_fg = pl.first_fg; a.K = pl.K; a.cand_cap = pl.cand_cap;
         a.converter = pl.converter; a.box_input = pl.box_input; a.score_thr = p->score_threshold;
-        a.xy_scale = p->xy_scale; a.wh_scale = p->wh_scale; a.iou_thr = p->overlap_threshold;
+        a.xy_scale = p->xy_scale; a.wh_scale = p->wh_scale;
+        nms_threshold_split(p->overlap_threshold, a);
         const int kwords = (pl.K + 31) / 32;
         const size_t key_slots = pl.cand_cap > kMaxPerClass ? pl.cand_cap : kMaxPerClass;
         const size_t smem = key_slots * 8 + (size_t)(pl.K + 1) * (8 + 16 + 4 + 4) + (size_t)pl.K * kwords * 4 + 64;

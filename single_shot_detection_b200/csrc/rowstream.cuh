@@ -21,9 +21,10 @@ namespace ssd {
 
 constexpr int kConsumerWarps = 8;
 constexpr int kStreamThreads = (kConsumerWarps + 1) * 32;
-constexpr int kStreamStages = 4;
+constexpr int kStreamStages = 3;
 constexpr int kMaxScoreCols = 1024;
 constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
 
 // exp(d) for the STREAMED row sums, d = x - max already rounded as the reference rounds it: one
 // FMUL + one MUFU.  Relative error <= 2^-22 per term, exp(0) == 1 exactly (rows whose scores tie in
@@ -34,6 +35,15 @@ __device__ __forceinline__ float fast_exp(float d) {
     return y;
 }
 
+// log for the STREAMED quantities (gate values, mining criterion): one MUFU + one FMUL, absolute
+// error ~1e-7 for the sums seen here (>= 1).  Both score passes use the same function, so the gate
+// value of an element is bit-identical in pass 1 and pass 2.
+__device__ __forceinline__ float fast_log(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return __fmul_rn(y, kLn2);
+}
+
 // Tiling of a [B images x A rows x C cols] array.  Work item = `group_tiles` consecutive tiles of
 // one image; items are dealt round-robin to CTAs.  Tiles never cross an image boundary.
 struct ScoreGrid {
@@ -42,36 +52,39 @@ struct ScoreGrid {
     int stage_bytes;          // bytes per ring stage (logit tile + side array, 16-byte multiples)
     int side_offset;          // byte offset of the side array inside a stage
     int nblk, split;          // post-processor block-max bookkeeping (unused by mining)
+    int step_img, step_grp;   // gridDim.x decomposed as step_img * groups_per_image + step_grp
     int64_t total_floats;     // B*A*C
     int64_t total_rows;       // B*A
 };
 
 struct TileCursor {
-    int item, tile, tile_end;
+    int item, img, grp, tile, tile_end;
     __device__ __forceinline__ void start(const ScoreGrid& g) {
         item = blockIdx.x;
+        img = item / g.groups_per_image;
+        grp = item - img * g.groups_per_image;
         open(g);
     }
     __device__ __forceinline__ void open(const ScoreGrid& g) {
-        if (item < g.num_items) {
-            const int grp = item % g.groups_per_image;
-            tile = grp * g.group_tiles;
-            tile_end = min(tile + g.group_tiles, g.tiles_per_image);
-        }
+        tile = grp * g.group_tiles;
+        tile_end = min(tile + g.group_tiles, g.tiles_per_image);
     }
     __device__ __forceinline__ bool valid(const ScoreGrid& g) const { return item < g.num_items; }
-    __device__ __forceinline__ int image(const ScoreGrid& g) const { return item / g.groups_per_image; }
-    __device__ __forceinline__ int group(const ScoreGrid& g) const { return item % g.groups_per_image; }
+    __device__ __forceinline__ int image(const ScoreGrid&) const { return img; }
+    __device__ __forceinline__ int group(const ScoreGrid&) const { return grp; }
     __device__ __forceinline__ bool last_of_item() const { return tile + 1 == tile_end; }
     __device__ __forceinline__ void next(const ScoreGrid& g) {
         if (++tile == tile_end) {
             item += gridDim.x;
+            img += g.step_img;
+            grp += g.step_grp;
+            if (grp >= g.groups_per_image) { grp -= g.groups_per_image; ++img; }
             open(g);
         }
     }
     __device__ __forceinline__ int rows(const ScoreGrid& g) const { return min(g.tile_rows, g.A - tile * g.tile_rows); }
     __device__ __forceinline__ int64_t first_row(const ScoreGrid& g) const {
-        return (int64_t)image(g) * g.A + (int64_t)tile * g.tile_rows;
+        return (int64_t)img * g.A + (int64_t)tile * g.tile_rows;
     }
 };
 
@@ -172,54 +185,77 @@ struct RowLanes {
     __device__ __forceinline__ RowLanes() : sub(lane_id() % Q), rl(lane_id() / Q) {}
 };
 
-// Load the NREG register slice of one row from a staged tile; out-of-range slots get -inf
-// (exp(-inf - m) == 0 and max(-inf, x) == x, so no further predication is needed).
-template <int Q, int NREG>
-__device__ __forceinline__ void load_row_slice(float (&v)[NREG], const float* row, int sub, int C, bool row_valid) {
+// Slots [0, IFULL) hold a valid column for every lane and every C of the dispatch bucket; the
+// remaining slots may fall past the end of the row and are forced to -inf with a per-lane bit mask
+// (exp(-inf - m) == 0 and max(-inf, x) == x, so nothing downstream needs a predicate).
+template <int Q, int NREG, int CMIN>
+struct RowShape {
+    static constexpr int kFull = CMIN / Q < NREG ? CMIN / Q : NREG;      // slots valid for every lane
+    static constexpr int kMasked = NREG - kFull;
+    uint32_t keep[kMasked > 0 ? kMasked : 1];
+    __device__ __forceinline__ RowShape(int sub, int C) {
 #pragma unroll
-    for (int i = 0; i < NREG; ++i) {
-        const int col = sub + i * Q;
-        v[i] = (row_valid && col < C) ? row[col] : -INFINITY;
+        for (int j = 0; j < kMasked; ++j) keep[j] = (sub + (kFull + j) * Q < C) ? 0xFFFFFFFFu : 0u;
     }
-}
+    // Loads are unconditional: rows past the end of a partial tile and columns past the end of the
+    // row read whatever is in the stage (which has slack for it); the caller discards those.
+    __device__ __forceinline__ void load(float (&v)[NREG], const float* row, int sub) const {
+#pragma unroll
+        for (int i = 0; i < NREG; ++i) {
+            float x = row[sub + i * Q];
+            if (i >= kFull) {
+                const uint32_t k = keep[i - kFull];
+                x = __uint_as_float((__float_as_uint(x) & k) | (~k & 0xFF800000u));
+            }
+            v[i] = x;
+        }
+    }
+};
 
-// row max and sum of exp(x - max) over the Q lanes that own the row (invalid rows: m = 0, sum = 0)
+// row max and sum of exp(x - max) over the Q lanes that own the row
 template <int Q, int NREG>
-__device__ __forceinline__ void row_max_sum(const float (&v)[NREG], bool row_valid, float& m, float& sum) {
+__device__ __forceinline__ void row_max_sum(const float (&v)[NREG], float& m, float& sum) {
     m = v[0];
 #pragma unroll
     for (int i = 1; i < NREG; ++i) m = fmaxf(m, v[i]);
     m = group_max<Q>(m);
-    if (!row_valid) m = 0.f;
     sum = 0.f;
 #pragma unroll
     for (int i = 0; i < NREG; ++i) sum = __fadd_rn(sum, fast_exp(__fsub_rn(v[i], m)));
     sum = group_sum<Q>(sum);
 }
 
-// Dispatch table C -> (Q, NREG).  NREG*Q >= C.
-#define SSD_DISPATCH_ROW_SHAPE(C, CALL)                      \
-    do {                                                     \
-        if ((C) <= 8) { CALL(1, 8); }                        \
-        else if ((C) <= 24) { CALL(4, 6); }                  \
-        else if ((C) <= 32) { CALL(4, 8); }                  \
-        else if ((C) <= 64) { CALL(8, 8); }                  \
-        else if ((C) <= 88) { CALL(8, 11); }                 \
-        else if ((C) <= 128) { CALL(8, 16); }                \
-        else if ((C) <= 256) { CALL(32, 8); }                \
-        else { CALL(32, 32); }                               \
+// Dispatch table C -> (Q, NREG, CMIN): NREG*Q >= C, CMIN = smallest C of the bucket.
+#define SSD_DISPATCH_ROW_SHAPE(C, CALL)                          \
+    do {                                                         \
+        if ((C) <= 8) { CALL(1, 8, 1); }                         \
+        else if ((C) <= 16) { CALL(2, 8, 9); }                   \
+        else if ((C) <= 24) { CALL(4, 6, 17); }                  \
+        else if ((C) <= 32) { CALL(4, 8, 25); }                  \
+        else if ((C) <= 64) { CALL(8, 8, 33); }                  \
+        else if ((C) <= 88) { CALL(8, 11, 65); }                 \
+        else if ((C) <= 128) { CALL(8, 16, 89); }                \
+        else if ((C) <= 256) { CALL(32, 8, 129); }               \
+        else { CALL(32, 32, 257); }                              \
     } while (0)
 
 inline int lanes_per_row(int C) {
     int q = 0;
-#define SSD_Q_(QQ, NN) q = QQ
+#define SSD_Q_(QQ, NN, CM) q = QQ
     SSD_DISPATCH_ROW_SHAPE(C, SSD_Q_);
 #undef SSD_Q_
     return q;
 }
+inline int slots_per_row(int C) {
+    int n = 0;
+#define SSD_N_(QQ, NN, CM) n = QQ * NN
+    SSD_DISPATCH_ROW_SHAPE(C, SSD_N_);
+#undef SSD_N_
+    return n;
+}
 
 // Host: tile geometry.  tile_rows is a multiple of the rows all consumer warps cover in one step.
-inline void plan_tiles(ScoreGrid& g, int images, int A, int C, bool with_side, int target_tile_bytes = 12 * 1024) {
+inline void plan_tiles(ScoreGrid& g, int images, int A, int C, bool with_side, int target_tile_bytes = 24 * 1024) {
     const int quantum = kConsumerWarps * (32 / lanes_per_row(C));
     int rows = target_tile_bytes / (C * 4);
     rows = rows / quantum * quantum;
@@ -231,21 +267,28 @@ inline void plan_tiles(ScoreGrid& g, int images, int A, int C, bool with_side, i
     g.group_tiles = 1;
     g.groups_per_image = g.tiles_per_image;
     g.num_items = images * g.groups_per_image;
-    const size_t tile_bytes = round_up((size_t)rows * C * 4 + 32, 16);
+    // head alignment slack (<= 12 bytes) + the columns an unconditional row load may overshoot
+    const size_t tile_bytes = round_up((size_t)rows * C * 4 + 16 + (size_t)(slots_per_row(C) - C) * 4 + 16, 16);
     g.side_offset = (int)tile_bytes;
     g.stage_bytes = (int)(tile_bytes + (with_side ? round_up((size_t)rows * 8 + 32, 16) : 0));
     g.total_floats = (int64_t)images * A * C;
     g.total_rows = (int64_t)images * A;
     g.first_fg = 0; g.nblk = 0; g.split = 1;
+    g.step_img = 0; g.step_grp = 0;
 }
 inline size_t stream_smem_bytes(const ScoreGrid& g) { return 128 + (size_t)kStreamStages * g.stage_bytes; }
-inline int stream_grid(const ScoreGrid& g) {
-    // resident CTAs per SM by shared memory (227 KB usable), at most 4; grid = a whole number of waves
-    int per_sm = (int)((size_t)(220 * 1024) / (stream_smem_bytes(g) + 1024));
+__device__ __forceinline__ size_t stream_smem_bytes_dev(const ScoreGrid& g) { return 128 + (size_t)kStreamStages * g.stage_bytes; }
+// Grid size (a whole number of resident waves) and the cursor's stride decomposition.
+inline int stream_grid(ScoreGrid& g, size_t extra_smem = 0) {
+    int per_sm = (int)((size_t)(224 * 1024) / (stream_smem_bytes(g) + extra_smem + 1024));
     if (per_sm > 4) per_sm = 4;
     if (per_sm < 1) per_sm = 1;
     int grid = per_sm * sm_count();
-    return grid < g.num_items ? grid : g.num_items;
+    if (grid > g.num_items) grid = g.num_items;
+    if (grid < 1) grid = 1;
+    g.step_img = grid / g.groups_per_image;
+    g.step_grp = grid % g.groups_per_image;
+    return grid;
 }
 
 }  // namespace ssd

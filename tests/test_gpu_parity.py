@@ -434,6 +434,38 @@ def test_nms_api_vs_torchvision_golden(dev):
         assert torch.equal(sk.cpu(), torch.from_numpy(z[f"topk_kept_scores_{i}"])), i
 
 
+def test_nms_threshold_boundaries_exact(dev):
+    """The overlap test is `(double)fp32(inter/union) > threshold`.  The kernel evaluates it without a
+    division (exact product in double against the rounding midpoint): thresholds placed exactly on,
+    one double-ulp below / above and one float-ulp around achieved IoU values must give torchvision's
+    keep list, as must negative, zero and > 1 thresholds (division path)."""
+    import torchvision
+    _, _, _, _, _, box_utils = _modules()
+    gen = torch.Generator().manual_seed(77)
+    n = 160
+    xy = torch.randint(0, 40, (n, 2), generator=gen).float()
+    wh = torch.randint(1, 24, (n, 2), generator=gen).float()
+    boxes = torch.cat([xy, xy + wh], dim=1)
+    boxes[5] = boxes[4]                                    # duplicates (IoU exactly 1)
+    boxes[9, 2:] = boxes[9, :2]                            # zero-area box
+    scores = torch.rand((n,), generator=gen)
+    iou = torchvision.ops.box_iou(boxes, boxes)
+    vals = torch.unique(iou[(iou > 0.05) & (iou < 0.95)])
+    picks = vals[torch.linspace(0, vals.numel() - 1, 12).long()].tolist()
+    thresholds = [0.0, -0.25, 1.0, 1.5, 0.45, 0.5, 1e-35]
+    for v in picks:
+        v32 = np.float32(v)
+        d = float(v32)
+        thresholds += [d, float(np.nextafter(d, 0.0)), float(np.nextafter(d, 1.0)),
+                       float(np.nextafter(v32, np.float32(0))), float(np.nextafter(v32, np.float32(1)))]
+    bd, sd = boxes.to(dev), scores.to(dev)
+    for thr in thresholds:
+        ref = torchvision.ops.nms(boxes, scores, thr).tolist()
+        assert ora.greedy_nms(boxes.numpy(), scores.numpy(), thr).tolist() == ref, thr
+        (_, _), keep = box_utils.nms(bd, sd, thr, 0.01, None)
+        assert keep.cpu().tolist() == ref, thr
+
+
 def test_postprocessor_interface(dev):
     _, _, bc, _, pp, _ = _modules()
     coder = bc.BoxCoder(10.0, 5.0)
