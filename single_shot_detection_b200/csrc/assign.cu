@@ -66,6 +66,8 @@ assign_targets_kernel(const float4* __restrict__ anchors, const float* __restric
                       const int32_t* __restrict__ gt_offsets, int A, int chunk, float matched_thr,
                       float unmatched_thr, int force_match, float* __restrict__ target, int32_t* __restrict__ match_out,
                       int32_t* __restrict__ stats) {
+    griddep_wait();
+    griddep_launch_dependents();
     cg::cluster_group cluster = cg::this_cluster();
     const int csize = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
@@ -109,15 +111,33 @@ assign_targets_kernel(const float4* __restrict__ anchors, const float* __restric
                 ab = corners_of(anchors[a]);
                 aarea = clamped_area(ab.x, ab.y, ab.z, ab.w);
             }
-            float best_iou = -INFINITY;
+            // IoU 0 against every box so far: the state torch.max would be in after a row of zeros
+            float best_iou = 0.f;
             int best_g = 0;
+            const bool a_degenerate = !(aarea > 0.f);
+#pragma unroll 2
             for (int g = 0; g < G; ++g) {
-                const float v = iou_exact(gbox[g], garea[g], ab, aarea);
+                const float4 gb = gbox[g];
+                const float iw = fmaxf(fsub(fminf(gb.z, ab.z), fmaxf(gb.x, ab.x)), 0.f);
+                const float ih = fmaxf(fsub(fminf(gb.w, ab.w), fmaxf(gb.y, ab.y)), 0.f);
+                const float inter = fmul(iw, ih);
+                // Disjoint pairs have IoU +0 exactly: they can neither raise the anchor's running
+                // maximum nor beat the (0, anchor 0) entry every GT starts with, so the divide and
+                // both argmax updates are skipped unless some lane of the warp overlaps this box.
+                // (0/0 -> NaN needs both areas to be zero / NaN; NaN inter is not == 0.)
+                bool live = valid && !(inter == 0.f);
+                if (a_degenerate && valid) live = live || !(garea[g] > 0.f);
+                if (!__any_sync(FULL, live)) continue;
+                float v = 0.f;
+                if (live) {
+                    const float uni = fsub(fadd(garea[g], aarea), inter);
+                    v = (inter == 0.f && uni > 0.f) ? 0.f : fdiv(inter, uni);
+                }
                 // torch.max(dim=0): first maximum wins, NaN propagates and sticks
                 if (!(v <= best_iou) && !(best_iou != best_iou)) { best_iou = v; best_g = g; }
                 // per-GT argmax over anchors
-                uint32_t key = valid ? ordered_key(v) : 0u;
-                if (valid && v != v) key = 0xFFFFFFFFu;
+                uint32_t key = live ? ordered_key(v) : 0u;
+                if (live && v != v) key = 0xFFFFFFFFu;
                 const uint32_t wmax = __reduce_max_sync(FULL, key);
                 if (wmax > 0x80000000u) {               // somebody overlaps (key(+0) == 0x80000000)
                     const unsigned bal = __ballot_sync(FULL, key == wmax);
@@ -224,6 +244,8 @@ assign_targets_kernel(const float4* __restrict__ anchors, const float* __restric
 // ---------------------------------------------------------------------------------------------
 __global__ void pairwise_iou_kernel(const float4* __restrict__ a, int na, const float4* __restrict__ b, int nb,
                                     float* __restrict__ out) {
+    griddep_wait();
+    griddep_launch_dependents();
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y;
     if (j >= nb) return;
@@ -240,6 +262,8 @@ __global__ void pairwise_iou_kernel(const float4* __restrict__ a, int na, const 
 __global__ void __launch_bounds__(1024)
 match_per_prediction_kernel(const float* __restrict__ w, int G, int A, float matched_thr, float unmatched_thr,
                             int force_match, long long* __restrict__ box_idx, unsigned long long* __restrict__ best) {
+    griddep_wait();
+    griddep_launch_dependents();
     // best[G] lives in global scratch (single CTA, so plain atomics + __syncthreads order it)
     // generic weights (may be negative): start below every real key
     for (int g = threadIdx.x; g < G; g += blockDim.x) best[g] = 0ull;
@@ -295,9 +319,8 @@ extern "C" int ssd_pairwise_iou(const float* a_corners, int num_a, const float* 
                 "ssd_pairwise_iou: boxes must be 16-byte aligned");
     SSD_REQUIRE(num_a <= 65535, SSD_ERR_UNSUPPORTED, "ssd_pairwise_iou: more than 65535 rows");
     dim3 grid((num_b + 255) / 256, num_a);
-    pairwise_iou_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)a_corners, num_a,
-                                                                  (const float4*)b_corners, num_b, out);
-    SSD_CUDA(cudaGetLastError());
+    SSD_CUDA(launch_pdl(pairwise_iou_kernel, grid, dim3(256), 0, (cudaStream_t)stream, (const float4*)a_corners, num_a,
+                        (const float4*)b_corners, num_b, out));
     count_launch();
     return SSD_OK;
 }
@@ -315,10 +338,9 @@ extern "C" int ssd_match_per_prediction(const float* weights, int num_gt, int nu
         SSD_CUDA(cudaMalloc(&g_match_scratch, sizeof(unsigned long long) * kMaxGtPerImage));
         g_match_scratch_cap = kMaxGtPerImage;
     }
-    match_per_prediction_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(weights, num_gt, num_anchors, matched_threshold,
-                                                                       unmatched_threshold, force_match,
-                                                                       (long long*)box_idx_out, g_match_scratch);
-    SSD_CUDA(cudaGetLastError());
+    SSD_CUDA(launch_pdl(match_per_prediction_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, weights, num_gt,
+                        num_anchors, matched_threshold, unmatched_threshold, force_match, (long long*)box_idx_out,
+                        g_match_scratch));
     count_launch();
     return SSD_OK;
 }
@@ -361,13 +383,15 @@ extern "C" int ssd_assign_targets(const float* anchors, const float* gt_rows, in
     cfg.blockDim = dim3(kAssignThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cl;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     LaunchTimer lt_("assign", st);
     SSD_CUDA(cudaLaunchKernelEx(&cfg, assign_targets_kernel, (const float4*)anchors, gt_rows, gt_cols, gt_offsets,
                                 num_anchors, chunk, matched_threshold, unmatched_threshold, force_match, target_out,

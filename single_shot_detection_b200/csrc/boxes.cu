@@ -61,6 +61,8 @@ template <int OP, bool VEC4>
 __global__ void __launch_bounds__(256)
 box_transform_kernel(const float* __restrict__ src, int64_t src_stride, float* dst, int64_t dst_stride,
                      const float4* __restrict__ priors, int64_t rows, int A, float xy, float wh, float eps) {
+    griddep_wait();
+    griddep_launch_dependents();
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
     Box b = load_box<VEC4>(src + r * src_stride);
@@ -87,9 +89,11 @@ static int launch_box(bool vec4, const float* src, int64_t ss, float* dst, int64
     const unsigned blocks = (unsigned)((rows + 255) / 256);
     LaunchTimer lt_("box", st);
     if (vec4)
-        box_transform_kernel<OP, true><<<blocks, 256, 0, st>>>(src, ss, dst, ds, (const float4*)priors, rows, A, xy, wh, eps);
+        SSD_CUDA(launch_pdl(box_transform_kernel<OP, true>, dim3(blocks), dim3(256), 0, st, src, ss, dst, ds,
+                            (const float4*)priors, rows, A, xy, wh, eps));
     else
-        box_transform_kernel<OP, false><<<blocks, 256, 0, st>>>(src, ss, dst, ds, (const float4*)priors, rows, A, xy, wh, eps);
+        SSD_CUDA(launch_pdl(box_transform_kernel<OP, false>, dim3(blocks), dim3(256), 0, st, src, ss, dst, ds,
+                            (const float4*)priors, rows, A, xy, wh, eps));
     SSD_CUDA(cudaGetLastError());
     count_launch();
     return SSD_OK;

@@ -65,6 +65,32 @@ __device__ __forceinline__ float key_to_float(uint32_t k) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// programmatic dependent launch: every kernel of this library is launched with the
+// programmatic-stream-serialization attribute and starts with griddep_wait(), so the launch
+// latency and prologue of kernel N+1 overlap the tail of kernel N (also inside captured graphs).
+// griddep_wait() returns once the preceding grid in the stream has completed and flushed; since
+// every kernel waits before it finishes, completion is transitive along the chain.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
+// ---------------------------------------------------------------------------------------------
 // warp helpers
 // ---------------------------------------------------------------------------------------------
 constexpr unsigned FULL = 0xFFFFFFFFu;

@@ -59,6 +59,8 @@ mining_loss_kernel(const float* __restrict__ logits, const long long* __restrict
                    int* __restrict__ hist, ScoreGrid g) {
     extern __shared__ __align__(128) unsigned char smem[];
     stream_init(smem);
+    griddep_wait();
+    griddep_launch_dependents();
     if (warp_id() == kConsumerWarps) {
         producer_loop(smem, g, logits, reinterpret_cast<const unsigned long long*>(cls), policy_evict_first());
         return;
@@ -98,6 +100,8 @@ mining_loss_kernel(const float* __restrict__ logits, const long long* __restrict
 template <bool CLS_FLOAT>
 __global__ void mining_keys_from_loss_kernel(const float* __restrict__ loss, const void* __restrict__ cls, int cls_stride,
                                              uint32_t* __restrict__ keys, int* __restrict__ hist, int A, int64_t n) {
+    griddep_wait();
+    griddep_launch_dependents();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     long long c;
@@ -108,6 +112,8 @@ __global__ void mining_keys_from_loss_kernel(const float* __restrict__ loss, con
 }
 
 __global__ void positive_mask_kernel(const long long* __restrict__ cls, uint8_t* __restrict__ mask, int64_t n) {
+    griddep_wait();
+    griddep_launch_dependents();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         const long long c = cls[i];
@@ -159,6 +165,8 @@ mining_select_kernel(const uint32_t* __restrict__ keys, const int* __restrict__ 
                      int ratio_is_integer, double min_negatives, uint8_t* __restrict__ mask,
                      int32_t* __restrict__ stats) {
     __shared__ SelShared sh;
+    griddep_wait();
+    griddep_launch_dependents();
     const int b = blockIdx.x;
     const uint32_t* gk = keys + (size_t)b * A;
     const int* gh = hist + (size_t)b * kHistStride;
@@ -332,9 +340,8 @@ extern "C" int ssd_positive_mask(const int64_t* target_classes, int64_t count, u
     SSD_REQUIRE(target_classes && mask_out, SSD_ERR_INVALID_ARGUMENT, "ssd_positive_mask: null pointer");
     const int threads = 256;
     const int64_t blocks = (count + threads - 1) / threads;
-    positive_mask_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
-        (const long long*)target_classes, mask_out, count);
-    SSD_CUDA(cudaGetLastError());
+    SSD_CUDA(launch_pdl(positive_mask_kernel, dim3((unsigned)blocks), dim3(threads), 0, (cudaStream_t)stream,
+                        (const long long*)target_classes, mask_out, count));
     count_launch();
     return SSD_OK;
 }
@@ -359,7 +366,8 @@ static int launch_mining_keys(const float* logits, const int64_t* target_classes
         auto kern = mining_loss_kernel<QQ, NN, CM>;                                                                    \
         SSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
         LaunchTimer lt_("mining_loss", st);                                                            \
-        kern<<<grid, kStreamThreads, smem, st>>>(logits, (const long long*)target_classes, keys, hist, g);           \
+        SSD_CUDA(launch_pdl(kern, dim3(grid), dim3(kStreamThreads), smem, st, logits,                               \
+                            (const long long*)target_classes, keys, hist, g));                                      \
     } while (0)
     SSD_DISPATCH_ROW_SHAPE(num_cols, SSD_LAUNCH_MINING);
 #undef SSD_LAUNCH_MINING
@@ -408,9 +416,9 @@ extern "C" int ssd_hard_negative_mask(const float* logits, const int64_t* target
         SSD_CUDA(cudaMemsetAsync(hist, 0, hist_bytes(batch), st));
         const int threads = 256;
         LaunchTimer lt_("keys_from_loss", st);
-        mining_keys_from_loss_kernel<false><<<(unsigned)((total_rows + threads - 1) / threads), threads, 0, st>>>(
-            loss_override, target_classes, 1, keys, hist, num_anchors, total_rows);
-        SSD_CUDA(cudaGetLastError());
+        SSD_CUDA(launch_pdl(mining_keys_from_loss_kernel<false>, dim3((unsigned)((total_rows + threads - 1) / threads)),
+                            dim3(threads), 0, st, loss_override, (const void*)target_classes, 1, keys, hist, num_anchors,
+                            total_rows));
         count_launch();
     } else {
         const int rc = launch_mining_keys(logits, target_classes, batch, num_anchors, num_cols, keys, hist, st);
@@ -418,9 +426,8 @@ extern "C" int ssd_hard_negative_mask(const float* logits, const int64_t* target
     }
 
     LaunchTimer lt_("mining_select", st);
-    mining_select_kernel<<<batch, kSelThreads, 0, st>>>(keys, hist, num_anchors, ratio, ratio_is_integer,
-                                                        min_negatives, mask_out, stats_out);
-    SSD_CUDA(cudaGetLastError());
+    SSD_CUDA(launch_pdl(mining_select_kernel, dim3(batch), dim3(kSelThreads), 0, st, (const uint32_t*)keys,
+                        (const int*)hist, num_anchors, ratio, ratio_is_integer, min_negatives, mask_out, stats_out));
     count_launch();
     return SSD_OK;
 }

@@ -143,6 +143,8 @@ score_pass1_kernel(const float* __restrict__ scores, ScoreGrid g, float2* __rest
                    float* __restrict__ blockmax) {
     extern __shared__ __align__(128) unsigned char smem[];
     stream_init(smem);
+    griddep_wait();
+    griddep_launch_dependents();
     if (warp_id() == kConsumerWarps) {
         producer_loop(smem, g, scores, nullptr, policy_evict_last());      // pass 2 re-reads the same bytes
         return;
@@ -266,6 +268,8 @@ class_gate_kernel(const float* __restrict__ blockmax, int C, int first_fg, int n
                   float score_thr, float* __restrict__ gate, int* __restrict__ cand_count, int* __restrict__ status,
                   int* __restrict__ score_hist, int hist_words) {
     extern __shared__ __align__(16) uint32_t skey[];          // [merged blocks][kGateCols + 1]
+    griddep_wait();
+    griddep_launch_dependents();
     const int b = blockIdx.y;
     const int c0 = blockIdx.x * kGateCols;
     const int lane = lane_id();
@@ -376,6 +380,8 @@ score_pass2_kernel(const float* __restrict__ scores, ScoreGrid g, const float2* 
                    const float* __restrict__ gate, int* __restrict__ cand_count, uint2* __restrict__ cand, int cand_cap) {
     extern __shared__ __align__(128) unsigned char smem[];
     stream_init(smem);
+    griddep_wait();
+    griddep_launch_dependents();
     if (warp_id() == kConsumerWarps) {
         producer_loop(smem, g, scores,
                       CONV == SSD_CONVERT_SOFTMAX ? reinterpret_cast<const unsigned long long*>(rowstat) : nullptr,
@@ -596,6 +602,28 @@ __device__ int exact_select_column(const NmsArgs& a, int img, int col, const flo
     return k;
 }
 
+// torchvision's overlap test `(double)fp32(inter / union) > threshold` for one pair of corner boxes
+// (areas unclamped, intersection sides clamped at 0).  Fast form: no division (see
+// nms_threshold_split); `slow` reports the pairs that need the literal division instead.
+__device__ __forceinline__ bool pair_suppressed(const NmsArgs& a, float4 bi, float ai, float4 bj, float aj, bool& slow) {
+    const float iw = fmaxf(0.f, fsub(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)));
+    const float ih = fmaxf(0.f, fsub(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)));
+    const float inter = fmul(iw, ih);
+    const float uni = fsub(fadd(ai, aj), inter);
+    const bool fast = a.exact_mul && inter > 0.f && uni > 0.f;
+    // disjoint boxes give +0 (or 0/0): never above a non-negative threshold
+    slow = !fast && (inter != 0.f || a.iou_thr < 0.0);
+    const double lhs = (double)inter, rhs = a.iou_mid * (double)uni;
+    return fast && (lhs > rhs || (lhs == rhs && a.iou_even));
+}
+__device__ __noinline__ bool pair_suppressed_slow(const NmsArgs& a, float4 bi, float ai, float4 bj, float aj) {
+    const float iw = fmaxf(0.f, fsub(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)));
+    const float ih = fmaxf(0.f, fsub(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)));
+    const float inter = fmul(iw, ih);
+    const float uni = fsub(fadd(ai, aj), inter);
+    return (double)fdiv(inter, uni) > a.iou_thr;           // float-vs-double compare
+}
+
 constexpr int kRankSortMax = 256;     // candidate lists up to this size are sorted by ranking
 
 __global__ void __launch_bounds__(kNmsThreads)
@@ -607,6 +635,8 @@ segment_nms_kernel(NmsArgs a, const float* __restrict__ scores, const float2* __
     __shared__ uint32_t s_hist[2048];
     __shared__ int s_misc[4 + kNmsThreads / 32];
     __shared__ int s_valid, s_nkeep;
+    griddep_wait();
+    griddep_launch_dependents();
     const int seg = blockIdx.x;
     const int img = seg / a.Cf;
     const int lane = lane_id();
@@ -714,39 +744,43 @@ segment_nms_kernel(NmsArgs a, const float* __restrict__ scores, const float2* __
     }
     __syncthreads();
 
-    // ---- IoU bit matrix: bit j of row i set <=> box i suppresses box j (j > i).  The n(n-1)/2 pairs
-    //      are dealt out flat over the CTA so every lane has work; suppressing pairs are rare and are
-    //      recorded with a shared-memory atomicOr. ----
-    for (int t = threadIdx.x; t < n * words; t += blockDim.x) mask[t] = 0u;
-    __syncthreads();
-    {
-        int i = 0, off = threadIdx.x;                 // pair (i, i + 1 + off)
-        for (;;) {
-            while (i < n - 1 && off >= n - 1 - i) { off -= n - 1 - i; ++i; }
-            if (i >= n - 1) break;
-            const int j = i + 1 + off;
-            const float4 bi = sbox[i], bj = sbox[j];
-            const float iw = fmaxf(0.f, fsub(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)));
-            const float ih = fmaxf(0.f, fsub(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)));
-            const float inter = fmul(iw, ih);
-            if (inter != 0.f) {                       // disjoint boxes: IoU is +0 (or 0/0, never > thr)
-                const float uni = fsub(fadd(sarea[i], sarea[j]), inter);
-                bool sup;
-                if (a.exact_mul && inter > 0.f && uni > 0.f) {
-                    // RN(inter / uni) >= T32  <=>  inter > M * uni, or == with T32 even; the product of a
-                    // 25-bit and a 24-bit significand is exact in double (see nms_threshold_split)
-                    const double lhs = (double)inter, rhs = a.iou_mid * (double)uni;
-                    sup = lhs > rhs || (lhs == rhs && a.iou_even);
-                } else {
-                    sup = (double)fdiv(inter, uni) > a.iou_thr;           // float-vs-double compare
-                }
-                if (sup) atomicOr(&mask[(size_t)i * words + (j >> 5)], 1u << (j & 31));
-            } else if (a.iou_thr < 0.0) {
-                // a negative threshold suppresses disjoint boxes too (0 > thr); uni > 0 assumed as in torchvision's 0/uni
-                const float uni = fsub(fadd(sarea[i], sarea[j]), inter);
-                if ((double)fdiv(inter, uni) > a.iou_thr) atomicOr(&mask[(size_t)i * words + (j >> 5)], 1u << (j & 31));
+    // ---- IoU bit matrix: bit j of row i set <=> box i suppresses box j (j > i).  A warp takes a row,
+    //      its lanes a word of 32 columns (ballot -> one store); a short last word (n mod 32 <= 8) is
+    //      done transposed -- lanes over rows, a loop over its few columns -- instead of with 32-lane
+    //      items that would be mostly idle. ----
+    const int tail = n & 31;
+    const bool tail_transposed = tail != 0 && tail <= 8 && words > 1;
+    const int words_main = tail_transposed ? words - 1 : words;
+    const int nwarps = blockDim.x >> 5;
+    for (int i = warp_id(); i < n; i += nwarps) {
+        const float4 bi = sbox[i];
+        const float ai = sarea[i];
+        for (int w = i >> 5; w < words_main; ++w) {
+            const int j = (w << 5) + lane;
+            const bool in_range = j > i && j < n;
+            const int jj = in_range ? j : i;
+            bool slow;
+            bool sup = pair_suppressed(a, bi, ai, sbox[jj], sarea[jj], slow);
+            if (__any_sync(FULL, slow && in_range)) {
+                if (slow) sup = pair_suppressed_slow(a, bi, ai, sbox[jj], sarea[jj]);
             }
-            off += blockDim.x;
+            const uint32_t bits = __ballot_sync(FULL, sup && in_range);
+            if (lane == 0) mask[(size_t)i * words + w] = bits;
+        }
+    }
+    if (tail_transposed) {
+        const int j0 = n - tail;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const float4 bi = sbox[i];
+            const float ai = sarea[i];
+            uint32_t bits = 0u;
+            for (int j = max(j0, i + 1); j < n; ++j) {
+                bool slow;
+                bool sup = pair_suppressed(a, bi, ai, sbox[j], sarea[j], slow);
+                if (slow) sup = pair_suppressed_slow(a, bi, ai, sbox[j], sarea[j]);
+                bits |= sup ? 1u << (j & 31) : 0u;
+            }
+            mask[(size_t)i * words + words - 1] = bits;
         }
     }
     __syncthreads();
@@ -827,6 +861,8 @@ image_topk_kernel(int Cf, int K, int T, int det_cap, const int* __restrict__ kep
                   int* __restrict__ det_anchor) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ TopkShared sh;
+    griddep_wait();
+    griddep_launch_dependents();
     const int img = blockIdx.x;
     const int lane = lane_id();
     const int tid = threadIdx.x;
@@ -1020,6 +1056,8 @@ image_topk_kernel(int Cf, int K, int T, int det_cap, const int* __restrict__ kep
 
 __global__ void widen_keep_kernel(const int* __restrict__ src, const int* __restrict__ count, long long* __restrict__ dst,
                                   int cap) {
+    griddep_wait();
+    griddep_launch_dependents();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < cap && i < count[0]) dst[i] = src[i];
 }
@@ -1057,7 +1095,7 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
         auto launch = [&](auto kern) -> int {                                                                          \
             SSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem));    \
             LaunchTimer lt_("pass1", st);                                                            \
-            kern<<<grid, kStreamThreads, stream_smem, st>>>(scores, g, rowstat, blockmax);                          \
+            SSD_CUDA(launch_pdl(kern, dim3(grid), dim3(kStreamThreads), stream_smem, st, scores, g, rowstat, blockmax)); \
             return SSD_OK;                                                                                             \
         };                                                                                                             \
         int rc;                                                                                                        \
@@ -1076,9 +1114,9 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
         const int nm = (pl.nblk + merge - 1) / merge;
         const size_t gsmem = (size_t)nm * (kGateCols + 1) * sizeof(uint32_t);
         dim3 ggrid((pl.C + kGateCols - 1) / kGateCols, pl.B);
-        class_gate_kernel<<<ggrid, kGateThreads, gsmem, st>>>(blockmax, pl.C, pl.first_fg, pl.nblk, pl.K, pl.converter,
-                                                               p->score_threshold, gate, cand_count, status,
-                                                               score_hist, pl.B * kScoreBins);
+        SSD_CUDA(launch_pdl(class_gate_kernel, ggrid, dim3(kGateThreads), gsmem, st, (const float*)blockmax, pl.C,
+                            pl.first_fg, pl.nblk, pl.K, pl.converter, p->score_threshold, gate, cand_count, status,
+                            score_hist, pl.B * kScoreBins));
         SSD_CUDA(cudaGetLastError());
     count_launch();
     }
@@ -1088,7 +1126,8 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
         auto launch = [&](auto kern) -> int {                                                                          \
             SSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass2_smem));    \
             LaunchTimer lt_("pass2", st);                                                            \
-            kern<<<grid, kStreamThreads, pass2_smem, st>>>(scores, g, rowstat, gate, cand_count, cand, pl.cand_cap); \
+            SSD_CUDA(launch_pdl(kern, dim3(grid), dim3(kStreamThreads), pass2_smem, st, scores, g,                   \
+                                (const float2*)rowstat, (const float*)gate, cand_count, cand, pl.cand_cap));         \
             return SSD_OK;                                                                                             \
         };                                                                                                             \
         int rc;                                                                                                        \
@@ -1112,9 +1151,9 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
         const size_t smem = key_slots * 8 + (size_t)(pl.K + 1) * (8 + 16 + 4 + 4) + (size_t)pl.K * kwords * 4 + 64;
         SSD_CUDA(cudaFuncSetAttribute(segment_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         LaunchTimer lt_("nms", st);
-        segment_nms_kernel<<<pl.B * pl.Cf, kNmsThreads, smem, st>>>(a, scores, rowstat, cand_count, cand,
-                                                                     (const float4*)boxes, (const float4*)priors,
-                                                                     kept_count, kept, status, score_hist);
+        SSD_CUDA(launch_pdl(segment_nms_kernel, dim3(pl.B * pl.Cf), dim3(kNmsThreads), smem, st, a, scores,
+                            (const float2*)rowstat, (const int*)cand_count, (const uint2*)cand, (const float4*)boxes,
+                            (const float4*)priors, kept_count, kept, status, score_hist));
         SSD_CUDA(cudaGetLastError());
     count_launch();
     }
@@ -1126,8 +1165,9 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
         SSD_REQUIRE(smem <= 224 * 1024, SSD_ERR_UNSUPPORTED, "ssd_postprocess: final top-k needs %zu bytes of shared memory", smem);
         SSD_CUDA(cudaFuncSetAttribute(image_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         LaunchTimer lt_("topk", st);
-        image_topk_kernel<<<pl.B, kTopkThreads, smem, st>>>(pl.Cf, pl.K, pl.T, pl.det_cap, kept_count, kept, score_hist, dets_out,
-                                                             count_out, anchor_out);
+        SSD_CUDA(launch_pdl(image_topk_kernel, dim3(pl.B), dim3(kTopkThreads), smem, st, pl.Cf, pl.K, pl.T, pl.det_cap,
+                            (const int*)kept_count, (const float*)kept, (const int*)score_hist, dets_out, count_out,
+                            anchor_out));
         SSD_CUDA(cudaGetLastError());
     count_launch();
     }
@@ -1204,7 +1244,8 @@ extern "C" int ssd_nms(const float* corner_boxes, const float* scores, int num_b
     int* anchors = (int*)(ws + pl.off_anchor_tmp);
     const int rc2 = run_postprocess(pl, &p, scores, corner_boxes, nullptr, dets, count_out, anchors, nullptr, ws, st);
     if (rc2 != SSD_OK) return rc2;
-    widen_keep_kernel<<<(max_per_class + 127) / 128, 128, 0, st>>>(anchors, count_out, (long long*)keep_out, max_per_class);
+    SSD_CUDA(launch_pdl(widen_keep_kernel, dim3((max_per_class + 127) / 128), dim3(128), 0, st, (const int*)anchors,
+                        (const int*)count_out, (long long*)keep_out, max_per_class));
     SSD_CUDA(cudaGetLastError());
     count_launch();
     return SSD_OK;
