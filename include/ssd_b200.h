@@ -70,6 +70,12 @@ SSD_API int ssd_b200_device_check(void);
  * writes "label:mean_us:count,..." into buf; returns the number of characters written. */
 SSD_API void ssd_b200_timing_enable(int on);
 SSD_API size_t ssd_b200_timing_report(char* buf, size_t capacity);
+/* Diagnostics: device-side timeline.  `device_slots` points to ssd_b200_trace_slots() pairs of
+ * uint64 in device memory (initialise every pair to {UINT64_MAX, 0}); every kernel of the library
+ * then records min(start) / max(end) of %globaltimer in its slot -- also inside a replayed CUDA
+ * graph.  Pass NULL to switch the trace off (the default). */
+SSD_API int ssd_b200_trace_enable(unsigned long long* device_slots);
+SSD_API int ssd_b200_trace_slots(void);
 
 /* ------------------------------------------------------------------------------------------
  * a2  bf/utils/box_utils.py:83-101  iou(a, b) -- pairwise IoU of corner boxes.

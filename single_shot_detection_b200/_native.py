@@ -48,6 +48,8 @@ _SIGNATURES = {
     "ssd_b200_device_check": (c_int, []),
     "ssd_b200_timing_enable": (None, [c_int]),
     "ssd_b200_timing_report": (c_size_t, [ctypes.c_char_p, c_size_t]),
+    "ssd_b200_trace_enable": (c_int, [c_void_p]),
+    "ssd_b200_trace_slots": (c_int, []),
     "ssd_pairwise_iou": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "ssd_match_per_prediction": (c_int, [c_void_p, c_int, c_int, c_float, c_float, c_int, c_void_p, c_void_p]),
     "ssd_assign_targets": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_float, c_int,

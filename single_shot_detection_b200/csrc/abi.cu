@@ -89,6 +89,22 @@ extern "C" int ssd_b200_device_check(void) {
     return SSD_OK;
 }
 
+namespace ssd {
+cudaError_t set_trace_assign(unsigned long long*);
+cudaError_t set_trace_boxes(unsigned long long*);
+cudaError_t set_trace_mining(unsigned long long*);
+cudaError_t set_trace_postprocess(unsigned long long*);
+}  // namespace ssd
+
+extern "C" int ssd_b200_trace_enable(unsigned long long* device_slots) {
+    SSD_CUDA(ssd::set_trace_assign(device_slots));
+    SSD_CUDA(ssd::set_trace_boxes(device_slots));
+    SSD_CUDA(ssd::set_trace_mining(device_slots));
+    SSD_CUDA(ssd::set_trace_postprocess(device_slots));
+    return SSD_OK;
+}
+extern "C" int ssd_b200_trace_slots(void) { return ssd::kTraceSlots; }
+
 extern "C" void ssd_b200_timing_enable(int on) {
     ssd::g_timing = on != 0;
     ssd::g_timing_used = 0;

@@ -66,6 +66,7 @@ assign_targets_kernel(const float4* __restrict__ anchors, const float* __restric
                       const int32_t* __restrict__ gt_offsets, int A, int chunk, float matched_thr,
                       float unmatched_thr, int force_match, float* __restrict__ target, int32_t* __restrict__ match_out,
                       int32_t* __restrict__ stats) {
+    KernelTrace trace_(TR_ASSIGN);
     griddep_wait();
     griddep_launch_dependents();
     cg::cluster_group cluster = cg::this_cluster();
@@ -399,3 +400,5 @@ extern "C" int ssd_assign_targets(const float* anchors, const float* gt_rows, in
     count_launch();
     return SSD_OK;
 }
+
+SSD_DEFINE_TRACE_SETTER(set_trace_assign)

@@ -61,6 +61,7 @@ template <int OP, bool VEC4>
 __global__ void __launch_bounds__(256)
 box_transform_kernel(const float* __restrict__ src, int64_t src_stride, float* dst, int64_t dst_stride,
                      const float4* __restrict__ priors, int64_t rows, int A, float xy, float wh, float eps) {
+    KernelTrace trace_(TR_BOX0 + OP);
     griddep_wait();
     griddep_launch_dependents();
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -138,3 +139,5 @@ extern "C" int ssd_box_transform(int op, const float* src, int64_t src_row_strid
 #undef SSD_BOX_CASE
     return SSD_ERR_INVALID_ARGUMENT;
 }
+
+SSD_DEFINE_TRACE_SETTER(set_trace_boxes)

@@ -65,6 +65,40 @@ __device__ __forceinline__ float key_to_float(uint32_t k) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// device-side timeline (diagnostics): when a trace buffer is installed (ssd_b200_trace_enable),
+// every kernel records min(start) / max(end) of %globaltimer over its warps in its slot, so the
+// real overlap of the launches inside a replayed CUDA graph can be read back.  One pointer per
+// translation unit (no relocatable device code); a null pointer costs one load and a branch.
+// ---------------------------------------------------------------------------------------------
+enum TraceSlot {
+    TR_ASSIGN = 0, TR_MINING_LOSS, TR_MINING_KEYS, TR_MINING_SELECT, TR_PASS1, TR_GATE, TR_PASS2, TR_NMS, TR_TOPK,
+    TR_MISC, TR_BOX0 = 10, kTraceSlots = 24
+};
+static __device__ unsigned long long* tu_trace_buf = nullptr;
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+struct KernelTrace {
+    unsigned long long* p;
+    __device__ __forceinline__ explicit KernelTrace(int slot) {
+        p = tu_trace_buf;
+        if (p != nullptr) {
+            p += 2 * slot;
+            if ((threadIdx.x & 31) == 0) atomicMin(p, global_ns());
+        }
+    }
+    __device__ __forceinline__ ~KernelTrace() {
+        if (p != nullptr && (threadIdx.x & 31) == 0) atomicMax(p + 1, global_ns());
+    }
+};
+#define SSD_DEFINE_TRACE_SETTER(name)                                                            \
+    namespace ssd {                                                                              \
+    cudaError_t name(unsigned long long* buf) { return cudaMemcpyToSymbol(tu_trace_buf, &buf, sizeof(buf)); } \
+    }
+
+// ---------------------------------------------------------------------------------------------
 // programmatic dependent launch: every kernel of this library is launched with the
 // programmatic-stream-serialization attribute and starts with griddep_wait(), so the launch
 // latency and prologue of kernel N+1 overlap the tail of kernel N (also inside captured graphs).

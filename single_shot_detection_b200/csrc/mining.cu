@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(kStreamThreads)
 mining_loss_kernel(const float* __restrict__ logits, const long long* __restrict__ cls, uint32_t* __restrict__ keys,
                    int* __restrict__ hist, ScoreGrid g) {
     extern __shared__ __align__(128) unsigned char smem[];
+    KernelTrace trace_(TR_MINING_LOSS);
     stream_init(smem);
     griddep_wait();
     griddep_launch_dependents();
@@ -78,6 +79,7 @@ mining_loss_kernel(const float* __restrict__ logits, const long long* __restrict
         const int wbase = warp_id() * rows_per_warp;
 #pragma unroll 2
         for (int step = 0; step < rows_per_warp; step += RowLanes<Q>::kRowsPerWarpStep) {
+            if (wbase + step >= rows) break;            // the rest of a partial tile (warp-uniform)
             const int lr = wbase + step + ln.rl;
             float v[NREG];
             shape.load(v, tile.logits + (size_t)lr * g.C, ln.sub);
@@ -100,6 +102,7 @@ mining_loss_kernel(const float* __restrict__ logits, const long long* __restrict
 template <bool CLS_FLOAT>
 __global__ void mining_keys_from_loss_kernel(const float* __restrict__ loss, const void* __restrict__ cls, int cls_stride,
                                              uint32_t* __restrict__ keys, int* __restrict__ hist, int A, int64_t n) {
+    KernelTrace trace_(TR_MINING_KEYS);
     griddep_wait();
     griddep_launch_dependents();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -165,6 +168,7 @@ mining_select_kernel(const uint32_t* __restrict__ keys, const int* __restrict__ 
                      int ratio_is_integer, double min_negatives, uint8_t* __restrict__ mask,
                      int32_t* __restrict__ stats) {
     __shared__ SelShared sh;
+    KernelTrace trace_(TR_MINING_SELECT);
     griddep_wait();
     griddep_launch_dependents();
     const int b = blockIdx.x;
@@ -431,3 +435,5 @@ extern "C" int ssd_hard_negative_mask(const float* logits, const int64_t* target
     count_launch();
     return SSD_OK;
 }
+
+SSD_DEFINE_TRACE_SETTER(set_trace_mining)

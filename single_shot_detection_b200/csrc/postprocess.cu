@@ -47,7 +47,10 @@ struct PostPlan {
     int cand_cap;            // candidate slots per (image, class)
     // workspace offsets (bytes)
     size_t off_rowstat, off_blockmax, off_gate, off_cand_count, off_cand, off_kept_count, off_kept, off_status,
-        off_anchor_tmp, off_score_hist;
+        off_anchor_tmp, off_score_hist, off_bhist;
+    size_t zero_begin, zero_bytes;   // counters and histograms: one memset per call
+    bool gate_hist;                  // gates from a histogram of the block maxima (SOFTMAX / SIGMOID)
+    float bin_lo, bin_scale;
     size_t total_bytes;
 };
 
@@ -55,6 +58,11 @@ constexpr int kKeptCols = 6;          // x1,y1,x2,y2,score,anchor(bits)
 constexpr int kScoreBins = 4096;      // per-image histogram of the kept scores (final top-k)
 constexpr int kTopkBoundaryCap = 1024;
 constexpr int kQueueCap = 96;         // pass-2 survivor queue: entries per warp
+// Class gates from a histogram of the block maxima: kGateBins linear bins over [lo, lo + kGateBins / scale)
+// in the gate domain (log-probability / logit), two 16-bit counters per word.  The range starts
+// just below the score threshold -- nothing under it can become a detection -- see gate_range().
+constexpr int kGateBins = 256;
+constexpr int kGateWords = kGateBins / 2;
 constexpr size_t kQueueBytes = (size_t)kConsumerWarps * kQueueCap * 3 * sizeof(uint32_t);
 
 // Monotone (non-decreasing) map of a kept score to a histogram bin; probabilities spread over the
@@ -67,6 +75,21 @@ __device__ __forceinline__ int score_bin(float v) {
 constexpr int kMaxPerClass = 512;
 constexpr int kNmsThreads = 128;
 constexpr int kTopkThreads = 512;
+
+// Bin range of the block-maximum histograms.  SOFTMAX: log-probabilities from just under
+// log(threshold) (at least -16) up to 0; SIGMOID: logits from just under logit(threshold) in steps
+// of 1/32.  Values outside clamp to the end bins; the first bin stands for "-inf".
+static void gate_range(int converter, float score_thr, float& lo, float& scale) {
+    if (converter == SSD_CONVERT_SOFTMAX) {
+        lo = -16.f;
+        if (score_thr > 0.f && score_thr < 1.f) lo = fmaxf(-16.f, logf(score_thr) - 0.05f);
+        scale = (float)kGateBins / -lo;
+    } else {
+        lo = -16.f;
+        if (score_thr > 0.f && score_thr < 1.f) lo = fmaxf(-16.f, logf(score_thr / (1.f - score_thr)) - 0.05f);
+        scale = 32.f;
+    }
+}
 
 static int make_plan(const ssd_postprocess_params* p, PostPlan& pl) {
     SSD_REQUIRE(p != nullptr, SSD_ERR_INVALID_ARGUMENT, "ssd_postprocess: null params");
@@ -110,7 +133,7 @@ static int make_plan(const ssd_postprocess_params* p, PostPlan& pl) {
     g.split = split;
     g.nblk = g.groups_per_image * kConsumerWarps * split;
     pl.nblk = g.nblk;
-    pl.grid = stream_grid(g, kQueueBytes);
+    pl.grid = stream_grid(g, kQueueBytes + round_up((size_t)pl.C * sizeof(float), 16));
     int cap = 512;                        // power of two (the segment sort pads to one), >= 8K
     while (cap < 8 * pl.K && cap < 4096) cap <<= 1;
     pl.cand_cap = cap;
@@ -118,16 +141,26 @@ static int make_plan(const ssd_postprocess_params* p, PostPlan& pl) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += round_up(bytes, 256); return o; };
     const size_t BA = (size_t)pl.B * A1 + 2;
+    // block counts stay below 65536 (16-bit histogram counters) for every supported A
+    // Few columns: the gates come from histograms inside pass 2 (one launch less).  Many columns
+    // (COCO's 81): a pass-2 CTA would spend longer on its image's gates than the separate
+    // class_gate launch costs, measured in the step graph (profiles/), so that one stays.
+    pl.gate_hist = pl.converter != SSD_CONVERT_IDENTITY && pl.nblk < 65536 && pl.C <= 32;
+    { const char* e = getenv("SSD_GATE"); if (e) pl.gate_hist = e[0] == 'h' && pl.converter != SSD_CONVERT_IDENTITY; }
+    gate_range(pl.converter, p->score_threshold, pl.bin_lo, pl.bin_scale);
     pl.off_rowstat = take(BA * sizeof(float2));
-    pl.off_blockmax = take((size_t)pl.B * pl.nblk * pl.C * sizeof(float));
+    pl.off_blockmax = take(pl.gate_hist ? 0 : (size_t)pl.B * pl.nblk * pl.C * sizeof(float));
     pl.off_gate = take((size_t)pl.B * pl.C * sizeof(float));
-    pl.off_cand_count = take((size_t)pl.B * pl.Cf * sizeof(int));
     pl.off_cand = take((size_t)pl.B * pl.Cf * pl.cand_cap * sizeof(uint2));
     pl.off_kept_count = take((size_t)pl.B * pl.Cf * sizeof(int));
     pl.off_kept = take((size_t)pl.B * pl.Cf * pl.K * kKeptCols * sizeof(float));
-    pl.off_status = take(4 * sizeof(int));
     pl.off_anchor_tmp = take((size_t)pl.B * (pl.det_cap > 0 ? pl.det_cap : 1) * sizeof(int));
+    pl.zero_begin = off;
+    pl.off_bhist = take(pl.gate_hist ? (size_t)pl.B * pl.C * kGateWords * sizeof(uint32_t) : 0);
+    pl.off_cand_count = take((size_t)pl.B * pl.Cf * sizeof(int));
+    pl.off_status = take(4 * sizeof(int));
     pl.off_score_hist = take((size_t)pl.B * kScoreBins * sizeof(int));
+    pl.zero_bytes = off - pl.zero_begin;
     pl.total_bytes = off;
     return SSD_OK;
 }
@@ -137,11 +170,30 @@ static int make_plan(const ssd_postprocess_params* p, PostPlan& pl) {
 //    SOFTMAX: gate value of an element = its log-probability  x - (max + log(sum));
 //    SIGMOID / IDENTITY: the raw value (both converters are monotone per element).
 // ---------------------------------------------------------------------------------------------
+// Histogram of the block maxima of one (image, column): bin = floor((g - lo) * scale), clamped; the
+// lower edge of a bin, lo + bin / scale, can exceed a value of the bin only by the rounding of these
+// few operations -- far inside the slack gate_from_kth subtracts.
+struct GateBins {
+    float lo, scale;
+};
+__device__ __forceinline__ int gate_bin(float gval, GateBins gb) {
+    const float s = fminf(fmaxf(__fmul_rn(__fsub_rn(gval, gb.lo), gb.scale), 0.f), (float)(kGateBins - 1));
+    return (int)s;                      // NaN -> 0
+}
+__device__ __forceinline__ void bump_gate_bin(uint32_t* __restrict__ words, float gval, GateBins gb) {
+    const int b = gate_bin(gval, gb);
+    atomicAdd(words + (b >> 1), (b & 1) ? 0x10000u : 1u);
+}
+__device__ __forceinline__ float gate_bin_edge(int bin, GateBins gb) {
+    return bin <= 0 ? -INFINITY : __fadd_rn(gb.lo, __fdiv_rn((float)bin, gb.scale));
+}
+
 template <int Q, int NREG, int CMIN, int CONV>
 __global__ void __launch_bounds__(kStreamThreads)
 score_pass1_kernel(const float* __restrict__ scores, ScoreGrid g, float2* __restrict__ rowstat,
-                   float* __restrict__ blockmax) {
+                   float* __restrict__ blockmax, uint32_t* __restrict__ bhist, GateBins gbins) {
     extern __shared__ __align__(128) unsigned char smem[];
+    KernelTrace trace_(TR_PASS1);
     stream_init(smem);
     griddep_wait();
     griddep_launch_dependents();
@@ -165,6 +217,7 @@ score_pass1_kernel(const float* __restrict__ scores, ScoreGrid g, float2* __rest
         const int wbase = warp_id() * rows_per_warp;
 #pragma unroll 2
         for (int step = 0; step < rows_per_warp; step += RowLanes<Q>::kRowsPerWarpStep) {
+            if (wbase + step >= rows) break;            // the rest of a partial tile (warp-uniform)
             const int lr = wbase + step + ln.rl;
             const bool valid = lr < rows;
             float v[NREG];
@@ -185,22 +238,44 @@ score_pass1_kernel(const float* __restrict__ scores, ScoreGrid g, float2* __rest
         }
         consumer_release(smem, k);
         if (cur.last_of_item()) {
-            // merge the row slots of the warp down to `split` blocks, then one vector per block
-#pragma unroll
-            for (int i = 0; i < NREG; ++i) {
-                float x = cmax[i];
-#pragma unroll
-                for (int o = Q; o < 32; o <<= 1)
-                    if (o >= Q * g.split) x = fmaxf(x, __shfl_xor_sync(FULL, x, o));
-                cmax[i] = x;
-            }
-            if (ln.rl < g.split) {
-                float* dst = blockmax + ((size_t)cur.image(g) * g.nblk +
-                                         ((size_t)cur.group(g) * kConsumerWarps + warp_id()) * g.split + ln.rl) * g.C;
+            if (Q == 1 && g.split == 1) {
+                // row-per-lane shape: one CREDUX per column, lane c keeps column c, one coalesced store
+                float mine = -INFINITY;
 #pragma unroll
                 for (int i = 0; i < NREG; ++i) {
-                    const int col = ln.sub + i * Q;
-                    if (col < g.C) dst[col] = cmax[i];
+                    const float r = warp_max(cmax[i]);
+                    if (lane_id() == i) mine = r;
+                }
+                if (lane_id() < g.C) {
+                    if (bhist != nullptr)
+                        bump_gate_bin(bhist + ((size_t)cur.image(g) * g.C + lane_id()) * kGateWords, mine, gbins);
+                    else
+                        blockmax[((size_t)cur.image(g) * g.nblk + (size_t)cur.group(g) * kConsumerWarps + warp_id()) * g.C +
+                                 lane_id()] = mine;
+                }
+            } else {
+                // merge the row slots of the warp down to `split` blocks, then one vector per block
+#pragma unroll
+                for (int i = 0; i < NREG; ++i) {
+                    float x = cmax[i];
+#pragma unroll
+                    for (int o = Q; o < 32; o <<= 1)
+                        if (o >= Q * g.split) x = fmaxf(x, __shfl_xor_sync(FULL, x, o));
+                    cmax[i] = x;
+                }
+                if (ln.rl < g.split) {
+                    float* dst = blockmax + ((size_t)cur.image(g) * g.nblk +
+                                             ((size_t)cur.group(g) * kConsumerWarps + warp_id()) * g.split + ln.rl) * g.C;
+#pragma unroll
+                    for (int i = 0; i < NREG; ++i) {
+                        const int col = ln.sub + i * Q;
+                        if (col < g.C) {
+                            if (bhist != nullptr)
+                                bump_gate_bin(bhist + ((size_t)cur.image(g) * g.C + col) * kGateWords, cmax[i], gbins);
+                            else
+                                dst[col] = cmax[i];
+                        }
+                    }
                 }
             }
 #pragma unroll
@@ -265,24 +340,17 @@ constexpr int kGateBits = 20;                // resolved MSBs of the K-th larges
 // (a slightly smaller key).  Both only let a few more candidates through.
 __global__ void __launch_bounds__(kGateThreads)
 class_gate_kernel(const float* __restrict__ blockmax, int C, int first_fg, int nblk, int K, int converter,
-                  float score_thr, float* __restrict__ gate, int* __restrict__ cand_count, int* __restrict__ status,
-                  int* __restrict__ score_hist, int hist_words) {
+                  float score_thr, float* __restrict__ gate) {
     extern __shared__ __align__(16) uint32_t skey[];          // [merged blocks][kGateCols + 1]
+    KernelTrace trace_(TR_GATE);
     griddep_wait();
     griddep_launch_dependents();
     const int b = blockIdx.y;
     const int c0 = blockIdx.x * kGateCols;
     const int lane = lane_id();
-    if (b == 0 && blockIdx.x == 0 && threadIdx.x < 4 && status != nullptr) status[threadIdx.x] = 0;
     const int merge = (nblk + 32 * kGateKeysPerLane - 1) / (32 * kGateKeysPerLane);
     const int nm = (nblk + merge - 1) / merge;                 // merged blocks, <= 512
     const float* src = blockmax + (size_t)b * nblk * C;
-    // zero the per-image score histograms for the NMS kernel (grid-stride over the whole array)
-    {
-        const int nthreads = gridDim.x * gridDim.y * kGateThreads;
-        const int gtid = (blockIdx.y * gridDim.x + blockIdx.x) * kGateThreads + threadIdx.x;
-        for (int i = gtid; i < hist_words; i += nthreads) score_hist[i] = 0;
-    }
     // coalesced load: 8 consecutive columns of one block row per 8 threads, four rows in flight
     if (merge == 1) {
         const int total = nm * kGateCols;
@@ -344,10 +412,7 @@ class_gate_kernel(const float* __restrict__ blockmax, int C, int first_fg, int n
         kth = T < 0x00800000u ? -INFINITY : key_to_float(T);
         if (kth != kth) kth = -INFINITY;
     }
-    if (lane == 0) {
-        gate[b * C + col] = gate_from_kth(converter, score_thr, kth);
-        cand_count[b * (C - first_fg) + (col - first_fg)] = 0;
-    }
+    if (lane == 0) gate[b * C + col] = gate_from_kth(converter, score_thr, kth);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -374,11 +439,68 @@ struct CandQueue {
     }
 };
 
+// Gates of one image from the block-maximum histograms (consumer warps only; a warp per column,
+// kGateBatch columns' loads in flight).  Lane l holds bins 8 l .. 8 l + 7 of a column (four words);
+// the gate is the lower edge of the highest bin whose suffix count reaches K -- a lower bound of
+// the K-th largest block maximum, hence of the K-th largest score of the class.
+struct GateHist {
+    const uint32_t* bhist;      // nullptr: gates are read from the `gate` array (class_gate_kernel)
+    int K, converter;
+    float score_thr;
+    GateBins bins;
+};
+constexpr int kGateBatch = 4;
+__device__ __forceinline__ void image_gates(const GateHist& gh, const ScoreGrid& g, int img, float* __restrict__ sgate) {
+    const int lane = lane_id();
+    static_assert(kGateWords == 32 * 4, "four words per lane");
+    const uint4* base = reinterpret_cast<const uint4*>(gh.bhist + (size_t)img * g.C * kGateWords) + lane;
+    for (int col0 = g.first_fg + warp_id(); col0 < g.C; col0 += kConsumerWarps * kGateBatch) {
+        uint4 h[kGateBatch];
+#pragma unroll
+        for (int u = 0; u < kGateBatch; ++u) {
+            const int col = col0 + u * kConsumerWarps;
+            h[u] = col < g.C ? base[(size_t)col * (kGateWords / 4)] : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < kGateBatch; ++u) {
+            const int col = col0 + u * kConsumerWarps;
+            if (col >= g.C) break;
+            const uint32_t w[4] = {h[u].x, h[u].y, h[u].z, h[u].w};
+            int own = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) own += (int)(w[j] & 0xFFFFu) + (int)(w[j] >> 16);
+            int incl = own;                               // suffix sum towards higher lanes (= higher bins)
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_down_sync(FULL, incl, o);
+                if (lane + o < 32) incl += t;
+            }
+            int above = incl - own;
+            int bin = -1;
+            if (above < gh.K && incl >= gh.K) {
+#pragma unroll
+                for (int j = 7; j >= 0; --j) {
+                    const int c = (int)((w[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu);
+                    if (bin < 0 && above + c >= gh.K) bin = 8 * lane + j;
+                    above += c;
+                }
+            }
+            const unsigned found = __ballot_sync(FULL, bin >= 0);
+            if (bin >= 0) sgate[col] = gate_from_kth(gh.converter, gh.score_thr, gate_bin_edge(bin, gh.bins));
+            if (found == 0u && lane == 0) sgate[col] = gate_from_kth(gh.converter, gh.score_thr, -INFINITY);
+        }
+    }
+    for (int c = threadIdx.x; c < g.first_fg; c += kConsumerWarps * 32) sgate[c] = INFINITY;
+}
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory"); }
+
 template <int Q, int NREG, int CMIN, int CONV>
 __global__ void __launch_bounds__(kStreamThreads)
 score_pass2_kernel(const float* __restrict__ scores, ScoreGrid g, const float2* __restrict__ rowstat,
-                   const float* __restrict__ gate, int* __restrict__ cand_count, uint2* __restrict__ cand, int cand_cap) {
+                   const float* __restrict__ gate, GateHist gh, int* __restrict__ cand_count, uint2* __restrict__ cand,
+                   int cand_cap) {
     extern __shared__ __align__(128) unsigned char smem[];
+    KernelTrace trace_(TR_PASS2);
     stream_init(smem);
     griddep_wait();
     griddep_launch_dependents();
@@ -397,6 +519,7 @@ score_pass2_kernel(const float* __restrict__ scores, ScoreGrid g, const float2* 
         uint32_t* base = reinterpret_cast<uint32_t*>(smem + stream_smem_bytes_dev(g)) + warp_id() * kQueueCap * 3;
         q.seg = base; q.anchor = base + kQueueCap; q.val = base + 2 * kQueueCap; q.n = 0;
     }
+    float* sgate = reinterpret_cast<float*>(smem + stream_smem_bytes_dev(g) + kQueueBytes);      // [C]
     const unsigned lt_mask = (1u << lane_id()) - 1u;
 
     float gv[NREG];
@@ -409,16 +532,24 @@ score_pass2_kernel(const float* __restrict__ scores, ScoreGrid g, const float2* 
         const int img = cur.image(g);
         if (img != cur_image) {                 // per-lane slice of this image's gates
             cur_image = img;
+            const float* gsrc = gate + (size_t)img * g.C;
+            if (gh.bhist != nullptr) {
+                consumer_barrier();             // everybody is done with the previous image's gates
+                image_gates(gh, g, img, sgate);
+                consumer_barrier();
+                gsrc = sgate;
+            }
 #pragma unroll
             for (int i = 0; i < NREG; ++i) {
                 const int col = ln.sub + i * Q;
-                gv[i] = (col < g.C) ? gate[(size_t)img * g.C + col] : INFINITY;
+                gv[i] = (col < g.C) ? gsrc[col] : INFINITY;
             }
         }
         const StagedTile tile = consumer_acquire(smem, g, k, r0);
         const int a0 = cur.tile * g.tile_rows;
         const int wbase = warp_id() * rows_per_warp;
         for (int step = 0; step < rows_per_warp; step += RowLanes<Q>::kRowsPerWarpStep) {
+            if (wbase + step >= rows) break;            // the rest of a partial tile (warp-uniform)
             const int lr = wbase + step + ln.rl;
             const bool valid = lr < rows;
             float v[NREG];
@@ -635,6 +766,7 @@ segment_nms_kernel(NmsArgs a, const float* __restrict__ scores, const float2* __
     __shared__ uint32_t s_hist[2048];
     __shared__ int s_misc[4 + kNmsThreads / 32];
     __shared__ int s_valid, s_nkeep;
+    KernelTrace trace_(TR_NMS);
     griddep_wait();
     griddep_launch_dependents();
     const int seg = blockIdx.x;
@@ -861,6 +993,7 @@ image_topk_kernel(int Cf, int K, int T, int det_cap, const int* __restrict__ kep
                   int* __restrict__ det_anchor) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ TopkShared sh;
+    KernelTrace trace_(TR_TOPK);
     griddep_wait();
     griddep_launch_dependents();
     const int img = blockIdx.x;
@@ -1088,14 +1221,21 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
     const ScoreGrid& g = pl.g;
     const int grid = pl.grid;
     const size_t stream_smem = stream_smem_bytes(g);
-    const size_t pass2_smem = stream_smem + kQueueBytes;
+    const size_t pass2_smem = stream_smem + kQueueBytes + round_up((size_t)pl.C * sizeof(float), 16);
+    uint32_t* bhist = pl.gate_hist ? (uint32_t*)(ws + pl.off_bhist) : nullptr;
+    GateBins gbins;
+    gbins.lo = pl.bin_lo; gbins.scale = pl.bin_scale;
+
+    // counters, histograms and the status words start at zero
+    SSD_CUDA(cudaMemsetAsync(ws + pl.zero_begin, 0, pl.zero_bytes, st));
 
 #define SSD_LAUNCH_PASS1(QQ, NN, CM)                                                                                     \
     do {                                                                                                               \
         auto launch = [&](auto kern) -> int {                                                                          \
             SSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem));    \
             LaunchTimer lt_("pass1", st);                                                            \
-            SSD_CUDA(launch_pdl(kern, dim3(grid), dim3(kStreamThreads), stream_smem, st, scores, g, rowstat, blockmax)); \
+            SSD_CUDA(launch_pdl(kern, dim3(grid), dim3(kStreamThreads), stream_smem, st, scores, g, rowstat, blockmax, \
+                                bhist, gbins));                                                                 \
             return SSD_OK;                                                                                             \
         };                                                                                                             \
         int rc;                                                                                                        \
@@ -1108,26 +1248,28 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
     SSD_CUDA(cudaGetLastError());
     count_launch();
 
-    {
+    if (!pl.gate_hist) {
         LaunchTimer lt_("gate", st);
         const int merge = (pl.nblk + 32 * kGateKeysPerLane - 1) / (32 * kGateKeysPerLane);
         const int nm = (pl.nblk + merge - 1) / merge;
         const size_t gsmem = (size_t)nm * (kGateCols + 1) * sizeof(uint32_t);
         dim3 ggrid((pl.C + kGateCols - 1) / kGateCols, pl.B);
         SSD_CUDA(launch_pdl(class_gate_kernel, ggrid, dim3(kGateThreads), gsmem, st, (const float*)blockmax, pl.C,
-                            pl.first_fg, pl.nblk, pl.K, pl.converter, p->score_threshold, gate, cand_count, status,
-                            score_hist, pl.B * kScoreBins));
+                            pl.first_fg, pl.nblk, pl.K, pl.converter, p->score_threshold, gate));
         SSD_CUDA(cudaGetLastError());
-    count_launch();
+        count_launch();
     }
 
+    GateHist gh;
+    gh.bhist = bhist; gh.K = pl.K; gh.converter = pl.converter; gh.score_thr = p->score_threshold;
+    gh.bins = gbins;
 #define SSD_LAUNCH_PASS2(QQ, NN, CM)                                                                                     \
     do {                                                                                                               \
         auto launch = [&](auto kern) -> int {                                                                          \
             SSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pass2_smem));    \
             LaunchTimer lt_("pass2", st);                                                            \
             SSD_CUDA(launch_pdl(kern, dim3(grid), dim3(kStreamThreads), pass2_smem, st, scores, g,                   \
-                                (const float2*)rowstat, (const float*)gate, cand_count, cand, pl.cand_cap));         \
+                                (const float2*)rowstat, (const float*)gate, gh, cand_count, cand, pl.cand_cap));     \
             return SSD_OK;                                                                                             \
         };                                                                                                             \
         int rc;                                                                                                        \
@@ -1250,3 +1392,5 @@ extern "C" int ssd_nms(const float* corner_boxes, const float* scores, int num_b
     count_launch();
     return SSD_OK;
 }
+
+SSD_DEFINE_TRACE_SETTER(set_trace_postprocess)

@@ -15,6 +15,8 @@
 // addresses and sizes; rows are 4*C bytes, so tile starts are only 4-byte aligned in general).
 #pragma once
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ssd {
@@ -45,22 +47,31 @@ __device__ __forceinline__ float fast_log(float x) {
 }
 
 // Tiling of a [B images x A rows x C cols] array.  Work item = `group_tiles` consecutive tiles of
-// one image; items are dealt round-robin to CTAs.  Tiles never cross an image boundary.
+// one image; every CTA takes a contiguous range of items.  Tiles never cross an image boundary.
 struct ScoreGrid {
     int A, C, first_fg;
     int tile_rows, tiles_per_image, group_tiles, groups_per_image, num_items;
     int stage_bytes;          // bytes per ring stage (logit tile + side array, 16-byte multiples)
     int side_offset;          // byte offset of the side array inside a stage
     int nblk, split;          // post-processor block-max bookkeeping (unused by mining)
-    int step_img, step_grp;   // gridDim.x decomposed as step_img * groups_per_image + step_grp
+    int step_img, step_grp;   // gridDim.x decomposed as step_img * groups_per_image + step_grp (round-robin)
+    int contiguous;           // item dealing, see TileCursor
     int64_t total_floats;     // B*A*C
     int64_t total_rows;       // B*A
 };
 
 struct TileCursor {
-    int item, img, grp, tile, tile_end;
+    int item, item_end, img, grp, tile, tile_end;
+    // contiguous: CTA c owns the item range [c * n / grid, (c + 1) * n / grid) -- at most two images
+    // per CTA unless an image has fewer items than a CTA's share; otherwise items are dealt round-robin.
     __device__ __forceinline__ void start(const ScoreGrid& g) {
-        item = blockIdx.x;
+        if (g.contiguous) {
+            item = (int)(((int64_t)blockIdx.x * g.num_items) / gridDim.x);
+            item_end = (int)(((int64_t)(blockIdx.x + 1) * g.num_items) / gridDim.x);
+        } else {
+            item = blockIdx.x;
+            item_end = g.num_items;
+        }
         img = item / g.groups_per_image;
         grp = item - img * g.groups_per_image;
         open(g);
@@ -69,16 +80,21 @@ struct TileCursor {
         tile = grp * g.group_tiles;
         tile_end = min(tile + g.group_tiles, g.tiles_per_image);
     }
-    __device__ __forceinline__ bool valid(const ScoreGrid& g) const { return item < g.num_items; }
+    __device__ __forceinline__ bool valid(const ScoreGrid&) const { return item < item_end; }
     __device__ __forceinline__ int image(const ScoreGrid&) const { return img; }
     __device__ __forceinline__ int group(const ScoreGrid&) const { return grp; }
     __device__ __forceinline__ bool last_of_item() const { return tile + 1 == tile_end; }
     __device__ __forceinline__ void next(const ScoreGrid& g) {
         if (++tile == tile_end) {
-            item += gridDim.x;
-            img += g.step_img;
-            grp += g.step_grp;
-            if (grp >= g.groups_per_image) { grp -= g.groups_per_image; ++img; }
+            if (g.contiguous) {
+                ++item;
+                if (++grp == g.groups_per_image) { grp = 0; ++img; }
+            } else {
+                item += gridDim.x;
+                img += g.step_img;
+                grp += g.step_grp;
+                if (grp >= g.groups_per_image) { grp -= g.groups_per_image; ++img; }
+            }
             open(g);
         }
     }
@@ -212,23 +228,54 @@ struct RowShape {
     }
 };
 
-// row max and sum of exp(x - max) over the Q lanes that own the row
+// three-input maximum (FMNMX3 on sm_100a); NaN operands are dropped like fmaxf
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+// warp-wide maximum in one instruction (CREDUX.MAX.F32 on sm_100a); NaN lanes are dropped
+__device__ __forceinline__ float warp_max(float x) {
+    float y;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// row max and sum of exp(x - max) over the Q lanes that own the row.  The order of the maxima is
+// immaterial; the sum is a streamed quantity (see fast_exp) accumulated in three independent chains.
 template <int Q, int NREG>
 __device__ __forceinline__ void row_max_sum(const float (&v)[NREG], float& m, float& sum) {
-    m = v[0];
+    float ma = v[0], mb = v[0];
+    int i = 1;
 #pragma unroll
-    for (int i = 1; i < NREG; ++i) m = fmaxf(m, v[i]);
-    m = group_max<Q>(m);
-    sum = 0.f;
+    for (; i + 3 < NREG; i += 4) {
+        ma = max3(ma, v[i], v[i + 1]);
+        mb = max3(mb, v[i + 2], v[i + 3]);
+    }
 #pragma unroll
-    for (int i = 0; i < NREG; ++i) sum = __fadd_rn(sum, fast_exp(__fsub_rn(v[i], m)));
-    sum = group_sum<Q>(sum);
+    for (; i < NREG; ++i) ma = fmaxf(ma, v[i]);
+    m = group_max<Q>(fmaxf(ma, mb));
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NREG; j += 3) {
+        s0 = __fadd_rn(s0, fast_exp(__fsub_rn(v[j], m)));
+        if (j + 1 < NREG) s1 = __fadd_rn(s1, fast_exp(__fsub_rn(v[j + 1], m)));
+        if (j + 2 < NREG) s2 = __fadd_rn(s2, fast_exp(__fsub_rn(v[j + 2], m)));
+    }
+    sum = group_sum<Q>(__fadd_rn(__fadd_rn(s0, s1), s2));
 }
 
 // Dispatch table C -> (Q, NREG, CMIN): NREG*Q >= C, CMIN = smallest C of the bucket.
+// Odd C <= 32 (VOC's 21 columns) take the row-per-lane shape Q == 1: lane l walks row l of the warp
+// step at a stride of C words -- C odd, so the 32 lanes hit 32 different banks -- with no lane idle,
+// no shuffle in the row reductions and ~3x fewer warp instructions per element than a split row.
 #define SSD_DISPATCH_ROW_SHAPE(C, CALL)                          \
     do {                                                         \
         if ((C) <= 8) { CALL(1, 8, 1); }                         \
+        else if ((C) == 21) { CALL(1, 21, 21); }                 \
+        else if (((C) & 1) && (C) <= 16) { CALL(1, 16, 9); }     \
+        else if (((C) & 1) && (C) <= 24) { CALL(1, 24, 17); }    \
+        else if (((C) & 1) && (C) <= 32) { CALL(1, 32, 25); }    \
         else if ((C) <= 16) { CALL(2, 8, 9); }                   \
         else if ((C) <= 24) { CALL(4, 6, 17); }                  \
         else if ((C) <= 32) { CALL(4, 8, 25); }                  \
@@ -275,10 +322,11 @@ inline void plan_tiles(ScoreGrid& g, int images, int A, int C, bool with_side, i
     g.total_rows = (int64_t)images * A;
     g.first_fg = 0; g.nblk = 0; g.split = 1;
     g.step_img = 0; g.step_grp = 0;
+    { const char* e = getenv("SSD_CURSOR"); g.contiguous = (e && e[0] == 'r') ? 0 : 1; }
 }
 inline size_t stream_smem_bytes(const ScoreGrid& g) { return 128 + (size_t)kStreamStages * g.stage_bytes; }
 __device__ __forceinline__ size_t stream_smem_bytes_dev(const ScoreGrid& g) { return 128 + (size_t)kStreamStages * g.stage_bytes; }
-// Grid size (a whole number of resident waves) and the cursor's stride decomposition.
+// Grid size: a whole number of resident waves.
 inline int stream_grid(ScoreGrid& g, size_t extra_smem = 0) {
     int per_sm = (int)((size_t)(224 * 1024) / (stream_smem_bytes(g) + extra_smem + 1024));
     if (per_sm > 4) per_sm = 4;

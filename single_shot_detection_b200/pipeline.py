@@ -76,13 +76,16 @@ class AnchorPipeline:
         batch, num_anchors = target.shape[:2]
         classes = target[..., CLASS_INDEX].long()
         mask = self.sampler(scores.view(batch, num_anchors, -1), classes)
+        self._encode_target_boxes(target, anchors)
+        return mask
+
+    def _encode_target_boxes(self, target, anchors):
         target_locs = target[..., LOC_INDEX_START:LOC_INDEX_END]
         if self.fuse_encode:
             self.box_coder.encode_corners_(target_locs, anchors)
         else:
-            box_utils.to_centroids(target_locs, inplace=True)
-            self.box_coder.encode_box(target_locs, anchors, inplace=True)
-        return mask
+            box_utils.to_centroids(target_locs, inplace=True)                  # multibox_loss.py:81
+            self.box_coder.encode_box(target_locs, anchors, inplace=True)      # multibox_loss.py:82
 
     # -- device-resident, sync-free -------------------------------------------------------------
     def step_device(self, packed: PackedGroundTruth, anchors_dev, scores_dev, locs_dev,
@@ -94,13 +97,22 @@ class AnchorPipeline:
         so they are enqueued on two streams (fork / join with events; capturable into one graph
         with two parallel branches)."""
         main = torch.cuda.current_stream()
-        side = self._side_stream()
+        side, side2 = self._side_streams()
         side.wait_stream(main)
         with torch.cuda.stream(side):
             target = self.target_assigner.encode_packed(packed, anchors_dev)
-            mask = self._sample_and_encode(target, anchors_dev, scores_dev)
+            classes = target[..., CLASS_INDEX].long()                      # multibox_loss.py:49
+            assigned = torch.cuda.Event()
+            assigned.record(side)
+            batch, num_anchors = target.shape[:2]
+            mask = self.sampler(scores_dev.view(batch, num_anchors, -1), classes)
+        with torch.cuda.stream(side2):
+            # the box encoding only needs the assignment: a third branch next to sampler and post-processor
+            side2.wait_event(assigned)
+            self._encode_target_boxes(target, anchors_dev)
         dets, counts, det_anchors, status = self.postprocessor.postprocess_padded((scores_dev, locs_dev), anchors_dev)
         main.wait_stream(side)
+        main.wait_stream(side2)
         mining = _sampler.hard_negative_mining.last_stats if self.cfg["sampler"] == "hard_negative_mining" else None
         stats, shard = None, None
         if shard_capacity is not None:
@@ -110,9 +122,9 @@ class AnchorPipeline:
         return StepOutput(target, mask, dets, counts, det_anchors, status, stats, shard,
                           self.target_assigner.last_stats, mining)
 
-    def _side_stream(self):
+    def _side_streams(self):
         if self._side is None:
-            self._side = torch.cuda.Stream()
+            self._side = (torch.cuda.Stream(), torch.cuda.Stream())
         return self._side
 
     def capture(self, packed: PackedGroundTruth, anchors_dev, scores_dev, locs_dev, warmup: int = 2,
