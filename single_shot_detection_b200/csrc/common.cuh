@@ -89,6 +89,14 @@ struct KernelTrace {
             if ((threadIdx.x & 31) == 0) atomicMin(p, global_ns());
         }
     }
+    // phase marks of one CTA (the middle one of the grid): slot 16 + k holds {time, 0}
+    __device__ __forceinline__ void mark(int k) const {
+        if (p != nullptr && threadIdx.x == 0 && blockIdx.x == gridDim.x / 2 && k < 8) {
+            unsigned long long* q = tu_trace_buf + 2 * (16 + k);
+            q[0] = global_ns();
+            q[1] = 1;
+        }
+    }
     __device__ __forceinline__ ~KernelTrace() {
         if (p != nullptr && (threadIdx.x & 31) == 0) atomicMax(p + 1, global_ns());
     }

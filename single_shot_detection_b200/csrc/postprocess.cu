@@ -47,7 +47,7 @@ struct PostPlan {
     int cand_cap;            // candidate slots per (image, class)
     // workspace offsets (bytes)
     size_t off_rowstat, off_blockmax, off_gate, off_cand_count, off_cand, off_kept_count, off_kept, off_status,
-        off_anchor_tmp, off_score_hist, off_bhist;
+        off_anchor_tmp, off_score_hist, off_bhist, off_image_done;
     size_t zero_begin, zero_bytes;   // counters and histograms: one memset per call
     bool gate_hist;                  // gates from a histogram of the block maxima (SOFTMAX / SIGMOID)
     float bin_lo, bin_scale;
@@ -55,7 +55,7 @@ struct PostPlan {
 };
 
 constexpr int kKeptCols = 6;          // x1,y1,x2,y2,score,anchor(bits)
-constexpr int kScoreBins = 4096;      // per-image histogram of the kept scores (final top-k)
+constexpr int kScoreBins = 2048;      // per-image histogram of the kept scores (final top-k)
 constexpr int kTopkBoundaryCap = 1024;
 constexpr int kQueueCap = 96;         // pass-2 survivor queue: entries per warp
 // Class gates from a histogram of the block maxima: kGateBins linear bins over [lo, lo + kGateBins / scale)
@@ -160,6 +160,7 @@ static int make_plan(const ssd_postprocess_params* p, PostPlan& pl) {
     pl.off_cand_count = take((size_t)pl.B * pl.Cf * sizeof(int));
     pl.off_status = take(4 * sizeof(int));
     pl.off_score_hist = take((size_t)pl.B * kScoreBins * sizeof(int));
+    pl.off_image_done = take((size_t)pl.B * sizeof(int));
     pl.zero_bytes = off - pl.zero_begin;
     pl.total_bytes = off;
     return SSD_OK;
@@ -620,6 +621,9 @@ struct NmsArgs {
     // exact division-free form of `(double)RN32(inter / uni) > iou_thr` (see nms_threshold_split)
     double iou_mid;
     int iou_even, exact_mul;
+    // fp32 screen (see pair_screen): threshold * (1 -/+ 4e-7), valid for thresholds in [0, 1e30)
+    float iou_lo, iou_hi;
+    int screen;
 };
 
 // torchvision compares the fp32 quotient with the double threshold.  Let T32 be the smallest float
@@ -638,6 +642,14 @@ static void nms_threshold_split(double thr, NmsArgs& a) {
     a.iou_mid = ((double)p32 + (double)t32) * 0.5;
     a.iou_even = (bits & 1u) == 0u;
     a.exact_mul = 1;
+}
+static void nms_threshold_screen(double thr, NmsArgs& a) {
+    a.screen = 0; a.iou_lo = 0.f; a.iou_hi = 0.f;
+    if (!(thr >= 0.0 && thr < 1e30)) return;
+    a.iou_lo = nextafterf((float)(thr * (1.0 - 4e-7)), -INFINITY);
+    a.iou_hi = nextafterf((float)(thr * (1.0 + 4e-7)), INFINITY);
+    if (a.iou_lo < 0.f) a.iou_lo = 0.f;
+    a.screen = 1;
 }
 
 __device__ __forceinline__ float exact_score(int converter, float x, float2 st) {
@@ -734,49 +746,347 @@ __device__ int exact_select_column(const NmsArgs& a, int img, int col, const flo
 }
 
 // torchvision's overlap test `(double)fp32(inter / union) > threshold` for one pair of corner boxes
-// (areas unclamped, intersection sides clamped at 0).  Fast form: no division (see
-// nms_threshold_split); `slow` reports the pairs that need the literal division instead.
-__device__ __forceinline__ bool pair_suppressed(const NmsArgs& a, float4 bi, float ai, float4 bj, float aj, bool& slow) {
+// (areas unclamped, intersection sides clamped at 0), in three tiers:
+//   * disjoint boxes (inter == 0) never exceed a non-negative threshold (0/u, -0 or 0/0 -> NaN);
+//   * fp32 screen: inter against union * threshold with a 4e-7 relative guard band on both sides
+//     (the product is off by <= 2^-24 relative, the rounding midpoint by <= 2^-24 more);
+//   * anything inside the band, non-positive unions, NaNs and negative thresholds take the exact
+//     form: the division-free double comparison (see nms_threshold_split) or the literal division.
+// Returns 0 = keep, 1 = suppress, 2 = undecided (exact form needed).
+__device__ __forceinline__ int pair_screen(const NmsArgs& a, float4 bi, float ai, float4 bj, float aj) {
     const float iw = fmaxf(0.f, fsub(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)));
     const float ih = fmaxf(0.f, fsub(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)));
     const float inter = fmul(iw, ih);
+    if (inter == 0.f) return 0;
     const float uni = fsub(fadd(ai, aj), inter);
-    const bool fast = a.exact_mul && inter > 0.f && uni > 0.f;
-    // disjoint boxes give +0 (or 0/0): never above a non-negative threshold
-    slow = !fast && (inter != 0.f || a.iou_thr < 0.0);
-    const double lhs = (double)inter, rhs = a.iou_mid * (double)uni;
-    return fast && (lhs > rhs || (lhs == rhs && a.iou_even));
+    const bool ok = inter > 0.f && uni > 0.f;
+    if (ok && inter > fmul(uni, a.iou_hi)) return 1;
+    if (ok && inter < fmul(uni, a.iou_lo)) return 0;
+    return 2;
 }
-__device__ __noinline__ bool pair_suppressed_slow(const NmsArgs& a, float4 bi, float ai, float4 bj, float aj) {
+__device__ __noinline__ bool pair_suppressed_exact(const NmsArgs& a, float4 bi, float ai, float4 bj, float aj) {
     const float iw = fmaxf(0.f, fsub(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)));
     const float ih = fmaxf(0.f, fsub(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)));
     const float inter = fmul(iw, ih);
     const float uni = fsub(fadd(ai, aj), inter);
+    if (a.exact_mul && inter > 0.f && uni > 0.f) {
+        const double lhs = (double)inter, rhs = a.iou_mid * (double)uni;
+        return lhs > rhs || (lhs == rhs && a.iou_even);
+    }
     return (double)fdiv(inter, uni) > a.iou_thr;           // float-vs-double compare
+}
+__device__ __forceinline__ bool pair_suppressed(const NmsArgs& a, float4 bi, float ai, float4 bj, float aj, bool active) {
+    int r = 2;
+    if (a.screen) r = active ? pair_screen(a, bi, ai, bj, aj) : 0;
+    else if (!active) r = 0;
+    if (__any_sync(FULL, r == 2)) {
+        if (r == 2) r = pair_suppressed_exact(a, bi, ai, bj, aj) ? 1 : 0;
+    }
+    return r == 1;
 }
 
 constexpr int kRankSortMax = 256;     // candidate lists up to this size are sorted by ranking
 
-__global__ void __launch_bounds__(kNmsThreads)
-segment_nms_kernel(NmsArgs a, const float* __restrict__ scores, const float2* __restrict__ rowstat,
-                   const int* __restrict__ cand_count, const uint2* __restrict__ cand,
-                   const float4* __restrict__ boxes, const float4* __restrict__ priors, int* __restrict__ kept_count,
-                   float* __restrict__ kept, int* __restrict__ status, int* __restrict__ score_hist) {
+// ---------------------------------------------------------------------------------------------
+// 5. final top-k of one image (postprocessor.py:68-74), run by the LAST segment CTA of the image
+//    (or by image_topk_kernel when its shared memory does not fit next to the NMS arrays)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void write_det_row(float* dets, int* anchors, const float* kept, int K, int cls, int slot,
+                                              int out_row) {
+    const float* src = kept + ((size_t)cls * K + slot) * kKeptCols;
+    float* o = dets + (size_t)out_row * 6;
+    o[0] = src[0]; o[1] = src[1]; o[2] = src[2]; o[3] = src[3];
+    o[4] = (float)(cls + 1);                                           // postprocessor.py:66
+    o[5] = src[4];
+    if (anchors != nullptr) anchors[out_row] = (int)__float_as_uint(src[5]);
+}
+
+template <int THREADS>
+struct TopkShared {
+    int wsum[THREADS / 32];
+    int warp_tot[THREADS / 32];
+    int cnt[4];
+    int n_total, n_sel, n_cand, cut_bin, above, in_bin;
+};
+
+struct TopkArgs {
+    int Cf, K, T, det_cap;
+    const int* kept_count;
+    const float* kept;
+    const int* score_hist;
+    float* dets;
+    int* det_count;
+    int* det_anchor;
+};
+
+__host__ __device__ inline size_t topk_smem_bytes(int Cf, int T) {
+    int t2 = 32;
+    while (t2 < T) t2 <<= 1;
+    return round_up((size_t)(Cf + 1) * 4, 16) * 2 + (size_t)(T > 0 ? t2 : 0) * 8 + (size_t)kTopkBoundaryCap * 8 + 64;
+}
+
+// The T best of the image's kept rows, descending score, ties by class-major position.  The NMS
+// CTAs have already histogrammed the kept scores, so the cut is found with one suffix scan; rows
+// above the cut bin are taken, the cut bin is ranked exactly.  A cut bin too crowded to rank
+// (scores tied en masse) falls back to a bit-wise bisection over the rows in global memory.
+template <int THREADS>
+__device__ void image_topk_body(unsigned char* smem, TopkShared<THREADS>& sh, const TopkArgs& ta, int img) {
+    const int lane = lane_id();
+    const int tid = threadIdx.x;
+    constexpr int nwarps = THREADS / 32;
+    constexpr int BPT = kScoreBins / THREADS;                  // histogram bins per thread
+    static_assert(BPT % 4 == 0 && BPT * THREADS == kScoreBins, "whole int4 loads per thread");
+    const int Cf = ta.Cf, K = ta.K, T = ta.T;
+    int t2 = 32;
+    while (t2 < T) t2 <<= 1;
+    const size_t offs_bytes = round_up((size_t)(Cf + 1) * 4, 16);
+    int* offs = reinterpret_cast<int*>(smem);                                            // [Cf + 1]
+    int* tie_base = reinterpret_cast<int*>(smem + offs_bytes);                           // [Cf + 1] fallback only
+    unsigned long long* sel = reinterpret_cast<unsigned long long*>(smem + 2 * offs_bytes);   // [t2]
+    unsigned long long* cand = sel + (T > 0 ? t2 : 0);                                   // [kTopkBoundaryCap] (later: sorted)
+    const int* kc = ta.kept_count + (size_t)img * Cf;
+    const float* kimg = ta.kept + (size_t)img * Cf * K * kKeptCols;
+    float* dimg = ta.dets + (size_t)img * ta.det_cap * 6;
+    int* aimg = ta.det_anchor ? ta.det_anchor + (size_t)img * ta.det_cap : nullptr;
+
+    // the histogram loads go out first (higher bins = larger scores)
+    int hb[BPT];
+    if (T > 0) {
+        const int4* h4 = reinterpret_cast<const int4*>(ta.score_hist + (size_t)img * kScoreBins) + (BPT / 4) * tid;
+#pragma unroll
+        for (int j = 0; j < BPT / 4; ++j) {
+            const int4 q = __ldcg(h4 + j);
+            hb[4 * j] = q.x; hb[4 * j + 1] = q.y; hb[4 * j + 2] = q.z; hb[4 * j + 3] = q.w;
+        }
+    }
+    // exclusive scan of the per-class counts (warp 0, 32 classes per round)
+    if (warp_id() == 0) {
+        int base = 0;
+        for (int c0 = 0; c0 < Cf; c0 += 32) {
+            const int c = c0 + lane;
+            const int v = c < Cf ? __ldcg(kc + c) : 0;
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (c < Cf) offs[c] = base + incl - v;
+            base += __shfl_sync(FULL, incl, 31);
+        }
+        if (lane == 0) {
+            offs[Cf] = base;
+            sh.n_total = base; sh.n_sel = 0; sh.n_cand = 0; sh.cut_bin = -1; sh.above = 0; sh.in_bin = 0;
+            sh.cnt[0] = sh.cnt[1] = sh.cnt[2] = sh.cnt[3] = 0;
+        }
+    }
+    __syncthreads();
+    const int n = sh.n_total;
+
+    if (T <= 0 || n <= T) {
+        // class-major order, descending score inside a class            postprocessor.py:68-70
+        for (int c = warp_id(); c < Cf; c += nwarps) {
+            const int cnt = offs[c + 1] - offs[c];
+            for (int t = lane; t < cnt; t += 32) write_det_row(dimg, aimg, kimg, K, c, t, offs[c] + t);
+        }
+        if (tid == 0) ta.det_count[img] = n;
+        return;
+    }
+
+    // ---- cut bin: above(bin) < T <= above(bin) + hist[bin] ----
+    {
+        int own = 0;
+#pragma unroll
+        for (int j = 0; j < BPT; ++j) own += hb[j];
+        int incl = own;                                   // suffix sum inside the warp (towards higher lanes)
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_down_sync(FULL, incl, o);
+            if (lane + o < 32) incl += t;
+        }
+        if (lane == 0) sh.warp_tot[warp_id()] = incl;
+        __syncthreads();
+        const int wt = lane < nwarps ? sh.warp_tot[lane] : 0;
+        const int higher = __reduce_add_sync(FULL, lane > warp_id() ? wt : 0);
+        int above = higher + incl - own;
+        if (above < T && above + own >= T) {
+#pragma unroll
+            for (int j = BPT - 1; j >= 0; --j) {
+                if (above < T && above + hb[j] >= T) { sh.cut_bin = BPT * tid + j; sh.above = above; sh.in_bin = hb[j]; }
+                above += hb[j];
+            }
+        }
+        __syncthreads();
+    }
+    const int cut_bin = sh.cut_bin, in_bin = sh.in_bin;
+    const int need = T - sh.above;                        // rows wanted from the cut bin, 1..in_bin
+
+    if (in_bin <= kTopkBoundaryCap) {
+        // one pass over the kept rows: composite = (score key, ~class-major position).  Flat over the
+        // Cf x K slots, four independent loads in flight per thread.
+        const int slots = Cf * K;
+        for (int s0 = tid; s0 < slots; s0 += 4 * THREADS) {
+            float sc[4];
+            int pos[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int s = s0 + u * THREADS;
+                const int c = s < slots ? s / K : 0;
+                const int t = s - c * K;
+                const bool ok = s < slots && t < offs[c + 1] - offs[c];
+                pos[u] = ok ? offs[c] + t : -1;
+                sc[u] = ok ? kimg[(size_t)s * kKeptCols + 4] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (pos[u] < 0) continue;
+                const int bin = score_bin(sc[u]);
+                if (bin >= cut_bin) {
+                    const unsigned long long comp = ((unsigned long long)ordered_key(sc[u]) << 32) |
+                                                    (unsigned long long)(0xFFFFFFFFu - (uint32_t)pos[u]);
+                    if (bin > cut_bin || need == in_bin) sel[atomicAdd(&sh.n_sel, 1)] = comp;
+                    else cand[atomicAdd(&sh.n_cand, 1)] = comp;
+                }
+            }
+        }
+        __syncthreads();
+        if (need < in_bin) {
+            const int nc = sh.n_cand;
+            for (int i = tid; i < nc; i += THREADS) {
+                const unsigned long long me = cand[i];
+                int rank = 0;
+                for (int j = 0; j < nc; ++j) rank += cand[j] > me;
+                if (rank < need) sel[atomicAdd(&sh.n_sel, 1)] = me;
+            }
+            __syncthreads();
+        }
+    } else {
+        // crowded cut bin: S = the T-th largest score key by bit-wise bisection over the rows (read
+        // from global memory every pass -- slow, but only for en-masse ties).  One barrier per bit;
+        // the counters rotate over four slots (slot p+2 is cleared while p is in use).
+        auto count_keys = [&](uint32_t trial, bool strict) {
+            int c_ = 0;
+            for (int c = warp_id(); c < Cf; c += nwarps) {
+                const int cnt = offs[c + 1] - offs[c];
+                for (int t = lane; t < cnt; t += 32) {
+                    const uint32_t key = ordered_key(kimg[((size_t)c * K + t) * kKeptCols + 4]);
+                    c_ += strict ? key > trial : key >= trial;
+                }
+            }
+            return __reduce_add_sync(FULL, c_);
+        };
+        uint32_t S = 0u;
+        for (int bit = 31, pass = 0; bit >= 0; --bit, ++pass) {
+            const uint32_t trial = S | (1u << bit);
+            const int c = count_keys(trial, false);
+            if (lane == 0 && c) atomicAdd(&sh.cnt[pass & 3], c);
+            if (tid == 0) sh.cnt[(pass + 2) & 3] = 0;
+            __syncthreads();
+            if (sh.cnt[pass & 3] >= T) S = trial;
+        }
+        const int gt = count_keys(S, true);
+        __syncthreads();                                   // every thread is done reading cnt[]
+        if (tid == 0) sh.cnt[0] = 0;
+        __syncthreads();
+        if (lane == 0 && gt) atomicAdd(&sh.cnt[0], gt);
+        // ties per class, then their exclusive scan: ties are taken from the front (position order)
+        for (int c = warp_id(); c < Cf; c += nwarps) {
+            const int cnt = offs[c + 1] - offs[c];
+            int ties = 0;
+            for (int t = lane; t < cnt; t += 32) ties += ordered_key(kimg[((size_t)c * K + t) * kKeptCols + 4]) == S;
+            ties = __reduce_add_sync(FULL, ties);
+            if (lane == 0) tie_base[c] = ties;
+        }
+        __syncthreads();
+        if (warp_id() == 0) {
+            int base = 0;
+            for (int c0 = 0; c0 < Cf; c0 += 32) {
+                const int c = c0 + lane;
+                const int v = c < Cf ? tie_base[c] : 0;
+                int incl = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                if (c < Cf) tie_base[c] = base + incl - v;
+                base += __shfl_sync(FULL, incl, 31);
+            }
+        }
+        __syncthreads();
+        const int need_ties = T - sh.cnt[0];               // >= 1
+        for (int c = warp_id(); c < Cf; c += nwarps) {
+            const int cnt = offs[c + 1] - offs[c];
+            int running = tie_base[c];
+            for (int t0 = 0; t0 < cnt; t0 += 32) {
+                const int t = t0 + lane;
+                const uint32_t key = t < cnt ? ordered_key(kimg[((size_t)c * K + t) * kKeptCols + 4]) : 0u;
+                const bool tie = t < cnt && key == S;
+                const unsigned bal = __ballot_sync(FULL, tie);
+                const int trank = running + __popc(bal & ((1u << lane) - 1u));
+                if (t < cnt && (key > S || (tie && trank < need_ties)))
+                    sel[atomicAdd(&sh.n_sel, 1)] = ((unsigned long long)key << 32) |
+                                                   (unsigned long long)(0xFFFFFFFFu - (uint32_t)(offs[c] + t));
+                running += __popc(bal);
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- order the T selected rows: descending score, ties by class-major position ----
+    const unsigned long long* ordered;
+    if (T <= kTopkBoundaryCap) {
+        unsigned long long* sorted = cand;                 // the candidates are no longer needed
+        for (int r = tid; r < T; r += THREADS) {
+            const unsigned long long me = sel[r];
+            int rank = 0;
+            for (int j = 0; j < T; ++j) rank += sel[j] > me;
+            sorted[rank] = me;
+        }
+        ordered = sorted;
+        __syncthreads();
+    } else {
+        for (int i = T + tid; i < t2; i += THREADS) sel[i] = 0ull;
+        bitonic_sort_desc(sel, t2);
+        ordered = sel;
+    }
+    for (int r = tid; r < T; r += THREADS) {
+        const int pos = (int)(0xFFFFFFFFu - (uint32_t)(ordered[r] & 0xFFFFFFFFull));
+        int c_lo = 0, c_hi = Cf;               // largest c with offs[c] <= pos
+        while (c_hi - c_lo > 1) {
+            const int mid = (c_lo + c_hi) >> 1;
+            if (offs[mid] <= pos) c_lo = mid; else c_hi = mid;
+        }
+        write_det_row(dimg, aimg, kimg, K, c_lo, pos - offs[c_lo], r);
+    }
+    if (tid == 0) ta.det_count[img] = T;
+}
+
+__global__ void __launch_bounds__(kTopkThreads)
+image_topk_kernel(TopkArgs ta) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint32_t s_hist[2048];
-    __shared__ int s_misc[4 + kNmsThreads / 32];
-    __shared__ int s_valid, s_nkeep;
-    KernelTrace trace_(TR_NMS);
+    __shared__ TopkShared<kTopkThreads> sh;
+    KernelTrace trace_(TR_TOPK);
     griddep_wait();
     griddep_launch_dependents();
+    image_topk_body<kTopkThreads>(smem, sh, ta, blockIdx.x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 4. segment_nms: one CTA per (image, foreground class)
+// ---------------------------------------------------------------------------------------------
+// Returns the number of kept rows of the segment (kept_count[seg] is written by the caller).
+__device__ int nms_segment(const KernelTrace& tr, const NmsArgs& a, unsigned char* smem, uint32_t* s_hist, int* s_misc, int& s_valid, int& s_nkeep,
+                           const float* __restrict__ scores, const float2* __restrict__ rowstat,
+                           const int* __restrict__ cand_count, const uint2* __restrict__ cand,
+                           const float4* __restrict__ boxes, const float4* __restrict__ priors, float* __restrict__ kept,
+                           int* __restrict__ status, int* __restrict__ score_hist) {
     const int seg = blockIdx.x;
     const int img = seg / a.Cf;
     const int lane = lane_id();
+    tr.mark(0);
     int n_raw = cand_count[seg];
-    if (n_raw == 0) {
-        if (threadIdx.x == 0) kept_count[seg] = 0;
-        return;
-    }
+    if (n_raw == 0) return 0;
     // carve: keys[key_slots] u64 | sorted[K] u64 | box[K] float4 | area[K] | mask[K * kwords] | keep[K]
     const int key_slots = a.cand_cap > kMaxPerClass ? a.cand_cap : kMaxPerClass;
     const int kwords = (a.K + 31) >> 5;
@@ -789,14 +1099,15 @@ segment_nms_kernel(NmsArgs a, const float* __restrict__ scores, const float2* __
 
     const bool overflow = n_raw > a.cand_cap;
     if (threadIdx.x == 0) s_valid = 0;
+    if (threadIdx.x == 0 && status != nullptr) {
+        if (n_raw > kRankSortMax) atomicAdd(&status[2], 1);
+        atomicMax(&status[3], n_raw);
+    }
     if (overflow) {
         // the candidate list is incomplete: redo this (image, class) exactly from the score column
         if (threadIdx.x == 0 && status != nullptr) atomicAdd(&status[1], 1);
         n_raw = exact_select_column(a, img, a.first_fg + (seg - img * a.Cf), scores, rowstat, keys, s_hist, s_misc);
-        if (n_raw == 0) {
-            if (threadIdx.x == 0) kept_count[seg] = 0;
-            return;
-        }
+        if (n_raw == 0) return 0;
         if (threadIdx.x == 0) s_valid = n_raw;
     }
     __syncthreads();
@@ -828,11 +1139,9 @@ segment_nms_kernel(NmsArgs a, const float* __restrict__ scores, const float2* __
         for (int t = n_raw + threadIdx.x; t < fill; t += blockDim.x) keys[t] = 0ull;
     }
     __syncthreads();
+    tr.mark(1);
     const int n = min(s_valid, a.K);             // box_utils.py:186-188 top-k
-    if (n == 0) {
-        if (threadIdx.x == 0) kept_count[seg] = 0;
-        return;
-    }
+    if (n == 0) return 0;
 
     // ---- order: (score desc, anchor asc) ----
     if (by_rank) {
@@ -856,8 +1165,9 @@ segment_nms_kernel(NmsArgs a, const float* __restrict__ scores, const float2* __
         __syncthreads();
     }
     const int words = (n + 31) >> 5;
+    tr.mark(2);
 
-    // ---- boxes of the n best: decode + to_corners only these ----
+    // ---- boxes of the n best: decode + to_corners only these; the diagonal mask words start at 0 ----
     for (int t = threadIdx.x; t < n; t += blockDim.x) {
         const uint32_t anchor = 0xFFFFFFFFu - (uint32_t)(sorted[t] & 0xFFFFFFFFull);
         float4 bx = boxes[(size_t)img * a.A + anchor];
@@ -873,49 +1183,78 @@ segment_nms_kernel(NmsArgs a, const float* __restrict__ scores, const float2* __
         }
         sbox[t] = bx;
         sarea[t] = fmul(fsub(bx.z, bx.x), fsub(bx.w, bx.y));          // torchvision: unclamped area
+        mask[(size_t)t * words + (t >> 5)] = 0u;
     }
     __syncthreads();
+    tr.mark(3);
 
-    // ---- IoU bit matrix: bit j of row i set <=> box i suppresses box j (j > i).  A warp takes a row,
-    //      its lanes a word of 32 columns (ballot -> one store); a short last word (n mod 32 <= 8) is
-    //      done transposed -- lanes over rows, a loop over its few columns -- instead of with 32-lane
-    //      items that would be mostly idle. ----
+    // ---- IoU bit matrix: bit j of row i set <=> box i suppresses box j (j > i) ----
+    const int nwarps = blockDim.x >> 5;
+    // (a) words right of the diagonal: a warp takes a row, its lanes the 32 columns of a word
+    //     (ballot -> one store).  A short last word (n mod 32 <= 8) is done transposed -- lanes over
+    //     rows, a loop over its few columns -- instead of with mostly idle 32-lane items.
     const int tail = n & 31;
     const bool tail_transposed = tail != 0 && tail <= 8 && words > 1;
     const int words_main = tail_transposed ? words - 1 : words;
-    const int nwarps = blockDim.x >> 5;
     for (int i = warp_id(); i < n; i += nwarps) {
         const float4 bi = sbox[i];
         const float ai = sarea[i];
-        for (int w = i >> 5; w < words_main; ++w) {
-            const int j = (w << 5) + lane;
-            const bool in_range = j > i && j < n;
-            const int jj = in_range ? j : i;
-            bool slow;
-            bool sup = pair_suppressed(a, bi, ai, sbox[jj], sarea[jj], slow);
-            if (__any_sync(FULL, slow && in_range)) {
-                if (slow) sup = pair_suppressed_slow(a, bi, ai, sbox[jj], sarea[jj]);
+        // four words per round: the loads and tests of a round are independent, the stores come last
+        for (int w0 = (i >> 5) + 1; w0 < words_main; w0 += 4) {
+            uint32_t bits[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = ((w0 + u) << 5) + lane;
+                const bool in_range = j < n && w0 + u < words_main;
+                const int jj = in_range ? j : i;
+                const bool sup = pair_suppressed(a, bi, ai, sbox[jj], sarea[jj], in_range);
+                bits[u] = __ballot_sync(FULL, sup);
             }
-            const uint32_t bits = __ballot_sync(FULL, sup && in_range);
-            if (lane == 0) mask[(size_t)i * words + w] = bits;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (lane == 0 && w0 + u < words_main) mask[(size_t)i * words + w0 + u] = bits[u];
         }
     }
     if (tail_transposed) {
         const int j0 = n - tail;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        for (int i0 = warp_id() * 32; i0 < j0; i0 += nwarps * 32) {
+            const int i = i0 + lane;                   // i < j0 always (j0 is a multiple of 32)
             const float4 bi = sbox[i];
             const float ai = sarea[i];
             uint32_t bits = 0u;
-            for (int j = max(j0, i + 1); j < n; ++j) {
-                bool slow;
-                bool sup = pair_suppressed(a, bi, ai, sbox[j], sarea[j], slow);
-                if (slow) sup = pair_suppressed_slow(a, bi, ai, sbox[j], sarea[j]);
+            for (int j = j0; j < n; ++j) {
+                const bool sup = pair_suppressed(a, bi, ai, sbox[j], sarea[j], true);
                 bits |= sup ? 1u << (j & 31) : 0u;
             }
             mask[(size_t)i * words + words - 1] = bits;
         }
     }
+    // (b) diagonal words: the 32 x 32 block of chunk c holds 496 unordered pairs; rotation d pairs
+    //     lane l with lane (l + d) mod 32, so 16 warp steps cover them all with every lane busy
+    //     (d == 16: half the lanes).  Suppressions are rare: shared-memory atomicOr.
+    for (int c = 0; c < words; ++c) {
+        const int r0 = c << 5;
+        const int rows_c = min(32, n - r0);
+        for (int d0 = 1 + 2 * warp_id(); d0 <= 16; d0 += 2 * nwarps) {
+            bool sup[2];
+            int row[2], bit[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int d = d0 + u;
+                const int o = (lane + d) & 31;
+                const int lo = min(lane, o), hi = max(lane, o);
+                const bool active = d <= 16 && hi < rows_c && (d < 16 || lane < 16);
+                const int i = r0 + (active ? lo : 0), j = r0 + (active ? hi : 0);
+                sup[u] = pair_suppressed(a, sbox[i], sarea[i], sbox[j], sarea[j], active);
+                row[u] = i; bit[u] = hi;
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                if (sup[u]) atomicOr(&mask[(size_t)row[u] * words + c], 1u << bit[u]);
+        }
+    }
     __syncthreads();
+    tr.mark(4);
 
     // ---- greedy sweep in score order (warp 0).  Lane l owns word l of the suppressed set; rows are
     //      resolved 32 at a time: the chunk's diagonal words are exchanged up front, the sequential
@@ -945,9 +1284,10 @@ segment_nms_kernel(NmsArgs a, const float* __restrict__ scores, const float2* __
             if ((kbits >> lane) & 1u) keep[nkeep + __popc(kbits & ((1u << lane) - 1u))] = r0 + lane;
             nkeep += __popc(kbits);
         }
-        if (lane == 0) { s_nkeep = nkeep; kept_count[seg] = nkeep; }
+        if (lane == 0) s_nkeep = nkeep;
     }
     __syncthreads();
+    tr.mark(5);
     const int nkeep = s_nkeep;
     float* out = kept + (size_t)seg * a.K * kKeptCols;
     for (int t = threadIdx.x; t < nkeep; t += blockDim.x) {
@@ -961,230 +1301,39 @@ segment_nms_kernel(NmsArgs a, const float* __restrict__ scores, const float2* __
         o[5] = __uint_as_float(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
         atomicAdd(score_hist + (size_t)img * kScoreBins + score_bin(score), 1);
     }
+    return nkeep;
 }
 
-// ---------------------------------------------------------------------------------------------
-// 5. image_topk: one CTA per image
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void write_det_row(float* dets, int* anchors, const float* kept, int K, int cls, int slot,
-                                              int out_row) {
-    const float* src = kept + ((size_t)cls * K + slot) * kKeptCols;
-    float* o = dets + (size_t)out_row * 6;
-    o[0] = src[0]; o[1] = src[1]; o[2] = src[2]; o[3] = src[3];
-    o[4] = (float)(cls + 1);                                           // postprocessor.py:66
-    o[5] = src[4];
-    if (anchors != nullptr) anchors[out_row] = (int)__float_as_uint(src[5]);
-}
-
-struct TopkShared {
-    int wsum[kTopkThreads / 32];
-    int warp_tot[kTopkThreads / 32];
-    int cnt[4];
-    int n_total, n_sel, n_tie, n_cand, cut_bin, above, in_bin;
-};
-
-// Final top-k (postprocessor.py:70-74): the T best of the image's kept rows, descending score,
-// ties by class-major position.  The NMS kernel has already histogrammed the kept scores, so the
-// cut is found with one suffix scan; rows above the cut bin are taken, the cut bin is ranked
-// exactly.  A cut bin too crowded to rank (scores tied en masse) falls back to a bit-wise bisection.
-__global__ void __launch_bounds__(kTopkThreads)
-image_topk_kernel(int Cf, int K, int T, int det_cap, const int* __restrict__ kept_count, const float* __restrict__ kept,
-                  const int* __restrict__ score_hist, float* __restrict__ dets, int* __restrict__ det_count,
-                  int* __restrict__ det_anchor) {
+__global__ void __launch_bounds__(kNmsThreads)
+segment_nms_kernel(NmsArgs a, TopkArgs ta, const float* __restrict__ scores, const float2* __restrict__ rowstat,
+                   const int* __restrict__ cand_count, const uint2* __restrict__ cand,
+                   const float4* __restrict__ boxes, const float4* __restrict__ priors, int* __restrict__ kept_count,
+                   float* __restrict__ kept, int* __restrict__ status, int* __restrict__ score_hist,
+                   int* __restrict__ image_done) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ TopkShared sh;
-    KernelTrace trace_(TR_TOPK);
+    __shared__ uint32_t s_hist[2048];
+    __shared__ int s_misc[4 + kNmsThreads / 32];
+    __shared__ int s_valid, s_nkeep, s_ticket;
+    KernelTrace trace_(TR_NMS);
     griddep_wait();
     griddep_launch_dependents();
-    const int img = blockIdx.x;
-    const int lane = lane_id();
-    const int tid = threadIdx.x;
-    constexpr int nwarps = kTopkThreads / 32;
-    int t2 = 32;
-    while (t2 < T) t2 <<= 1;
-    int* offs = reinterpret_cast<int*>(smem);                              // [Cf + 1]
-    unsigned long long* sel = reinterpret_cast<unsigned long long*>(smem + round_up((size_t)(Cf + 1) * 4, 16));   // [t2]
-    unsigned long long* cand = sel + t2;                                   // [kTopkBoundaryCap] (later: sorted)
-    uint32_t* skey = reinterpret_cast<uint32_t*>(cand + kTopkBoundaryCap); // [Cf*K] fallback only
-    const int* kc = kept_count + (size_t)img * Cf;
-    const float* kimg = kept + (size_t)img * Cf * K * kKeptCols;
-    float* dimg = dets + (size_t)img * det_cap * 6;
-    int* aimg = det_anchor ? det_anchor + (size_t)img * det_cap : nullptr;
-
-    // the histogram loads go out first (8 bins per thread, higher bins = larger scores)
-    static_assert(kScoreBins == 8 * kTopkThreads, "eight bins per thread");
-    int hb[8];
-    if (T > 0) {
-        const int4* h4 = reinterpret_cast<const int4*>(score_hist + (size_t)img * kScoreBins) + 2 * tid;
-        const int4 lo = h4[0], hi = h4[1];
-        hb[0] = lo.x; hb[1] = lo.y; hb[2] = lo.z; hb[3] = lo.w; hb[4] = hi.x; hb[5] = hi.y; hb[6] = hi.z; hb[7] = hi.w;
-    }
-    // exclusive scan of the per-class counts (warp 0, 32 classes per round)
-    if (warp_id() == 0) {
-        int base = 0;
-        for (int c0 = 0; c0 < Cf; c0 += 32) {
-            const int c = c0 + lane;
-            const int v = c < Cf ? kc[c] : 0;
-            int incl = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o) incl += t;
-            }
-            if (c < Cf) offs[c] = base + incl - v;
-            base += __shfl_sync(FULL, incl, 31);
-        }
-        if (lane == 0) {
-            offs[Cf] = base;
-            sh.n_total = base; sh.n_sel = 0; sh.n_tie = 0; sh.n_cand = 0; sh.cut_bin = -1; sh.above = 0; sh.in_bin = 0;
-            sh.cnt[0] = sh.cnt[1] = sh.cnt[2] = sh.cnt[3] = 0;
-        }
-    }
+    const int seg = blockIdx.x;
+    const int img = seg / a.Cf;
+    const int nkeep = nms_segment(trace_, a, smem, s_hist, s_misc, s_valid, s_nkeep, scores, rowstat, cand_count, cand, boxes,
+                                  priors, kept, status, score_hist);
+    if (threadIdx.x == 0) kept_count[seg] = nkeep;
+    trace_.mark(6);
+    if (image_done == nullptr) return;                     // the final top-k has its own launch
+    // The last segment of an image to finish runs the image's final top-k (fence + ticket: its
+    // reads of the other segments' kept rows, counts and histogram bumps are ordered after them).
+    __threadfence();
     __syncthreads();
-    const int n = sh.n_total;
-
-    if (T <= 0 || n <= T) {
-        // class-major order, descending score inside a class            postprocessor.py:68-70
-        for (int c = warp_id(); c < Cf; c += nwarps) {
-            const int cnt = offs[c + 1] - offs[c];
-            for (int t = lane; t < cnt; t += 32) write_det_row(dimg, aimg, kimg, K, c, t, offs[c] + t);
-        }
-        if (tid == 0) det_count[img] = n;
-        return;
-    }
-
-    // ---- cut bin: above(bin) < T <= above(bin) + hist[bin] ----
-    {
-        int own = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) own += hb[j];
-        int incl = own;                                   // suffix sum inside the warp (towards higher lanes)
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_down_sync(FULL, incl, o);
-            if (lane + o < 32) incl += t;
-        }
-        if (lane == 0) sh.warp_tot[warp_id()] = incl;
-        __syncthreads();
-        const int wt = lane < nwarps ? sh.warp_tot[lane] : 0;
-        const int higher = __reduce_add_sync(FULL, lane > warp_id() ? wt : 0);
-        int above = higher + incl - own;
-        if (above < T && above + own >= T) {
-#pragma unroll
-            for (int j = 7; j >= 0; --j) {
-                if (above < T && above + hb[j] >= T) { sh.cut_bin = 8 * tid + j; sh.above = above; sh.in_bin = hb[j]; }
-                above += hb[j];
-            }
-        }
-        __syncthreads();
-    }
-    const int cut_bin = sh.cut_bin, in_bin = sh.in_bin;
-    const int need = T - sh.above;                        // rows wanted from the cut bin, 1..in_bin
-
-    if (in_bin <= kTopkBoundaryCap) {
-        // one pass over the kept rows: composite = (score key, ~class-major position)
-        for (int c = warp_id(); c < Cf; c += nwarps) {
-            const int cnt = offs[c + 1] - offs[c];
-            for (int t = lane; t < cnt; t += 32) {
-                const float sc = kimg[((size_t)c * K + t) * kKeptCols + 4];
-                const int bin = score_bin(sc);
-                if (bin >= cut_bin) {
-                    const unsigned long long comp = ((unsigned long long)ordered_key(sc) << 32) |
-                                                    (unsigned long long)(0xFFFFFFFFu - (uint32_t)(offs[c] + t));
-                    if (bin > cut_bin || need == in_bin) sel[atomicAdd(&sh.n_sel, 1)] = comp;
-                    else cand[atomicAdd(&sh.n_cand, 1)] = comp;
-                }
-            }
-        }
-        __syncthreads();
-        if (need < in_bin) {
-            const int nc = sh.n_cand;
-            for (int i = tid; i < nc; i += kTopkThreads) {
-                const unsigned long long me = cand[i];
-                int rank = 0;
-                for (int j = 0; j < nc; ++j) rank += cand[j] > me;
-                if (rank < need) sel[atomicAdd(&sh.n_sel, 1)] = me;
-            }
-            __syncthreads();
-        }
-    } else {
-        // crowded cut bin: S = the T-th largest score key by bit-wise bisection over all rows.  One
-        // barrier per bit; the counters rotate over four slots (slot p+2 is cleared while p is in use).
-        for (int c = warp_id(); c < Cf; c += nwarps) {
-            const int cnt = offs[c + 1] - offs[c];
-            for (int t = lane; t < cnt; t += 32) skey[offs[c] + t] = ordered_key(kimg[((size_t)c * K + t) * kKeptCols + 4]);
-        }
-        __syncthreads();
-        uint32_t S = 0u;
-        for (int bit = 31, pass = 0; bit >= 0; --bit, ++pass) {
-            const uint32_t trial = S | (1u << bit);
-            int c = 0;
-            for (int i = tid; i < n; i += kTopkThreads) c += skey[i] >= trial;
-            c = __reduce_add_sync(FULL, c);
-            if (lane == 0 && c) atomicAdd(&sh.cnt[pass & 3], c);
-            if (tid == 0) sh.cnt[(pass + 2) & 3] = 0;
-            __syncthreads();
-            if (sh.cnt[pass & 3] >= T) S = trial;
-        }
-        int gt = 0;
-        for (int i = tid; i < n; i += kTopkThreads) gt += skey[i] > S;
-        gt = __reduce_add_sync(FULL, gt);
-        __syncthreads();                                   // every thread is done reading cnt[]
-        if (tid == 0) sh.cnt[0] = 0;
-        __syncthreads();
-        if (lane == 0 && gt) atomicAdd(&sh.cnt[0], gt);
-        __syncthreads();
-        const int need_ties = T - sh.cnt[0];               // >= 1
-        // ordered pass (position order) so that ties are taken from the front
-        for (int base = 0; base < n; base += kTopkThreads) {
-            const int i = base + tid;
-            const uint32_t key = i < n ? skey[i] : 0u;
-            const bool tie = i < n && key == S;
-            const unsigned bal = __ballot_sync(FULL, tie);
-            if (lane == 0) sh.wsum[warp_id()] = __popc(bal);
-            __syncthreads();
-            int before = sh.n_tie, total = 0;
-            for (int w = 0; w < nwarps; ++w) {
-                const int x = sh.wsum[w];
-                if (w < warp_id()) before += x;
-                total += x;
-            }
-            const int trank = before + __popc(bal & ((1u << lane) - 1u));
-            if (i < n && (key > S || (tie && trank < need_ties)))
-                sel[atomicAdd(&sh.n_sel, 1)] = ((unsigned long long)key << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)i);
-            __syncthreads();
-            if (tid == 0) sh.n_tie += total;
-            __syncthreads();
-        }
-    }
-
-    // ---- order the T selected rows: descending score, ties by class-major position ----
-    const unsigned long long* ordered;
-    if (T <= kTopkBoundaryCap) {
-        unsigned long long* sorted = cand;                 // the candidates are no longer needed
-        for (int r = tid; r < T; r += kTopkThreads) {
-            const unsigned long long me = sel[r];
-            int rank = 0;
-            for (int j = 0; j < T; ++j) rank += sel[j] > me;
-            sorted[rank] = me;
-        }
-        ordered = sorted;
-        __syncthreads();
-    } else {
-        for (int i = T + tid; i < t2; i += kTopkThreads) sel[i] = 0ull;
-        bitonic_sort_desc(sel, t2);
-        ordered = sel;
-    }
-    for (int r = tid; r < T; r += kTopkThreads) {
-        const int pos = (int)(0xFFFFFFFFu - (uint32_t)(ordered[r] & 0xFFFFFFFFull));
-        int c_lo = 0, c_hi = Cf;               // largest c with offs[c] <= pos
-        while (c_hi - c_lo > 1) {
-            const int mid = (c_lo + c_hi) >> 1;
-            if (offs[mid] <= pos) c_lo = mid; else c_hi = mid;
-        }
-        write_det_row(dimg, aimg, kimg, K, c_lo, pos - offs[c_lo], r);
-    }
-    if (tid == 0) det_count[img] = T;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(image_done + img, 1);
+    __syncthreads();
+    if (s_ticket != a.Cf - 1) return;
+    __threadfence();
+    TopkShared<kNmsThreads>& sh = *reinterpret_cast<TopkShared<kNmsThreads>*>(s_hist);
+    image_topk_body<kNmsThreads>(smem, sh, ta, img);
 }
 
 __global__ void widen_keep_kernel(const int* __restrict__ src, const int* __restrict__ count, long long* __restrict__ dst,
@@ -1217,6 +1366,7 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
     float* kept = (float*)(ws + pl.off_kept);
     int* status = (int*)(ws + pl.off_status);
     int* score_hist = (int*)(ws + pl.off_score_hist);
+    int* image_done = (int*)(ws + pl.off_image_done);
 
     const ScoreGrid& g = pl.g;
     const int grid = pl.grid;
@@ -1288,30 +1438,37 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
         a.converter = pl.converter; a.box_input = pl.box_input; a.score_thr = p->score_threshold;
         a.xy_scale = p->xy_scale; a.wh_scale = p->wh_scale;
         nms_threshold_split(p->overlap_threshold, a);
+        nms_threshold_screen(p->overlap_threshold, a);
+        TopkArgs ta;
+        ta.Cf = pl.Cf; ta.K = pl.K; ta.T = pl.T; ta.det_cap = pl.det_cap; ta.kept_count = kept_count; ta.kept = kept;
+        ta.score_hist = score_hist; ta.dets = dets_out; ta.det_count = count_out; ta.det_anchor = anchor_out;
         const int kwords = (pl.K + 31) / 32;
         const size_t key_slots = pl.cand_cap > kMaxPerClass ? pl.cand_cap : kMaxPerClass;
-        const size_t smem = key_slots * 8 + (size_t)(pl.K + 1) * (8 + 16 + 4 + 4) + (size_t)pl.K * kwords * 4 + 64;
+        const size_t nms_smem = key_slots * 8 + (size_t)(pl.K + 1) * (8 + 16 + 4 + 4) + (size_t)pl.K * kwords * 4 + 64;
+        // The final top-k can run in the last segment CTA of every image (fence + ticket) instead of
+        // in its own launch.  Measured on B200 (tools/graph_timeline.py) the 128-thread tail is slower
+        // than the launch it saves unless the batch is large, so it is opt-in: SSD_TOPK=fused.
+        const size_t topk_smem = topk_smem_bytes(pl.Cf, pl.T);
+        bool fused_topk = false;
+        { const char* e = getenv("SSD_TOPK"); if (e && e[0] == 'f') fused_topk = topk_smem <= nms_smem + 16 * 1024; }
+        const size_t smem = fused_topk && topk_smem > nms_smem ? topk_smem : nms_smem;
         SSD_CUDA(cudaFuncSetAttribute(segment_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        LaunchTimer lt_("nms", st);
-        SSD_CUDA(launch_pdl(segment_nms_kernel, dim3(pl.B * pl.Cf), dim3(kNmsThreads), smem, st, a, scores,
-                            (const float2*)rowstat, (const int*)cand_count, (const uint2*)cand, (const float4*)boxes,
-                            (const float4*)priors, kept_count, kept, status, score_hist));
-        SSD_CUDA(cudaGetLastError());
-    count_launch();
-    }
-    {
-        int t2 = 32;
-        while (t2 < pl.T) t2 <<= 1;
-        const size_t smem = round_up((size_t)(pl.Cf + 1) * 4, 16) + (size_t)(pl.T > 0 ? t2 : 0) * 8 +
-                            (size_t)kTopkBoundaryCap * 8 + round_up((size_t)pl.Cf * pl.K * 4, 16) + 64;
-        SSD_REQUIRE(smem <= 224 * 1024, SSD_ERR_UNSUPPORTED, "ssd_postprocess: final top-k needs %zu bytes of shared memory", smem);
-        SSD_CUDA(cudaFuncSetAttribute(image_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        LaunchTimer lt_("topk", st);
-        SSD_CUDA(launch_pdl(image_topk_kernel, dim3(pl.B), dim3(kTopkThreads), smem, st, pl.Cf, pl.K, pl.T, pl.det_cap,
-                            (const int*)kept_count, (const float*)kept, (const int*)score_hist, dets_out, count_out,
-                            anchor_out));
-        SSD_CUDA(cudaGetLastError());
-    count_launch();
+        {
+            LaunchTimer lt_("nms", st);
+            SSD_CUDA(launch_pdl(segment_nms_kernel, dim3(pl.B * pl.Cf), dim3(kNmsThreads), smem, st, a, ta, scores,
+                                (const float2*)rowstat, (const int*)cand_count, (const uint2*)cand, (const float4*)boxes,
+                                (const float4*)priors, kept_count, kept, status, score_hist,
+                                fused_topk ? image_done : (int*)nullptr));
+            count_launch();
+        }
+        if (!fused_topk) {
+            SSD_REQUIRE(topk_smem <= 224 * 1024, SSD_ERR_UNSUPPORTED,
+                        "ssd_postprocess: final top-k needs %zu bytes of shared memory", topk_smem);
+            SSD_CUDA(cudaFuncSetAttribute(image_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topk_smem));
+            LaunchTimer lt_("topk", st);
+            SSD_CUDA(launch_pdl(image_topk_kernel, dim3(pl.B), dim3(kTopkThreads), topk_smem, st, ta));
+            count_launch();
+        }
     }
     if (status_out != nullptr)
         SSD_CUDA(cudaMemcpyAsync(status_out, status, 4 * sizeof(int), cudaMemcpyDeviceToDevice, st));

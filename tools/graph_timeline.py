@@ -54,10 +54,13 @@ def main():
         torch.cuda.synchronize()
         lib.ssd_b200_trace_enable(None)
         t = buf.cpu()
-        used = [(int(t[i, 0]), int(t[i, 1]), i) for i in range(nslots) if int(t[i, 1]) > 0]
+        used = [(int(t[i, 0]), int(t[i, 1]), i) for i in range(min(nslots, 16)) if int(t[i, 1]) > 0]
+        marks = [int(t[i, 0]) for i in range(16, nslots) if int(t[i, 1]) == 1]
         t0 = min(u[0] for u in used)
         line = {NAMES.get(i, f"box_op{i - 10}"): [round((a - t0) / 1e3, 1), round((b - t0) / 1e3, 1)] for a, b, i in sorted(used)}
         line["span_us"] = round((max(u[1] for u in used) - t0) / 1e3, 1)
+        if marks:
+            line["marks_us"] = [round((m - t0) / 1e3, 1) for m in marks]
         print(json.dumps(line))
 
 
