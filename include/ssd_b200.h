@@ -104,11 +104,15 @@ SSD_API int ssd_match_per_prediction(const float* weights, int num_gt, int num_a
  *   target_out   [B,A,6] fp32, 8-byte aligned
  *   match_out    [B,A]   int32 matcher output per anchor, or NULL
  *   stats_out    [B,4]   int32 {positives, ignored, positives with NaN box, G_i}, or NULL
+ *   workspace    ssd_assign_workspace_bytes(batch, max_gt) bytes, 256-byte aligned (per-GT argmax
+ *                table and per-image counters; zeroed inside the call)
  * ---------------------------------------------------------------------------------------- */
+SSD_API size_t ssd_assign_workspace_bytes(int batch, int max_gt);
 SSD_API int ssd_assign_targets(const float* anchors, const float* gt_rows, int gt_cols,
                        const int32_t* gt_offsets, int max_gt, int batch, int num_anchors,
                        float matched_threshold, float unmatched_threshold, int force_match,
-                       float* target_out, int32_t* match_out, int32_t* stats_out, void* stream);
+                       float* target_out, int32_t* match_out, int32_t* stats_out, void* workspace,
+                       size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * a1/a6/a7  box format + coding, bf/utils/box_utils.py:16-36 and detection/box_coder.py:13-57.

@@ -52,8 +52,9 @@ _SIGNATURES = {
     "ssd_b200_trace_slots": (c_int, []),
     "ssd_pairwise_iou": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "ssd_match_per_prediction": (c_int, [c_void_p, c_int, c_int, c_float, c_float, c_int, c_void_p, c_void_p]),
+    "ssd_assign_workspace_bytes": (c_size_t, [c_int, c_int]),
     "ssd_assign_targets": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_float, c_int,
-                                   c_void_p, c_void_p, c_void_p, c_void_p]),
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ssd_box_transform": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_float,
                                   c_float, c_float, c_void_p]),
     "ssd_positive_mask": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),

@@ -1,35 +1,27 @@
 // Target assignment: detection/target_assigner.py:22-63 with detection/matcher.py:33-56 and
 // bf/utils/box_utils.py:16-23,38-101 fused into one launch for the whole batch.
 //
-// One thread-block CLUSTER per image.  The image's anchors are split across the CTAs of the
-// cluster; every thread owns one anchor at a time and walks the image's ground-truth boxes
-// (staged in shared memory):
+// Grid = (anchor blocks, images): one thread per anchor, every CTA stages its image's ground-truth
+// boxes in shared memory and walks them:
 //   * IoU in the reference's operation order, every fp32 op rounded separately (no FMA):
 //       inter = clamp(min(x2)-max(x1),0) * clamp(min(y2)-max(y1),0)
 //       iou   = inter / ((area_gt + area_anchor) - inter)                 box_utils.py:93-101
 //   * per-anchor running max over GT (first maximum wins = lowest GT index, NaN sticks),
 //   * per-GT argmax over anchors: warp REDUX max on the ordered IoU key, ballot for the lowest
-//     lane, one shared-memory atomicMax on a 64-bit (key, ~anchor) word per warp that beats the
-//     current best; after a cluster barrier every CTA reads its peers' tables through
-//     distributed shared memory and reduces them -- no global atomics, no second launch.
-//   * thresholds in fp32, then the forced match of every GT to its best anchor, colliding GTs
-//     resolved towards the highest GT index (sequential index_put semantics)  matcher.py:49-54
-//   * target rows written as coalesced float2 stores                target_assigner.py:38-58
-#include <cooperative_groups.h>
-
+//     lane, a shared-memory atomicMax on a 64-bit (key, ~anchor) word per warp that beats the
+//     CTA's best, then ONE global atomicMax per (CTA, GT) that saw an overlap at all;
+//   * thresholds in fp32 (matcher.py:49-50), target rows written as coalesced float2 stores
+//     (target_assigner.py:38-58);
+//   * the forced match of every GT to its best anchor (matcher.py:53-54) needs the argmax over ALL
+//     anchors of the image: the last CTA of an image to finish (fence + ticket) reads the merged
+//     table and rewrites those <= G rows, colliding GTs resolved towards the highest GT index
+//     (sequential index_put semantics).  No second launch, no cluster, any grid size.
 #include "common.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace ssd {
 
 constexpr int kAssignThreads = 256;
 constexpr int kMaxGtPerImage = 4096;
-constexpr int kForcedPending = -3;
-
-struct AssignSmem {
-    // dynamic layout: float4 gbox[G]; float garea[G]; float2 gcs[G]; u64 best[G]; int match[chunk]
-};
 
 __device__ __forceinline__ float clamped_area(float x1, float y1, float x2, float y2) {
     // (x2 - x1).clamp_(0) * (y2 - y1).clamp_(0)                      box_utils.py:46
@@ -55,40 +47,39 @@ __device__ __forceinline__ float4 corners_of(float4 c) {
     return make_float4(fsub(c.x, hw), fsub(c.y, hh), fadd(c.x, hw), fadd(c.y, hh));
 }
 
-__device__ __forceinline__ unsigned long long best_word(float iou, int anchor) {
-    uint32_t k = ordered_key(iou);
-    if (iou != iou) k = 0xFFFFFFFFu;                 // argmax treats NaN as the maximum
-    return ((unsigned long long)k << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)anchor);
+// Per-image scratch (zeroed by the caller's memset): [0] CTAs done, [1..3] positives / ignored /
+// positives with a NaN box, summed over the CTAs.
+constexpr int kAssignCounters = 4;
+
+__device__ __forceinline__ void row_class_counts(float cls, float4 bx, int& pos, int& ign, int& nan) {
+    const bool p = cls != (float)SSD_NEGATIVE_CLASS && cls != (float)SSD_IGNORE_CLASS;
+    pos = p;
+    ign = cls == (float)SSD_IGNORE_CLASS;
+    nan = p && (bx.x != bx.x || bx.y != bx.y || bx.z != bx.z || bx.w != bx.w);
 }
 
 __global__ void __launch_bounds__(kAssignThreads)
 assign_targets_kernel(const float4* __restrict__ anchors, const float* __restrict__ gt_rows, int gt_cols,
-                      const int32_t* __restrict__ gt_offsets, int A, int chunk, float matched_thr,
+                      const int32_t* __restrict__ gt_offsets, int A, int max_gt, float matched_thr,
                       float unmatched_thr, int force_match, float* __restrict__ target, int32_t* __restrict__ match_out,
-                      int32_t* __restrict__ stats) {
+                      int32_t* __restrict__ stats, int* __restrict__ counters, unsigned long long* __restrict__ gbest) {
     KernelTrace trace_(TR_ASSIGN);
     griddep_wait();
     griddep_launch_dependents();
-    cg::cluster_group cluster = cg::this_cluster();
-    const int csize = (int)cluster.num_blocks();
-    const int rank = (int)cluster.block_rank();
-    const int img = blockIdx.x / csize;
+    const int img = blockIdx.y;
     const int g0 = gt_offsets[img];
     const int G = gt_offsets[img + 1] - g0;
+    const int a_begin = blockIdx.x * kAssignThreads;
+    const int n_local = min(kAssignThreads, A - a_begin);
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // carve (all CTAs of the cluster use the same carve so mapped addresses line up)
     const int Gcap = G > 0 ? G : 1;
     float4* gbox = reinterpret_cast<float4*>(smem_raw);
-    unsigned long long* best = reinterpret_cast<unsigned long long*>(gbox + Gcap);
+    unsigned long long* best = reinterpret_cast<unsigned long long*>(gbox + Gcap);      // later: int anchor[G]
     float2* gcs = reinterpret_cast<float2*>(best + Gcap);
-    unsigned long long* merged = reinterpret_cast<unsigned long long*>(gcs + Gcap);
-    float* garea = reinterpret_cast<float*>(merged + Gcap);
-    int* match = reinterpret_cast<int*>(garea + Gcap);
-
-    const int a_begin = min(rank * chunk, A);
-    const int a_end = min(a_begin + chunk, A);
-    const int n_local = a_end - a_begin;
+    float* garea = reinterpret_cast<float*>(gcs + Gcap);
+    __shared__ int match[kAssignThreads];
+    __shared__ int s_last;
 
     for (int g = threadIdx.x; g < G; g += blockDim.x) {
         const float* row = gt_rows + (size_t)(g0 + g) * gt_cols;
@@ -96,105 +87,74 @@ assign_targets_kernel(const float4* __restrict__ anchors, const float* __restric
         gbox[g] = bx;
         garea[g] = clamped_area(bx.x, bx.y, bx.z, bx.w);
         gcs[g] = make_float2(row[SSD_CLASS_COL], row[SSD_SCORE_COL]);
-        best[g] = best_word(0.f, 0);      // an all-zero IoU row force-matches anchor 0
+        best[g] = 0ull;                   // nothing overlapping seen: stands for (IoU 0, anchor 0)
     }
     __syncthreads();
 
-    // ---- phase 1: per-anchor best GT, per-GT best anchor ----
-    if (G > 0) {
-        for (int base = 0; base < n_local; base += blockDim.x) {
-            const int la = base + threadIdx.x;
-            const bool valid = la < n_local;
-            const int a = a_begin + la;
-            float4 ab = make_float4(0.f, 0.f, 0.f, 0.f);
-            float aarea = 0.f;
-            if (valid) {
-                ab = corners_of(anchors[a]);
-                aarea = clamped_area(ab.x, ab.y, ab.z, ab.w);
-            }
-            // IoU 0 against every box so far: the state torch.max would be in after a row of zeros
-            float best_iou = 0.f;
-            int best_g = 0;
-            const bool a_degenerate = !(aarea > 0.f);
+    // ---- phase 1: per-anchor best GT, per-GT best anchor of this CTA ----
+    {
+        const int la = threadIdx.x;
+        const bool valid = la < n_local;
+        const int a = a_begin + la;
+        float4 ab = make_float4(0.f, 0.f, 0.f, 0.f);
+        float aarea = 0.f;
+        if (valid) {
+            ab = corners_of(anchors[a]);
+            aarea = clamped_area(ab.x, ab.y, ab.z, ab.w);
+        }
+        // IoU 0 against every box so far: the state torch.max would be in after a row of zeros
+        float best_iou = 0.f;
+        int best_g = 0;
+        const bool a_degenerate = !(aarea > 0.f);
 #pragma unroll 2
-            for (int g = 0; g < G; ++g) {
-                const float4 gb = gbox[g];
-                const float iw = fmaxf(fsub(fminf(gb.z, ab.z), fmaxf(gb.x, ab.x)), 0.f);
-                const float ih = fmaxf(fsub(fminf(gb.w, ab.w), fmaxf(gb.y, ab.y)), 0.f);
-                const float inter = fmul(iw, ih);
-                // Disjoint pairs have IoU +0 exactly: they can neither raise the anchor's running
-                // maximum nor beat the (0, anchor 0) entry every GT starts with, so the divide and
-                // both argmax updates are skipped unless some lane of the warp overlaps this box.
-                // (0/0 -> NaN needs both areas to be zero / NaN; NaN inter is not == 0.)
-                bool live = valid && !(inter == 0.f);
-                if (a_degenerate && valid) live = live || !(garea[g] > 0.f);
-                if (!__any_sync(FULL, live)) continue;
-                float v = 0.f;
-                if (live) {
-                    const float uni = fsub(fadd(garea[g], aarea), inter);
-                    v = (inter == 0.f && uni > 0.f) ? 0.f : fdiv(inter, uni);
+        for (int g = 0; g < G; ++g) {
+            const float4 gb = gbox[g];
+            const float iw = fmaxf(fsub(fminf(gb.z, ab.z), fmaxf(gb.x, ab.x)), 0.f);
+            const float ih = fmaxf(fsub(fminf(gb.w, ab.w), fmaxf(gb.y, ab.y)), 0.f);
+            const float inter = fmul(iw, ih);
+            // Disjoint pairs have IoU +0 exactly: they can neither raise the anchor's running
+            // maximum nor beat the (0, anchor 0) entry every GT starts with, so the divide and
+            // both argmax updates are skipped unless some lane of the warp overlaps this box.
+            // (0/0 -> NaN needs both areas to be zero / NaN; NaN inter is not == 0.)
+            bool live = valid && !(inter == 0.f);
+            if (a_degenerate && valid) live = live || !(garea[g] > 0.f);
+            if (!__any_sync(FULL, live)) continue;
+            float v = 0.f;
+            if (live) {
+                const float uni = fsub(fadd(garea[g], aarea), inter);
+                v = (inter == 0.f && uni > 0.f) ? 0.f : fdiv(inter, uni);
+            }
+            // torch.max(dim=0): first maximum wins, NaN propagates and sticks
+            if (!(v <= best_iou) && !(best_iou != best_iou)) { best_iou = v; best_g = g; }
+            // per-GT argmax over anchors
+            uint32_t key = live ? ordered_key(v) : 0u;
+            if (live && v != v) key = 0xFFFFFFFFu;
+            const uint32_t wmax = __reduce_max_sync(FULL, key);
+            if (wmax > 0x80000000u) {               // somebody overlaps (key(+0) == 0x80000000)
+                const unsigned bal = __ballot_sync(FULL, key == wmax);
+                if (lane_id() == __ffs(bal) - 1) {
+                    const unsigned long long w = ((unsigned long long)key << 32) |
+                                                 (unsigned long long)(0xFFFFFFFFu - (uint32_t)a);
+                    if (w > best[g]) atomicMax(&best[g], w);
                 }
-                // torch.max(dim=0): first maximum wins, NaN propagates and sticks
-                if (!(v <= best_iou) && !(best_iou != best_iou)) { best_iou = v; best_g = g; }
-                // per-GT argmax over anchors
-                uint32_t key = live ? ordered_key(v) : 0u;
-                if (live && v != v) key = 0xFFFFFFFFu;
-                const uint32_t wmax = __reduce_max_sync(FULL, key);
-                if (wmax > 0x80000000u) {               // somebody overlaps (key(+0) == 0x80000000)
-                    const unsigned bal = __ballot_sync(FULL, key == wmax);
-                    if (lane_id() == __ffs(bal) - 1) {
-                        const unsigned long long w = ((unsigned long long)key << 32) |
-                                                     (unsigned long long)(0xFFFFFFFFu - (uint32_t)a);
-                        if (w > best[g]) atomicMax(&best[g], w);
-                    }
-                }
-            }
-            if (valid) {
-                int m = best_g;
-                if (best_iou < unmatched_thr) m = SSD_NOT_MATCHED;              // matcher.py:49
-                else if (best_iou < matched_thr) m = SSD_IGNORE;                // matcher.py:50
-                match[la] = m;
             }
         }
-    } else {
-        for (int la = threadIdx.x; la < n_local; la += blockDim.x) match[la] = SSD_NOT_MATCHED;
+        int m = SSD_NOT_MATCHED;
+        if (G > 0) {
+            m = best_g;
+            if (best_iou < unmatched_thr) m = SSD_NOT_MATCHED;              // matcher.py:49
+            else if (best_iou < matched_thr) m = SSD_IGNORE;                // matcher.py:50
+        }
+        match[la] = m;
     }
+    __syncthreads();
 
-    // ---- merge the per-GT winners across the cluster through DSMEM ----
-    // Canonical DSMEM pattern: every CTA publishes its own table, cluster barrier, every CTA reads
-    // the peers' tables with remote loads and reduces locally.  (Remote atomics into one root
-    // table were observed NOT to be ordered by the cluster barrier on sm_100a.)
-    if (csize > 1 && G > 0 && force_match) {
-        __syncthreads();
-        cluster.sync();                                   // all local tables are final
+    // ---- phase 2: publish this CTA's per-GT winners ----
+    if (force_match) {
         for (int g = threadIdx.x; g < G; g += blockDim.x) {
-            unsigned long long m = best[g];
-            for (int r = 0; r < csize; ++r) {
-                if (r == rank) continue;
-                const unsigned long long* peer = cluster.map_shared_rank(best, r);
-                const unsigned long long v = peer[g];
-                m = v > m ? v : m;
-            }
-            merged[g] = m;
+            const unsigned long long w = best[g];
+            if (w != 0ull) atomicMax(&gbest[(size_t)img * max_gt + g], w);
         }
-        cluster.sync();                                   // nobody exits (or moves on) while peers still read
-        best = merged;
-    } else {
-        __syncthreads();
-    }
-
-    // ---- phase 2: forced matches (matcher.py:53-54), highest GT index wins a collision ----
-    if (force_match && G > 0) {
-        for (int g = threadIdx.x; g < G; g += blockDim.x) {
-            const int a = (int)(0xFFFFFFFFu - (uint32_t)(best[g] & 0xFFFFFFFFull));
-            if (a >= a_begin && a < a_end) match[a - a_begin] = kForcedPending;
-        }
-        __syncthreads();
-        for (int g = threadIdx.x; g < G; g += blockDim.x) {
-            const int a = (int)(0xFFFFFFFFu - (uint32_t)(best[g] & 0xFFFFFFFFull));
-            if (a >= a_begin && a < a_end) atomicMax(&match[a - a_begin], g);
-        }
-        __syncthreads();
     }
 
     // ---- phase 3: target rows, flat coalesced float2 stores over this CTA's [n_local, 6] slab ----
@@ -210,10 +170,9 @@ assign_targets_kernel(const float4* __restrict__ anchors, const float* __restric
             const float2 cs = gcs[m];
             v = part == 0 ? make_float2(bx.x, bx.y) : part == 1 ? make_float2(bx.z, bx.w) : cs;
             if (part == 2) {
-                const bool pos = cs.x != (float)SSD_NEGATIVE_CLASS && cs.x != (float)SSD_IGNORE_CLASS;
-                n_pos += pos;
-                n_ign += cs.x == (float)SSD_IGNORE_CLASS;
-                n_nan += pos && (bx.x != bx.x || bx.y != bx.y || bx.z != bx.z || bx.w != bx.w);
+                int p_, i_, n_;
+                row_class_counts(cs.x, bx, p_, i_, n_);
+                n_pos += p_; n_ign += i_; n_nan += n_;
             }
         } else if (m == SSD_IGNORE) {
             v = part == 2 ? make_float2((float)SSD_IGNORE_CLASS, (float)SSD_IGNORE_CLASS) : make_float2(0.f, 0.f);
@@ -223,20 +182,69 @@ assign_targets_kernel(const float4* __restrict__ anchors, const float* __restric
         }
         out[p] = v;
     }
-    if (match_out != nullptr) {
-        int32_t* mo = match_out + (size_t)img * A + a_begin;
-        for (int la = threadIdx.x; la < n_local; la += blockDim.x) mo[la] = match[la];
+    if (match_out != nullptr && threadIdx.x < n_local) match_out[(size_t)img * A + a_begin + threadIdx.x] = match[threadIdx.x];
+    int* cnt = counters + (size_t)img * kAssignCounters;
+    n_pos = __reduce_add_sync(FULL, n_pos);
+    n_ign = __reduce_add_sync(FULL, n_ign);
+    n_nan = __reduce_add_sync(FULL, n_nan);
+    if (lane_id() == 0) {
+        if (n_pos) atomicAdd(cnt + 1, n_pos);
+        if (n_ign) atomicAdd(cnt + 2, n_ign);
+        if (n_nan) atomicAdd(cnt + 3, n_nan);
     }
-    if (stats != nullptr) {
-        n_pos = __reduce_add_sync(FULL, n_pos);
-        n_ign = __reduce_add_sync(FULL, n_ign);
-        n_nan = __reduce_add_sync(FULL, n_nan);
-        if (lane_id() == 0) {
-            if (n_pos) atomicAdd(&stats[img * 4 + 0], n_pos);
-            if (n_ign) atomicAdd(&stats[img * 4 + 1], n_ign);
-            if (n_nan) atomicAdd(&stats[img * 4 + 2], n_nan);
+
+    // ---- phase 4: the last CTA of the image applies the forced matches and closes the statistics ----
+    // (the CTA barrier orders every thread's stores before thread 0's fence, which is cumulative)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(cnt, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (force_match && G > 0) {
+        int* ganchor = reinterpret_cast<int*>(best);                   // [G] (the 64-bit table is done with)
+        for (int g0_ = 0; g0_ < G; g0_ += blockDim.x) {
+            const int g = g0_ + threadIdx.x;
+            unsigned long long w = 0ull;
+            if (g < G) w = __ldcg(&gbest[(size_t)img * max_gt + g]);
+            if (g < G) ganchor[g] = w == 0ull ? 0 : (int)(0xFFFFFFFFu - (uint32_t)(w & 0xFFFFFFFFull));
         }
-        if (rank == 0 && threadIdx.x == 0) stats[img * 4 + 3] = G;
+        __syncthreads();
+        int d_pos = 0, d_ign = 0, d_nan = 0;
+        for (int g = threadIdx.x; g < G; g += blockDim.x) {
+            const int a = ganchor[g];
+            bool winner = true;                                        // the highest GT index wins a collision
+            for (int h = g + 1; h < G; ++h) winner = winner && ganchor[h] != a;
+            if (!winner) continue;
+            float* row = target + ((size_t)img * A + a) * SSD_TARGET_COLS;
+            const float2 o0 = __ldcg(reinterpret_cast<const float2*>(row));
+            const float2 o1 = __ldcg(reinterpret_cast<const float2*>(row) + 1);
+            const float2 o2 = __ldcg(reinterpret_cast<const float2*>(row) + 2);
+            int p_, i_, n_;
+            row_class_counts(o2.x, make_float4(o0.x, o0.y, o1.x, o1.y), p_, i_, n_);
+            d_pos -= p_; d_ign -= i_; d_nan -= n_;
+            const float4 bx = gbox[g];
+            const float2 cs = gcs[g];
+            row_class_counts(cs.x, bx, p_, i_, n_);
+            d_pos += p_; d_ign += i_; d_nan += n_;
+            reinterpret_cast<float2*>(row)[0] = make_float2(bx.x, bx.y);
+            reinterpret_cast<float2*>(row)[1] = make_float2(bx.z, bx.w);
+            reinterpret_cast<float2*>(row)[2] = cs;
+            if (match_out != nullptr) match_out[(size_t)img * A + a] = g;
+        }
+        if (d_pos) atomicAdd(cnt + 1, d_pos);
+        if (d_ign) atomicAdd(cnt + 2, d_ign);
+        if (d_nan) atomicAdd(cnt + 3, d_nan);
+        __threadfence();
+        __syncthreads();
+    }
+    if (stats != nullptr && threadIdx.x == 0) {
+        stats[img * 4 + 0] = atomicAdd(cnt + 1, 0);
+        stats[img * 4 + 1] = atomicAdd(cnt + 2, 0);
+        stats[img * 4 + 2] = atomicAdd(cnt + 3, 0);
+        stats[img * 4 + 3] = G;
     }
 }
 
@@ -346,57 +354,50 @@ extern "C" int ssd_match_per_prediction(const float* weights, int num_gt, int nu
     return SSD_OK;
 }
 
+extern "C" size_t ssd_assign_workspace_bytes(int batch, int max_gt) {
+    if (batch <= 0) return 256;
+    if (max_gt < 1) max_gt = 1;
+    return round_up((size_t)batch * kAssignCounters * sizeof(int), 256) +
+           round_up((size_t)batch * max_gt * sizeof(unsigned long long), 256);
+}
+
 extern "C" int ssd_assign_targets(const float* anchors, const float* gt_rows, int gt_cols, const int32_t* gt_offsets,
                                   int max_gt, int batch, int num_anchors, float matched_threshold,
                                   float unmatched_threshold, int force_match, float* target_out, int32_t* match_out,
-                                  int32_t* stats_out, void* stream) {
+                                  int32_t* stats_out, void* workspace, size_t workspace_bytes, void* stream) {
     SSD_REQUIRE(batch >= 0 && num_anchors >= 0 && max_gt >= 0, SSD_ERR_INVALID_ARGUMENT,
                 "ssd_assign_targets: negative shape");
     if (batch == 0 || num_anchors == 0) return SSD_OK;
-    SSD_REQUIRE(anchors && gt_offsets && target_out, SSD_ERR_INVALID_ARGUMENT, "ssd_assign_targets: null pointer");
+    SSD_REQUIRE(anchors && gt_offsets && target_out && workspace, SSD_ERR_INVALID_ARGUMENT,
+                "ssd_assign_targets: null pointer");
     SSD_REQUIRE(gt_rows || max_gt == 0, SSD_ERR_INVALID_ARGUMENT, "ssd_assign_targets: gt_rows is null");
     SSD_REQUIRE(gt_cols >= 6, SSD_ERR_INVALID_ARGUMENT, "ssd_assign_targets: gt rows need >= 6 columns, got %d", gt_cols);
     SSD_REQUIRE(matched_threshold >= unmatched_threshold, SSD_ERR_INVALID_ARGUMENT,
                 "ssd_assign_targets: matched_threshold < unmatched_threshold");
     SSD_REQUIRE(max_gt <= kMaxGtPerImage, SSD_ERR_UNSUPPORTED, "ssd_assign_targets: more than %d boxes per image",
                 kMaxGtPerImage);
+    SSD_REQUIRE(batch <= 65535, SSD_ERR_UNSUPPORTED, "ssd_assign_targets: more than 65535 images per call");
     SSD_REQUIRE(aligned(anchors, 16), SSD_ERR_MISALIGNED, "ssd_assign_targets: anchors not 16-byte aligned");
     SSD_REQUIRE(aligned(target_out, 8), SSD_ERR_MISALIGNED, "ssd_assign_targets: target not 8-byte aligned");
+    SSD_REQUIRE(aligned(workspace, 256), SSD_ERR_MISALIGNED, "ssd_assign_targets: workspace must be 256-byte aligned");
+    const size_t need = ssd_assign_workspace_bytes(batch, max_gt);
+    SSD_REQUIRE(workspace_bytes >= need, SSD_ERR_WORKSPACE, "ssd_assign_targets: workspace %zu < %zu bytes",
+                workspace_bytes, need);
     cudaStream_t st = (cudaStream_t)stream;
-    if (stats_out) SSD_CUDA(cudaMemsetAsync(stats_out, 0, sizeof(int32_t) * 4 * batch, st));
-
-    // cluster size: enough CTAs to cover the GPU about twice, at most 8 (portable limit)
-    int cl = 1;
-    const int want = (2 * sm_count() + batch - 1) / batch;
-    while (cl < 8 && cl < want) cl <<= 1;
-    while (cl > 1 && (num_anchors + cl - 1) / cl < kAssignThreads) cl >>= 1;
-    const int chunk = (num_anchors + cl - 1) / cl;
+    SSD_CUDA(cudaMemsetAsync(workspace, 0, need, st));
+    int* counters = (int*)workspace;
+    unsigned long long* gbest = (unsigned long long*)((unsigned char*)workspace +
+                                                      round_up((size_t)batch * kAssignCounters * sizeof(int), 256));
     const int gcap = max_gt > 0 ? max_gt : 1;
-    const size_t smem = (size_t)gcap * (sizeof(float4) + 2 * sizeof(unsigned long long) + sizeof(float2) + sizeof(float)) +
-                        (size_t)chunk * sizeof(int);
-    SSD_REQUIRE(smem <= 220 * 1024, SSD_ERR_UNSUPPORTED,
-                "ssd_assign_targets: %zu bytes of shared memory needed (anchors per CTA %d, boxes %d)", smem, chunk,
-                max_gt);
+    const size_t smem = (size_t)gcap * (sizeof(float4) + sizeof(unsigned long long) + sizeof(float2) + sizeof(float));
+    SSD_REQUIRE(smem <= 200 * 1024, SSD_ERR_UNSUPPORTED, "ssd_assign_targets: %zu bytes of shared memory needed (boxes %d)",
+                smem, max_gt);
     SSD_CUDA(cudaFuncSetAttribute(assign_targets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(batch * cl));
-    cfg.blockDim = dim3(kAssignThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cl;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 2;
+    dim3 grid((unsigned)((num_anchors + kAssignThreads - 1) / kAssignThreads), (unsigned)batch);
     LaunchTimer lt_("assign", st);
-    SSD_CUDA(cudaLaunchKernelEx(&cfg, assign_targets_kernel, (const float4*)anchors, gt_rows, gt_cols, gt_offsets,
-                                num_anchors, chunk, matched_threshold, unmatched_threshold, force_match, target_out,
-                                match_out, stats_out));
+    SSD_CUDA(launch_pdl(assign_targets_kernel, grid, dim3(kAssignThreads), smem, st, (const float4*)anchors, gt_rows,
+                        gt_cols, gt_offsets, num_anchors, gcap, matched_threshold, unmatched_threshold, force_match,
+                        target_out, match_out, stats_out, counters, gbest));
     count_launch();
     return SSD_OK;
 }

@@ -68,13 +68,14 @@ __device__ __forceinline__ float key_to_float(uint32_t k) {
 // device-side timeline (diagnostics): when a trace buffer is installed (ssd_b200_trace_enable),
 // every kernel records min(start) / max(end) of %globaltimer over its warps in its slot, so the
 // real overlap of the launches inside a replayed CUDA graph can be read back.  One pointer per
-// translation unit (no relocatable device code); a null pointer costs one load and a branch.
+// translation unit in constant memory (no relocatable device code); a null pointer costs one
+// constant load and a branch.
 // ---------------------------------------------------------------------------------------------
 enum TraceSlot {
     TR_ASSIGN = 0, TR_MINING_LOSS, TR_MINING_KEYS, TR_MINING_SELECT, TR_PASS1, TR_GATE, TR_PASS2, TR_NMS, TR_TOPK,
     TR_MISC, TR_BOX0 = 10, kTraceSlots = 24
 };
-static __device__ unsigned long long* tu_trace_buf = nullptr;
+static __constant__ unsigned long long* tu_trace_buf = nullptr;
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

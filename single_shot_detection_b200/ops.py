@@ -111,10 +111,12 @@ def _assign_targets(anchors: torch.Tensor, gt_rows: torch.Tensor, gt_offsets: to
     stats = torch.empty((batch, 4), dtype=torch.int32, device=dev)
     gt_cols = gt_rows.shape[1] if gt_rows.dim() == 2 else 6
     with torch.cuda.device(dev):
+        ws_bytes = N.lib().ssd_assign_workspace_bytes(batch, max_gt)
+        ws = workspace(ws_bytes, dev, "assign")
         N.check(N.lib().ssd_assign_targets(_ptr(anchors), _ptr(gt_rows) if gt_rows.numel() else None, gt_cols,
                                            _ptr(gt_offsets), max_gt, batch, num_anchors, matched_threshold,
                                            unmatched_threshold, int(force_match), _ptr(target), _ptr(match),
-                                           _ptr(stats), _stream()))
+                                           _ptr(stats), _ptr(ws), ws.numel(), _stream()))
     return target, match, stats
 
 

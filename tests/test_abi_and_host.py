@@ -50,7 +50,7 @@ def test_argument_validation_without_a_device():
     lib = N.lib()
     assert lib.ssd_box_transform(99, None, 4, None, 4, None, 1, 1, 1.0, 1.0, 0.0, None) == 1
     assert b"bad op" in lib.ssd_b200_last_error()
-    assert lib.ssd_assign_targets(None, None, 6, None, 0, -1, 10, 0.5, 0.5, 1, None, None, None, None) == 1
+    assert lib.ssd_assign_targets(None, None, 6, None, 0, -1, 10, 0.5, 0.5, 1, None, None, None, None, 0, None) == 1
     assert lib.ssd_hard_negative_mask(None, None, None, 1, 8, 3, 3.0, 1, 5.0, None, None, None, 0, None) == 1
     p = N.PostprocessParams()
     p.batch, p.num_anchors, p.num_cols, p.converter = 1, 8, 3, 7
