@@ -248,29 +248,23 @@ def run_ours(args):
     # ---- e2e: reference-shaped API, host buffers, H2D + D2H inside the timed region ----
     pipe_e = AnchorPipeline(w.cfg())
     T = w.max_total
-    dets_host = torch.empty((B * world, T, 6), dtype=torch.float32).pin_memory()
-    aux_host = torch.empty((B * world, 5), dtype=torch.int32).pin_memory()
 
-    def e2e_step(i):
-        gt, scores_h, locs_h = host_sets[i % nsets]
-        target, mask, dets = pipe_e.step(gt, anchors, scores_h, locs_h)     # list API: syncs on the counts
-        padded, counts, _, _ = pipe_e.postprocessor.last_padded
-        stats = matched_stats(pipe_e.target_assigner.last_stats, S.hard_negative_mining.last_stats
-                              if w.sampler == "hard_negative_mining" else None, counts)
-        if world > 1:
-            padded, counts, stats = sharding.all_gather_detections(padded, counts, stats, B * world)
-        dets_host.copy_(padded, non_blocking=True)
-        aux_host[:, 0].copy_(counts, non_blocking=True)
-        aux_host[:, 1:].copy_(stats, non_blocking=True)
+    # AnchorPipeline.stream: the reference-shaped step over a sequence of host batches, the H2D copies
+    # of batch i+1 overlapping the kernels of batch i; every batch's detections, counts and statistics
+    # are read back to pinned host memory before it is yielded (under torchrun: after the all-gather).
+    def e2e_run(n):
+        seen = 0
+        batches = (host_sets[i % nsets] for i in range(n))
+        for target, mask, dets in pipe_e.stream(batches, anchors, gather_batch=B * world if world > 1 else None):
+            seen += len(dets)
+        assert seen == n * B * world
         torch.cuda.current_stream().synchronize()
 
     e2e_steps = max(3, min(args.steps, 50))
-    for i in range(max(3, min(args.warmup, 5))):
-        e2e_step(i)
+    e2e_run(max(3, min(args.warmup, 5)))
     barrier()
     t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        e2e_step(i)
+    e2e_run(e2e_steps)
     barrier()
     e2e_s = time.perf_counter() - t0
     clock_info = clocks.stop() if rank == 0 else None
@@ -305,7 +299,8 @@ def run_ours(args):
                        "device_path": "CUDA graph replay per step"},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
-                    "path": "AnchorPipeline.step(list of GT, CPU anchors, pinned host scores/locs) -> list of detections"},
+                    "path": "AnchorPipeline.stream(batches of (list of GT, pinned host scores, locs), CPU anchors) -> "
+                            "(target, mask, list of host detections) per batch; H2D of batch i+1 overlaps batch i"},
             "gpu_launches": launches_per_step * args.steps,
             "launches_per_step": launches_per_step,
             "clocks": clock_info,

@@ -59,6 +59,9 @@ class AnchorPipeline:
         self.fuse_encode = False       # True: one pass for to_centroids+encode (same rounding)
         self._graph = None
         self._side = None
+        self._copy = None
+        self._stream_slots = None
+        self.last_host_stats = None    # [B, 5] int32 host: count, positives, hard negatives, ignored, detections
 
     # -- the reference-facing call -------------------------------------------------------------
     def step(self, ground_truth, anchors, scores, locs):
@@ -86,6 +89,111 @@ class AnchorPipeline:
         else:
             box_utils.to_centroids(target_locs, inplace=True)                  # multibox_loss.py:81
             self.box_coder.encode_box(target_locs, anchors, inplace=True)      # multibox_loss.py:82
+
+    # -- the same call over a sequence of host batches, software-pipelined ------------------------
+    def stream(self, batches, anchors, depth: int = 2, gather_batch: Optional[int] = None):
+        """Generator form of :meth:`step` for a sequence of ``(ground_truth, scores, locs)`` host batches
+        (what a data loader with pinned memory hands over): yields ``(target, mask, dets)`` per batch,
+        in order.  The host->device copies of batch ``i+1`` run on a copy stream while batch ``i``
+        computes, and the padded detections / counts / statistics of every batch are read back into
+        pinned host buffers, so ``dets`` is a list of HOST views ``[n_i, 6]``.  ``target`` and ``mask`` stay
+        on the device.  Every in-flight batch owns one of ``depth + 1`` static buffer sets with its own
+        captured step graph, so what a batch yields stays valid until ``depth`` further batches have
+        been yielded.
+
+        ``gather_batch``: under ``torch.distributed`` (one process per GPU, batch sharded by image)
+        the global batch size; the detections of all ranks are then exchanged with the one
+        all-gather of ``sharding`` before the read-back and ``dets`` covers the global batch."""
+        import collections
+        from . import sharding
+        device = torch.device("cuda", torch.cuda.current_device())
+        compute = torch.cuda.current_stream()
+        if self._copy is None:
+            self._copy = torch.cuda.Stream()
+        copy = self._copy
+        anchors_dev = _devcache.device_copy(anchors, device)
+        if self._stream_slots is None or len(self._stream_slots) != depth + 1:
+            self._stream_slots = []
+        slots = self._stream_slots  # depth + 1 static buffer sets, one captured step graph each (kept between calls)
+        queue = collections.deque()
+        issued = 0
+
+        def build_slots(ground_truth, scores, locs):
+            # static device inputs + one CUDA graph of the whole step per slot; ground-truth capacity
+            # per image is the next power of two >= 64 of what this batch needs
+            batch = len(ground_truth)
+            need = max([int(g.shape[0]) for g in ground_truth] + [1])
+            cap = 64
+            while cap < need:
+                cap *= 2
+            cols = min([int(g.shape[1]) for g in ground_truth if g.dim() == 2 and g.shape[0]] or [6])
+            compute.synchronize()
+            del slots[:]
+            for _ in range(depth + 1):
+                packed = PackedGroundTruth(torch.zeros((batch * cap, cols), dtype=torch.float32, device=device),
+                                           torch.zeros((batch + 1,), dtype=torch.int32, device=device), cap, batch)
+                scores_d = torch.zeros(scores.shape, dtype=torch.float32, device=device)
+                locs_d = torch.zeros(locs.shape, dtype=torch.float32, device=device)
+                runner = AnchorPipeline(self.cfg)
+                out = runner.capture(packed, anchors_dev, scores_d, locs_d, shard_capacity=batch)
+                rows = gather_batch if gather_batch is not None else batch
+                host = torch.empty((rows, out.shard.shape[1]), dtype=torch.float32).pin_memory()
+                slots.append({"packed": packed, "scores": scores_d, "locs": locs_d, "runner": runner, "out": out,
+                              "host": host, "ready": torch.cuda.Event(), "done": torch.cuda.Event(),
+                              "key": (tuple(scores.shape), tuple(locs.shape), batch, cols, gather_batch)})
+
+        def batch_key(ground_truth, scores, locs):
+            cols = min([int(g.shape[1]) for g in ground_truth if g.dim() == 2 and g.shape[0]] or [6])
+            return (tuple(scores.shape), tuple(locs.shape), len(ground_truth), cols, gather_batch)
+
+        def fits(ground_truth, scores, locs):
+            return (bool(slots) and slots[0]["key"] == batch_key(ground_truth, scores, locs)
+                    and max([int(g.shape[0]) for g in ground_truth] + [0]) <= slots[0]["packed"].max_gt)
+
+        def issue(batch):
+            nonlocal issued
+            ground_truth, scores, locs = batch
+            slot = slots[issued % (depth + 1)]        # its previous use was yielded >= 1 batch ago
+            issued += 1
+            with torch.cuda.stream(copy):
+                pack_ground_truth(ground_truth, device, out=slot["packed"])
+                slot["scores"].copy_(scores, non_blocking=True)
+                slot["locs"].copy_(locs, non_blocking=True)
+                slot["ready"].record(copy)
+            compute.wait_event(slot["ready"])
+            slot["runner"].replay()
+            shard = slot["out"].shard
+            if gather_batch is not None:
+                world = torch.distributed.get_world_size()
+                gathered = torch.empty((world * shard.shape[0], shard.shape[1]), dtype=shard.dtype, device=device)
+                torch.distributed.all_gather_into_tensor(gathered, shard)
+                shard = gathered
+                if gathered.shape[0] != gather_batch:
+                    dets, counts, stats = sharding.unpack_gathered(gathered, gather_batch, world, slot["out"].dets.shape[1])
+                    shard = sharding.pack_shard(dets, counts, stats, gather_batch)
+            slot["host"].copy_(shard, non_blocking=True)
+            slot["done"].record(compute)
+            return slot
+
+        def finish(slot):
+            slot["done"].synchronize()
+            host = slot["host"]
+            t = slot["out"].dets.shape[1]
+            ints = host.view(torch.int32)
+            self.last_host_stats = ints[:, t * 6:]
+            dets = host[:, : t * 6].view(host.shape[0], t, 6)
+            return slot["out"].target, slot["out"].mask, [dets[i, :n] for i, n in enumerate(ints[:, t * 6].tolist())]
+
+        for batch in batches:
+            if not fits(*batch):                      # first batch, new shapes or more boxes per image:
+                while queue:                          # drain, then (re)build the static buffers and graphs
+                    yield finish(queue.popleft())
+                build_slots(*batch)
+            queue.append(issue(batch))
+            if len(queue) >= depth:
+                yield finish(queue.popleft())
+        while queue:
+            yield finish(queue.popleft())
 
     # -- device-resident, sync-free -------------------------------------------------------------
     def step_device(self, packed: PackedGroundTruth, anchors_dev, scores_dev, locs_dev,

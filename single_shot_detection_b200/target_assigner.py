@@ -5,8 +5,8 @@
 (cx,cy,w,h) and returns ``target[B,A,6]`` fp32.  Unlike the reference -- which runs the whole
 thing on ``anchors.device``, i.e. on the CPU (detection/anchor_generators/_anchor_generator.py:4,18)
 -- the result lives on the GPU: the caller's ``target.to(device)`` (detection/init.py:115) becomes
-a no-op.  One cluster launch does IoU, both argmaxes, the forced match and the target write for
-the whole batch (csrc/assign.cu).
+a no-op.  One launch does IoU, both argmaxes, the forced match and the target write for the whole
+batch (csrc/assign.cu).
 """
 from __future__ import annotations
 
@@ -37,8 +37,13 @@ class PackedGroundTruth:
         self.rows, self.offsets, self.max_gt, self.batch = rows, offsets, max_gt, batch
 
 
-def pack_ground_truth(ground_truth: Sequence[torch.Tensor], device: torch.device) -> PackedGroundTruth:
-    """CSR-pack the list into ONE pinned staging buffer and ship it with one H2D copy."""
+def pack_ground_truth(ground_truth: Sequence[torch.Tensor], device: torch.device,
+                       out: Optional[PackedGroundTruth] = None) -> PackedGroundTruth:
+    """CSR-pack the list into ONE pinned staging buffer and ship it with one H2D copy.
+
+    ``out``: static device buffers to fill instead (CUDA-graph replay: ``out.rows`` [capacity, cols],
+    ``out.offsets`` [B+1], ``out.max_gt`` the capacity per image the graph was captured with);
+    raises ValueError when the batch does not fit."""
     batch = len(ground_truth)
     sizes = [int(g.shape[0]) for g in ground_truth]
     cols = min([int(g.shape[1]) for g in ground_truth if g.dim() == 2 and g.shape[0]] or [TARGET_SIZE])
@@ -64,6 +69,15 @@ def pack_ground_truth(ground_truth: Sequence[torch.Tensor], device: torch.device
             _devcache.mark_in_flight()
             return PackedGroundTruth(rows_dev, offsets_dev, max(sizes), batch)
         torch.cat([g[:, :cols] for g in ground_truth if g.shape[0]], dim=0, out=rows_host)
+    if out is not None:
+        if (batch != out.batch or total > out.rows.shape[0] or cols != out.rows.shape[1]
+                or (max(sizes) if sizes else 0) > out.max_gt):
+            raise ValueError("ground truth does not fit the static buffers")
+        out.offsets.copy_(off, non_blocking=True)
+        if total:
+            out.rows[:total].copy_(rows_host, non_blocking=True)
+        _devcache.mark_in_flight()
+        return out
     dev_words = stage[: head + total * cols].to(device, non_blocking=True)
     _devcache.mark_in_flight()
     offsets_dev = dev_words[: batch + 1].view(torch.int32)

@@ -532,3 +532,28 @@ def test_full_size_ssd300_b8_vs_oracle(dev):
     torch.testing.assert_close(target[..., :4].cpu()[pos], ref_target[..., :4][pos], rtol=REL, atol=1e-6)
     assert int((mask.cpu() != ref_mask).sum()) <= 8
     _compare_dets(dets, ref_dets, w.img)
+
+
+def test_stream_matches_step(dev):
+    """The software-pipelined form (H2D of batch i+1 under the kernels of batch i, detections read
+    back to pinned host memory) returns exactly what step() returns, batch by batch, in order."""
+    from single_shot_detection_b200.pipeline import AnchorPipeline
+    w = wl.WORKLOADS["ssd300_voc_b8"]
+    batches = []
+    for s in range(5):
+        anchors, gt, scores, locs = wl.make_inputs(w, seed=100 + s, batch=3 + (s % 2))
+        batches.append((gt, scores.pin_memory(), locs.pin_memory()))
+    ref_pipe = AnchorPipeline(w.cfg())
+    expected = []
+    for gt, scores, locs in batches:
+        target, mask, dets = ref_pipe.step(gt, anchors, scores, locs)
+        expected.append((target.cpu(), mask.cpu(), [d.cpu() for d in dets]))
+    pipe = AnchorPipeline(w.cfg())
+    seen = 0
+    for (target, mask, dets), (rt, rm, rd) in zip(pipe.stream(iter(batches), anchors), expected):
+        assert torch.equal(target.cpu(), rt) and torch.equal(mask.cpu(), rm)
+        assert len(dets) == len(rd)
+        for d, r in zip(dets, rd):
+            assert not d.is_cuda and torch.equal(d, r)
+        seen += 1
+    assert seen == len(batches)
