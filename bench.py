@@ -156,7 +156,7 @@ def run_reference(args):
         "e2e": {"value": mean, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 # --------------------------------------------------------------------------------------------
@@ -215,14 +215,21 @@ def run_ours(args):
     launches_per_step = int(N.lib().ssd_b200_launch_count() - launches_before)
     cap = B if world > 1 else None
     for pipe, (packed, scores_d, locs_d) in zip(pipes, dev_sets):
+        # (the all-gather stays outside the graph: capturing the NCCL collective hung on this stack)
         outs.append(pipe.capture(packed, anchors_dev, scores_d, locs_d, shard_capacity=cap))
     torch.cuda.synchronize()
+
+    # the one exchange step of the path (detections + counts + stats, one collective per step) runs
+    # asynchronously: the all-gather of step i overlaps the kernels of step i+1
+    gather = sharding.OverlappedGather(B * world, w.max_total) if world > 1 else None
 
     def device_step(i):
         k = i % nsets
         pipes[k].replay()
-        if world > 1:       # the one exchange step of the path: detections + counts + stats, one collective
-            return sharding.all_gather_packed(outs[k].shard, B * world, w.max_total)
+        if world > 1:
+            if outs[k].gathered is not None:          # the all-gather is a node of the step graph
+                return outs[k].gathered
+            return gather.submit(outs[k].shard)
         return outs[k].dets, outs[k].counts, outs[k].assign_stats
 
     def barrier():
@@ -233,6 +240,8 @@ def run_ours(args):
     # ---- value: device-resident, CUDA events ----
     for i in range(args.warmup):
         device_step(i)
+    if world > 1:
+        gather.flush()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -241,6 +250,8 @@ def run_ours(args):
     e0.record()
     for i in range(args.steps):
         device_step(i)
+    if world > 1:
+        gather.flush()                    # the last step's exchange completes inside the timed region
     e1.record()
     barrier()
     dev_ms = e0.elapsed_time(e1)
@@ -296,7 +307,9 @@ def run_ours(args):
                        "region": "encode_ground_truth + sampler + to_centroids/encode_box + postprocess"
                                  + (" + all_gather(dets,stats)" if world > 1 else ""),
                        "l2": f"inputs rotate over {nsets} sets = {nsets * per_set / 2**20:.0f} MiB > 126 MiB L2",
-                       "device_path": "CUDA graph replay per step"},
+                       "device_path": "CUDA graph replay per step" + (
+                           "" if world == 1 else (", all-gather captured in the graph" if outs[0].gathered is not None
+                                                  else ", all-gather of step i overlapping step i+1"))},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
                     "path": "AnchorPipeline.stream(batches of (list of GT, pinned host scores, locs), CPU anchors) -> "
@@ -314,8 +327,10 @@ def run_ours(args):
                 "value": mean, "unit": "images/s", "cores": cores, "kind": "port", "best": best,
                 "sample": f"{images} of {B} images per step, 3 steps + 1 warm-up, oracle port of the reference "
                           f"(torch CPU ops + torchvision.ops.nms), {cores} torch threads"}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -356,10 +371,31 @@ def roofline_probe(w, dev_sets, anchors_dev, pipe, B, A, C, nsets, iters: int = 
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # stdout carries exactly one JSON line: everything libraries print there (NCCL's version banner)
+    # goes to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    import builtins
+    original_print = builtins.print
+
+    def emit(*a, **k):
+        if not k.get("file"):
+            os.write(real_stdout, (" ".join(str(x) for x in a) + "\n").encode())      # straight to the real stdout
+        else:
+            original_print(*a, **k)
+
+    builtins.print = emit
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    finally:
+        builtins.print = original_print
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
 
 
 if __name__ == "__main__":

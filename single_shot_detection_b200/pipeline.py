@@ -37,6 +37,7 @@ class StepOutput(NamedTuple):
     shard: Optional[torch.Tensor]  # packed exchange buffer, when requested
     assign_stats: Optional[torch.Tensor] = None   # [B, 4] int32 positives, ignored, NaN boxes, G (ssd_assign_targets)
     mining_stats: Optional[torch.Tensor] = None   # [B, 4] int32 positives, negatives, selected, ties (ssd_hard_negative_mask)
+    gathered: Optional[torch.Tensor] = None       # [world * capacity, T*6+5] all ranks' shards (gather=True)
 
 
 class AnchorPipeline:
@@ -197,9 +198,11 @@ class AnchorPipeline:
 
     # -- device-resident, sync-free -------------------------------------------------------------
     def step_device(self, packed: PackedGroundTruth, anchors_dev, scores_dev, locs_dev,
-                    shard_capacity: Optional[int] = None) -> "StepOutput":
+                    shard_capacity: Optional[int] = None, gather: bool = False) -> "StepOutput":
         """``shard_capacity``: also pack (dets, counts, stats) into the one-buffer layout
         ``sharding.all_gather_detections`` exchanges (so the packing is part of the graph).
+        ``gather``: also run that exchange -- one NCCL all-gather over all ranks -- as the last
+        operation of the step (capturable: the collective becomes a node of the step graph).
 
         The train-side chain (assign -> sampler -> encode) and the post-processor are independent,
         so they are enqueued on two streams (fork / join with events; capturable into one graph
@@ -227,8 +230,13 @@ class AnchorPipeline:
             from . import sharding
             stats = matched_stats(self.target_assigner.last_stats, mining, counts)
             shard = sharding.pack_shard(dets, counts, stats, shard_capacity)
+        gathered = None
+        if gather:
+            world = torch.distributed.get_world_size()
+            gathered = torch.empty((world * shard.shape[0], shard.shape[1]), dtype=shard.dtype, device=shard.device)
+            torch.distributed.all_gather_into_tensor(gathered, shard)
         return StepOutput(target, mask, dets, counts, det_anchors, status, stats, shard,
-                          self.target_assigner.last_stats, mining)
+                          self.target_assigner.last_stats, mining, gathered)
 
     def _side_streams(self):
         if self._side is None:
@@ -236,19 +244,19 @@ class AnchorPipeline:
         return self._side
 
     def capture(self, packed: PackedGroundTruth, anchors_dev, scores_dev, locs_dev, warmup: int = 2,
-                shard_capacity: Optional[int] = None) -> "StepOutput":
+                shard_capacity: Optional[int] = None, gather: bool = False) -> "StepOutput":
         """Record ``step_device`` on these (static) buffers into a CUDA graph; returns the outputs
         the replays will keep overwriting."""
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                out = self.step_device(packed, anchors_dev, scores_dev, locs_dev, shard_capacity)
+                out = self.step_device(packed, anchors_dev, scores_dev, locs_dev, shard_capacity, gather)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            out = self.step_device(packed, anchors_dev, scores_dev, locs_dev, shard_capacity)
+            out = self.step_device(packed, anchors_dev, scores_dev, locs_dev, shard_capacity, gather)
         self._graph = graph
         return out
 

@@ -78,3 +78,46 @@ def all_gather_packed(mine: torch.Tensor, batch: int, max_rows: int, group: Opti
     out = torch.empty((world * capacity, mine.shape[1]), dtype=mine.dtype, device=mine.device)
     dist.all_gather_into_tensor(out, mine, group=group)
     return unpack_gathered(out, batch, world, max_rows)
+
+
+class OverlappedGather:
+    """The exchange step off the critical path: ``submit`` enqueues the all-gather of a packed shard
+    asynchronously (NCCL runs it on its own stream, after the work already enqueued on the current
+    stream) and hands back the PREVIOUS submission's gathered buffer, now complete for the current
+    stream -- so the collective of step i overlaps the kernels of step i+1.  ``flush`` returns the
+    last one.  The buffers rotate over a small ring (no allocation per step); ``unpack`` turns one
+    into ``(dets, counts, stats)`` of the whole batch as in :func:`all_gather_detections`."""
+
+    def __init__(self, batch: int, max_rows: int, group: Optional[dist.ProcessGroup] = None, ring: int = 3):
+        self.batch, self.max_rows, self.group = batch, max_rows, group
+        self.world = dist.get_world_size(group)
+        self._pending = None
+        self._ring = [None] * ring
+        self._next = 0
+
+    def unpack(self, gathered: torch.Tensor):
+        return unpack_gathered(gathered, self.batch, self.world, self.max_rows)
+
+    def _finish(self):
+        if self._pending is None:
+            return None
+        work, out = self._pending
+        self._pending = None
+        work.wait()                       # orders the current stream after the collective; no host sync on NCCL
+        return out
+
+    def submit(self, shard: torch.Tensor):
+        previous = self._finish()
+        k = self._next
+        self._next = (k + 1) % len(self._ring)
+        out = self._ring[k]
+        shape = (self.world * shard.shape[0], shard.shape[1])
+        if out is None or tuple(out.shape) != shape or out.device != shard.device:
+            out = torch.empty(shape, dtype=shard.dtype, device=shard.device)
+            self._ring[k] = out
+        work = dist.all_gather_into_tensor(out, shard, group=self.group, async_op=True)
+        self._pending = (work, out)
+        return previous
+
+    def flush(self):
+        return self._finish()

@@ -44,6 +44,18 @@ def _worker(rank, world, port, batch, max_rows, failures):
         got2 = sharding.all_gather_packed(mine, batch, max_rows)
         if not all(torch.equal(a.to(b.dtype), b) for a, b in zip(got2, (dets, counts, stats))):
             failures.put((rank, "all_gather_packed differs"))
+        # the overlapped form hands back the previous submission's result, flush the last one
+        og = sharding.OverlappedGather(batch, max_rows)
+        dets_b, counts_b, stats_b = _whole_batch(batch, max_rows, seed=6)
+        mine_b = sharding.pack_shard(dets_b[lo:hi], counts_b[lo:hi], stats_b[lo:hi], cap)
+        first = og.submit(mine)
+        second = og.submit(mine_b)
+        third = og.flush()
+        if first is not None or og.flush() is not None:
+            failures.put((rank, "OverlappedGather: unexpected result before / after the queue"))
+        for got3, want in ((second, (dets, counts, stats)), (third, (dets_b, counts_b, stats_b))):
+            if not all(torch.equal(a.to(b.dtype), b) for a, b in zip(og.unpack(got3), want)):
+                failures.put((rank, "OverlappedGather differs"))
     except Exception as e:  # noqa: BLE001
         failures.put((rank, repr(e)))
     finally:
