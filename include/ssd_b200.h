@@ -170,6 +170,33 @@ SSD_API int ssd_hard_negative_mask(const float* logits, const int64_t* target_cl
                            size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * a10 / f1  detection/losses/multibox_loss.py:56-92  masked multibox losses, forward + gradient.
+ *     class_loss = classification_loss(scores[sampled_mask], classes[sampled_mask]) (reduction sum),
+ *     loc_loss   = SmoothL1Loss(sum)(locs[positive], target_locs[positive]); both are scaled by
+ *     their weight and divided by max(#positives, 1); loss = class_loss + loc_loss.
+ *     kind SSD_LOSS_SOFTMAX_CE: torch CrossEntropyLoss(ignore_index = -1) over the C columns;
+ *     kind SSD_LOSS_SIGMOID_FOCAL: bf/modules/losses.py:34-54 with the one-hot soft target
+ *     (column class-1, value = ground-truth score) of multibox_loss.py:64-67; as in the reference
+ *     this term is the MEAN over the sampled anchors (its constructor never receives
+ *     reduction='sum': bf/utils/misc_utils.py:21-29 filters the keyword out), NaN for an empty mask.
+ *   logits       [B,A,C]  fp32
+ *   locs         [B,A,4]  fp32, 16-byte aligned
+ *   target       [B,A,6]  fp32 rows (encoded box, class, score): AFTER to_centroids + encode_box
+ *   sampled_mask [B,A]    uint8 (the sampler's output)
+ *   grad_logits  [B,A,C]  d loss / d logits, or NULL      (dense: zero rows outside the mask)
+ *   grad_locs    [B,A,4]  d loss / d locs, 16-byte aligned, or NULL
+ *   loss_out     [3]      fp32 {loss, class_loss, loc_loss}
+ * ---------------------------------------------------------------------------------------- */
+#define SSD_LOSS_SOFTMAX_CE 0
+#define SSD_LOSS_SIGMOID_FOCAL 1
+SSD_API size_t ssd_multibox_loss_workspace_bytes(int batch, int num_anchors);
+SSD_API int ssd_multibox_loss(const float* logits, const float* locs, const float* target,
+                      const uint8_t* sampled_mask, int batch, int num_anchors, int num_cols, int kind,
+                      float gamma, float alpha, float class_weight, float loc_weight,
+                      float* grad_logits, float* grad_locs, float* loss_out, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * a7+a8+a9  detection/postprocessor.py:24-78  Postprocessor.postprocess, including
  *           bf/utils/box_utils.py:165-194 nms (top-k + torchvision.ops.nms semantics).
  * ---------------------------------------------------------------------------------------- */

@@ -486,6 +486,45 @@ def multibox_loss_ce_smoothl1(scores: torch.Tensor, locs: torch.Tensor, priors: 
     return class_loss + loc_loss, class_loss, loc_loss
 
 
+def sigmoid_focal_loss_rows(prediction: torch.Tensor, target: torch.Tensor, gamma: float, alpha: float):
+    """Per-row SigmoidFocalLoss terms, bf/modules/losses.py:42-52 (before the reduction)."""
+    alpha_weight = target * alpha + (1.0 - target) * (1.0 - alpha)
+    pb = torch.sigmoid(prediction)
+    pb = pb * target + (1.0 - pb) * (1.0 - target)
+    cross_entropy = F.binary_cross_entropy_with_logits(prediction, target, reduction="none")
+    return (alpha_weight * (1.0 - pb).pow(gamma) * cross_entropy).sum(dim=-1)
+
+
+def multibox_loss_focal_smoothl1(scores: torch.Tensor, locs: torch.Tensor, target: torch.Tensor,
+                                 sampled_mask: torch.Tensor, encoded_target_locs: torch.Tensor,
+                                 gamma: float = 2.0, alpha: float = 0.25):
+    """SigmoidFocal + SmoothL1 triple: the MULTICLASS branch of MultiboxLoss.forward
+    (multibox_loss.py:60-67): one-hot target at column class-1 scaled by the GT score.
+
+    The classification term is the MEAN over the sampled anchors, not the sum: MultiboxLoss passes
+    reduction='sum' (multibox_loss.py:24), but get_ctor wraps the constructor in filter_kwargs
+    (bf/utils/misc_utils.py:21-29), which keeps only keywords NAMED in the signature --
+    SigmoidFocalLoss.__init__(self, gamma, alpha, **kwargs) names neither `reduction` nor
+    `ignore_index`, so _Loss falls back to its default reduction='mean' (losses.py:11).  The golden
+    fixtures (the reference's own output) pin this; an empty mask gives NaN as torch's mean does."""
+    b, a = target.shape[:2]
+    cls = target[..., CLS_COL].long()
+    pos = positives_mask(cls)
+    logits = scores.view(b, a, -1)[sampled_mask]
+    cls_s = cls[sampled_mask]
+    score_s = target[..., SCORE_COL][sampled_mask]
+    class_target = torch.zeros_like(logits)
+    m = positives_mask(cls_s)
+    class_target[m, cls_s[m] - 1] = score_s[m]
+    class_loss = sigmoid_focal_loss_rows(logits, class_target, gamma, alpha).mean()
+    loc_loss = F.smooth_l1_loss(locs.view(b, a, 4)[pos].view(-1, 4),
+                                encoded_target_locs[pos].view(-1, 4), reduction="sum")
+    div = pos.sum().clamp(min=1).float()
+    class_loss = class_loss / div
+    loc_loss = loc_loss / div
+    return class_loss + loc_loss, class_loss, loc_loss
+
+
 # --------------------------------------------------------------------------------------
 # whole timed region (SURVEY.md §8 d) as the reference executes it on the CPU
 # --------------------------------------------------------------------------------------

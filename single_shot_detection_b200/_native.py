@@ -26,6 +26,7 @@ BOX_TO_CORNERS, BOX_TO_CENTROIDS, BOX_TO_CENTROIDS_INPLACE, BOX_ENCODE, BOX_ENCO
     BOX_DECODE_INPLACE, BOX_CENTROIDS_ENCODE_INPLACE, BOX_DECODE_TO_CORNERS = range(9)
 # ssd_converter / ssd_box_input
 CONVERT_SOFTMAX, CONVERT_SIGMOID, CONVERT_IDENTITY = 0, 1, 2
+LOSS_SOFTMAX_CE, LOSS_SIGMOID_FOCAL = 0, 1
 BOXES_ENCODED, BOXES_CORNERS = 0, 1
 
 
@@ -63,6 +64,9 @@ _SIGNATURES = {
     "ssd_hard_negative_workspace_bytes": (c_size_t, [c_int, c_int]),
     "ssd_hard_negative_mask": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_int, c_double,
                                        c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ssd_multibox_loss_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "ssd_multibox_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float,
+                                  c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ssd_postprocess_workspace_bytes": (c_size_t, [POINTER(PostprocessParams)]),
     "ssd_postprocess": (c_int, [POINTER(PostprocessParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -29,6 +29,8 @@ _LIB.define("postprocess(Tensor scores, Tensor boxes, Tensor? priors, int conver
             "int box_input, float xy_scale, float wh_scale, float score_threshold, int max_per_class, "
             "float overlap_threshold, int max_total) -> (Tensor, Tensor, Tensor, Tensor)")
 _LIB.define("nms(Tensor boxes, Tensor scores, int max_per_class, float overlap_threshold) -> (Tensor, Tensor)")
+_LIB.define("multibox_loss(Tensor scores, Tensor locs, Tensor target, Tensor sampled_mask, int kind, float gamma, "
+            "float alpha, float class_weight, float loc_weight, bool need_grad) -> (Tensor, Tensor, Tensor)")
 
 
 def _stream() -> int:
@@ -239,7 +241,34 @@ def _nms(boxes: torch.Tensor, scores: torch.Tensor, max_per_class: int, overlap_
     return keep, count
 
 
-for _name, _fn in [("pairwise_iou", _pairwise_iou), ("match_per_prediction", _match_per_prediction),
+def _multibox_loss(scores: torch.Tensor, locs: torch.Tensor, target: torch.Tensor, sampled_mask: torch.Tensor,
+                   kind: int, gamma: float, alpha: float, class_weight: float, loc_weight: float, need_grad: bool):
+    """(loss3 [3], grad_scores like scores, grad_locs like locs); the gradients are empty tensors when
+    ``need_grad`` is false.  ``target`` rows hold the ENCODED boxes (after to_centroids + encode_box)."""
+    N.require_device()
+    batch, num_anchors = int(target.shape[0]), int(target.shape[1])
+    scores_c, locs_c = _f32c(scores.detach()), _f32c(locs.detach())
+    target_c = _f32c(target.detach())
+    mask = sampled_mask if sampled_mask.is_contiguous() else sampled_mask.contiguous()
+    if mask.dtype != torch.bool and mask.dtype != torch.uint8:
+        mask = mask != 0
+    num_cols = scores_c.numel() // max(batch * num_anchors, 1)
+    dev = target_c.device
+    loss3 = torch.empty((3,), dtype=torch.float32, device=dev)
+    grad_scores = torch.empty(scores.shape if need_grad else (0,), dtype=torch.float32, device=dev)
+    grad_locs = torch.empty(locs.shape if need_grad else (0,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        nbytes = N.lib().ssd_multibox_loss_workspace_bytes(batch, num_anchors)
+        ws = workspace(nbytes, dev, "loss")
+        N.check(N.lib().ssd_multibox_loss(_ptr(scores_c), _ptr(locs_c), _ptr(target_c), _ptr(mask), batch, num_anchors,
+                                          num_cols, kind, gamma, alpha, class_weight, loc_weight,
+                                          _ptr(grad_scores) if need_grad else None,
+                                          _ptr(grad_locs) if need_grad else None, _ptr(loss3), _ptr(ws), ws.numel(),
+                                          _stream()))
+    return loss3, grad_scores, grad_locs
+
+
+for _name, _fn in [("multibox_loss", _multibox_loss), ("pairwise_iou", _pairwise_iou), ("match_per_prediction", _match_per_prediction),
                    ("assign_targets", _assign_targets), ("box_transform", _box_transform),
                    ("box_transform_", _box_transform_), ("positive_mask", _positive_mask),
                    ("hard_negative_mask", _hard_negative_mask), ("postprocess", _postprocess), ("nms", _nms)]:

@@ -557,3 +557,76 @@ def test_stream_matches_step(dev):
             assert not d.is_cuda and torch.equal(d, r)
         seen += 1
     assert seen == len(batches)
+
+
+# ----------------------------------------------------------------------------------------------
+# masked multibox losses (a10 / f1): fused forward + gradient
+# ----------------------------------------------------------------------------------------------
+def _loss_module(w):
+    import functools
+    from single_shot_detection_b200 import box_coder, multibox_loss, sampler
+    coder = box_coder.BoxCoder(w.xy_scale, w.wh_scale, w.eps)
+    if w.converter == "SOFTMAX":
+        smp = functools.partial(sampler.hard_negative_mining, negative_per_positive_ratio=w.ratio,
+                                min_negative_per_image=w.min_neg)
+        return multibox_loss.MultiboxLoss(smp, coder, {"name": "CrossEntropyLoss"}, {"name": "SmoothL1Loss"})
+    return multibox_loss.MultiboxLoss(sampler.naive_sampler, coder,
+                                      {"name": "SigmoidFocalLoss", "gamma": 2.0, "alpha": 0.25},
+                                      {"name": "SmoothL1Loss"})
+
+
+def test_multibox_loss_vs_reference_golden(case, dev):
+    """(loss, class_loss, loc_loss) of the reference's own MultiboxLoss on the fixtures, 1e-5 relative."""
+    crit = _loss_module(case.w)
+    target = case.target.clone().to(dev)
+    loss3 = crit((case.scores.to(dev), case.locs.to(dev)), case.anchors, target)
+    got = [float(x) for x in loss3]
+    np.testing.assert_allclose(got, case.loss3, rtol=REL)
+    # the box columns of `target` were encoded in place, as the reference's forward does
+    pos = ora.positives_mask(case.target[..., 4].long())
+    torch.testing.assert_close(target[..., :4].cpu()[pos], case.enc_inplace[pos], rtol=REL, atol=1e-6)
+
+
+@pytest.mark.parametrize("kind", ["ce", "focal"])
+def test_multibox_loss_gradients_vs_autograd(dev, kind):
+    """Dense gradients of the fused pass against torch autograd through the oracle's loss, with the
+    SAME sampler mask and encoded targets; unequal weights and a non-unit upstream gradient."""
+    from single_shot_detection_b200 import _native as N
+    from single_shot_detection_b200.multibox_loss import _FusedMultiboxLoss
+    w = wl.WORKLOADS["tiny_voc_b3" if kind == "ce" else "tiny_sigmoid_b2"]
+    anchors, gt, scores, locs = wl.make_inputs(w, seed=77, batch=4)
+    b, a = 4, anchors.shape[0]
+    target = ora.assign_targets(gt, anchors, w.matched_threshold, w.unmatched_threshold)
+    cls = target[..., 4].long()
+    if kind == "ce":
+        mask = ora.mine_hard_negatives(scores.view(b, a, -1), cls, 3, 5, canonical=True)
+        mask[0, :7] = True                      # a few extra anchors, including ignored ones if any
+    else:
+        mask = ora.positives_mask(cls)
+        mask[1, :9] = True                      # negatives in the mask: all-zero focal targets
+        target[..., 5] = torch.where(ora.positives_mask(cls), torch.rand(cls.shape) * 0.5 + 0.5, target[..., 5])
+    tl = target[..., :4]
+    ora.centroids_from_corners(tl, inplace=True)
+    ora.encode_boxes(tl, anchors, w.xy_scale, w.wh_scale, w.eps, inplace=True)
+    cw, lw = 1.7, 0.6
+    s_ref = scores.clone().requires_grad_(True)
+    l_ref = locs.clone().requires_grad_(True)
+    if kind == "ce":
+        _, c_ref, r_ref = ora.multibox_loss_ce_smoothl1(s_ref, l_ref, anchors, target, mask, tl)
+    else:
+        _, c_ref, r_ref = ora.multibox_loss_focal_smoothl1(s_ref, l_ref, target, mask, tl)
+    ref3 = torch.stack([cw * c_ref + lw * r_ref, cw * c_ref, lw * r_ref])
+    up = torch.tensor([0.9, 0.3, -0.2])
+    (ref3 * up).sum().backward()
+
+    s_dev = scores.to(dev).requires_grad_(True)
+    l_dev = locs.to(dev).requires_grad_(True)
+    loss3 = _FusedMultiboxLoss.apply(s_dev, l_dev, target.to(dev), mask.to(dev),
+                                     N.LOSS_SOFTMAX_CE if kind == "ce" else N.LOSS_SIGMOID_FOCAL, 2.0, 0.25, cw, lw)
+    torch.testing.assert_close(loss3.cpu(), ref3.detach(), rtol=REL, atol=1e-7)
+    (loss3 * up.to(dev)).sum().backward()
+    scale = float(s_ref.grad.abs().max())
+    torch.testing.assert_close(s_dev.grad.cpu(), s_ref.grad, rtol=1e-4, atol=1e-6 * max(scale, 1e-3))
+    torch.testing.assert_close(l_dev.grad.cpu(), l_ref.grad, rtol=1e-4, atol=1e-7)
+    # rows outside the masks carry exactly zero gradient
+    assert float(s_dev.grad.view(b, a, -1)[~mask.to(dev)].abs().max()) == 0.0

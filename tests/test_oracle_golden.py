@@ -143,16 +143,17 @@ def test_postprocess_stage_exact(case):
 
 def test_loss_with_oracle_sampler_and_coder(case):
     w = case.w
-    if w.converter != "SOFTMAX":
-        pytest.skip("CE/SmoothL1 restated only for the softmax configs")
     cls = case.target[..., 4].long()
-    mask = ora.mine_hard_negatives(case.scores.view(case.B, case.A, case.C), cls, w.ratio, w.min_neg,
-                                   canonical=False)
     t = case.target.clone()
     tl = t[..., 0:4]
     ora.centroids_from_corners(tl, inplace=True)
     ora.encode_boxes(tl, case.anchors, w.xy_scale, w.wh_scale, w.eps, inplace=True)
-    loss3 = ora.multibox_loss_ce_smoothl1(case.scores, case.locs, case.anchors, case.target, mask, tl)
+    if w.converter == "SOFTMAX":
+        mask = ora.mine_hard_negatives(case.scores.view(case.B, case.A, case.C), cls, w.ratio, w.min_neg,
+                                       canonical=False)
+        loss3 = ora.multibox_loss_ce_smoothl1(case.scores, case.locs, case.anchors, case.target, mask, tl)
+    else:       # the sigmoid configs: naive sampler + SigmoidFocalLoss(gamma=2, alpha=.25), make_golden.py
+        loss3 = ora.multibox_loss_focal_smoothl1(case.scores, case.locs, case.target, ora.positives_mask(cls), tl)
     np.testing.assert_allclose([float(x) for x in loss3], case.loss3, rtol=1e-5)
 
 
