@@ -128,7 +128,7 @@ static int make_plan(const ssd_postprocess_params* p, PostPlan& pl) {
     g.num_items = pl.B * g.groups_per_image;
     // fewer rows per block than a warp sees in one tile: keep `split` row slots separate
     int split = 1;
-    const int slots = 32 / lanes_per_row(pl.C);           // row slots per warp step
+    const int slots = 32 / lanes_per_row(pl.C, true);     // row slots per warp step of pass 1
     while (split < slots && rows_per_warp_tile * gt / split > (want_rows > 0 ? want_rows : 1)) split <<= 1;
     g.split = split;
     g.nblk = g.groups_per_image * kConsumerWarps * split;
@@ -1393,7 +1393,7 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
         else rc = launch(score_pass1_kernel<QQ, NN, CM, SSD_CONVERT_IDENTITY>);                                            \
         if (rc != SSD_OK) return rc;                                                                                   \
     } while (0)
-    SSD_DISPATCH_ROW_SHAPE(pl.C, SSD_LAUNCH_PASS1);
+    SSD_DISPATCH_ROW_SHAPE_PASS1(pl.C, SSD_LAUNCH_PASS1);
 #undef SSD_LAUNCH_PASS1
     SSD_CUDA(cudaGetLastError());
     count_launch();

@@ -269,7 +269,13 @@ __device__ __forceinline__ void row_max_sum(const float (&v)[NREG], float& m, fl
 // Odd C <= 32 (VOC's 21 columns) take the row-per-lane shape Q == 1: lane l walks row l of the warp
 // step at a stride of C words -- C odd, so the 32 lanes hit 32 different banks -- with no lane idle,
 // no shuffle in the row reductions and ~3x fewer warp instructions per element than a split row.
-#define SSD_DISPATCH_ROW_SHAPE(C, CALL)                          \
+// WIDE81: the shape for COCO's 81 columns.  Four lanes x 21 registers (no padding slot, fewer
+// instructions per row) is faster for the kernels that only reduce ROWS (mining criterion, pass 2);
+// pass 1 also keeps per-lane COLUMN maxima that are merged across the row slots of the warp, which
+// is cheaper with eight lanes x 11 registers (measured, profiles/).
+#define SSD_DISPATCH_ROW_SHAPE(C, CALL) SSD_DISPATCH_ROW_SHAPE_(C, CALL, 1)
+#define SSD_DISPATCH_ROW_SHAPE_PASS1(C, CALL) SSD_DISPATCH_ROW_SHAPE_(C, CALL, 0)
+#define SSD_DISPATCH_ROW_SHAPE_(C, CALL, WIDE81)                 \
     do {                                                         \
         if ((C) <= 8) { CALL(1, 8, 1); }                         \
         else if ((C) == 21) { CALL(1, 21, 21); }                 \
@@ -280,30 +286,37 @@ __device__ __forceinline__ void row_max_sum(const float (&v)[NREG], float& m, fl
         else if ((C) <= 24) { CALL(4, 6, 17); }                  \
         else if ((C) <= 32) { CALL(4, 8, 25); }                  \
         else if ((C) <= 64) { CALL(8, 8, 33); }                  \
+        else if ((C) == 81 && (WIDE81)) { CALL(4, 21, 81); }     \
         else if ((C) <= 88) { CALL(8, 11, 65); }                 \
         else if ((C) <= 128) { CALL(8, 16, 89); }                \
         else if ((C) <= 256) { CALL(32, 8, 129); }               \
         else { CALL(32, 32, 257); }                              \
     } while (0)
 
-inline int lanes_per_row(int C) {
+inline int lanes_per_row(int C, bool pass1 = false) {
     int q = 0;
 #define SSD_Q_(QQ, NN, CM) q = QQ
-    SSD_DISPATCH_ROW_SHAPE(C, SSD_Q_);
+    if (pass1) SSD_DISPATCH_ROW_SHAPE_PASS1(C, SSD_Q_);
+    else SSD_DISPATCH_ROW_SHAPE(C, SSD_Q_);
 #undef SSD_Q_
     return q;
 }
+// register slots per row (>= C): the widest of the shapes any kernel uses for this C
 inline int slots_per_row(int C) {
-    int n = 0;
+    int n = 0, n1 = 0;
 #define SSD_N_(QQ, NN, CM) n = QQ * NN
     SSD_DISPATCH_ROW_SHAPE(C, SSD_N_);
 #undef SSD_N_
-    return n;
+#define SSD_N_(QQ, NN, CM) n1 = QQ * NN
+    SSD_DISPATCH_ROW_SHAPE_PASS1(C, SSD_N_);
+#undef SSD_N_
+    return n > n1 ? n : n1;
 }
 
 // Host: tile geometry.  tile_rows is a multiple of the rows all consumer warps cover in one step.
 inline void plan_tiles(ScoreGrid& g, int images, int A, int C, bool with_side, int target_tile_bytes = 24 * 1024) {
-    const int quantum = kConsumerWarps * (32 / lanes_per_row(C));
+    const int q_min = lanes_per_row(C) < lanes_per_row(C, true) ? lanes_per_row(C) : lanes_per_row(C, true);
+    const int quantum = kConsumerWarps * (32 / q_min);        // a whole number of warp steps for every kernel
     int rows = target_tile_bytes / (C * 4);
     rows = rows / quantum * quantum;
     if (rows > 4 * quantum) rows = 4 * quantum;
