@@ -288,6 +288,28 @@ def run_ours(args):
     # ---- roofline: the dominant kernel alone, CUDA events, rotating (cold-L2) inputs ----
     roof = roofline_probe(w, dev_sets, anchors_dev, pipes[0], B, A, C, nsets)
 
+    # ---- per-kernel times in context (library event timers around every launch of an eager step) ----
+    import ctypes
+    lib = N.lib()
+    for i in range(3):
+        k = i % nsets
+        pipes[0].step_device(dev_sets[k][0], anchors_dev, dev_sets[k][1], dev_sets[k][2])
+    torch.cuda.synchronize()
+    lib.ssd_b200_timing_enable(1)
+    for i in range(20):
+        k = i % nsets
+        pipes[0].step_device(dev_sets[k][0], anchors_dev, dev_sets[k][1], dev_sets[k][2])
+    buf = ctypes.create_string_buffer(4096)
+    lib.ssd_b200_timing_report(buf, 4096)
+    lib.ssd_b200_timing_enable(0)
+    kernels_us = {kv.split(":")[0]: float(kv.split(":")[1]) for kv in buf.value.decode().split(",") if kv}
+    num_fg = C - (1 if w.converter == "SOFTMAX" else 0)
+    pair_tests = B * num_fg * w.max_per_class * (w.max_per_class - 1) // 2
+    nms_info = {"kernel": "segment_nms_kernel", "us_in_step": kernels_us.get("nms"),
+                "pair_tests_per_launch": pair_tests,
+                "pair_tests_per_s": pair_tests / (kernels_us["nms"] * 1e-6) if kernels_us.get("nms") else None,
+                "note": "K(K-1)/2 IoU tests per (image, class) at K = max_per_class; bound by the ALU pipe, not HBM"}
+
     # max over ranks
     t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
@@ -318,6 +340,8 @@ def run_ours(args):
             "launches_per_step": launches_per_step,
             "clocks": clock_info,
             "roofline": roof,
+            "kernels_us": kernels_us,
+            "nms": nms_info,
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
@@ -363,10 +387,16 @@ def roofline_probe(w, dev_sets, anchors_dev, pipe, B, A, C, nsets, iters: int = 
     us = 1e3 * e0.elapsed_time(e1) / iters
     algo_bytes = B * A * (4 * C + 8 + 4)          # logits + int64 class read, uint32 key written
     achieved = algo_bytes / (us * 1e-6) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` capture per workload
+    # (profiles/r01_ncu_full.md); None for a workload that has no committed capture
+    traffic = {"ssd300_voc_b32": 25841664, "ssd512_coco_b32": 266480000}.get(w.name)
     return {"bound": "hbm", "kernel": "mining_loss_kernel (ssd_mining_keys)", "achieved": achieved, "peak": peak,
-            "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "traffic_source": "profiles/r01_ncu_full.md" if traffic else None,
             "algorithmic_bytes_per_launch": algo_bytes, "us_per_launch": us,
-            "note": "launches back-to-back on one stream, inputs rotate over sets larger than L2"}
+            "note": "the logit-streaming kernel of the sampler (4C+12 algorithmic bytes per anchor), launched back to back "
+                    "on one stream incl. its histogram memset, inputs rotating over sets larger than L2; the largest kernel "
+                    "of the step, segment_nms_kernel, is ALU bound and reported under 'nms'"}
 
 
 def main():

@@ -133,8 +133,11 @@ class AnchorPipeline:
             for _ in range(depth + 1):
                 packed = PackedGroundTruth(torch.zeros((batch * cap, cols), dtype=torch.float32, device=device),
                                            torch.zeros((batch + 1,), dtype=torch.int32, device=device), cap, batch)
-                scores_d = torch.zeros(scores.shape, dtype=torch.float32, device=device)
-                locs_d = torch.zeros(locs.shape, dtype=torch.float32, device=device)
+                # (the capture warm-up runs on this batch's data: all-zero logits would tie en masse and
+                # take the post-processor's slow exact fallback)
+                scores_d = scores.to(device=device, dtype=torch.float32).contiguous()
+                locs_d = locs.to(device=device, dtype=torch.float32).contiguous()
+                pack_ground_truth(ground_truth, device, out=packed)
                 runner = AnchorPipeline(self.cfg)
                 out = runner.capture(packed, anchors_dev, scores_d, locs_d, shard_capacity=batch)
                 rows = gather_batch if gather_batch is not None else batch
