@@ -786,6 +786,12 @@ __device__ __forceinline__ bool pair_suppressed(const NmsArgs& a, float4 bi, flo
 }
 
 constexpr int kRankSortMax = 256;     // candidate lists up to this size are sorted by ranking
+// 64-bit sort slots at the head of the NMS kernel's shared memory; later reused as the per-warp pair
+// lists of the overlap filter (kNmsThreads / 32 warps x 1024 16-bit codes), hence at least 1024
+__host__ __device__ inline int nms_key_slots(int cand_cap) {
+    const int lo = kMaxPerClass > 256 * (kNmsThreads / 32) ? kMaxPerClass : 256 * (kNmsThreads / 32);
+    return cand_cap > lo ? cand_cap : lo;
+}
 
 // ---------------------------------------------------------------------------------------------
 // 5. final top-k of one image (postprocessor.py:68-74), run by the LAST segment CTA of the image
@@ -1087,13 +1093,14 @@ __device__ int nms_segment(const KernelTrace& tr, const NmsArgs& a, unsigned cha
     tr.mark(0);
     int n_raw = cand_count[seg];
     if (n_raw == 0) return 0;
-    // carve: keys[key_slots] u64 | sorted[K] u64 | box[K] float4 | area[K] | mask[K * kwords] | keep[K]
-    const int key_slots = a.cand_cap > kMaxPerClass ? a.cand_cap : kMaxPerClass;
+    // carve: keys[key_slots] u64 | sorted[K] u64 | box[K] float4 | fbox[K] float4 | area[K] | mask[K * kwords] | keep[K]
+    const int key_slots = nms_key_slots(a.cand_cap);
     const int kwords = (a.K + 31) >> 5;
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem);
     unsigned long long* sorted = keys + key_slots;
     float4* sbox = reinterpret_cast<float4*>(sorted + ((a.K + 1) & ~1));          // 16-byte aligned
-    float* sarea = reinterpret_cast<float*>(sbox + a.K);
+    float4* fbox = sbox + a.K;                 // the boxes as the overlap filter sees them (NaN if degenerate)
+    float* sarea = reinterpret_cast<float*>(fbox + a.K);
     uint32_t* mask = reinterpret_cast<uint32_t*>(sarea + a.K);
     int* keep = reinterpret_cast<int*>(mask + (size_t)a.K * kwords);
 
@@ -1183,75 +1190,72 @@ __device__ int nms_segment(const KernelTrace& tr, const NmsArgs& a, unsigned cha
         }
         sbox[t] = bx;
         sarea[t] = fmul(fsub(bx.z, bx.x), fsub(bx.w, bx.y));          // torchvision: unclamped area
-        mask[(size_t)t * words + (t >> 5)] = 0u;
+        // a box without positive extent intersects nothing (the clamped side is 0): NaN fails every compare
+        const bool extent = bx.z > bx.x && bx.w > bx.y;
+        fbox[t] = extent ? bx : make_float4(NAN, NAN, NAN, NAN);
+        for (int w = 0; w < words; ++w) mask[(size_t)t * words + w] = 0u;
     }
     __syncthreads();
     tr.mark(3);
 
     // ---- IoU bit matrix: bit j of row i set <=> box i suppresses box j (j > i) ----
+    // Two tiers per 32 x 32 block (row chunk c, column word w >= c), one warp per block:
+    //  (1) overlap filter, lanes = rows: the 32 boxes of the word are broadcast one by one and every
+    //      lane collects a bit per column whose box intersects its row's box with positive extent
+    //      (four compares).  A pair that fails this has intersection 0 (or NaN) and can never exceed
+    //      a non-negative threshold -- for random boxes that is ~90 % of the pairs;
+    //  (2) the surviving pairs are compacted into a per-warp list (16-bit row/column codes in the
+    //      shared memory the sort no longer needs) and only those take the IoU test, lanes = pairs,
+    //      every lane busy; suppressions are recorded with a shared-memory atomicOr.
     const int nwarps = blockDim.x >> 5;
-    // (a) words right of the diagonal: a warp takes a row, its lanes the 32 columns of a word
-    //     (ballot -> one store).  A short last word (n mod 32 <= 8) is done transposed -- lanes over
-    //     rows, a loop over its few columns -- instead of with mostly idle 32-lane items.
-    const int tail = n & 31;
-    const bool tail_transposed = tail != 0 && tail <= 8 && words > 1;
-    const int words_main = tail_transposed ? words - 1 : words;
-    for (int i = warp_id(); i < n; i += nwarps) {
-        const float4 bi = sbox[i];
-        const float ai = sarea[i];
-        // four words per round: the loads and tests of a round are independent, the stores come last
-        for (int w0 = (i >> 5) + 1; w0 < words_main; w0 += 4) {
-            uint32_t bits[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int j = ((w0 + u) << 5) + lane;
-                const bool in_range = j < n && w0 + u < words_main;
-                const int jj = in_range ? j : i;
-                const bool sup = pair_suppressed(a, bi, ai, sbox[jj], sarea[jj], in_range);
-                bits[u] = __ballot_sync(FULL, sup);
+    unsigned short* plist = reinterpret_cast<unsigned short*>(keys) + (size_t)warp_id() * 1024;     // [1024] per warp
+    const int nblocks = words * (words + 1) / 2;
+    for (int blk = warp_id(); blk < nblocks; blk += nwarps) {
+        // blk -> (c, w) with c <= w, enumerated word-major: w = 0: (0,0); w = 1: (0,1), (1,1); ...
+        int w = 0;
+        while ((w + 1) * (w + 2) / 2 <= blk) ++w;
+        const int c = blk - w * (w + 1) / 2;
+        const int i = (c << 5) + lane;                      // this lane's row
+        const int j0 = w << 5;
+        const int cols = min(32, n - j0);
+        uint32_t bits = 0u;
+        if (a.screen) {
+            const float4 bi = i < n ? fbox[i] : make_float4(NAN, NAN, NAN, NAN);
+#pragma unroll 8
+            for (int jj = 0; jj < cols; ++jj) {
+                const float4 bj = fbox[j0 + jj];            // same address for every lane: broadcast
+                const bool hit = bi.z > bj.x && bj.z > bi.x && bi.w > bj.y && bj.w > bi.y;
+                bits |= hit ? 1u << jj : 0u;
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (lane == 0 && w0 + u < words_main) mask[(size_t)i * words + w0 + u] = bits[u];
+        } else {
+            bits = i < n ? (cols == 32 ? ~0u : (1u << cols) - 1u) : 0u;      // negative threshold: every pair counts
         }
-    }
-    if (tail_transposed) {
-        const int j0 = n - tail;
-        for (int i0 = warp_id() * 32; i0 < j0; i0 += nwarps * 32) {
-            const int i = i0 + lane;                   // i < j0 always (j0 is a multiple of 32)
-            const float4 bi = sbox[i];
-            const float ai = sarea[i];
-            uint32_t bits = 0u;
-            for (int j = j0; j < n; ++j) {
-                const bool sup = pair_suppressed(a, bi, ai, sbox[j], sarea[j], true);
-                bits |= sup ? 1u << (j & 31) : 0u;
-            }
-            mask[(size_t)i * words + words - 1] = bits;
-        }
-    }
-    // (b) diagonal words: the 32 x 32 block of chunk c holds 496 unordered pairs; rotation d pairs
-    //     lane l with lane (l + d) mod 32, so 16 warp steps cover them all with every lane busy
-    //     (d == 16: half the lanes).  Suppressions are rare: shared-memory atomicOr.
-    for (int c = 0; c < words; ++c) {
-        const int r0 = c << 5;
-        const int rows_c = min(32, n - r0);
-        for (int d0 = 1 + 2 * warp_id(); d0 <= 16; d0 += 2 * nwarps) {
-            bool sup[2];
-            int row[2], bit[2];
+        if (c == w) bits &= lane == 31 ? 0u : ~0u << (lane + 1);             // diagonal block: only j > i
+        // compaction: exclusive prefix of the popcounts, then every lane writes its (row, column) codes
+        const int mine = __popc(bits);
+        int incl = mine;
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int d = d0 + u;
-                const int o = (lane + d) & 31;
-                const int lo = min(lane, o), hi = max(lane, o);
-                const bool active = d <= 16 && hi < rows_c && (d < 16 || lane < 16);
-                const int i = r0 + (active ? lo : 0), j = r0 + (active ? hi : 0);
-                sup[u] = pair_suppressed(a, sbox[i], sarea[i], sbox[j], sarea[j], active);
-                row[u] = i; bit[u] = hi;
-            }
-#pragma unroll
-            for (int u = 0; u < 2; ++u)
-                if (sup[u]) atomicOr(&mask[(size_t)row[u] * words + c], 1u << bit[u]);
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += t;
         }
+        const int total = __shfl_sync(FULL, incl, 31);
+        int pos = incl - mine;
+        while (bits) {
+            const int jj = __ffs(bits) - 1;
+            bits &= bits - 1;
+            plist[pos++] = (unsigned short)((lane << 5) | jj);
+        }
+        __syncwarp();
+        for (int e0 = 0; e0 < total; e0 += 32) {
+            const int e = e0 + lane;
+            const bool active = e < total;
+            const int code = active ? plist[e] : 0;
+            const int pi = (c << 5) + (code >> 5), pj = j0 + (code & 31);
+            const bool sup = pair_suppressed(a, sbox[pi], sarea[pi], sbox[pj], sarea[pj], active);
+            if (sup) atomicOr(&mask[(size_t)pi * words + w], 1u << (code & 31));
+        }
+        __syncwarp();
     }
     __syncthreads();
     tr.mark(4);
@@ -1443,8 +1447,8 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
         ta.Cf = pl.Cf; ta.K = pl.K; ta.T = pl.T; ta.det_cap = pl.det_cap; ta.kept_count = kept_count; ta.kept = kept;
         ta.score_hist = score_hist; ta.dets = dets_out; ta.det_count = count_out; ta.det_anchor = anchor_out;
         const int kwords = (pl.K + 31) / 32;
-        const size_t key_slots = pl.cand_cap > kMaxPerClass ? pl.cand_cap : kMaxPerClass;
-        const size_t nms_smem = key_slots * 8 + (size_t)(pl.K + 1) * (8 + 16 + 4 + 4) + (size_t)pl.K * kwords * 4 + 64;
+        const size_t key_slots = nms_key_slots(pl.cand_cap);
+        const size_t nms_smem = key_slots * 8 + (size_t)(pl.K + 1) * (8 + 16 + 16 + 4 + 4) + (size_t)pl.K * kwords * 4 + 64;
         // The final top-k can run in the last segment CTA of every image (fence + ticket) instead of
         // in its own launch.  Measured on B200 (tools/graph_timeline.py) the 128-thread tail is slower
         // than the launch it saves unless the batch is large, so it is opt-in: SSD_TOPK=fused.
