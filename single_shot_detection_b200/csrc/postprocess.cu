@@ -1091,6 +1091,8 @@ __device__ int nms_segment(const KernelTrace& tr, const NmsArgs& a, unsigned cha
     const int img = seg / a.Cf;
     const int lane = lane_id();
     tr.mark(0);
+    // the first candidate of every thread is requested together with the count (one round trip less)
+    const uint2 first_cand = cand[(size_t)seg * a.cand_cap + threadIdx.x];
     int n_raw = cand_count[seg];
     if (n_raw == 0) return 0;
     // carve: keys[key_slots] u64 | sorted[K] u64 | box[K] float4 | fbox[K] float4 | area[K] | mask[K * kwords] | keep[K]
@@ -1129,7 +1131,7 @@ __device__ int nms_segment(const KernelTrace& tr, const NmsArgs& a, unsigned cha
         for (int t = threadIdx.x; t < fill; t += blockDim.x) {
             unsigned long long key = 0ull;
             if (t < n_raw) {
-                const uint2 e = cand[(size_t)seg * a.cand_cap + t];
+                const uint2 e = t == (int)threadIdx.x ? first_cand : cand[(size_t)seg * a.cand_cap + t];
                 float2 st = make_float2(0.f, 1.f);
                 if (a.converter == SSD_CONVERT_SOFTMAX) st = rowstat[(size_t)img * a.A + e.x];
                 const float p = exact_score(a.converter, __uint_as_float(e.y), st);
@@ -1260,32 +1262,35 @@ __device__ int nms_segment(const KernelTrace& tr, const NmsArgs& a, unsigned cha
     __syncthreads();
     tr.mark(4);
 
-    // ---- greedy sweep in score order (warp 0).  Lane l owns word l of the suppressed set; rows are
-    //      resolved 32 at a time: the chunk's diagonal words are exchanged up front, the sequential
-    //      part is a register-only chain, the kept rows' mask words are pre-loaded. ----
+    // ---- greedy sweep in score order (warp 0), 32 rows at a time, lanes = rows of the chunk.
+    //      Lane w also owns word w of the suppressed set.  Only rows that suppress something inside
+    //      the chunk take part in the sequential chain (a row with an empty diagonal word changes
+    //      nothing; whether it is kept can be read off the final set, since later rows never touch
+    //      its bit); the words right of the diagonal are OR-reduced over the kept rows (REDUX). ----
     if (warp_id() == 0) {
         uint32_t removed = 0u;
         int nkeep = 0;
         for (int c = 0; c < words; ++c) {
             const int r0 = c << 5;
             const int rows_c = min(32, n - r0);
-            uint32_t later[32];                       // mask[r0 + l][lane] for the words after this chunk
-#pragma unroll
-            for (int l = 0; l < 32; ++l)
-                later[l] = (l < rows_c && lane > c && lane < words) ? mask[(size_t)(r0 + l) * words + lane] : 0u;
-            const uint32_t diag = lane < rows_c ? mask[(size_t)(r0 + lane) * words + c] : 0u;
+            const uint32_t* row = mask + (size_t)(r0 + lane) * words;
+            const uint32_t diag = lane < rows_c ? row[c] : 0u;
             uint32_t cur = __shfl_sync(FULL, removed, c);
             if (rows_c < 32) cur |= ~0u << rows_c;
-            uint32_t kbits = 0u;
-#pragma unroll
-            for (int l = 0; l < 32; ++l) {
+            unsigned todo = __ballot_sync(FULL, diag != 0u);
+            while (todo) {
+                const int l = __ffs(todo) - 1;
+                todo &= todo - 1;
                 const uint32_t d = __shfl_sync(FULL, diag, l);
-                if (!((cur >> l) & 1u)) { cur |= d; kbits |= 1u << l; }
+                if (!((cur >> l) & 1u)) cur |= d;
             }
-#pragma unroll
-            for (int l = 0; l < 32; ++l)
-                if ((kbits >> l) & 1u) removed |= later[l];
-            if ((kbits >> lane) & 1u) keep[nkeep + __popc(kbits & ((1u << lane) - 1u))] = r0 + lane;
+            const uint32_t kbits = ~cur;
+            const bool kept_row = (kbits >> lane) & 1u;
+            for (int w = c + 1; w < words; ++w) {
+                const uint32_t r = __reduce_or_sync(FULL, kept_row ? row[w] : 0u);
+                if (lane == w) removed |= r;
+            }
+            if (kept_row) keep[nkeep + __popc(kbits & ((1u << lane) - 1u))] = r0 + lane;
             nkeep += __popc(kbits);
         }
         if (lane == 0) s_nkeep = nkeep;
