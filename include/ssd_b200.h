@@ -244,6 +244,32 @@ SSD_API int ssd_nms(const float* corner_boxes, const float* scores, int num_boxe
             double overlap_threshold, int64_t* keep_out, int32_t* count_out, void* workspace,
             size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * f2  detection/metrics/mean_average_precision.py:10-116 + the accumulation loop of bf/eval.py:54-70
+ *     (the consumer of the post-processor's output).
+ *   ssd_map_append: compacts one batch of padded detections (dets [B, T, 6] + counts [B], as
+ *     ssd_postprocess writes them) into rows [capacity, 7] = (image id, x1, y1, x2, y2, class, score),
+ *     image id = image_base + b (eval.py:55-58), starting at *cursor_in; writes cursor_out[0] =
+ *     *cursor_in + sum(counts) and cursor_out[1] = capacity (rows past the capacity are dropped: the
+ *     caller compares the two).  cursor_in and cursor_out are two different int64[2] device words.
+ *   ssd_mean_average_precision: preds [count, 7] in any order; ground truth as for
+ *     ssd_assign_targets (a 7th "difficult" column is honoured when use_difficult);  classes are
+ *     0 .. num_classes-1 (detections of any other class never enter the mean).
+ *     ap_out [num_classes] fp32: AP per class, -1 for a class without (non-difficult) ground truth;
+ *     map_out double[2] = (mAP, number of classes in the mean);  order_out [count] uint32 = the
+ *     class-major / descending-score order the matching used;  flags_out [count] uint8 in that
+ *     order: 1 = true positive, 2 = false positive, 0 = neither (matched a difficult box).
+ *     voc != 0: 11-point interpolated AP, else area under the precision envelope.
+ * ---------------------------------------------------------------------------------------- */
+SSD_API size_t ssd_map_workspace_bytes(int64_t count, int total_gt, int num_classes);
+SSD_API int ssd_map_append(const float* dets, const int32_t* counts, int batch, int max_total, int image_base,
+                   float* rows, int64_t capacity, const int64_t* cursor_in, int64_t* cursor_out, void* stream);
+SSD_API int ssd_mean_average_precision(const float* preds, int64_t count, const float* gt_rows, int gt_cols,
+                               const int32_t* gt_offsets, int num_images, int total_gt, int num_classes,
+                               float iou_threshold, int use_difficult, int voc, float* ap_out, double* map_out,
+                               uint8_t* flags_out, uint32_t* order_out, void* workspace, size_t workspace_bytes,
+                               void* stream);
+
 #ifdef __cplusplus
 }
 #endif
