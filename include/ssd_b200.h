@@ -83,6 +83,10 @@ SSD_API int ssd_b200_trace_slots(void);
  * ---------------------------------------------------------------------------------------- */
 SSD_API int ssd_pairwise_iou(const float* a_corners, int num_a, const float* b_corners, int num_b,
                      float* out, void* stream);
+/* f4  bf/utils/box_utils.py:104-143  generalized_iou(a, b, cartesian): iou - (enclosing - union) / enclosing.
+ *     cartesian != 0: out [num_a, num_b]; else element-wise, num_a == num_b, out [num_a]. */
+SSD_API int ssd_generalized_iou(const float* a_corners, int num_a, const float* b_corners, int num_b,
+                        int cartesian, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * a3  detection/matcher.py:33-56  match_per_prediction(weights, matched, unmatched, force)
@@ -216,6 +220,10 @@ typedef struct {
     double overlap_threshold;    /* NMS IoU threshold, compared as (double)iou > threshold   */
     int32_t max_total;           /* T; <= 0 means no final top-k                             */
     int32_t det_capacity;        /* rows per image in dets_out; >= min(T or inf, Cf*K)       */
+    int32_t soft_nms;            /* != 0: soft-NMS (box_utils.py:145-163) instead of hard NMS */
+    float soft_sigma;            /* Gaussian decay exp(-iou^2 / sigma)                       */
+    float soft_threshold;        /* threshold of the soft-NMS loop (Postprocessor: = score_threshold) */
+    int32_t reserved_;
 } ssd_postprocess_params;
 
 SSD_API size_t ssd_postprocess_workspace_bytes(const ssd_postprocess_params* p);
@@ -244,6 +252,13 @@ SSD_API int ssd_nms(const float* corner_boxes, const float* scores, int num_boxe
             double overlap_threshold, int64_t* keep_out, int32_t* count_out, void* workspace,
             size_t workspace_bytes, void* stream);
 
+/* f4  bf/utils/box_utils.py:145-163  nms(..., soft=True): Gaussian soft-NMS of one box set, the
+ *     reference's loop statement by statement (including its loop condition on the SUM of the
+ *     remaining indices).  keep_out[i] = input row of the i-th PICKED box (pick order). */
+SSD_API int ssd_soft_nms(const float* corner_boxes, const float* scores, int num_boxes, int max_per_class,
+                 float score_threshold, float sigma, int64_t* keep_out, int32_t* count_out, void* workspace,
+                 size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * f2  detection/metrics/mean_average_precision.py:10-116 + the accumulation loop of bf/eval.py:54-70
  *     (the consumer of the post-processor's output).
@@ -269,6 +284,24 @@ SSD_API int ssd_mean_average_precision(const float* preds, int64_t count, const 
                                float iou_threshold, int use_difficult, int voc, float* ap_out, double* map_out,
                                uint8_t* flags_out, uint32_t* order_out, void* workspace, size_t workspace_bytes,
                                void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * f3  detection/anchor_generators/ssd.py:106-151, retina_net.py:28-54, detection/detector.py:82-86
+ *     the [A, 4] (cx, cy, w, h) anchor table of all levels, written on the device by one launch.
+ *   levels: HOST array.  Per level the cell centres are torch.linspace(x_start, x_end, cells_x) /
+ *   (y_start, y_end, cells_y) evaluated as ATen's fp32 CPU kernel does; wh holds the (w, h) of the
+ *   num_boxes boxes of a cell.  Layout per level: rows, then columns, then boxes (the head layout).
+ * ---------------------------------------------------------------------------------------- */
+#define SSD_MAX_ANCHOR_LEVELS 8
+#define SSD_MAX_BOXES_PER_CELL 16
+typedef struct {
+    int32_t cells_x, cells_y;
+    float x_start, x_end, y_start, y_end;
+    int32_t num_boxes;
+    float wh[2 * SSD_MAX_BOXES_PER_CELL];
+} SsdAnchorLevel;
+SSD_API int ssd_generate_anchors(const SsdAnchorLevel* levels, int num_levels, float* anchors_out,
+                         int64_t num_anchors, void* stream);
 
 #ifdef __cplusplus
 }

@@ -345,6 +345,49 @@ def greedy_nms(corner_boxes: np.ndarray, scores: np.ndarray, iou_threshold: floa
     return np.asarray(kept, dtype=np.int64)
 
 
+def gaussian_soft_nms(corner_boxes: torch.Tensor, scores: torch.Tensor, score_threshold: float,
+                      sigma: float = 0.5) -> torch.Tensor:
+    """Soft-NMS exactly as bf/utils/box_utils.py:145-163 runs it; returns the picked indices in pick
+    order (the reference returns ``(boxes[picked], scores[picked])`` with the INPUT scores).
+
+    Kept quirks: the loop head tests ``mask.nonzero().sum()`` -- the SUM OF THE INDICES of the mask,
+    so a mask whose only element is index 0 ends the loop (:151); the mask tested by the next loop head
+    is computed before the decay of this iteration (:156 vs :160); ``argmax`` runs over every
+    remaining score, above the threshold or not (:152).  Boxes areas are clamped (box_utils.area).
+    """
+    work = scores.clone()
+    mask = scores > score_threshold                                           # :147
+    area = box_area(corner_boxes)                                             # :148
+    picked: List[int] = []
+    while int(mask.nonzero().sum()) and len(picked) < scores.shape[0]:
+        idx = int(work.argmax())                                              # :152
+        work[idx] = 0                                                         # :153
+        picked.append(idx)
+        mask = work > score_threshold                                         # :156
+        inter_box = pairwise_overlap_box(corner_boxes[idx].unsqueeze(0), corner_boxes[mask]).squeeze(0)
+        inter = box_area(inter_box)                                           # :158
+        iou = inter / (area[idx] + area[mask] - inter)                        # :159
+        work[mask] = work[mask] * iou.pow(2).div_(sigma).neg_().exp_()        # :160
+    return torch.tensor(picked, dtype=torch.long)
+
+
+def generalized_iou(a: torch.Tensor, b: torch.Tensor, cartesian: bool = True) -> torch.Tensor:
+    """bf/utils/box_utils.py:104-143: iou - (enclosing - union) / enclosing for corner boxes."""
+    if cartesian:
+        inter = box_area(pairwise_overlap_box(a, b))
+        area_a = box_area(a).unsqueeze(1).expand_as(inter)
+        area_b = box_area(b).unsqueeze(0).expand_as(inter)
+        lo = torch.min(a[:, None, :2].expand(a.shape[0], b.shape[0], 2), b[None, :, :2].expand(a.shape[0], b.shape[0], 2))
+        hi = torch.max(a[:, None, 2:].expand(a.shape[0], b.shape[0], 2), b[None, :, 2:].expand(a.shape[0], b.shape[0], 2))
+    else:
+        inter = box_area(torch.cat([torch.max(a[..., :2], b[..., :2]), torch.min(a[..., 2:], b[..., 2:])], dim=-1))
+        area_a, area_b = box_area(a), box_area(b)
+        lo, hi = torch.min(a[..., :2], b[..., :2]), torch.max(a[..., 2:], b[..., 2:])
+    union = area_a + area_b - inter
+    enclosing = box_area(torch.cat([lo, hi], dim=-1))
+    return inter / union - (enclosing - union) / enclosing
+
+
 def select_top_scores(scores: torch.Tensor, k: int, canonical: bool = True) -> torch.Tensor:
     """Indices of the k largest scores.  Canonical: (score desc, index asc), returned in that
     order; otherwise ``torch.topk(sorted=False)`` as bf/utils/box_utils.py:186-187."""
@@ -356,8 +399,9 @@ def select_top_scores(scores: torch.Tensor, k: int, canonical: bool = True) -> t
 
 def class_nms(corner_boxes: torch.Tensor, scores: torch.Tensor, overlap_threshold: float,
               max_per_class: Optional[int] = None, canonical: bool = True,
-              use_torchvision: bool = False):
-    """Top-k then hard NMS for one class.  bf/utils/box_utils.py:165-194 (soft=False).
+              use_torchvision: bool = False, soft: Optional[Tuple[float, float]] = None):
+    """Top-k then hard NMS for one class (bf/utils/box_utils.py:165-194), or soft-NMS when
+    ``soft = (score_threshold, sigma)``.
 
     Returns ((boxes[keep], scores[keep]), keep, subset) where ``keep`` indexes the top-k
     ``subset`` (as in the reference) and ``subset`` maps back to the input rows (None when no
@@ -368,7 +412,9 @@ def class_nms(corner_boxes: torch.Tensor, scores: torch.Tensor, overlap_threshol
         subset = select_top_scores(scores, max_per_class, canonical)
         scores = scores[subset]
         corner_boxes = corner_boxes[subset]
-    if use_torchvision:
+    if soft is not None:
+        keep = gaussian_soft_nms(corner_boxes, scores, soft[0], soft[1])
+    elif use_torchvision:
         import torchvision
         keep = torchvision.ops.nms(corner_boxes, scores, overlap_threshold)
     else:
@@ -396,7 +442,7 @@ def detections_from_scores(fg_probs: torch.Tensor, corner_boxes: torch.Tensor,
                            score_threshold: float, overlap_threshold: float,
                            max_per_class: Optional[int], max_total: Optional[int],
                            canonical: bool = True, use_torchvision: bool = False,
-                           return_keep: bool = False):
+                           return_keep: bool = False, soft_sigma: Optional[float] = None):
     """Selection half of the post-processor (postprocessor.py:57-76): per class threshold ->
     top-k -> NMS -> concatenate -> optional final top-k.  Inputs are probabilities [B, A, Cf] and
     decoded corner boxes [B, A, 4], so a test can feed it the exact fp32 values another
@@ -416,7 +462,8 @@ def detections_from_scores(fg_probs: torch.Tensor, corner_boxes: torch.Tensor,
             above = col > score_threshold                               # :62 (fp32 compare)
             cand = torch.nonzero(above).view(-1)
             (b_keep, s_keep), keep, subset = class_nms(boxes[above], col[above], overlap_threshold,
-                                                       max_per_class, canonical, use_torchvision)
+                                                       max_per_class, canonical, use_torchvision,
+                                                       None if soft_sigma is None else (score_threshold, soft_sigma))
             src = cand if subset is None else cand[subset]
             per_class.append(src[keep])
             cls = torch.full((s_keep.shape[0], 1), float(c + 1))        # :66
@@ -439,7 +486,7 @@ def postprocess(scores: torch.Tensor, locs: torch.Tensor, priors: torch.Tensor, 
                 xy_scale: float, wh_scale: float, score_threshold: float,
                 overlap_threshold: float, max_per_class: Optional[int],
                 max_total: Optional[int], converter: str = "SOFTMAX",
-                canonical: bool = True, use_torchvision: bool = False):
+                canonical: bool = True, use_torchvision: bool = False, soft_sigma: Optional[float] = None):
     """Full post-processor.  detection/postprocessor.py:24-78."""
     batch = scores.shape[0]
     num_priors = priors.shape[0]
@@ -447,7 +494,7 @@ def postprocess(scores: torch.Tensor, locs: torch.Tensor, priors: torch.Tensor, 
     decoded = decode_boxes(locs.float().view(batch, num_priors, 4), priors, xy_scale, wh_scale)
     corners = corners_from_centroids(decoded)
     return detections_from_scores(probs, corners, score_threshold, overlap_threshold,
-                                  max_per_class, max_total, canonical, use_torchvision)
+                                  max_per_class, max_total, canonical, use_torchvision, soft_sigma=soft_sigma)
 
 
 def class_topk_boundary_tie(fg_probs: torch.Tensor, score_threshold: float,

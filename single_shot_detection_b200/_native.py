@@ -34,7 +34,8 @@ class PostprocessParams(Structure):
     _fields_ = [("batch", c_int32), ("num_anchors", c_int32), ("num_cols", c_int32), ("converter", c_int32),
                 ("first_fg_col", c_int32), ("box_input", c_int32), ("xy_scale", c_float), ("wh_scale", c_float),
                 ("score_threshold", c_float), ("max_per_class", c_int32), ("overlap_threshold", c_double),
-                ("max_total", c_int32), ("det_capacity", c_int32)]
+                ("max_total", c_int32), ("det_capacity", c_int32), ("soft_nms", c_int32), ("soft_sigma", c_float),
+                ("soft_threshold", c_float), ("reserved_", c_int32)]
 
 
 class NativeError(RuntimeError):
@@ -42,6 +43,19 @@ class NativeError(RuntimeError):
         super().__init__(f"{STATUS_NAMES.get(status, status)}: {message}")
         self.status = status
 
+
+MAX_ANCHOR_LEVELS = 8
+MAX_BOXES_PER_CELL = 16
+
+
+class AnchorLevel(Structure):
+    """SsdAnchorLevel of include/ssd_b200.h."""
+    _fields_ = [("cells_x", c_int32), ("cells_y", c_int32), ("x_start", c_float), ("x_end", c_float),
+                ("y_start", c_float), ("y_end", c_float), ("num_boxes", c_int32),
+                ("wh", c_float * (2 * MAX_BOXES_PER_CELL))]
+
+
+MAX_PER_CLASS = 512            # kMaxPerClass of csrc/postprocess.cu
 
 _SIGNATURES = {
     "ssd_b200_abi_version": (c_int, []),
@@ -58,6 +72,7 @@ _SIGNATURES = {
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ssd_box_transform": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_float,
                                   c_float, c_float, c_void_p]),
+    "ssd_generalized_iou": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "ssd_positive_mask": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "ssd_b200_launch_count": (ctypes.c_ulonglong, []),
     "ssd_mining_keys": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -72,10 +87,13 @@ _SIGNATURES = {
     "ssd_mean_average_precision": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float,
                                            c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                            c_void_p]),
+    "ssd_generate_anchors": (c_int, [POINTER(AnchorLevel), c_int, c_void_p, c_int64, c_void_p]),
     "ssd_postprocess_workspace_bytes": (c_size_t, [POINTER(PostprocessParams)]),
     "ssd_postprocess": (c_int, [POINTER(PostprocessParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ssd_nms_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "ssd_soft_nms": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_size_t,
+                             c_void_p]),
     "ssd_nms": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 

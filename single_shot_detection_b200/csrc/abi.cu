@@ -96,6 +96,7 @@ cudaError_t set_trace_mining(unsigned long long*);
 cudaError_t set_trace_postprocess(unsigned long long*);
 cudaError_t set_trace_loss(unsigned long long*);
 cudaError_t set_trace_metrics(unsigned long long*);
+cudaError_t set_trace_anchors(unsigned long long*);
 }  // namespace ssd
 
 extern "C" int ssd_b200_trace_enable(unsigned long long* device_slots) {
@@ -105,6 +106,7 @@ extern "C" int ssd_b200_trace_enable(unsigned long long* device_slots) {
     SSD_CUDA(ssd::set_trace_postprocess(device_slots));
     SSD_CUDA(ssd::set_trace_loss(device_slots));
     SSD_CUDA(ssd::set_trace_metrics(device_slots));
+    SSD_CUDA(ssd::set_trace_anchors(device_slots));
     return SSD_OK;
 }
 extern "C" int ssd_b200_trace_slots(void) { return ssd::kTraceSlots; }

@@ -267,6 +267,24 @@ __global__ void pairwise_iou_kernel(const float4* __restrict__ a, int na, const 
     out[(size_t)i * nb + j] = fdiv(inter, fsub(fadd(area_a, area_b), inter));
 }
 
+// bf/utils/box_utils.py:104-143 generalized IoU (https://arxiv.org/abs/1902.09630): iou - (enclosing - union) / enclosing.
+// cartesian: out[na, nb]; otherwise element-wise over na == nb rows (grid.y == 1, i = j).
+__global__ void generalized_iou_kernel(const float4* __restrict__ a, int na, const float4* __restrict__ b, int nb,
+                                       int cartesian, float* __restrict__ out) {
+    griddep_wait();
+    griddep_launch_dependents();
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nb) return;
+    const int i = cartesian ? blockIdx.y : j;
+    const float4 ga = a[i], gb = b[j];
+    const float area_a = clamped_area(ga.x, ga.y, ga.z, ga.w);
+    const float area_b = clamped_area(gb.x, gb.y, gb.z, gb.w);
+    const float inter = clamped_area(fmaxf(ga.x, gb.x), fmaxf(ga.y, gb.y), fminf(ga.z, gb.z), fminf(ga.w, gb.w));
+    const float uni = fsub(fadd(area_a, area_b), inter);
+    const float enc = clamped_area(fminf(ga.x, gb.x), fminf(ga.y, gb.y), fmaxf(ga.z, gb.z), fmaxf(ga.w, gb.w));
+    out[cartesian ? (size_t)i * nb + j : (size_t)j] = fsub(fdiv(inter, uni), fdiv(fsub(enc, uni), enc));
+}
+
 // one CTA: weights[G, A] -> box_idx[A].  Columns are walked by threads (coalesced along A).
 __global__ void __launch_bounds__(1024)
 match_per_prediction_kernel(const float* __restrict__ w, int G, int A, float matched_thr, float unmatched_thr,
@@ -330,6 +348,23 @@ extern "C" int ssd_pairwise_iou(const float* a_corners, int num_a, const float* 
     dim3 grid((num_b + 255) / 256, num_a);
     SSD_CUDA(launch_pdl(pairwise_iou_kernel, grid, dim3(256), 0, (cudaStream_t)stream, (const float4*)a_corners, num_a,
                         (const float4*)b_corners, num_b, out));
+    count_launch();
+    return SSD_OK;
+}
+
+extern "C" int ssd_generalized_iou(const float* a_corners, int num_a, const float* b_corners, int num_b, int cartesian,
+                                   float* out, void* stream) {
+    SSD_REQUIRE(num_a >= 0 && num_b >= 0, SSD_ERR_INVALID_ARGUMENT, "ssd_generalized_iou: negative size");
+    SSD_REQUIRE(cartesian || num_a == num_b, SSD_ERR_INVALID_ARGUMENT,
+                "ssd_generalized_iou: element-wise form needs as many a rows as b rows (%d vs %d)", num_a, num_b);
+    if (num_a == 0 || num_b == 0) return SSD_OK;
+    SSD_REQUIRE(a_corners && b_corners && out, SSD_ERR_INVALID_ARGUMENT, "ssd_generalized_iou: null pointer");
+    SSD_REQUIRE(aligned(a_corners, 16) && aligned(b_corners, 16), SSD_ERR_MISALIGNED,
+                "ssd_generalized_iou: boxes must be 16-byte aligned");
+    SSD_REQUIRE(!cartesian || num_a <= 65535, SSD_ERR_UNSUPPORTED, "ssd_generalized_iou: more than 65535 rows");
+    dim3 grid((num_b + 255) / 256, cartesian ? num_a : 1);
+    SSD_CUDA(launch_pdl(generalized_iou_kernel, grid, dim3(256), 0, (cudaStream_t)stream, (const float4*)a_corners, num_a,
+                        (const float4*)b_corners, num_b, cartesian, out));
     count_launch();
     return SSD_OK;
 }

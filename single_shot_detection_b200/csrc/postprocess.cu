@@ -51,6 +51,7 @@ struct PostPlan {
     size_t zero_begin, zero_bytes;   // counters and histograms: one memset per call
     bool gate_hist;                  // gates from a histogram of the block maxima (SOFTMAX / SIGMOID)
     float bin_lo, bin_scale;
+    float soft_thr;
     size_t total_bytes;
 };
 
@@ -107,6 +108,8 @@ static int make_plan(const ssd_postprocess_params* p, PostPlan& pl) {
     pl.B = p->batch; pl.A = p->num_anchors; pl.C = p->num_cols; pl.first_fg = p->first_fg_col;
     pl.Cf = pl.C - pl.first_fg; pl.K = p->max_per_class; pl.T = p->max_total; pl.det_cap = p->det_capacity;
     pl.converter = p->converter; pl.box_input = p->box_input;
+    pl.soft_thr = p->soft_threshold;
+    SSD_REQUIRE(!p->soft_nms || p->soft_sigma > 0.f, SSD_ERR_INVALID_ARGUMENT, "ssd_postprocess: soft-NMS needs sigma > 0");
     const long long all_rows = (long long)pl.Cf * pl.K;
     const long long need = (pl.T > 0 && pl.T < all_rows) ? pl.T : all_rows;
     SSD_REQUIRE(pl.det_cap >= need, SSD_ERR_INVALID_ARGUMENT,
@@ -624,6 +627,9 @@ struct NmsArgs {
     // fp32 screen (see pair_screen): threshold * (1 -/+ 4e-7), valid for thresholds in [0, 1e30)
     float iou_lo, iou_hi;
     int screen;
+    // soft-NMS (box_utils.py:145-163): Gaussian decay instead of the hard sweep
+    int soft;
+    float soft_thr, soft_sigma;
 };
 
 // torchvision compares the fp32 quotient with the double threshold.  Let T32 be the smallest float
@@ -1191,7 +1197,8 @@ __device__ int nms_segment(const KernelTrace& tr, const NmsArgs& a, unsigned cha
             bx = make_float4(fsub(cx, hw), fsub(cy, hh), fadd(cx, hw), fadd(cy, hh));
         }
         sbox[t] = bx;
-        sarea[t] = fmul(fsub(bx.z, bx.x), fsub(bx.w, bx.y));          // torchvision: unclamped area
+        sarea[t] = a.soft ? fmul(fmaxf(fsub(bx.z, bx.x), 0.f), fmaxf(fsub(bx.w, bx.y), 0.f))   // box_utils.area: clamped
+                          : fmul(fsub(bx.z, bx.x), fsub(bx.w, bx.y));                          // torchvision: unclamped
         // a box without positive extent intersects nothing (the clamped side is 0): NaN fails every compare
         const bool extent = bx.z > bx.x && bx.w > bx.y;
         fbox[t] = extent ? bx : make_float4(NAN, NAN, NAN, NAN);
@@ -1200,6 +1207,71 @@ __device__ int nms_segment(const KernelTrace& tr, const NmsArgs& a, unsigned cha
     __syncthreads();
     tr.mark(3);
 
+    if (a.soft) {
+        // ---- soft-NMS, box_utils.py:145-163, statement by statement (warp 0; lanes = candidates):
+        //        mask = scores > thr
+        //        while mask.nonzero().sum():                 <- the SUM OF THE INDICES: a mask whose only
+        //            idx = scores_copy.argmax()                 element is index 0 ends the loop
+        //            scores_copy[idx] = 0; picked += idx
+        //            mask = scores_copy > thr                <- tested by the NEXT loop head, before ...
+        //            scores_copy[mask] *= exp(-(iou(idx, mask) ** 2) / sigma)      ... this decay
+        //      Index 0 of the reference's subset is the lowest anchor (boolean-mask order); ties of
+        //      the argmax go to the lowest anchor as well. ----
+        float* sc = reinterpret_cast<float*>(mask);
+        for (int t = threadIdx.x; t < n; t += blockDim.x) sc[t] = key_to_float((uint32_t)(sorted[t] >> 32));
+        __syncthreads();
+        if (warp_id() == 0) {
+            unsigned long long lowest = ~0ull;
+            for (int t = lane; t < n; t += 32) {
+                const unsigned long long anchor = 0xFFFFFFFFull - (sorted[t] & 0xFFFFFFFFull);
+                lowest = min(lowest, (anchor << 32) | (unsigned long long)t);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) lowest = min(lowest, __shfl_xor_sync(FULL, lowest, o));
+            const int p0 = (int)(lowest & 0xFFFFFFFFull);
+            bool more = false;
+            for (int t = lane; t < n; t += 32) more |= sc[t] > a.soft_thr && t != p0;
+            more = __any_sync(FULL, more);
+            int nkeep = 0;
+            while (more && nkeep < n) {
+                // argmax over (score, lower anchor first): key = (ordered score, ~anchor) like `sorted`
+                unsigned long long best = 0ull;
+                int bt = 0;
+                for (int t = lane; t < n; t += 32) {
+                    const unsigned long long k = ((unsigned long long)ordered_key(sc[t]) << 32) | (sorted[t] & 0xFFFFFFFFull);
+                    if (k > best) { best = k; bt = t; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const unsigned long long ob = __shfl_xor_sync(FULL, best, o);
+                    const int ot = __shfl_xor_sync(FULL, bt, o);
+                    if (ob > best) { best = ob; bt = ot; }
+                }
+                if (lane == 0) { keep[nkeep] = bt; sc[bt] = 0.f; }
+                ++nkeep;
+                __syncwarp();
+                const float4 bi = sbox[bt];
+                const float ai = sarea[bt];
+                more = false;
+                for (int t = lane; t < n; t += 32) {
+                    const float v = sc[t];
+                    if (v > a.soft_thr) {
+                        more |= t != p0;
+                        const float4 bj = sbox[t];
+                        const float iw = fmaxf(fsub(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)), 0.f);
+                        const float ih = fmaxf(fsub(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)), 0.f);
+                        const float inter = fmul(iw, ih);
+                        const float iou = fdiv(inter, fsub(fadd(ai, sarea[t]), inter));
+                        sc[t] = fmul(v, expf(-fdiv(fmul(iou, iou), a.soft_sigma)));
+                    }
+                }
+                more = __any_sync(FULL, more);
+                __syncwarp();
+            }
+            if (lane == 0) s_nkeep = nkeep;
+        }
+        __syncthreads();
+    } else {
     // ---- IoU bit matrix: bit j of row i set <=> box i suppresses box j (j > i) ----
     // Two tiers per 32 x 32 block (row chunk c, column word w >= c), one warp per block:
     //  (1) overlap filter, lanes = rows: the 32 boxes of the word are broadcast one by one and every
@@ -1296,6 +1368,7 @@ __device__ int nms_segment(const KernelTrace& tr, const NmsArgs& a, unsigned cha
         if (lane == 0) s_nkeep = nkeep;
     }
     __syncthreads();
+    }   // hard NMS
     tr.mark(5);
     const int nkeep = s_nkeep;
     float* out = kept + (size_t)seg * a.K * kKeptCols;
@@ -1448,6 +1521,9 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
         a.xy_scale = p->xy_scale; a.wh_scale = p->wh_scale;
         nms_threshold_split(p->overlap_threshold, a);
         nms_threshold_screen(p->overlap_threshold, a);
+        a.soft = p->soft_nms != 0;
+        a.soft_sigma = p->soft_sigma;
+        a.soft_thr = pl.soft_thr;
         TopkArgs ta;
         ta.Cf = pl.Cf; ta.K = pl.K; ta.T = pl.T; ta.det_cap = pl.det_cap; ta.kept_count = kept_count; ta.kept = kept;
         ta.score_hist = score_hist; ta.dets = dets_out; ta.det_count = count_out; ta.det_anchor = anchor_out;
@@ -1555,6 +1631,41 @@ extern "C" int ssd_nms(const float* corner_boxes, const float* scores, int num_b
     SSD_CUDA(launch_pdl(widen_keep_kernel, dim3((max_per_class + 127) / 128), dim3(128), 0, st, (const int*)anchors,
                         (const int*)count_out, (long long*)keep_out, max_per_class));
     SSD_CUDA(cudaGetLastError());
+    count_launch();
+    return SSD_OK;
+}
+
+// ---- box_utils.nms(soft=True): the same call with the Gaussian sweep ----
+extern "C" int ssd_soft_nms(const float* corner_boxes, const float* scores, int num_boxes, int max_per_class,
+                            float score_threshold, float sigma, int64_t* keep_out, int32_t* count_out, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+    SSD_REQUIRE(num_boxes >= 0, SSD_ERR_INVALID_ARGUMENT, "ssd_soft_nms: negative box count");
+    SSD_REQUIRE(count_out != nullptr, SSD_ERR_INVALID_ARGUMENT, "ssd_soft_nms: null count_out");
+    SSD_REQUIRE(sigma > 0.f, SSD_ERR_INVALID_ARGUMENT, "ssd_soft_nms: sigma must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (num_boxes == 0) {
+        SSD_CUDA(cudaMemsetAsync(count_out, 0, sizeof(int32_t), st));
+        return SSD_OK;
+    }
+    ssd_postprocess_params p;
+    nms_params(num_boxes, max_per_class, 0.5, p);
+    p.soft_nms = 1; p.soft_sigma = sigma; p.soft_threshold = score_threshold;
+    PostPlan pl;
+    const int rc = make_plan(&p, pl);
+    if (rc != SSD_OK) return rc;
+    SSD_REQUIRE(corner_boxes && scores && keep_out && workspace, SSD_ERR_INVALID_ARGUMENT, "ssd_soft_nms: null pointer");
+    SSD_REQUIRE(aligned(corner_boxes, 16) && aligned(scores, 16), SSD_ERR_MISALIGNED,
+                "ssd_soft_nms: boxes and scores must be 16-byte aligned");
+    SSD_REQUIRE(aligned(workspace, 256), SSD_ERR_MISALIGNED, "ssd_soft_nms: workspace must be 256-byte aligned");
+    SSD_REQUIRE(workspace_bytes >= ssd_nms_workspace_bytes(num_boxes, max_per_class), SSD_ERR_WORKSPACE,
+                "ssd_soft_nms: workspace too small");
+    unsigned char* ws = (unsigned char*)workspace;
+    float* dets = (float*)(ws + pl.total_bytes);
+    int* anchors = (int*)(ws + pl.off_anchor_tmp);
+    const int rc2 = run_postprocess(pl, &p, scores, corner_boxes, nullptr, dets, count_out, anchors, nullptr, ws, st);
+    if (rc2 != SSD_OK) return rc2;
+    SSD_CUDA(launch_pdl(widen_keep_kernel, dim3((max_per_class + 127) / 128), dim3(128), 0, st, (const int*)anchors,
+                        (const int*)count_out, (long long*)keep_out, max_per_class));
     count_launch();
     return SSD_OK;
 }

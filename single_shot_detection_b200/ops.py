@@ -16,6 +16,7 @@ from . import _native as N
 _LIB = torch.library.Library("ssd_b200", "DEF")
 
 _LIB.define("pairwise_iou(Tensor a, Tensor b) -> Tensor")
+_LIB.define("generalized_iou(Tensor a, Tensor b, bool cartesian) -> Tensor")
 _LIB.define("match_per_prediction(Tensor weights, float matched_threshold, float unmatched_threshold, "
             "bool force_match) -> Tensor")
 _LIB.define("assign_targets(Tensor anchors, Tensor gt_rows, Tensor gt_offsets, int max_gt, "
@@ -27,8 +28,9 @@ _LIB.define("hard_negative_mask(Tensor? logits, Tensor target_classes, Tensor? l
             "bool ratio_is_integer, float min_negatives) -> (Tensor, Tensor)")
 _LIB.define("postprocess(Tensor scores, Tensor boxes, Tensor? priors, int converter, int first_fg_col, "
             "int box_input, float xy_scale, float wh_scale, float score_threshold, int max_per_class, "
-            "float overlap_threshold, int max_total) -> (Tensor, Tensor, Tensor, Tensor)")
+            "float overlap_threshold, int max_total, float soft_sigma=0.0) -> (Tensor, Tensor, Tensor, Tensor)")
 _LIB.define("nms(Tensor boxes, Tensor scores, int max_per_class, float overlap_threshold) -> (Tensor, Tensor)")
+_LIB.define("soft_nms(Tensor boxes, Tensor scores, int max_per_class, float score_threshold, float sigma) -> (Tensor, Tensor)")
 _LIB.define("multibox_loss(Tensor scores, Tensor locs, Tensor target, Tensor sampled_mask, int kind, float gamma, "
             "float alpha, float class_weight, float loc_weight, bool need_grad) -> (Tensor, Tensor, Tensor)")
 
@@ -88,6 +90,17 @@ def _pairwise_iou(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
     with torch.cuda.device(a.device):
         N.check(N.lib().ssd_pairwise_iou(_ptr(a), a.shape[0], _ptr(b), b.shape[0], _ptr(out), _stream()))
+    return out
+
+
+def _generalized_iou(a: torch.Tensor, b: torch.Tensor, cartesian: bool) -> torch.Tensor:
+    N.require_device()
+    a, b = _f32c(a), _f32c(b)
+    shape = (a.shape[0], b.shape[0]) if cartesian else (a.shape[0],)
+    out = torch.empty(shape, dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        N.check(N.lib().ssd_generalized_iou(_ptr(a), a.shape[0], _ptr(b), b.shape[0], int(cartesian), _ptr(out),
+                                            _stream()))
     return out
 
 
@@ -197,7 +210,7 @@ def det_capacity(num_fg: int, max_per_class: int, max_total: int) -> int:
 
 def _postprocess(scores: torch.Tensor, boxes: torch.Tensor, priors: Optional[torch.Tensor], converter: int,
                  first_fg_col: int, box_input: int, xy_scale: float, wh_scale: float, score_threshold: float,
-                 max_per_class: int, overlap_threshold: float, max_total: int):
+                 max_per_class: int, overlap_threshold: float, max_total: int, soft_sigma: float = 0.0):
     N.require_device()
     scores = _f32c(scores.detach())
     boxes = _f32c(boxes.detach())
@@ -212,6 +225,7 @@ def _postprocess(scores: torch.Tensor, boxes: torch.Tensor, priors: Optional[tor
     p.max_per_class, p.overlap_threshold, p.max_total = max_per_class, overlap_threshold, max_total
     cap = det_capacity(num_cols - first_fg_col, max_per_class, max_total)
     p.det_capacity = cap
+    p.soft_nms, p.soft_sigma, p.soft_threshold = int(soft_sigma > 0.0), soft_sigma, score_threshold
     dets = torch.empty((batch, cap, 6), dtype=torch.float32, device=dev)
     counts = torch.empty((batch,), dtype=torch.int32, device=dev)
     anchors = torch.empty((batch, cap), dtype=torch.int32, device=dev)
@@ -238,6 +252,21 @@ def _nms(boxes: torch.Tensor, scores: torch.Tensor, max_per_class: int, overlap_
         ws = workspace(max(nbytes, 256), dev, "nms")
         N.check(N.lib().ssd_nms(_ptr(boxes), _ptr(scores), n, max_per_class, overlap_threshold, _ptr(keep),
                                 _ptr(count), _ptr(ws), ws.numel(), _stream()))
+    return keep, count
+
+
+def _soft_nms(boxes: torch.Tensor, scores: torch.Tensor, max_per_class: int, score_threshold: float, sigma: float):
+    N.require_device()
+    boxes, scores = _f32c(boxes), _f32c(scores)
+    n = scores.numel()
+    dev = boxes.device
+    keep = torch.empty((max_per_class,), dtype=torch.int64, device=dev)
+    count = torch.zeros((1,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        nbytes = N.lib().ssd_nms_workspace_bytes(n, max_per_class)
+        ws = workspace(max(nbytes, 256), dev, "nms")
+        N.check(N.lib().ssd_soft_nms(_ptr(boxes), _ptr(scores), n, max_per_class, score_threshold, sigma, _ptr(keep),
+                                     _ptr(count), _ptr(ws), ws.numel(), _stream()))
     return keep, count
 
 
@@ -268,10 +297,10 @@ def _multibox_loss(scores: torch.Tensor, locs: torch.Tensor, target: torch.Tenso
     return loss3, grad_scores, grad_locs
 
 
-for _name, _fn in [("multibox_loss", _multibox_loss), ("pairwise_iou", _pairwise_iou), ("match_per_prediction", _match_per_prediction),
+for _name, _fn in [("multibox_loss", _multibox_loss), ("pairwise_iou", _pairwise_iou), ("generalized_iou", _generalized_iou), ("match_per_prediction", _match_per_prediction),
                    ("assign_targets", _assign_targets), ("box_transform", _box_transform),
                    ("box_transform_", _box_transform_), ("positive_mask", _positive_mask),
-                   ("hard_negative_mask", _hard_negative_mask), ("postprocess", _postprocess), ("nms", _nms)]:
+                   ("hard_negative_mask", _hard_negative_mask), ("postprocess", _postprocess), ("nms", _nms), ("soft_nms", _soft_nms)]:
     _LIB.impl(_name, _fn, "CUDA")
 
 OPS = torch.ops.ssd_b200

@@ -27,8 +27,6 @@ class Postprocessor(object):
         self.score_converter = score_converter
         if score_converter not in _CONVERTERS:
             raise ValueError(f'Wrong value for score_converter: {score_converter}')
-        if nms.get('soft', False):
-            raise NotImplementedError('soft-NMS is not part of the accelerated path (SURVEY.md §8f)')
         if nms.get('max_per_class') is None:
             raise NotImplementedError('max_per_class=None (NMS over every candidate) is not supported; '
                                       'every reference sample sets it (100)')
@@ -47,7 +45,8 @@ class Postprocessor(object):
         return OPS.postprocess(b_scores, b_boxes, priors_dev, converter, first_fg, N.BOXES_ENCODED,
                                float(self.box_coder.xy_scale), float(self.box_coder.wh_scale),
                                float(self.score_threshold), int(self._nms_cfg['max_per_class']),
-                               float(self._nms_cfg['overlap_threshold']), max_total)
+                               float(self._nms_cfg['overlap_threshold']), max_total,
+                               float(self._nms_cfg.get('sigma', 0.5)) if self._nms_cfg.get('soft', False) else 0.0)
 
     def postprocess(self, prediction, priors):
         """

@@ -100,6 +100,17 @@ def build_anchors(w: Workload) -> torch.Tensor:
     return _anchors.retina_anchor_table((w.img, w.img), sizes, list(ratios), min_level, scale, spl)
 
 
+def build_anchor_generators(w: Workload):
+    """The workload's per-level generators (anchor_generators.py: the table is written on the GPU)."""
+    from . import anchor_generators as ag
+    if w.anchor_kind == "ssd":
+        lo, hi, ratios = w.anchor_args
+        return ag.build_ssd_anchor_generators(num_scales=len(w.fmaps), min_scale=lo, max_scale=hi,
+                                              aspect_ratios=[list(r) for r in ratios])
+    ratios, min_level, scale, spl = w.anchor_args
+    return ag.build_retina_anchor_generators(list(ratios), min_level, min_level + len(w.fmaps) - 1, scale, spl)
+
+
 def make_ground_truth(batch: int, img: int, num_fg: int, max_gt: int, gen: torch.Generator,
                       extra_col: bool = False, mixup: Optional[float] = None) -> List[torch.Tensor]:
     """List of [G_i, 6(+1)] fp32 rows (x1,y1,x2,y2,class,score[,difficult])."""

@@ -40,9 +40,11 @@ def test_library_loads_and_exports_every_declared_symbol():
 
 
 def test_postprocess_params_struct_matches_header_layout():
-    # int32 x6, float x3, int32, double, int32 x2 -> the double sits at offset 40 on every LP64 ABI
+    # int32 x6, float x3, int32, double, int32 x3, float x2, int32 -> the double sits at offset 40 on every LP64 ABI
     assert N.PostprocessParams.overlap_threshold.offset == 40
-    assert ctypes.sizeof(N.PostprocessParams) == 56
+    assert N.PostprocessParams.soft_nms.offset == 56
+    assert ctypes.sizeof(N.PostprocessParams) == 72
+    assert ctypes.sizeof(N.AnchorLevel) == 7 * 4 + 2 * N.MAX_BOXES_PER_CELL * 4
 
 
 def test_argument_validation_without_a_device():
@@ -106,3 +108,28 @@ def test_cpu_tensors_are_rejected_not_silently_computed():
         box_utils.to_corners(torch.zeros(3, 4))
     with pytest.raises(TypeError):
         box_utils.iou(torch.zeros(3, 4), torch.zeros(2, 4))
+
+
+def test_anchor_generator_shapes_match_reference_tables():
+    """Host half of the device anchor generator: the per-level (w, h) scalars and the linspace end points
+    reproduce the tables the reference's own generators produced (tests/golden/anchors.npz); the cell
+    centres themselves are written by the kernel (-m gpu)."""
+    import numpy as np
+    import torch
+    import golden_io as gio
+    from single_shot_detection_b200 import workloads as wl
+    z = gio.load("anchors.npz")
+    for name in z.files:
+        w = wl.WORKLOADS[name]
+        table = z[name]
+        first = 0
+        for gen, cells in zip(wl.build_anchor_generators(w), w.fmaps):
+            lvl = gen._level((w.img, w.img), (cells, cells))
+            n = cells * cells * gen.num_boxes
+            block = table[first: first + n].reshape(cells, cells, gen.num_boxes, 4)
+            wh = np.array(list(lvl.wh)[: 2 * gen.num_boxes], dtype=np.float32).reshape(-1, 2)
+            assert np.array_equal(block[0, 0, :, 2:], wh), name
+            assert np.float32(lvl.x_start) == block[0, 0, 0, 0] and np.float32(lvl.x_end) == block[0, -1, 0, 0], name
+            assert np.float32(lvl.y_start) == block[0, 0, 0, 1] and np.float32(lvl.y_end) == block[-1, 0, 0, 1], name
+            first += n
+        assert first == table.shape[0]

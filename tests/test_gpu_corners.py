@@ -1,0 +1,100 @@
+"""GPU parity of the optional API corners: soft-NMS (stand-alone and inside the
+post-processor), generalized IoU, the numpy route of box_utils, match_bipartite -- against the values
+the reference produced (tests/golden/corners.npz) and against the oracle.
+
+Bars: picked indices / keep lists exact; scores and boxes 1e-5 relative; GIoU bit exact (add / sub /
+mul / div only, every op separately rounded)."""
+import numpy as np
+import pytest
+import torch
+
+import golden_io as gio
+from oracle import anchor_pipeline_oracle as ora
+from single_shot_detection_b200 import workloads as wl
+
+pytestmark = pytest.mark.gpu
+REL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda", 0)
+
+
+def test_soft_nms_matches_reference_picks(dev):
+    from single_shot_detection_b200 import box_utils
+    z = gio.load("corners.npz")
+    for i in range(int(z["num_soft"])):
+        boxes, scores = torch.from_numpy(z[f"soft_boxes_{i}"]), torch.from_numpy(z[f"soft_scores_{i}"])
+        thr, sigma, k = (float(x) for x in z[f"soft_cfg_{i}"])
+        (bk, sk), picked = box_utils.nms(boxes.to(dev), scores.to(dev), overlap_threshold=.45, score_threshold=thr,
+                                         max_per_class=None if k < 0 else int(k), soft=True, sigma=sigma)
+        assert np.array_equal(picked.cpu().numpy(), z[f"soft_picked_{i}"]), i
+        want = z[f"soft_out_{i}"]
+        assert np.array_equal(torch.cat([bk.reshape(-1, 4), sk.reshape(-1, 1)], 1).cpu().numpy(), want), i
+
+
+def test_soft_nms_random_vs_oracle(dev):
+    from single_shot_detection_b200 import box_utils
+    gen = torch.Generator().manual_seed(3)
+    for n, thr, sigma in [(3, .1, .5), (33, .05, .5), (200, .3, .25), (400, .5, .5), (512, .45, 2.0)]:
+        c = torch.rand((n, 2), generator=gen) * 200
+        s = torch.rand((n, 2), generator=gen) * 70 + 10
+        boxes = torch.cat([c - s / 2, c + s / 2], 1)
+        scores = torch.rand((n,), generator=gen)
+        want = ora.gaussian_soft_nms(boxes, scores, thr, sigma)
+        (_, sk), picked = box_utils.nms(boxes.to(dev), scores.to(dev), .45, thr, soft=True, sigma=sigma)
+        assert torch.equal(picked.cpu(), want), n
+        assert torch.equal(sk.cpu(), scores[want])
+
+
+def test_postprocessor_with_soft_nms_matches_reference(dev):
+    from single_shot_detection_b200 import box_coder, postprocessor
+    z = gio.load("corners.npz")
+    for m in range(int(z["num_post"])):
+        w = wl.WORKLOADS[str(z[f"post_workload_{m}"])]
+        anchors = wl.build_anchors(w)
+        scores, locs = torch.from_numpy(z[f"post_scores_{m}"]), torch.from_numpy(z[f"post_locs_{m}"])
+        want = gio.split_ragged(z[f"post_det_flat_{m}"], z[f"post_det_off_{m}"])
+        post = postprocessor.Postprocessor(box_coder.BoxCoder(w.xy_scale, w.wh_scale), score_threshold=.2,
+                                           nms={"max_per_class": 100, "overlap_threshold": .45, "soft": True, "sigma": .5},
+                                           score_converter=w.converter, max_total=40)
+        got = post.postprocess((scores.to(dev), locs.to(dev)), anchors)
+        assert len(got) == len(want)
+        for g, r in zip(got, want):
+            assert g.shape == r.shape
+            assert torch.equal(g[:, 4].cpu(), r[:, 4])                                   # classes, row by row
+            np.testing.assert_allclose(g.cpu().numpy(), r.numpy(), rtol=REL, atol=1e-5)
+
+
+def test_generalized_iou_bit_exact(dev):
+    from single_shot_detection_b200 import box_utils
+    z = gio.load("corners.npz")
+    a, b = torch.from_numpy(z["giou_a"]).to(dev), torch.from_numpy(z["giou_b"]).to(dev)
+    assert np.array_equal(box_utils.generalized_iou(a, b).cpu().numpy(), z["giou_cartesian"])
+    assert np.array_equal(box_utils.generalized_iou(a, b[:37], cartesian=False).cpu().numpy(), z["giou_elementwise"])
+
+
+def test_numpy_route_of_box_utils(dev):
+    """bf/preprocessing/functional/box.py:68-69 calls intersection / iou with numpy arrays."""
+    from single_shot_detection_b200 import box_utils
+    z = gio.load("corners.npz")
+    a, b = z["giou_a"], z["giou_b"]
+    got = box_utils.iou(a, b)
+    assert isinstance(got, np.ndarray) and got.dtype == np.float32
+    assert np.array_equal(got, ora.pairwise_iou(torch.from_numpy(a), torch.from_numpy(b)).numpy(), equal_nan=True)
+    region = np.array([40., 40, 220, 260], dtype=np.float32)
+    inter = box_utils.intersection(region[np.newaxis], a, zero_incorrect=True).squeeze()
+    lo = np.maximum(region[:2], a[:, :2])
+    hi = np.minimum(region[2:], a[:, 2:])
+    want = np.concatenate([lo, hi], axis=1)
+    want[(hi < lo).any(axis=1)] = 0
+    assert np.array_equal(inter, want)
+    elementwise = box_utils.iou(a, inter, cartesian=False)
+    assert elementwise.shape == (a.shape[0],)
+    (bk, sk), keep = box_utils.nms(a, np.linspace(0.2, 0.9, a.shape[0]).astype(np.float32), .45, .01, max_per_class=20)
+    assert isinstance(keep, np.ndarray) and bk.shape[0] == keep.shape[0] == sk.shape[0]
+    sc = np.linspace(0.2, 0.9, a.shape[0]).astype(np.float32)
+    subset = np.arange(a.shape[0] - 20, a.shape[0])                              # the 20 best (scores increase)
+    assert np.array_equal(keep, subset[ora.greedy_nms(a[subset], sc[subset], .45)])

@@ -630,3 +630,40 @@ def test_multibox_loss_gradients_vs_autograd(dev, kind):
     torch.testing.assert_close(l_dev.grad.cpu(), l_ref.grad, rtol=1e-4, atol=1e-7)
     # rows outside the masks carry exactly zero gradient
     assert float(s_dev.grad.view(b, a, -1)[~mask.to(dev)].abs().max()) == 0.0
+
+
+# ----------------------------------------------------------------------------------------------
+# anchor tables written on the device
+# ----------------------------------------------------------------------------------------------
+def test_device_anchor_tables_bit_exact_vs_reference_tables(dev):
+    from single_shot_detection_b200 import anchor_generators as ag
+    z = gio.load("anchors.npz")
+    for name in z.files:
+        w = wl.WORKLOADS[name]
+        gens = wl.build_anchor_generators(w)
+        table = ag.generate_anchors(gens, (w.img, w.img), [(s, s) for s in w.fmaps], dev)
+        assert table.is_cuda and torch.equal(table.cpu(), torch.from_numpy(z[name])), name
+        # per-level API of the reference: [H, W, boxes, 4]
+        img = torch.empty((1, 3, w.img, w.img))
+        fm = torch.empty((1, 1, w.fmaps[0], w.fmaps[0]), device=dev)
+        lvl = gens[0].generate(img, fm)
+        n = w.fmaps[0] ** 2 * gens[0].num_boxes
+        assert lvl.shape == (w.fmaps[0], w.fmaps[0], gens[0].num_boxes, 4)
+        assert torch.equal(lvl.reshape(-1, 4).cpu(), torch.from_numpy(z[name][:n]))
+
+
+def test_device_linspace_matches_torch_cpu_for_odd_sizes(dev):
+    """Cell centres for every map size 1..70 at several image sizes, non-square maps and explicit steps:
+    the kernel's fma form of torch.linspace against the CPU kernel of the installed torch."""
+    from single_shot_detection_b200 import anchor_generators as ag
+    for img_w, img_h in [(300, 300), (512, 384), (500, 333), (321, 1025)]:
+        for cells in list(range(1, 71)) + [100, 128, 129]:
+            fm = (cells, max(1, (cells * 3) // 4))
+            for step in (None, 8):
+                gen = ag.SsdAnchorGenerator([1.0, 2.0], min_scale=0.2, max_scale=0.4, step=step)
+                got = ag.generate_anchors([gen], (img_w, img_h), [fm], dev, cache=False).cpu().view(fm[1], fm[0], -1, 4)
+                sw, sh = (step, step) if step else (img_w / fm[0], img_h / fm[1])
+                xs = torch.linspace(0.5 * sw, (0.5 + fm[0] - 1) * sw, fm[0])
+                ys = torch.linspace(0.5 * sh, (0.5 + fm[1] - 1) * sh, fm[1])
+                assert torch.equal(got[0, :, 0, 0], xs), (img_w, cells, step)
+                assert torch.equal(got[:, 0, 0, 1], ys), (img_h, cells, step)

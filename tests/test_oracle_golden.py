@@ -199,3 +199,43 @@ def test_matcher_tie_rules_known_answers():
     assert idx.tolist() == [0, 0]
     gt, an = ora.greedy_bipartite_match(torch.tensor([[0.9, 0.8, 0.1], [0.85, 0.1, 0.2]]))
     assert an.tolist() == [0, 2]
+
+
+# ----------------------------------------------------------------------------------------------
+# optional API corners: soft-NMS, generalized IoU -- tests/golden/corners.npz
+# ----------------------------------------------------------------------------------------------
+def test_soft_nms_oracle_matches_reference_picks():
+    z = gio.load("corners.npz")
+    for i in range(int(z["num_soft"])):
+        boxes, scores = torch.from_numpy(z[f"soft_boxes_{i}"]), torch.from_numpy(z[f"soft_scores_{i}"])
+        thr, sigma, k = (float(x) for x in z[f"soft_cfg_{i}"])
+        assert k < 0 or k >= boxes.shape[0]                       # no unsorted top-k in the fixtures
+        picked = ora.gaussian_soft_nms(boxes, scores, thr, sigma)
+        assert np.array_equal(picked.numpy(), z[f"soft_picked_{i}"]), i
+        out = torch.cat([boxes[picked].reshape(-1, 4), scores[picked].reshape(-1, 1)], dim=1)
+        assert np.array_equal(out.numpy(), z[f"soft_out_{i}"]), i
+    # the loop head tests the SUM of the remaining indices: a lone box (index 0) is never picked
+    assert z["soft_picked_0"].size == 0
+
+
+def test_soft_postprocess_oracle_matches_reference():
+    z = gio.load("corners.npz")
+    for m in range(int(z["num_post"])):
+        w = wl.WORKLOADS[str(z[f"post_workload_{m}"])]
+        anchors = wl.build_anchors(w)
+        scores, locs = torch.from_numpy(z[f"post_scores_{m}"]), torch.from_numpy(z[f"post_locs_{m}"])
+        want = gio.split_ragged(z[f"post_det_flat_{m}"], z[f"post_det_off_{m}"])
+        got = ora.postprocess(scores, locs, anchors, xy_scale=w.xy_scale, wh_scale=w.wh_scale, score_threshold=.2,
+                              overlap_threshold=.45, max_per_class=100, max_total=40, converter=w.converter,
+                              canonical=False, soft_sigma=.5)
+        for g, r in zip(got, want):
+            assert g.shape == r.shape
+            np.testing.assert_allclose(g.numpy(), r.numpy(), rtol=1e-6, atol=1e-6)
+
+
+def test_generalized_iou_oracle_matches_reference():
+    z = gio.load("corners.npz")
+    a, b = torch.from_numpy(z["giou_a"]), torch.from_numpy(z["giou_b"])
+    assert np.array_equal(ora.generalized_iou(a, b).numpy(), z["giou_cartesian"])
+    assert np.array_equal(ora.generalized_iou(a, b[:37], cartesian=False).numpy(), z["giou_elementwise"])
+    assert z["giou_cartesian"][3, 5] == 1.0
