@@ -1,6 +1,6 @@
 // Hard-negative mining (detection/sampler.py:12-25) and the naive sampler (sampler.py:9-10).
 //
-// Two launches (plus one memset node for the histograms):
+// Two launches, no memset and no global atomics:
 //   1. mining_loss_kernel   -- streams logits[B, A, C] once (TMA bulk -> smem ring, class ids as a
 //      side array of the same ring), computes the mining criterion
 //          loss = -log_softmax(x)[0] = (max + log(sum exp(x - max))) - x0
@@ -8,13 +8,13 @@
 //          0           anchor is ignored (class -1): never selected
 //          0xFFFFFFFF  anchor is positive: always selected
 //          otherwise   ordered_key(loss) of a negative (class 0) anchor
-//      and bumps a per-image histogram of the negative losses (kLossBins monotone bins, resolution
-//      1/128) with fire-and-forget global reductions.  This is the HBM-bound kernel: 4*C + 8 bytes
-//      read, 4 bytes written per anchor.
-//   2. mining_select_kernel -- one CTA per image: k = min(max(n_pos*ratio, min_neg), n_neg) exactly
-//      as the reference derives it (int64 or fp32 arithmetic depending on the Python type of
-//      `ratio`); a suffix scan of the histogram finds the bin that holds the k-th largest loss; one
-//      pass over the keys selects everything above that bin and collects the handful of keys inside
+//      This is the HBM-bound kernel: 4*C + 8 bytes read, 4 bytes written per anchor.
+//   2. mining_select_kernel -- one CTA per image: a first pass over the image's keys (35 KB for
+//      SSD300, L2 resident: the previous launch just wrote them) builds the histogram of the negative
+//      losses in shared memory (kLossBins monotone bins, resolution 1/128) and counts the positives;
+//      k = min(max(n_pos*ratio, min_neg), n_neg) exactly as the reference derives it (int64 or fp32
+//      arithmetic depending on the Python type of `ratio`); a suffix scan of the histogram finds the
+//      bin that holds the k-th largest loss; a second pass over the keys selects everything above that bin and collects the handful of keys inside
 //      it, which are ranked exactly (key desc, anchor asc).  Loss ties across the cut
 //      (implementation-defined in the reference, whose argsort is unstable) go to the lower anchor.
 //      A boundary bin too crowded to rank in shared memory (heavily tied losses) falls back to an
@@ -45,18 +45,11 @@ __device__ __forceinline__ int loss_bin(float v) {
 }
 __device__ __forceinline__ int key_bin(uint32_t key) { return loss_bin(key_to_float(key)); }
 
-__device__ __forceinline__ void publish_key(uint32_t key, float loss, uint32_t* __restrict__ keys, int64_t row,
-                                            int* __restrict__ hist_img) {
-    keys[row] = key;
-    if (key == kKeyPositive) atomicAdd(hist_img + kLossBins, 1);
-    else if (key != kKeyIgnored) atomicAdd(hist_img + key_bin(key), 1);
-    (void)loss;
-}
 
 template <int Q, int NREG, int CMIN>
 __global__ void __launch_bounds__(kStreamThreads)
 mining_loss_kernel(const float* __restrict__ logits, const long long* __restrict__ cls, uint32_t* __restrict__ keys,
-                   int* __restrict__ hist, ScoreGrid g) {
+                   ScoreGrid g) {
     extern __shared__ __align__(128) unsigned char smem[];
     KernelTrace trace_(TR_MINING_LOSS);
     stream_init(smem);
@@ -74,7 +67,6 @@ mining_loss_kernel(const float* __restrict__ logits, const long long* __restrict
     for (int k = 0; cur.valid(g); ++k, cur.next(g)) {
         const int64_t r0 = cur.first_row(g);
         const int rows = cur.rows(g);
-        int* hist_img = hist + (size_t)cur.image(g) * kHistStride;
         const StagedTile tile = consumer_acquire(smem, g, k, r0);
         const int wbase = warp_id() * rows_per_warp;
 #pragma unroll 2
@@ -89,7 +81,7 @@ mining_loss_kernel(const float* __restrict__ logits, const long long* __restrict
                 // v[0] of lane sub == 0 is column 0
                 const float loss = __fsub_rn(__fadd_rn(m, fast_log(sum)), v[0]);
                 const long long c = (long long)tile.side[lr];
-                publish_key(mining_key(loss, c), loss, keys, r0 + lr, hist_img);
+                keys[r0 + lr] = mining_key(loss, c);
             }
         }
         consumer_release(smem, k);
@@ -101,7 +93,7 @@ mining_loss_kernel(const float* __restrict__ logits, const long long* __restrict
 // `cls_stride` floats, else int64 contiguous.
 template <bool CLS_FLOAT>
 __global__ void mining_keys_from_loss_kernel(const float* __restrict__ loss, const void* __restrict__ cls, int cls_stride,
-                                             uint32_t* __restrict__ keys, int* __restrict__ hist, int A, int64_t n) {
+                                             uint32_t* __restrict__ keys, int64_t n) {
     KernelTrace trace_(TR_MINING_KEYS);
     griddep_wait();
     griddep_launch_dependents();
@@ -110,8 +102,7 @@ __global__ void mining_keys_from_loss_kernel(const float* __restrict__ loss, con
     long long c;
     if (CLS_FLOAT) c = (long long)reinterpret_cast<const float*>(cls)[i * cls_stride];
     else c = reinterpret_cast<const long long*>(cls)[i];
-    const float l = loss[i];
-    publish_key(mining_key(l, c), l, keys, i, hist + (size_t)(i / A) * kHistStride);
+    keys[i] = mining_key(loss[i], c);
 }
 
 __global__ void positive_mask_kernel(const long long* __restrict__ cls, uint8_t* __restrict__ mask, int64_t n) {
@@ -137,6 +128,7 @@ struct SelShared {
     int n_neg, cut_bin, above, in_bin;
     int n_cand;
     unsigned long long cand[kBoundaryCap];
+    alignas(16) int hist[kHistStride];           // [kLossBins] = positives
 };
 
 // block-wide sum of four per-thread counters; result valid for every thread
@@ -164,7 +156,7 @@ __device__ __forceinline__ void block_sum4(SelShared& sh, int (&c)[4]) {
 }
 
 __global__ void __launch_bounds__(kSelThreads)
-mining_select_kernel(const uint32_t* __restrict__ keys, const int* __restrict__ hist, int A, double ratio,
+mining_select_kernel(const uint32_t* __restrict__ keys, int A, double ratio,
                      int ratio_is_integer, double min_negatives, uint8_t* __restrict__ mask,
                      int32_t* __restrict__ stats) {
     __shared__ SelShared sh;
@@ -173,14 +165,37 @@ mining_select_kernel(const uint32_t* __restrict__ keys, const int* __restrict__ 
     griddep_launch_dependents();
     const int b = blockIdx.x;
     const uint32_t* gk = keys + (size_t)b * A;
-    const int* gh = hist + (size_t)b * kHistStride;
     uint8_t* gm = mask + (size_t)b * A;
     const int tid = threadIdx.x;
     static_assert(kLossBins == 4 * kSelThreads, "four bins per thread");
 
+    // ---- histogram of the image's negative losses (+ the positives count) in shared memory ----
+    reinterpret_cast<int4*>(sh.hist)[tid] = make_int4(0, 0, 0, 0);
+    if (tid < kHistStride - kLossBins) sh.hist[kLossBins + tid] = 0;
+    __syncthreads();
+    {
+        int pos = 0;
+        for (int a0 = tid; a0 < A; a0 += 8 * kSelThreads) {
+            uint32_t kk[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int a = a0 + u * kSelThreads;
+                kk[u] = a < A ? gk[a] : kKeyIgnored;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t key = kk[u];
+                if (key == kKeyPositive) ++pos;
+                else if (key != kKeyIgnored) atomicAdd(&sh.hist[key_bin(key)], 1);
+            }
+        }
+        pos = __reduce_add_sync(FULL, pos);
+        if (lane_id() == 0 && pos) atomicAdd(&sh.hist[kLossBins], pos);
+    }
+    __syncthreads();
     // ---- suffix scan of the histogram: thread t owns bins 4t..4t+3, higher bins = larger losses ----
-    const int4 h4 = reinterpret_cast<const int4*>(gh)[tid];
-    const int n_pos = gh[kLossBins];
+    const int4 h4 = reinterpret_cast<const int4*>(sh.hist)[tid];
+    const int n_pos = sh.hist[kLossBins];
     const int own = h4.x + h4.y + h4.z + h4.w;
     int incl = own;                                   // inclusive suffix sum inside the warp (towards higher lanes)
 #pragma unroll
@@ -351,16 +366,14 @@ extern "C" int ssd_positive_mask(const int64_t* target_classes, int64_t count, u
 }
 
 static size_t keys_bytes(int batch, int num_anchors) { return round_up((size_t)batch * num_anchors * sizeof(uint32_t), 256); }
-static size_t hist_bytes(int batch) { return round_up((size_t)batch * kHistStride * sizeof(int), 256); }
 
 // keys + histograms of the whole batch from the logits
 static int launch_mining_keys(const float* logits, const int64_t* target_classes, int batch, int num_anchors,
-                              int num_cols, uint32_t* keys, int* hist, cudaStream_t st) {
+                              int num_cols, uint32_t* keys, cudaStream_t st) {
     SSD_REQUIRE(num_cols >= 1 && num_cols <= kMaxScoreCols, SSD_ERR_UNSUPPORTED,
                 "mining: num_cols %d outside 1..%d", num_cols, kMaxScoreCols);
     SSD_REQUIRE(aligned(logits, 16), SSD_ERR_MISALIGNED, "mining: logits not 16-byte aligned");
     SSD_REQUIRE(aligned(target_classes, 16), SSD_ERR_MISALIGNED, "mining: target_classes not 16-byte aligned");
-    SSD_CUDA(cudaMemsetAsync(hist, 0, hist_bytes(batch), st));
     ScoreGrid g;
     plan_tiles(g, batch, num_anchors, num_cols, true);
     const int grid = stream_grid(g);
@@ -371,7 +384,7 @@ static int launch_mining_keys(const float* logits, const int64_t* target_classes
         SSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
         LaunchTimer lt_("mining_loss", st);                                                            \
         SSD_CUDA(launch_pdl(kern, dim3(grid), dim3(kStreamThreads), smem, st, logits,                               \
-                            (const long long*)target_classes, keys, hist, g));                                      \
+                            (const long long*)target_classes, keys, g));                                      \
     } while (0)
     SSD_DISPATCH_ROW_SHAPE(num_cols, SSD_LAUNCH_MINING);
 #undef SSD_LAUNCH_MINING
@@ -382,7 +395,7 @@ static int launch_mining_keys(const float* logits, const int64_t* target_classes
 
 extern "C" size_t ssd_hard_negative_workspace_bytes(int batch, int num_anchors) {
     if (batch <= 0 || num_anchors <= 0) return 256;
-    return keys_bytes(batch, num_anchors) + hist_bytes(batch);
+    return keys_bytes(batch, num_anchors);
 }
 
 extern "C" int ssd_mining_keys(const float* logits, const int64_t* target_classes, int batch, int num_anchors,
@@ -394,9 +407,7 @@ extern "C" int ssd_mining_keys(const float* logits, const int64_t* target_classe
                 "ssd_mining_keys: null pointer");
     SSD_REQUIRE(workspace_bytes >= ssd_hard_negative_workspace_bytes(batch, num_anchors), SSD_ERR_WORKSPACE,
                 "ssd_mining_keys: workspace too small");
-    int* hist = (int*)((unsigned char*)workspace + keys_bytes(batch, num_anchors));
-    return launch_mining_keys(logits, target_classes, batch, num_anchors, num_cols, keys_out, hist,
-                              (cudaStream_t)stream);
+    return launch_mining_keys(logits, target_classes, batch, num_anchors, num_cols, keys_out, (cudaStream_t)stream);
 }
 
 extern "C" int ssd_hard_negative_mask(const float* logits, const int64_t* target_classes, const float* loss_override,
@@ -413,25 +424,22 @@ extern "C" int ssd_hard_negative_mask(const float* logits, const int64_t* target
     SSD_REQUIRE(aligned(workspace, 256), SSD_ERR_MISALIGNED, "ssd_hard_negative_mask: workspace must be 256-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     uint32_t* keys = (uint32_t*)workspace;
-    int* hist = (int*)((unsigned char*)workspace + keys_bytes(batch, num_anchors));
     const int64_t total_rows = (int64_t)batch * num_anchors;
 
     if (loss_override != nullptr) {
-        SSD_CUDA(cudaMemsetAsync(hist, 0, hist_bytes(batch), st));
         const int threads = 256;
         LaunchTimer lt_("keys_from_loss", st);
         SSD_CUDA(launch_pdl(mining_keys_from_loss_kernel<false>, dim3((unsigned)((total_rows + threads - 1) / threads)),
-                            dim3(threads), 0, st, loss_override, (const void*)target_classes, 1, keys, hist, num_anchors,
-                            total_rows));
+                            dim3(threads), 0, st, loss_override, (const void*)target_classes, 1, keys, total_rows));
         count_launch();
     } else {
-        const int rc = launch_mining_keys(logits, target_classes, batch, num_anchors, num_cols, keys, hist, st);
+        const int rc = launch_mining_keys(logits, target_classes, batch, num_anchors, num_cols, keys, st);
         if (rc != SSD_OK) return rc;
     }
 
     LaunchTimer lt_("mining_select", st);
     SSD_CUDA(launch_pdl(mining_select_kernel, dim3(batch), dim3(kSelThreads), 0, st, (const uint32_t*)keys,
-                        (const int*)hist, num_anchors, ratio, ratio_is_integer, min_negatives, mask_out, stats_out));
+                        num_anchors, ratio, ratio_is_integer, min_negatives, mask_out, stats_out));
     count_launch();
     return SSD_OK;
 }

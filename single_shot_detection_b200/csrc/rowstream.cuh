@@ -314,7 +314,12 @@ inline int slots_per_row(int C) {
 }
 
 // Host: tile geometry.  tile_rows is a multiple of the rows all consumer warps cover in one step.
+inline int env_int(const char* name, int fallback) {
+    const char* e = getenv(name);
+    return (e && e[0]) ? atoi(e) : fallback;
+}
 inline void plan_tiles(ScoreGrid& g, int images, int A, int C, bool with_side, int target_tile_bytes = 24 * 1024) {
+    target_tile_bytes = env_int("SSD_TILE_BYTES", target_tile_bytes);          // tuning knob (tools/kernel_times.sh)
     const int q_min = lanes_per_row(C) < lanes_per_row(C, true) ? lanes_per_row(C) : lanes_per_row(C, true);
     const int quantum = kConsumerWarps * (32 / q_min);        // a whole number of warp steps for every kernel
     int rows = target_tile_bytes / (C * 4);
@@ -343,6 +348,7 @@ __device__ __forceinline__ size_t stream_smem_bytes_dev(const ScoreGrid& g) { re
 inline int stream_grid(ScoreGrid& g, size_t extra_smem = 0) {
     int per_sm = (int)((size_t)(224 * 1024) / (stream_smem_bytes(g) + extra_smem + 1024));
     if (per_sm > 4) per_sm = 4;
+    per_sm = env_int("SSD_CTAS_PER_SM", per_sm);                                // tuning knob
     if (per_sm < 1) per_sm = 1;
     int grid = per_sm * sm_count();
     if (grid > g.num_items) grid = g.num_items;
