@@ -173,6 +173,13 @@ SSD_API int ssd_hard_negative_mask(const float* logits, const int64_t* target_cl
                            uint8_t* mask_out, int32_t* stats_out, void* workspace,
                            size_t workspace_bytes, void* stream);
 
+/* The selection alone, on the RAW criterion keys ssd_postprocess_pass1 emits (ordered_key(-log_softmax[0]),
+ * class-agnostic) + the classes: int64 [B,A] (class_stride == 0) or the class column of fp32 target rows
+ * (`classes` = &target[0][0][4], class_stride = 6 floats).  No workspace. */
+SSD_API int ssd_hard_negative_mask_from_keys(const uint32_t* loss_keys, const void* classes, int class_stride,
+                                     int batch, int num_anchors, double ratio, int ratio_is_integer,
+                                     double min_negatives, uint8_t* mask_out, int32_t* stats_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * a10 / f1  detection/losses/multibox_loss.py:56-92  masked multibox losses, forward + gradient.
  *     class_loss = classification_loss(scores[sampled_mask], classes[sampled_mask]) (reduction sum),
@@ -223,7 +230,7 @@ typedef struct {
     int32_t soft_nms;            /* != 0: soft-NMS (box_utils.py:145-163) instead of hard NMS */
     float soft_sigma;            /* Gaussian decay exp(-iou^2 / sigma)                       */
     float soft_threshold;        /* threshold of the soft-NMS loop (Postprocessor: = score_threshold) */
-    int32_t reserved_;
+    int32_t resume_after_pass1;  /* != 0: ssd_postprocess_pass1 already ran on this workspace    */
 } ssd_postprocess_params;
 
 SSD_API size_t ssd_postprocess_workspace_bytes(const ssd_postprocess_params* p);
@@ -240,6 +247,15 @@ SSD_API size_t ssd_postprocess_workspace_bytes(const ssd_postprocess_params* p);
 SSD_API int ssd_postprocess(const ssd_postprocess_params* p, const float* scores, const float* boxes,
                     const float* priors, float* dets_out, int32_t* count_out, int32_t* anchor_out,
                     int32_t* status_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* The first launch of ssd_postprocess on its own: row statistics (max, sum exp) and the gate bookkeeping
+ * go into the workspace; with loss_keys_out != NULL (SOFTMAX only) the same streamed read of the logits
+ * also emits the hard-negative-mining criterion of detection/sampler.py:13 per anchor as an order-
+ * preserving uint32 key [B,A] (for ssd_hard_negative_mask_from_keys) -- in an eval step
+ * (detection/init.py:117-122) sampler and post-processor see the same logits, so one read serves both.
+ * Finish with ssd_postprocess(resume_after_pass1 = 1) on the same workspace. */
+SSD_API int ssd_postprocess_pass1(const ssd_postprocess_params* p, const float* scores, uint32_t* loss_keys_out,
+                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * a9  bf/utils/box_utils.py:165-194  nms(boxes, scores, overlap_threshold, score_threshold,
@@ -302,6 +318,19 @@ typedef struct {
 } SsdAnchorLevel;
 SSD_API int ssd_generate_anchors(const SsdAnchorLevel* levels, int num_levels, float* anchors_out,
                          int64_t num_anchors, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * e   the exchange step (no reference equivalent): pack the local images' padded
+ *     detections [B,T,6], counts [B] and statistics into shard_out [capacity, T*6 + 5] fp32 words:
+ *     T*6 detection words, then int32 {count, positives, hard negatives selected, ignored,
+ *     detections}; rows >= batch are padding with count = -1.  assign_stats = stats_out of
+ *     ssd_assign_targets, mining_stats = stats_out of ssd_hard_negative_mask (either may be NULL).
+ *     stats_out [B,4] int32 (optional) receives the four statistics.  The buffer is what ONE
+ *     all-gather (NCCL over NVLink) moves.
+ * ---------------------------------------------------------------------------------------- */
+SSD_API int ssd_pack_shard(const float* dets, const int32_t* counts, const int32_t* assign_stats,
+                   const int32_t* mining_stats, int batch, int max_total, int capacity, float* shard_out,
+                   int32_t* stats_out, void* stream);
 
 #ifdef __cplusplus
 }

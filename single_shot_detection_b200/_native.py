@@ -35,7 +35,7 @@ class PostprocessParams(Structure):
                 ("first_fg_col", c_int32), ("box_input", c_int32), ("xy_scale", c_float), ("wh_scale", c_float),
                 ("score_threshold", c_float), ("max_per_class", c_int32), ("overlap_threshold", c_double),
                 ("max_total", c_int32), ("det_capacity", c_int32), ("soft_nms", c_int32), ("soft_sigma", c_float),
-                ("soft_threshold", c_float), ("reserved_", c_int32)]
+                ("soft_threshold", c_float), ("resume_after_pass1", c_int32)]
 
 
 class NativeError(RuntimeError):
@@ -79,6 +79,9 @@ _SIGNATURES = {
     "ssd_hard_negative_workspace_bytes": (c_size_t, [c_int, c_int]),
     "ssd_hard_negative_mask": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_int, c_double,
                                        c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ssd_hard_negative_mask_from_keys": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_int, c_double,
+                                                 c_void_p, c_void_p, c_void_p]),
+    "ssd_postprocess_pass1": (c_int, [POINTER(PostprocessParams), c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ssd_multibox_loss_workspace_bytes": (c_size_t, [c_int, c_int]),
     "ssd_multibox_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float,
                                   c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -87,6 +90,7 @@ _SIGNATURES = {
     "ssd_mean_average_precision": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float,
                                            c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                            c_void_p]),
+    "ssd_pack_shard": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "ssd_generate_anchors": (c_int, [POINTER(AnchorLevel), c_int, c_void_p, c_int64, c_void_p]),
     "ssd_postprocess_workspace_bytes": (c_size_t, [POINTER(PostprocessParams)]),
     "ssd_postprocess": (c_int, [POINTER(PostprocessParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

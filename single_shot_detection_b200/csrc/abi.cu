@@ -36,6 +36,28 @@ int sm_count() {
 
 __global__ void probe_kernel(int* out) { *out = 100; }
 
+// Scratch zeroing as a KERNEL node: inside a captured step graph a memset node in front of a branch was
+// observed (tools/graph_timeline.py) to queue behind the kernels of an unrelated branch -- the
+// post-processor's first pass then started only after the target assignment had finished.  A kernel
+// launched with programmatic stream serialization has no such coupling and overlaps its successor's
+// prologue.
+__global__ void __launch_bounds__(256) zero_kernel(uint4* __restrict__ p, size_t n16) {
+    griddep_wait();
+    griddep_launch_dependents();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
+        p[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+cudaError_t zero_async(void* p, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return cudaSuccess;
+    if (!aligned(p, 16) || (bytes & 15)) return cudaMemsetAsync(p, 0, bytes, st);
+    const size_t n16 = bytes / 16;
+    size_t blocks = (n16 + 255) / 256;
+    if (blocks > 592) blocks = 592;
+    const cudaError_t e = launch_pdl(zero_kernel, dim3((unsigned)blocks), dim3(256), 0, st, (uint4*)p, n16);
+    if (e == cudaSuccess) count_launch();
+    return e;
+}
+
 // ---- optional per-launch timing (diagnostics; off by default, not capturable into a graph) ----
 constexpr int kTimingSlots = 8192;
 static bool g_timing = false;
@@ -97,6 +119,7 @@ cudaError_t set_trace_postprocess(unsigned long long*);
 cudaError_t set_trace_loss(unsigned long long*);
 cudaError_t set_trace_metrics(unsigned long long*);
 cudaError_t set_trace_anchors(unsigned long long*);
+cudaError_t set_trace_exchange(unsigned long long*);
 }  // namespace ssd
 
 extern "C" int ssd_b200_trace_enable(unsigned long long* device_slots) {
@@ -107,6 +130,7 @@ extern "C" int ssd_b200_trace_enable(unsigned long long* device_slots) {
     SSD_CUDA(ssd::set_trace_loss(device_slots));
     SSD_CUDA(ssd::set_trace_metrics(device_slots));
     SSD_CUDA(ssd::set_trace_anchors(device_slots));
+    SSD_CUDA(ssd::set_trace_exchange(device_slots));
     return SSD_OK;
 }
 extern "C" int ssd_b200_trace_slots(void) { return ssd::kTraceSlots; }

@@ -1,15 +1,17 @@
 // Target assignment: detection/target_assigner.py:22-63 with detection/matcher.py:33-56 and
 // bf/utils/box_utils.py:16-23,38-101 fused into one launch for the whole batch.
 //
-// Grid = (anchor blocks, images): one thread per anchor, every CTA stages its image's ground-truth
-// boxes in shared memory and walks them:
+// Grid = (anchor blocks, images): 1024 anchors per CTA, four per thread (strided by the CTA width, so
+// every access stays coalesced); every CTA stages its image's ground-truth boxes in shared memory and
+// walks them:
 //   * IoU in the reference's operation order, every fp32 op rounded separately (no FMA):
 //       inter = clamp(min(x2)-max(x1),0) * clamp(min(y2)-max(y1),0)
 //       iou   = inter / ((area_gt + area_anchor) - inter)                 box_utils.py:93-101
 //   * per-anchor running max over GT (first maximum wins = lowest GT index, NaN sticks),
-//   * per-GT argmax over anchors: warp REDUX max on the ordered IoU key, ballot for the lowest
-//     lane, a shared-memory atomicMax on a 64-bit (key, ~anchor) word per warp that beats the
-//     CTA's best, then ONE global atomicMax per (CTA, GT) that saw an overlap at all;
+//   * per-GT argmax over anchors: the thread's best of its four, warp REDUX max on the ordered IoU
+//     key, REDUX min on the anchor among its holders, a shared-memory atomicMax on a 64-bit
+//     (key, ~anchor) word per warp that beats the CTA's best, then ONE global atomicMax per (CTA, GT)
+//     that saw an overlap at all;
 //   * thresholds in fp32 (matcher.py:49-50), target rows written as coalesced float2 stores
 //     (target_assigner.py:38-58);
 //   * the forced match of every GT to its best anchor (matcher.py:53-54) needs the argmax over ALL
@@ -21,6 +23,12 @@
 namespace ssd {
 
 constexpr int kAssignThreads = 256;
+// Anchors per thread: 1024 anchors per CTA keep the grid at ~1/4 of a wave of thread slots (SSD300 b32:
+// 288 CTAs), so the launch ramp is short, the kernel leaves room for the post-processor's first pass that
+// runs beside it in the step graph, GT staging / per-GT atomics / tickets are amortised over 4x the work,
+// and the four independent IoU chains per thread hide the shared-memory and divide latencies.
+constexpr int kAssignPerThread = 4;
+constexpr int kAssignTile = kAssignThreads * kAssignPerThread;
 constexpr int kMaxGtPerImage = 4096;
 
 __device__ __forceinline__ float clamped_area(float x1, float y1, float x2, float y2) {
@@ -65,12 +73,11 @@ assign_targets_kernel(const float4* __restrict__ anchors, const float* __restric
                       int32_t* __restrict__ stats, int* __restrict__ counters, unsigned long long* __restrict__ gbest) {
     KernelTrace trace_(TR_ASSIGN);
     griddep_wait();
-    griddep_launch_dependents();
     const int img = blockIdx.y;
     const int g0 = gt_offsets[img];
     const int G = gt_offsets[img + 1] - g0;
-    const int a_begin = blockIdx.x * kAssignThreads;
-    const int n_local = min(kAssignThreads, A - a_begin);
+    const int a_begin = blockIdx.x * kAssignTile;
+    const int n_local = min(kAssignTile, A - a_begin);
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int Gcap = G > 0 ? G : 1;
@@ -78,8 +85,24 @@ assign_targets_kernel(const float4* __restrict__ anchors, const float* __restric
     unsigned long long* best = reinterpret_cast<unsigned long long*>(gbox + Gcap);      // later: int anchor[G]
     float2* gcs = reinterpret_cast<float2*>(best + Gcap);
     float* garea = reinterpret_cast<float*>(gcs + Gcap);
-    __shared__ int match[kAssignThreads];
+    __shared__ int match[kAssignTile];
     __shared__ int s_last;
+
+    // the anchors do not depend on the ground truth: their loads go out before the staging barrier
+    float4 ab[kAssignPerThread];
+    float aarea[kAssignPerThread];
+    bool valid[kAssignPerThread];
+#pragma unroll
+    for (int j = 0; j < kAssignPerThread; ++j) {
+        const int la = threadIdx.x + j * kAssignThreads;
+        valid[j] = la < n_local;
+        ab[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        aarea[j] = 0.f;
+        if (valid[j]) {
+            ab[j] = corners_of(anchors[a_begin + la]);
+            aarea[j] = clamped_area(ab[j].x, ab[j].y, ab[j].z, ab[j].w);
+        }
+    }
 
     for (int g = threadIdx.x; g < G; g += blockDim.x) {
         const float* row = gt_rows + (size_t)(g0 + g) * gt_cols;
@@ -90,64 +113,75 @@ assign_targets_kernel(const float4* __restrict__ anchors, const float* __restric
         best[g] = 0ull;                   // nothing overlapping seen: stands for (IoU 0, anchor 0)
     }
     __syncthreads();
+    trace_.mark(0);
 
     // ---- phase 1: per-anchor best GT, per-GT best anchor of this CTA ----
     {
-        const int la = threadIdx.x;
-        const bool valid = la < n_local;
-        const int a = a_begin + la;
-        float4 ab = make_float4(0.f, 0.f, 0.f, 0.f);
-        float aarea = 0.f;
-        if (valid) {
-            ab = corners_of(anchors[a]);
-            aarea = clamped_area(ab.x, ab.y, ab.z, ab.w);
-        }
         // IoU 0 against every box so far: the state torch.max would be in after a row of zeros
-        float best_iou = 0.f;
-        int best_g = 0;
-        const bool a_degenerate = !(aarea > 0.f);
-#pragma unroll 2
+        float best_iou[kAssignPerThread];
+        int best_g[kAssignPerThread];
+#pragma unroll
+        for (int j = 0; j < kAssignPerThread; ++j) { best_iou[j] = 0.f; best_g[j] = 0; }
+#pragma unroll 1
         for (int g = 0; g < G; ++g) {
             const float4 gb = gbox[g];
-            const float iw = fmaxf(fsub(fminf(gb.z, ab.z), fmaxf(gb.x, ab.x)), 0.f);
-            const float ih = fmaxf(fsub(fminf(gb.w, ab.w), fmaxf(gb.y, ab.y)), 0.f);
-            const float inter = fmul(iw, ih);
-            // Disjoint pairs have IoU +0 exactly: they can neither raise the anchor's running
-            // maximum nor beat the (0, anchor 0) entry every GT starts with, so the divide and
-            // both argmax updates are skipped unless some lane of the warp overlaps this box.
-            // (0/0 -> NaN needs both areas to be zero / NaN; NaN inter is not == 0.)
-            bool live = valid && !(inter == 0.f);
-            if (a_degenerate && valid) live = live || !(garea[g] > 0.f);
-            if (!__any_sync(FULL, live)) continue;
-            float v = 0.f;
-            if (live) {
-                const float uni = fsub(fadd(garea[g], aarea), inter);
-                v = (inter == 0.f && uni > 0.f) ? 0.f : fdiv(inter, uni);
+            const float ga = garea[g];
+            float inter[kAssignPerThread];
+            bool live[kAssignPerThread];
+            bool any_live = false;
+#pragma unroll
+            for (int j = 0; j < kAssignPerThread; ++j) {
+                const float iw = fmaxf(fsub(fminf(gb.z, ab[j].z), fmaxf(gb.x, ab[j].x)), 0.f);
+                const float ih = fmaxf(fsub(fminf(gb.w, ab[j].w), fmaxf(gb.y, ab[j].y)), 0.f);
+                inter[j] = fmul(iw, ih);
+                // Disjoint pairs have IoU +0 exactly: they can neither raise the anchor's running
+                // maximum nor beat the (0, anchor 0) entry every GT starts with, so the divide and
+                // both argmax updates are skipped unless some lane of the warp overlaps this box.
+                // (0/0 -> NaN needs both areas to be zero / NaN; NaN inter is not == 0.)
+                live[j] = valid[j] && !(inter[j] == 0.f);
+                if (valid[j] && !(aarea[j] > 0.f)) live[j] = live[j] || !(ga > 0.f);
+                any_live = any_live || live[j];
             }
-            // torch.max(dim=0): first maximum wins, NaN propagates and sticks
-            if (!(v <= best_iou) && !(best_iou != best_iou)) { best_iou = v; best_g = g; }
-            // per-GT argmax over anchors
-            uint32_t key = live ? ordered_key(v) : 0u;
-            if (live && v != v) key = 0xFFFFFFFFu;
-            const uint32_t wmax = __reduce_max_sync(FULL, key);
+            if (!__any_sync(FULL, any_live)) continue;
+            // this thread's best (key, anchor) for the box: j ascending = anchor ascending, strict > keeps the lower
+            uint32_t kbest = 0u;
+            uint32_t abest = 0xFFFFFFFFu;
+#pragma unroll
+            for (int j = 0; j < kAssignPerThread; ++j) {
+                if (!live[j]) continue;
+                const float uni = fsub(fadd(ga, aarea[j]), inter[j]);
+                const float v = (inter[j] == 0.f && uni > 0.f) ? 0.f : fdiv(inter[j], uni);
+                // torch.max(dim=0): first maximum wins, NaN propagates and sticks
+                if (!(v <= best_iou[j]) && !(best_iou[j] != best_iou[j])) { best_iou[j] = v; best_g[j] = g; }
+                uint32_t key = ordered_key(v);
+                if (v != v) key = 0xFFFFFFFFu;
+                if (key > kbest) { kbest = key; abest = (uint32_t)(a_begin + threadIdx.x + j * kAssignThreads); }
+            }
+            // per-GT argmax over anchors: largest key, lowest anchor among its holders
+            const uint32_t wmax = __reduce_max_sync(FULL, kbest);
             if (wmax > 0x80000000u) {               // somebody overlaps (key(+0) == 0x80000000)
-                const unsigned bal = __ballot_sync(FULL, key == wmax);
-                if (lane_id() == __ffs(bal) - 1) {
-                    const unsigned long long w = ((unsigned long long)key << 32) |
-                                                 (unsigned long long)(0xFFFFFFFFu - (uint32_t)a);
+                const uint32_t amin = __reduce_min_sync(FULL, kbest == wmax ? abest : 0xFFFFFFFFu);
+                if (lane_id() == 0) {
+                    const unsigned long long w = ((unsigned long long)wmax << 32) | (unsigned long long)(0xFFFFFFFFu - amin);
                     if (w > best[g]) atomicMax(&best[g], w);
                 }
             }
         }
-        int m = SSD_NOT_MATCHED;
-        if (G > 0) {
-            m = best_g;
-            if (best_iou < unmatched_thr) m = SSD_NOT_MATCHED;              // matcher.py:49
-            else if (best_iou < matched_thr) m = SSD_IGNORE;                // matcher.py:50
+#pragma unroll
+        for (int j = 0; j < kAssignPerThread; ++j) {
+            int m = SSD_NOT_MATCHED;
+            if (G > 0) {
+                m = best_g[j];
+                if (best_iou[j] < unmatched_thr) m = SSD_NOT_MATCHED;              // matcher.py:49
+                else if (best_iou[j] < matched_thr) m = SSD_IGNORE;                // matcher.py:50
+            }
+            match[threadIdx.x + j * kAssignThreads] = m;
         }
-        match[la] = m;
     }
     __syncthreads();
+    trace_.mark(1);
+    // dependents may be scheduled from here on (not earlier: an early dependent only squats on the SMs)
+    griddep_launch_dependents();
 
     // ---- phase 2: publish this CTA's per-GT winners ----
     if (force_match) {
@@ -182,7 +216,9 @@ assign_targets_kernel(const float4* __restrict__ anchors, const float* __restric
         }
         out[p] = v;
     }
-    if (match_out != nullptr && threadIdx.x < n_local) match_out[(size_t)img * A + a_begin + threadIdx.x] = match[threadIdx.x];
+    if (match_out != nullptr) {
+        for (int la = threadIdx.x; la < n_local; la += blockDim.x) match_out[(size_t)img * A + a_begin + la] = match[la];
+    }
     int* cnt = counters + (size_t)img * kAssignCounters;
     n_pos = __reduce_add_sync(FULL, n_pos);
     n_ign = __reduce_add_sync(FULL, n_ign);
@@ -196,11 +232,13 @@ assign_targets_kernel(const float4* __restrict__ anchors, const float* __restric
     // ---- phase 4: the last CTA of the image applies the forced matches and closes the statistics ----
     // (the CTA barrier orders every thread's stores before thread 0's fence, which is cumulative)
     __syncthreads();
+    trace_.mark(2);
     if (threadIdx.x == 0) {
         __threadfence();
         s_last = atomicAdd(cnt, 1) == (int)gridDim.x - 1;
     }
     __syncthreads();
+    trace_.mark(3);
     if (!s_last) return;
     __threadfence();
     if (force_match && G > 0) {
@@ -419,7 +457,7 @@ extern "C" int ssd_assign_targets(const float* anchors, const float* gt_rows, in
     SSD_REQUIRE(workspace_bytes >= need, SSD_ERR_WORKSPACE, "ssd_assign_targets: workspace %zu < %zu bytes",
                 workspace_bytes, need);
     cudaStream_t st = (cudaStream_t)stream;
-    SSD_CUDA(cudaMemsetAsync(workspace, 0, need, st));
+    SSD_CUDA(zero_async(workspace, need, st));
     int* counters = (int*)workspace;
     unsigned long long* gbest = (unsigned long long*)((unsigned char*)workspace +
                                                       round_up((size_t)batch * kAssignCounters * sizeof(int), 256));
@@ -428,7 +466,7 @@ extern "C" int ssd_assign_targets(const float* anchors, const float* gt_rows, in
     SSD_REQUIRE(smem <= 200 * 1024, SSD_ERR_UNSUPPORTED, "ssd_assign_targets: %zu bytes of shared memory needed (boxes %d)",
                 smem, max_gt);
     SSD_CUDA(cudaFuncSetAttribute(assign_targets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)((num_anchors + kAssignThreads - 1) / kAssignThreads), (unsigned)batch);
+    dim3 grid((unsigned)((num_anchors + kAssignTile - 1) / kAssignTile), (unsigned)batch);
     LaunchTimer lt_("assign", st);
     SSD_CUDA(launch_pdl(assign_targets_kernel, grid, dim3(kAssignThreads), smem, st, (const float4*)anchors, gt_rows,
                         gt_cols, gt_offsets, num_anchors, gcap, matched_threshold, unmatched_threshold, force_match,

@@ -90,10 +90,10 @@ static int launch_box(bool vec4, const float* src, int64_t ss, float* dst, int64
     const unsigned blocks = (unsigned)((rows + 255) / 256);
     LaunchTimer lt_("box", st);
     if (vec4)
-        SSD_CUDA(launch_pdl(box_transform_kernel<OP, true>, dim3(blocks), dim3(256), 0, st, src, ss, dst, ds,
+        SSD_CUDA(launch_plain(box_transform_kernel<OP, true>, dim3(blocks), dim3(256), 0, st, src, ss, dst, ds,
                             (const float4*)priors, rows, A, xy, wh, eps));
     else
-        SSD_CUDA(launch_pdl(box_transform_kernel<OP, false>, dim3(blocks), dim3(256), 0, st, src, ss, dst, ds,
+        SSD_CUDA(launch_plain(box_transform_kernel<OP, false>, dim3(blocks), dim3(256), 0, st, src, ss, dst, ds,
                             (const float4*)priors, rows, A, xy, wh, eps));
     SSD_CUDA(cudaGetLastError());
     count_launch();

@@ -33,6 +33,7 @@ int cuda_fail(cudaError_t e, const char* what);
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 __host__ __device__ inline size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 int sm_count();
+cudaError_t zero_async(void* p, size_t bytes, cudaStream_t st);   // scratch zeroing as a kernel node (abi.cu)
 void count_launch(int n = 1);      // bumps the library-wide kernel launch counter (ssd_b200_launch_count)
 // diagnostics: per-launch CUDA-event timing when enabled through ssd_b200_timing_enable()
 int timing_begin(const char* label, cudaStream_t st);
@@ -116,6 +117,30 @@ struct KernelTrace {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// WHERE a kernel triggers its dependents matters (tools/graph_timeline.py): the block scheduler places the
+// CTAs of concurrently pending grids in arrival order, so a dependent that was launched at the START of
+// its predecessor and cannot become fully resident yet (the NMS grid needs the shared memory pass 2 still
+// holds) blocks every grid that arrives after it -- the box transforms and the sampler's selection sat
+// behind it for ~14 us.  The long kernels therefore trigger when a CTA has finished its main loop: the
+// dependent's launch latency still overlaps the predecessor's tail, but nothing queues behind a grid
+// that cannot run.
+// A dependent launched early holds its thread slots / shared memory while it sits in griddep_wait():
+// small kernels with large grids that hang off a long-running predecessor (the box transforms after
+// the target assignment: 1092 CTAs x 256 threads) were observed to keep the post-processor's first
+// pass off the SMs for the whole assignment.  Those use launch_plain (full stream-order dependency).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_plain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cfg.attrs = nullptr;
+    cfg.numAttrs = 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,

@@ -54,7 +54,6 @@ mining_loss_kernel(const float* __restrict__ logits, const long long* __restrict
     KernelTrace trace_(TR_MINING_LOSS);
     stream_init(smem);
     griddep_wait();
-    griddep_launch_dependents();
     if (warp_id() == kConsumerWarps) {
         producer_loop(smem, g, logits, reinterpret_cast<const unsigned long long*>(cls), policy_evict_first());
         return;
@@ -86,6 +85,7 @@ mining_loss_kernel(const float* __restrict__ logits, const long long* __restrict
         }
         consumer_release(smem, k);
     }
+    griddep_launch_dependents();       // late: see the note at launch_pdl
 }
 
 // Criterion given (stage-boundary parity: identical fp32 inputs to the selection), or classes read
@@ -119,6 +119,20 @@ __global__ void positive_mask_kernel(const long long* __restrict__ cls, uint8_t*
 // per-image selection
 // ---------------------------------------------------------------------------------------------
 constexpr int kSelThreads = 1024;
+
+struct KeySource {
+    const uint32_t* keys;
+    const void* cls;
+    int stride;
+    __device__ __forceinline__ uint32_t key(int a) const {
+        const uint32_t k = keys[a];
+        if (cls == nullptr) return k;
+        const long long c = stride ? (long long)reinterpret_cast<const float*>(cls)[(size_t)a * stride]
+                                   : reinterpret_cast<const long long*>(cls)[a];
+        if (c == SSD_NEGATIVE_CLASS) return k == 0u ? 1u : (k == kKeyPositive ? kKeyPositive - 1u : k);
+        return c == SSD_IGNORE_CLASS ? kKeyIgnored : kKeyPositive;
+    }
+};
 
 struct SelShared {
     int warp_tot[32];
@@ -156,7 +170,7 @@ __device__ __forceinline__ void block_sum4(SelShared& sh, int (&c)[4]) {
 }
 
 __global__ void __launch_bounds__(kSelThreads)
-mining_select_kernel(const uint32_t* __restrict__ keys, int A, double ratio,
+mining_select_kernel(const uint32_t* __restrict__ keys, const void* __restrict__ cls, int cls_stride, int A, double ratio,
                      int ratio_is_integer, double min_negatives, uint8_t* __restrict__ mask,
                      int32_t* __restrict__ stats) {
     __shared__ SelShared sh;
@@ -165,6 +179,12 @@ mining_select_kernel(const uint32_t* __restrict__ keys, int A, double ratio,
     griddep_launch_dependents();
     const int b = blockIdx.x;
     const uint32_t* gk = keys + (size_t)b * A;
+    // cls == nullptr: the keys already carry the class (mining_loss_kernel).  Otherwise they are the RAW
+    // criterion (score_pass1_kernel) and the class comes from int64 [B, A] (cls_stride == 0) or from the
+    // class column of float target rows `cls_stride` floats apart.
+    const KeySource src{gk, cls == nullptr ? nullptr : (cls_stride ? (const void*)(reinterpret_cast<const float*>(cls) + (size_t)b * A * cls_stride)
+                                                                  : (const void*)(reinterpret_cast<const long long*>(cls) + (size_t)b * A)),
+                        cls_stride};
     uint8_t* gm = mask + (size_t)b * A;
     const int tid = threadIdx.x;
     static_assert(kLossBins == 4 * kSelThreads, "four bins per thread");
@@ -180,7 +200,7 @@ mining_select_kernel(const uint32_t* __restrict__ keys, int A, double ratio,
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int a = a0 + u * kSelThreads;
-                kk[u] = a < A ? gk[a] : kKeyIgnored;
+                kk[u] = a < A ? src.key(a) : kKeyIgnored;
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -258,7 +278,7 @@ mining_select_kernel(const uint32_t* __restrict__ keys, int A, double ratio,
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int a = a0 + u * kSelThreads;
-            kk[u] = a < A ? gk[a] : kKeyIgnored;
+            kk[u] = a < A ? src.key(a) : kKeyIgnored;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -300,7 +320,7 @@ mining_select_kernel(const uint32_t* __restrict__ keys, int A, double ratio,
                 int d[4] = {0, 0, 0, 0};
                 const uint32_t pre_hi = shift + 2 >= 32 ? 0u : prefix >> (shift + 2);
                 for (int a = tid; a < A; a += kSelThreads) {
-                    const uint32_t key = gk[a];
+                    const uint32_t key = src.key(a);
                     if (key != kKeyPositive && key != kKeyIgnored && key_bin(key) == cut_bin) {
                         const uint32_t khi = shift + 2 >= 32 ? 0u : key >> (shift + 2);
                         if (khi == pre_hi) d[(key >> shift) & 3u]++;
@@ -321,7 +341,7 @@ mining_select_kernel(const uint32_t* __restrict__ keys, int A, double ratio,
             for (int i = 0; i < rounds; ++i) {
                 const int a = i * kSelThreads + tid;
                 uint32_t key = kKeyIgnored;
-                if (a < A) key = gk[a];
+                if (a < A) key = src.key(a);
                 const bool member = a < A && key != kKeyPositive && key != kKeyIgnored && key_bin(key) == cut_bin;
                 const bool tie = member && key == thr_key;
                 const unsigned bal = __ballot_sync(FULL, tie);
@@ -439,7 +459,22 @@ extern "C" int ssd_hard_negative_mask(const float* logits, const int64_t* target
 
     LaunchTimer lt_("mining_select", st);
     SSD_CUDA(launch_pdl(mining_select_kernel, dim3(batch), dim3(kSelThreads), 0, st, (const uint32_t*)keys,
-                        num_anchors, ratio, ratio_is_integer, min_negatives, mask_out, stats_out));
+                        (const void*)nullptr, 0, num_anchors, ratio, ratio_is_integer, min_negatives, mask_out, stats_out));
+    count_launch();
+    return SSD_OK;
+}
+
+extern "C" int ssd_hard_negative_mask_from_keys(const uint32_t* loss_keys, const void* classes, int class_stride,
+                                                int batch, int num_anchors, double ratio, int ratio_is_integer,
+                                                double min_negatives, uint8_t* mask_out, int32_t* stats_out,
+                                                void* stream) {
+    SSD_REQUIRE(batch >= 0 && num_anchors >= 0 && class_stride >= 0, SSD_ERR_INVALID_ARGUMENT,
+                "ssd_hard_negative_mask_from_keys: negative shape");
+    if (batch == 0 || num_anchors == 0) return SSD_OK;
+    SSD_REQUIRE(loss_keys && classes && mask_out, SSD_ERR_INVALID_ARGUMENT, "ssd_hard_negative_mask_from_keys: null pointer");
+    LaunchTimer lt_("mining_select", (cudaStream_t)stream);
+    SSD_CUDA(launch_pdl(mining_select_kernel, dim3(batch), dim3(kSelThreads), 0, (cudaStream_t)stream, loss_keys, classes,
+                        class_stride, num_anchors, ratio, ratio_is_integer, min_negatives, mask_out, stats_out));
     count_launch();
     return SSD_OK;
 }

@@ -195,12 +195,12 @@ __device__ __forceinline__ float gate_bin_edge(int bin, GateBins gb) {
 template <int Q, int NREG, int CMIN, int CONV>
 __global__ void __launch_bounds__(kStreamThreads)
 score_pass1_kernel(const float* __restrict__ scores, ScoreGrid g, float2* __restrict__ rowstat,
-                   float* __restrict__ blockmax, uint32_t* __restrict__ bhist, GateBins gbins) {
+                   float* __restrict__ blockmax, uint32_t* __restrict__ bhist, GateBins gbins,
+                   uint32_t* __restrict__ loss_keys) {
     extern __shared__ __align__(128) unsigned char smem[];
     KernelTrace trace_(TR_PASS1);
     stream_init(smem);
     griddep_wait();
-    griddep_launch_dependents();
     if (warp_id() == kConsumerWarps) {
         producer_loop(smem, g, scores, nullptr, policy_evict_last());      // pass 2 re-reads the same bytes
         return;
@@ -233,6 +233,12 @@ score_pass1_kernel(const float* __restrict__ scores, ScoreGrid g, float2* __rest
                 // rows past the end of a partial tile: t = +inf turns every gate value into -inf / NaN,
                 // both of which fmaxf drops
                 const float t = valid ? __fadd_rn(m, fast_log(sum)) : INFINITY;
+                // the sampler's criterion -log_softmax(x)[0] = (max + log(sum)) - x0 falls out of the same row
+                // statistics (mining.cu, same operations): one streamed read of the logits serves both
+                if (loss_keys != nullptr && valid && ln.sub == 0) {
+                    const uint32_t lk = ordered_key(__fsub_rn(t, v[0]));
+                    loss_keys[r0 + lr] = lk == 0u ? 1u : lk;
+                }
 #pragma unroll
                 for (int i = 0; i < NREG; ++i) cmax[i] = fmaxf(cmax[i], __fsub_rn(v[i], t));
             } else {
@@ -287,6 +293,7 @@ score_pass1_kernel(const float* __restrict__ scores, ScoreGrid g, float2* __rest
         }
         cur.next(g);
     }
+    griddep_launch_dependents();       // late: see the note at launch_pdl
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -507,7 +514,6 @@ score_pass2_kernel(const float* __restrict__ scores, ScoreGrid g, const float2* 
     KernelTrace trace_(TR_PASS2);
     stream_init(smem);
     griddep_wait();
-    griddep_launch_dependents();
     if (warp_id() == kConsumerWarps) {
         producer_loop(smem, g, scores,
                       CONV == SSD_CONVERT_SOFTMAX ? reinterpret_cast<const unsigned long long*>(rowstat) : nullptr,
@@ -592,6 +598,7 @@ score_pass2_kernel(const float* __restrict__ scores, ScoreGrid g, const float2* 
         }
         consumer_release(smem, k);
     }
+    griddep_launch_dependents();       // late: see the note at launch_pdl
     q.flush(cand_count, cand, cand_cap);
 }
 
@@ -1398,11 +1405,11 @@ segment_nms_kernel(NmsArgs a, TopkArgs ta, const float* __restrict__ scores, con
     __shared__ int s_valid, s_nkeep, s_ticket;
     KernelTrace trace_(TR_NMS);
     griddep_wait();
-    griddep_launch_dependents();
     const int seg = blockIdx.x;
     const int img = seg / a.Cf;
     const int nkeep = nms_segment(trace_, a, smem, s_hist, s_misc, s_valid, s_nkeep, scores, rowstat, cand_count, cand, boxes,
                                   priors, kept, status, score_hist);
+    griddep_launch_dependents();       // late: see the note at launch_pdl
     if (threadIdx.x == 0) kept_count[seg] = nkeep;
     trace_.mark(6);
     if (image_done == nullptr) return;                     // the final top-k has its own launch
@@ -1436,9 +1443,11 @@ extern "C" size_t ssd_postprocess_workspace_bytes(const ssd_postprocess_params* 
     return pl.total_bytes;
 }
 
+constexpr int kStagePass1 = 1, kStageRest = 2;
 static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, const float* scores,
                            const float* boxes, const float* priors, float* dets_out, int32_t* count_out,
-                           int32_t* anchor_out, int32_t* status_out, unsigned char* ws, cudaStream_t st) {
+                           int32_t* anchor_out, int32_t* status_out, unsigned char* ws, cudaStream_t st,
+                           int stages = kStagePass1 | kStageRest, uint32_t* loss_keys = nullptr) {
     float2* rowstat = (float2*)(ws + pl.off_rowstat);
     float* blockmax = (float*)(ws + pl.off_blockmax);
     float* gate = (float*)(ws + pl.off_gate);
@@ -1458,8 +1467,9 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
     GateBins gbins;
     gbins.lo = pl.bin_lo; gbins.scale = pl.bin_scale;
 
+    if (stages & kStagePass1) {
     // counters, histograms and the status words start at zero
-    SSD_CUDA(cudaMemsetAsync(ws + pl.zero_begin, 0, pl.zero_bytes, st));
+    SSD_CUDA(zero_async(ws + pl.zero_begin, pl.zero_bytes, st));
 
 #define SSD_LAUNCH_PASS1(QQ, NN, CM)                                                                                     \
     do {                                                                                                               \
@@ -1467,7 +1477,7 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
             SSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem));    \
             LaunchTimer lt_("pass1", st);                                                            \
             SSD_CUDA(launch_pdl(kern, dim3(grid), dim3(kStreamThreads), stream_smem, st, scores, g, rowstat, blockmax, \
-                                bhist, gbins));                                                                 \
+                                bhist, gbins, loss_keys));                                                      \
             return SSD_OK;                                                                                             \
         };                                                                                                             \
         int rc;                                                                                                        \
@@ -1479,6 +1489,8 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
 #undef SSD_LAUNCH_PASS1
     SSD_CUDA(cudaGetLastError());
     count_launch();
+    }
+    if (!(stages & kStageRest)) return SSD_OK;
 
     if (!pl.gate_hist) {
         LaunchTimer lt_("gate", st);
@@ -1583,7 +1595,26 @@ extern "C" int ssd_postprocess(const ssd_postprocess_params* p, const float* sco
     SSD_REQUIRE(workspace_bytes >= pl.total_bytes, SSD_ERR_WORKSPACE, "ssd_postprocess: workspace %zu < %zu bytes",
                 workspace_bytes, pl.total_bytes);
     return run_postprocess(pl, p, scores, boxes, priors, dets_out, count_out, anchor_out, status_out,
-                           (unsigned char*)workspace, st);
+                           (unsigned char*)workspace, st, p->resume_after_pass1 ? kStageRest : (kStagePass1 | kStageRest));
+}
+
+// Pass 1 alone (memset + row statistics + gate bookkeeping), optionally emitting the sampler's
+// criterion; ssd_postprocess with resume_after_pass1 = 1 on the SAME workspace finishes the job.
+extern "C" int ssd_postprocess_pass1(const ssd_postprocess_params* p, const float* scores, uint32_t* loss_keys_out,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
+    PostPlan pl;
+    const int rc = make_plan(p, pl);
+    if (rc != SSD_OK) return rc;
+    if (pl.B == 0 || pl.A == 0) return SSD_OK;
+    SSD_REQUIRE(scores && workspace, SSD_ERR_INVALID_ARGUMENT, "ssd_postprocess_pass1: null pointer");
+    SSD_REQUIRE(loss_keys_out == nullptr || pl.converter == SSD_CONVERT_SOFTMAX, SSD_ERR_INVALID_ARGUMENT,
+                "ssd_postprocess_pass1: the mining criterion needs the SOFTMAX converter");
+    SSD_REQUIRE(aligned(scores, 16), SSD_ERR_MISALIGNED, "ssd_postprocess_pass1: scores must be 16-byte aligned");
+    SSD_REQUIRE(aligned(workspace, 256), SSD_ERR_MISALIGNED, "ssd_postprocess_pass1: workspace must be 256-byte aligned");
+    SSD_REQUIRE(workspace_bytes >= pl.total_bytes, SSD_ERR_WORKSPACE, "ssd_postprocess_pass1: workspace %zu < %zu bytes",
+                workspace_bytes, pl.total_bytes);
+    return run_postprocess(pl, p, scores, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, (unsigned char*)workspace,
+                           (cudaStream_t)stream, kStagePass1, loss_keys_out);
 }
 
 // ---- box_utils.nms for one box set: the same machinery with B = 1, one score column ----

@@ -208,36 +208,104 @@ def det_capacity(num_fg: int, max_per_class: int, max_total: int) -> int:
     return min(rows, max_total) if max_total > 0 else rows
 
 
+def _post_params(scores, boxes, converter, first_fg_col, box_input, xy_scale, wh_scale, score_threshold, max_per_class,
+                 overlap_threshold, max_total, soft_sigma):
+    batch = scores.shape[0]
+    num_anchors = boxes.numel() // max(4 * batch, 1)
+    num_cols = scores.numel() // max(batch * num_anchors, 1)
+    p = N.PostprocessParams()
+    p.batch, p.num_anchors, p.num_cols = batch, num_anchors, num_cols
+    p.converter, p.first_fg_col, p.box_input = converter, first_fg_col, box_input
+    p.xy_scale, p.wh_scale, p.score_threshold = xy_scale, wh_scale, score_threshold
+    p.max_per_class, p.overlap_threshold, p.max_total = max_per_class, overlap_threshold, max_total
+    p.det_capacity = det_capacity(num_cols - first_fg_col, max_per_class, max_total)
+    p.soft_nms, p.soft_sigma, p.soft_threshold = int(soft_sigma > 0.0), soft_sigma, score_threshold
+    return p
+
+
+def _post_workspace(p, dev):
+    nbytes = N.lib().ssd_postprocess_workspace_bytes(ctypes.byref(p))
+    if nbytes == 0:
+        N.check(N.lib().ssd_postprocess(ctypes.byref(p), None, None, None, None, None, None, None, None, 0, None))
+    return workspace(nbytes, dev, "postprocess")
+
+
+def _post_finish(p, scores, boxes, priors, ws):
+    dev = scores.device
+    batch, cap = p.batch, p.det_capacity
+    dets = torch.empty((batch, cap, 6), dtype=torch.float32, device=dev)
+    counts = torch.empty((batch,), dtype=torch.int32, device=dev)
+    anchors = torch.empty((batch, cap), dtype=torch.int32, device=dev)
+    status = torch.empty((4,), dtype=torch.int32, device=dev)
+    N.check(N.lib().ssd_postprocess(ctypes.byref(p), _ptr(scores), _ptr(boxes), _ptr(priors), _ptr(dets),
+                                    _ptr(counts), _ptr(anchors), _ptr(status), _ptr(ws), ws.numel(), _stream()))
+    return dets, counts, anchors, status
+
+
 def _postprocess(scores: torch.Tensor, boxes: torch.Tensor, priors: Optional[torch.Tensor], converter: int,
                  first_fg_col: int, box_input: int, xy_scale: float, wh_scale: float, score_threshold: float,
                  max_per_class: int, overlap_threshold: float, max_total: int, soft_sigma: float = 0.0):
     N.require_device()
     scores = _f32c(scores.detach())
     boxes = _f32c(boxes.detach())
-    batch = scores.shape[0]
-    num_anchors = boxes.numel() // max(4 * batch, 1)
-    num_cols = scores.numel() // max(batch * num_anchors, 1)
+    p = _post_params(scores, boxes, converter, first_fg_col, box_input, xy_scale, wh_scale, score_threshold,
+                     max_per_class, overlap_threshold, max_total, soft_sigma)
+    with torch.cuda.device(scores.device):
+        return _post_finish(p, scores, boxes, priors, _post_workspace(p, scores.device))
+
+
+class PostprocessInFlight:
+    """The post-processor split after its first launch (ssd_postprocess_pass1): ``loss_keys`` [B, A] int32
+    holds the sampler's raw criterion keys when requested; :meth:`finish` enqueues the remaining launches
+    on the CURRENT stream.  Between the two the caller may record an event, so that the selection of the
+    sampler (another stream) waits for pass 1 only."""
+
+    def __init__(self, p, scores, boxes, priors, ws, loss_keys):
+        self.p, self.scores, self.boxes, self.priors, self.ws, self.loss_keys = p, scores, boxes, priors, ws, loss_keys
+
+    def finish(self):
+        self.p.resume_after_pass1 = 1
+        with torch.cuda.device(self.scores.device):
+            return _post_finish(self.p, self.scores, self.boxes, self.priors, self.ws)
+
+
+def postprocess_begin(scores: torch.Tensor, boxes: torch.Tensor, priors: Optional[torch.Tensor], converter: int,
+                      first_fg_col: int, box_input: int, xy_scale: float, wh_scale: float, score_threshold: float,
+                      max_per_class: int, overlap_threshold: float, max_total: int, soft_sigma: float = 0.0,
+                      want_loss_keys: bool = False) -> PostprocessInFlight:
+    N.require_device()
+    scores = _f32c(scores.detach())
+    boxes = _f32c(boxes.detach())
+    p = _post_params(scores, boxes, converter, first_fg_col, box_input, xy_scale, wh_scale, score_threshold,
+                     max_per_class, overlap_threshold, max_total, soft_sigma)
     dev = scores.device
-    p = N.PostprocessParams()
-    p.batch, p.num_anchors, p.num_cols = batch, num_anchors, num_cols
-    p.converter, p.first_fg_col, p.box_input = converter, first_fg_col, box_input
-    p.xy_scale, p.wh_scale, p.score_threshold = xy_scale, wh_scale, score_threshold
-    p.max_per_class, p.overlap_threshold, p.max_total = max_per_class, overlap_threshold, max_total
-    cap = det_capacity(num_cols - first_fg_col, max_per_class, max_total)
-    p.det_capacity = cap
-    p.soft_nms, p.soft_sigma, p.soft_threshold = int(soft_sigma > 0.0), soft_sigma, score_threshold
-    dets = torch.empty((batch, cap, 6), dtype=torch.float32, device=dev)
-    counts = torch.empty((batch,), dtype=torch.int32, device=dev)
-    anchors = torch.empty((batch, cap), dtype=torch.int32, device=dev)
-    status = torch.empty((4,), dtype=torch.int32, device=dev)
+    keys = torch.empty((p.batch, p.num_anchors), dtype=torch.int32, device=dev) if want_loss_keys else None
     with torch.cuda.device(dev):
-        nbytes = N.lib().ssd_postprocess_workspace_bytes(ctypes.byref(p))
-        if nbytes == 0:
-            N.check(N.lib().ssd_postprocess(ctypes.byref(p), None, None, None, None, None, None, None, None, 0, None))
-        ws = workspace(nbytes, dev, "postprocess")
-        N.check(N.lib().ssd_postprocess(ctypes.byref(p), _ptr(scores), _ptr(boxes), _ptr(priors), _ptr(dets),
-                                        _ptr(counts), _ptr(anchors), _ptr(status), _ptr(ws), ws.numel(), _stream()))
-    return dets, counts, anchors, status
+        ws = _post_workspace(p, dev)
+        N.check(N.lib().ssd_postprocess_pass1(ctypes.byref(p), _ptr(scores), _ptr(keys), _ptr(ws), ws.numel(), _stream()))
+    return PostprocessInFlight(p, scores, boxes, priors, ws, keys)
+
+
+def hard_negative_mask_from_keys(loss_keys: torch.Tensor, target: torch.Tensor, ratio: float, ratio_is_integer: bool,
+                                 min_negatives: float):
+    """Selection on the raw criterion keys of :func:`postprocess_begin`; the classes are read straight from
+    the class column of ``target`` [B, A, 6] fp32 (no ``.long()`` copy) or from an int64 [B, A] tensor."""
+    N.require_device()
+    batch, num_anchors = loss_keys.shape
+    dev = loss_keys.device
+    if target.dtype == torch.int64:
+        cls = target if target.is_contiguous() else target.contiguous()
+        cls_ptr, stride = cls.data_ptr(), 0
+    else:
+        assert target.dtype == torch.float32 and target.is_contiguous() and target.shape[-1] >= 5
+        cls_ptr, stride = target.data_ptr() + 4 * 4, int(target.shape[-1])
+    mask = torch.empty((batch, num_anchors), dtype=torch.bool, device=dev)
+    stats = torch.empty((batch, 4), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib().ssd_hard_negative_mask_from_keys(loss_keys.data_ptr(), cls_ptr, stride, batch, num_anchors,
+                                                         float(ratio), int(ratio_is_integer), float(min_negatives),
+                                                         _ptr(mask), _ptr(stats), _stream()))
+    return mask, stats
 
 
 def _nms(boxes: torch.Tensor, scores: torch.Tensor, max_per_class: int, overlap_threshold: float):

@@ -58,6 +58,7 @@ class AnchorPipeline:
             {"max_per_class": cfg["max_per_class"], "overlap_threshold": cfg["overlap_threshold"]},
             score_converter=cfg["converter"], max_total=cfg["max_total"])
         self.fuse_encode = False       # True: one pass for to_centroids+encode (same rounding)
+        self.share_logit_pass = True   # eval step: mining criterion out of the post-processor's first pass
         self._graph = None
         self._side = None
         self._copy = None
@@ -72,9 +73,22 @@ class AnchorPipeline:
         scores = scores if scores.is_cuda else scores.to(device, non_blocking=True)
         locs = locs if locs.is_cuda else locs.to(device, non_blocking=True)
         target = self.target_assigner.encode_ground_truth(ground_truth, anchors)
-        mask = self._sample_and_encode(target, anchors, scores)
-        dets = self.postprocessor.postprocess((scores, locs), anchors)
+        if self._shares_logit_pass():
+            flight = self.postprocessor.begin_padded((scores, locs), anchors, want_loss_keys=True)
+            mask = _sampler.hard_negative_mining_from_keys(flight.loss_keys, target, self.cfg.get("ratio"),
+                                                           self.cfg.get("min_neg"))
+            self._encode_target_boxes(target, anchors)
+            dets = self.postprocessor.to_list(*flight.finish())
+        else:
+            mask = self._sample_and_encode(target, anchors, scores)
+            dets = self.postprocessor.postprocess((scores, locs), anchors)
         return target, mask, dets
+
+    def _shares_logit_pass(self) -> bool:
+        # eval step: sampler and post-processor see the same logits, so the post-processor's first pass
+        # also emits the mining criterion and the sampler only runs its selection (one read fewer)
+        return (self.share_logit_pass and self.cfg["sampler"] == "hard_negative_mining"
+                and self.cfg["converter"] == "SOFTMAX")
 
     def _sample_and_encode(self, target, anchors, scores):
         batch, num_anchors = target.shape[:2]
@@ -213,26 +227,41 @@ class AnchorPipeline:
         main = torch.cuda.current_stream()
         side, side2 = self._side_streams()
         side.wait_stream(main)
+        batch = packed.batch
+        share = self._shares_logit_pass()
+        # Branch layout (measured with tools/graph_timeline.py): a kernel behind a CROSS-stream edge of the
+        # captured graph started ~10 us after its dependency had finished, a same-stream successor starts at
+        # once.  So the train-side chain stays on ONE side stream -- assign -> to_centroids -> encode_box ->
+        # selection -- and only the selection has a second (event) dependency, on the post-processor's pass 1.
         with torch.cuda.stream(side):
             target = self.target_assigner.encode_packed(packed, anchors_dev)
-            classes = target[..., CLASS_INDEX].long()                      # multibox_loss.py:49
-            assigned = torch.cuda.Event()
-            assigned.record(side)
-            batch, num_anchors = target.shape[:2]
-            mask = self.sampler(scores_dev.view(batch, num_anchors, -1), classes)
-        with torch.cuda.stream(side2):
-            # the box encoding only needs the assignment: a third branch next to sampler and post-processor
-            side2.wait_event(assigned)
-            self._encode_target_boxes(target, anchors_dev)
-        dets, counts, det_anchors, status = self.postprocessor.postprocess_padded((scores_dev, locs_dev), anchors_dev)
+            if not share:
+                classes = target[..., CLASS_INDEX].long()                      # multibox_loss.py:49 (before the boxes change)
+            else:
+                classes = None
+        if share:
+            flight = self.postprocessor.begin_padded((scores_dev, locs_dev), anchors_dev, want_loss_keys=True)
+            keyed = torch.cuda.Event()
+            keyed.record(main)
+        with torch.cuda.stream(side):
+            self._encode_target_boxes(target, anchors_dev)                     # touches columns 0-3 only
+            if share:
+                side.wait_event(keyed)
+                mask = _sampler.hard_negative_mining_from_keys(flight.loss_keys, target, self.cfg.get("ratio"),
+                                                               self.cfg.get("min_neg"))
+            else:
+                num_anchors = target.shape[1]
+                mask = self.sampler(scores_dev.view(batch, num_anchors, -1), classes)
+        if share:
+            dets, counts, det_anchors, status = flight.finish()
+        else:
+            dets, counts, det_anchors, status = self.postprocessor.postprocess_padded((scores_dev, locs_dev), anchors_dev)
         main.wait_stream(side)
-        main.wait_stream(side2)
         mining = _sampler.hard_negative_mining.last_stats if self.cfg["sampler"] == "hard_negative_mining" else None
         stats, shard = None, None
         if shard_capacity is not None:
             from . import sharding
-            stats = matched_stats(self.target_assigner.last_stats, mining, counts)
-            shard = sharding.pack_shard(dets, counts, stats, shard_capacity)
+            shard, stats = sharding.pack_shard_device(dets, counts, self.target_assigner.last_stats, mining, shard_capacity)
         gathered = None
         if gather:
             world = torch.distributed.get_world_size()
@@ -258,7 +287,13 @@ class AnchorPipeline:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        # The post-processor chain (pass 1 -> pass 2 -> NMS -> top-k) is the longest branch: it is captured
+        # on a HIGH-priority stream (the priority becomes an attribute of its kernel nodes), the assignment /
+        # sampler / encode branches on default-priority side streams, so that whenever CTAs of both are
+        # pending the block scheduler places the critical chain first.
+        import os
+        prio = os.environ.get("SSD_GRAPH_PRIORITY", "1") != "0"
+        with torch.cuda.graph(graph, stream=torch.cuda.Stream(priority=-1) if prio else None):
             out = self.step_device(packed, anchors_dev, scores_dev, locs_dev, shard_capacity, gather)
         self._graph = graph
         return out

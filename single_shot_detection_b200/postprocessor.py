@@ -48,6 +48,24 @@ class Postprocessor(object):
                                float(self._nms_cfg['overlap_threshold']), max_total,
                                float(self._nms_cfg.get('sigma', 0.5)) if self._nms_cfg.get('soft', False) else 0.0)
 
+    def begin_padded(self, prediction, priors, want_loss_keys=False):
+        """First launch only (row statistics; with ``want_loss_keys`` also the sampler's criterion, see
+        ops.postprocess_begin); ``.finish()`` on the result enqueues the rest and returns what
+        :meth:`postprocess_padded` returns."""
+        from . import ops
+        b_scores, b_boxes = prediction
+        if not b_scores.is_cuda:
+            raise TypeError('Postprocessor needs CUDA predictions (no CPU fallback)')
+        priors_dev = _devcache.device_copy(priors, b_scores.device)
+        converter, first_fg = _CONVERTERS[self.score_converter]
+        max_total = int(self.max_total) if self.max_total is not None else 0
+        return ops.postprocess_begin(b_scores, b_boxes, priors_dev, converter, first_fg, N.BOXES_ENCODED,
+                                     float(self.box_coder.xy_scale), float(self.box_coder.wh_scale),
+                                     float(self.score_threshold), int(self._nms_cfg['max_per_class']),
+                                     float(self._nms_cfg['overlap_threshold']), max_total,
+                                     float(self._nms_cfg.get('sigma', 0.5)) if self._nms_cfg.get('soft', False) else 0.0,
+                                     want_loss_keys)
+
     def postprocess(self, prediction, priors):
         """
         Args:
@@ -58,7 +76,10 @@ class Postprocessor(object):
         Returns:
             processed: list(:len Batch) of torch.tensor(:shape [Boxes_i, 6] ~ {[0-3] - box, [4] - class, [5] - score})
         """
-        dets, counts, anchors, status = self.postprocess_padded(prediction, priors)
+        return self.to_list(*self.postprocess_padded(prediction, priors))
+
+    def to_list(self, dets, counts, anchors, status):
+        """Padded device output -> the reference's list of ``[n_i, 6]`` views (one host sync: the counts)."""
         self.last_padded = (dets, counts, anchors, status)
         host = _devcache.pinned_buffer("post_counts", (counts.numel() + 4,), torch.int32)
         host[: counts.numel()].copy_(counts, non_blocking=True)

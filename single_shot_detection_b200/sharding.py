@@ -41,6 +41,23 @@ def pack_shard(dets: torch.Tensor, counts: torch.Tensor, stats: torch.Tensor, ca
     return buf
 
 
+def pack_shard_device(dets: torch.Tensor, counts: torch.Tensor, assign_stats: Optional[torch.Tensor],
+                      mining_stats: Optional[torch.Tensor], capacity: int):
+    """:func:`pack_shard` + ``pipeline.matched_stats`` for CUDA tensors in ONE launch (csrc/exchange.cu):
+    -> (shard [capacity, T*6 + 5], stats [B, 4] int32)."""
+    from . import _native as N
+    N.require_device()
+    n, t = int(dets.shape[0]), int(dets.shape[1])
+    shard = torch.empty((capacity, t * 6 + 5), dtype=torch.float32, device=dets.device)
+    stats = torch.empty((n, 4), dtype=torch.int32, device=dets.device)
+    with torch.cuda.device(dets.device):
+        N.check(N.lib().ssd_pack_shard(dets.data_ptr(), counts.data_ptr(),
+                                       None if assign_stats is None else assign_stats.data_ptr(),
+                                       None if mining_stats is None else mining_stats.data_ptr(), n, t, capacity,
+                                       shard.data_ptr(), stats.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    return shard, stats
+
+
 def unpack_gathered(gathered: torch.Tensor, batch: int, world: int, max_rows: int):
     """Inverse of pack_shard over the concatenation of all ranks' buffers."""
     capacity = gathered.shape[0] // world

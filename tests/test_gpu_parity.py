@@ -667,3 +667,59 @@ def test_device_linspace_matches_torch_cpu_for_odd_sizes(dev):
                 ys = torch.linspace(0.5 * sh, (0.5 + fm[1] - 1) * sh, fm[1])
                 assert torch.equal(got[0, :, 0, 0], xs), (img_w, cells, step)
                 assert torch.equal(got[:, 0, 0, 1], ys), (img_h, cells, step)
+
+
+def test_pack_shard_kernel_equals_tensor_op_packing(dev):
+    """csrc/exchange.cu against the tensor-op packing the gloo tests exercise on the CPU (sharding.pack_shard)."""
+    from single_shot_detection_b200 import sharding
+    from single_shot_detection_b200.pipeline import matched_stats
+    gen = torch.Generator().manual_seed(11)
+    for n, t, cap in [(5, 7, 5), (3, 200, 8), (0, 4, 2), (32, 200, 32)]:
+        dets = torch.rand((n, t, 6), generator=gen)
+        counts = torch.randint(0, t + 1, (n,), generator=gen, dtype=torch.int32)
+        a_stats = torch.randint(0, 99, (n, 4), generator=gen, dtype=torch.int32)
+        m_stats = torch.randint(0, 99, (n, 4), generator=gen, dtype=torch.int32)
+        want_stats = matched_stats(a_stats, m_stats, counts)
+        want = sharding.pack_shard(dets, counts, want_stats, cap)
+        got, got_stats = sharding.pack_shard_device(dets.to(dev), counts.to(dev), a_stats.to(dev), m_stats.to(dev), cap)
+        assert torch.equal(got.cpu().view(torch.int32), want.view(torch.int32)), (n, t, cap)
+        assert torch.equal(got_stats.cpu(), want_stats)
+        got2, _ = sharding.pack_shard_device(dets.to(dev), counts.to(dev), a_stats.to(dev), None, cap)
+        want2 = sharding.pack_shard(dets, counts, matched_stats(a_stats, None, counts), cap)
+        assert torch.equal(got2.cpu().view(torch.int32), want2.view(torch.int32))
+
+
+# ----------------------------------------------------------------------------------------------
+# eval step: the mining criterion out of the post-processor's first pass (one read of the logits)
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,batch", [("ssd300_voc_b8", 8), ("tiny_voc_b3", 3), ("ssd_mb2_coco_b64", 6)])
+def test_shared_logit_pass_equals_separate_calls(dev, name, batch):
+    from single_shot_detection_b200.pipeline import AnchorPipeline
+    from single_shot_detection_b200.target_assigner import pack_ground_truth
+    w = wl.WORKLOADS[name]
+    anchors, gt, scores, locs = wl.make_inputs(w, seed=5, batch=batch)
+    outs = []
+    for share in (False, True):
+        pipe = AnchorPipeline(w.cfg())
+        pipe.share_logit_pass = share
+        packed = pack_ground_truth(gt, dev)
+        out = pipe.step_device(packed, anchors.to(dev), scores.to(dev), locs.to(dev))
+        torch.cuda.synchronize()
+        outs.append(out)
+    a, b = outs
+    assert torch.equal(a.target, b.target)
+    assert torch.equal(a.dets, b.dets) and torch.equal(a.counts, b.counts)
+    assert torch.equal(a.mining_stats[:, :3], b.mining_stats[:, :3])           # positives, negatives, selected
+    diff = (a.mask != b.mask)
+    if w.num_score_cols == 21 or w.num_score_cols <= 8:
+        assert not bool(diff.any())          # same row shape in both kernels: bit-identical criterion
+    else:
+        # C = 81: pass 1 sums a row over 8 lanes, the sampler's own kernel over 4 -- the criterion can differ
+        # in the last bit, which may swap two anchors exactly at the cut
+        assert int(diff.sum()) <= 2 * batch
+    # and the list API takes the same route
+    pipe = AnchorPipeline(w.cfg())
+    target, mask, dets = pipe.step(gt, anchors, scores.to(dev), locs.to(dev))
+    assert torch.equal(mask, b.mask) and torch.equal(target, b.target)
+    for i, d in enumerate(dets):
+        assert torch.equal(d, b.dets[i, : int(b.counts[i])])
