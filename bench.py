@@ -359,9 +359,13 @@ def run_ours(args):
 
 
 def roofline_probe(w, dev_sets, anchors_dev, pipe, B, A, C, nsets, iters: int = 50):
-    """Time the logit-streaming kernel that dominates the step, alone, with CUDA events."""
+    """Time the logit-streaming kernels alone (CUDA events on the launching stream, launches back to back,
+    inputs rotating over sets larger than L2).  The roofline entry is the one that runs in the step: the
+    post-processor's first pass (row statistics + gate bookkeeping + the sampler's criterion); the sampler's
+    own streaming kernel (train steps, no post-processor) is reported beside it."""
     import ctypes
     from single_shot_detection_b200 import _native as N
+    from single_shot_detection_b200 import ops
     peak, peak_src = measured_peaks()
     dev = anchors_dev.device
     stream = torch.cuda.current_stream().cuda_stream
@@ -369,34 +373,65 @@ def roofline_probe(w, dev_sets, anchors_dev, pipe, B, A, C, nsets, iters: int = 
     cls = [torch.zeros((B, A), dtype=torch.int64, device=dev) for _ in range(nsets)]
     lib = N.lib()
 
-    ws = torch.empty((lib.ssd_hard_negative_workspace_bytes(B, A),), dtype=torch.uint8, device=dev)
+    def timed(launch):
+        for i in range(5):
+            launch(i % nsets)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            launch(i % nsets)
+        e1.record()
+        torch.cuda.synchronize()
+        return 1e3 * e0.elapsed_time(e1) / iters
 
-    def launch(k):
+    ws = torch.empty((max(lib.ssd_hard_negative_workspace_bytes(B, A), 256),), dtype=torch.uint8, device=dev)
+
+    def mining(k):
         N.check(lib.ssd_mining_keys(dev_sets[k][1].data_ptr(), cls[k].data_ptr(), B, A, C, keys.data_ptr(),
                                     ws.data_ptr(), ws.numel(), stream))
 
-    for i in range(5):
-        launch(i % nsets)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(iters):
-        launch(i % nsets)
-    e1.record()
-    torch.cuda.synchronize()
-    us = 1e3 * e0.elapsed_time(e1) / iters
     algo_bytes = B * A * (4 * C + 8 + 4)          # logits + int64 class read, uint32 key written
-    achieved = algo_bytes / (us * 1e-6) / 1e9
+    us_mining = timed(mining)
+    other = {"mining_loss_kernel (ssd_mining_keys, the sampler alone)": {
+        "us_per_launch": us_mining, "achieved": algo_bytes / (us_mining * 1e-6) / 1e9,
+        "frac": algo_bytes / (us_mining * 1e-6) / 1e9 / peak, "algorithmic_bytes_per_launch": algo_bytes}}
+    if w.converter != "SOFTMAX" or w.sampler != "hard_negative_mining":
+        # no shared pass in this configuration: the sampler's kernel is not in the step either (naive sampler);
+        # pass 1 without the criterion output is the step's streaming kernel
+        want_keys = False
+        algo_p1 = B * A * (4 * C)
+    else:
+        want_keys = True
+        algo_p1 = B * A * (4 * C + 8 + 4)          # logits read, (max, sum) float2 + uint32 criterion key written
+    post = pipe.postprocessor
+    conv, first_fg = {"SOFTMAX": (N.CONVERT_SOFTMAX, 1), "SIGMOID": (N.CONVERT_SIGMOID, 0)}[w.converter]
+    p = ops._post_params(dev_sets[0][1], dev_sets[0][2], conv, first_fg, N.BOXES_ENCODED, float(w.xy_scale),
+                         float(w.wh_scale), float(w.score_threshold), int(w.max_per_class), float(w.overlap_threshold),
+                         int(w.max_total or 0), 0.0)
+    pws = ops._post_workspace(p, dev)
+
+    def pass1(k):
+        N.check(lib.ssd_postprocess_pass1(ctypes.byref(p), dev_sets[k][1].data_ptr(), keys.data_ptr() if want_keys else None,
+                                          pws.data_ptr(), pws.numel(), stream))
+
+    us = timed(pass1)
+    achieved = algo_p1 / (us * 1e-6) / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` capture per workload
     # (profiles/r01_ncu_full.md); None for a workload that has no committed capture
-    traffic = {"ssd300_voc_b32": 25841664, "ssd512_coco_b32": 266480000}.get(w.name)
-    return {"bound": "hbm", "kernel": "mining_loss_kernel (ssd_mining_keys)", "achieved": achieved, "peak": peak,
+    traffic = NCU_TRAFFIC.get(w.name)
+    return {"bound": "hbm", "kernel": "score_pass1_kernel (ssd_postprocess_pass1)", "achieved": achieved, "peak": peak,
             "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "traffic_source": "profiles/r01_ncu_full.md" if traffic else None,
-            "algorithmic_bytes_per_launch": algo_bytes, "us_per_launch": us,
-            "note": "the logit-streaming kernel of the sampler (4C+12 algorithmic bytes per anchor), launched back to back "
-                    "on one stream incl. its histogram memset, inputs rotating over sets larger than L2; the largest kernel "
-                    "of the step, segment_nms_kernel, is ALU bound and reported under 'nms'"}
+            "algorithmic_bytes_per_launch": algo_p1, "us_per_launch": us, "other_streaming_kernels": other,
+            "note": "the streaming kernel of the step: one read of the logits yields the row statistics, the gate "
+                    "bookkeeping and the sampler's criterion (4C read + 12 written bytes per anchor); the call is timed "
+                    "back to back on one stream INCLUDING its scratch-zeroing kernel, inputs rotating over sets larger "
+                    "than L2; the largest kernel of the step, segment_nms_kernel, is ALU bound and reported under 'nms'"}
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel (profiles/r01_ncu_full.md)
+NCU_TRAFFIC = {}
 
 
 def main():

@@ -42,6 +42,7 @@ __global__ void probe_kernel(int* out) { *out = 100; }
 // launched with programmatic stream serialization has no such coupling and overlaps its successor's
 // prologue.
 __global__ void __launch_bounds__(256) zero_kernel(uint4* __restrict__ p, size_t n16) {
+    KernelTrace trace_(n16 > 4096 ? TR_MISC : TR_MINING_KEYS);     // (diagnostics: large / small zeroing)
     griddep_wait();
     griddep_launch_dependents();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
@@ -120,6 +121,7 @@ cudaError_t set_trace_loss(unsigned long long*);
 cudaError_t set_trace_metrics(unsigned long long*);
 cudaError_t set_trace_anchors(unsigned long long*);
 cudaError_t set_trace_exchange(unsigned long long*);
+cudaError_t set_trace_abi(unsigned long long*);
 }  // namespace ssd
 
 extern "C" int ssd_b200_trace_enable(unsigned long long* device_slots) {
@@ -131,6 +133,7 @@ extern "C" int ssd_b200_trace_enable(unsigned long long* device_slots) {
     SSD_CUDA(ssd::set_trace_metrics(device_slots));
     SSD_CUDA(ssd::set_trace_anchors(device_slots));
     SSD_CUDA(ssd::set_trace_exchange(device_slots));
+    SSD_CUDA(ssd::set_trace_abi(device_slots));
     return SSD_OK;
 }
 extern "C" int ssd_b200_trace_slots(void) { return ssd::kTraceSlots; }
@@ -162,3 +165,5 @@ extern "C" size_t ssd_b200_timing_report(char* buf, size_t capacity) {
     g_timing_used = 0;
     return off;
 }
+
+SSD_DEFINE_TRACE_SETTER(set_trace_abi)

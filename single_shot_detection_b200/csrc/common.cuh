@@ -129,6 +129,15 @@ __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("grid
 // small kernels with large grids that hang off a long-running predecessor (the box transforms after
 // the target assignment: 1092 CTAs x 256 threads) were observed to keep the post-processor's first
 // pass off the SMs for the whole assignment.  Those use launch_plain (full stream-order dependency).
+// Every kernel of the library asks for the same shared-memory carve-out (the maximum: the streaming
+// kernels need 3 x 72 KB per SM).  Kernels with different carve-outs cannot share an SM, and switching
+// costs a reconfiguration: with mixed preferences the post-processor's first pass started ~5 us after
+// the zeroing kernel in front of it had finished (tools/graph_timeline.py).
+template <typename F>
+inline void prefer_max_shared(F kern) {
+    static_cast<void>(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+}
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_plain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                                 Args&&... args) {
@@ -139,6 +148,7 @@ inline cudaError_t launch_plain(void (*kern)(KArgs...), dim3 grid, dim3 block, s
     cfg.stream = st;
     cfg.attrs = nullptr;
     cfg.numAttrs = 0;
+    prefer_max_shared(kern);
     return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
@@ -155,6 +165,7 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    prefer_max_shared(kern);
     return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 

@@ -42,13 +42,14 @@ namespace ssd {
 struct PostPlan {
     int B, A, C, Cf, first_fg, K, T, det_cap, converter, box_input;
     ScoreGrid g;             // tiling of the streaming kernels (shared by both passes)
-    int grid;                // CTAs of the streaming kernels
+    int grid;                // CTAs of pass 2
+    int grid1;               // CTAs of pass 1 (less shared memory per CTA: one more per SM)
     int nblk;                // row blocks per image
     int cand_cap;            // candidate slots per (image, class)
     // workspace offsets (bytes)
     size_t off_rowstat, off_blockmax, off_gate, off_cand_count, off_cand, off_kept_count, off_kept, off_status,
         off_anchor_tmp, off_score_hist, off_bhist, off_image_done;
-    size_t zero_begin, zero_bytes;   // counters and histograms: one memset per call
+    size_t zero_begin, zero_bytes;   // counters and histograms of the LATER launches: zeroed by pass 1 itself
     bool gate_hist;                  // gates from a histogram of the block maxima (SOFTMAX / SIGMOID)
     float bin_lo, bin_scale;
     float soft_thr;
@@ -64,6 +65,7 @@ constexpr int kQueueCap = 96;         // pass-2 survivor queue: entries per warp
 // just below the score threshold -- nothing under it can become a detection -- see gate_range().
 constexpr int kGateBins = 256;
 constexpr int kGateWords = kGateBins / 2;
+constexpr int kGateStride = kGateWords + 1;      // shared-memory histogram of pass 2: words per column
 constexpr size_t kQueueBytes = (size_t)kConsumerWarps * kQueueCap * 3 * sizeof(uint32_t);
 
 // Monotone (non-decreasing) map of a kept score to a histogram bin; probabilities spread over the
@@ -136,7 +138,11 @@ static int make_plan(const ssd_postprocess_params* p, PostPlan& pl) {
     g.split = split;
     g.nblk = g.groups_per_image * kConsumerWarps * split;
     pl.nblk = g.nblk;
-    pl.grid = stream_grid(g, kQueueBytes + round_up((size_t)pl.C * sizeof(float), 16));
+    pl.gate_hist = pl.converter != SSD_CONVERT_IDENTITY && pl.nblk < 65536 && pl.C <= 32;
+    { const char* e = getenv("SSD_GATE"); if (e) pl.gate_hist = e[0] == 'h' && pl.converter != SSD_CONVERT_IDENTITY && pl.C <= 64; }
+    { ScoreGrid g1 = g; pl.grid1 = stream_grid(g1); }
+    pl.grid = stream_grid(g, kQueueBytes + round_up((size_t)pl.C * sizeof(float), 16) +
+                                 (pl.gate_hist ? (size_t)pl.C * kGateStride * sizeof(uint32_t) : 0));
     int cap = 512;                        // power of two (the segment sort pads to one), >= 8K
     while (cap < 8 * pl.K && cap < 4096) cap <<= 1;
     pl.cand_cap = cap;
@@ -148,18 +154,16 @@ static int make_plan(const ssd_postprocess_params* p, PostPlan& pl) {
     // Few columns: the gates come from histograms inside pass 2 (one launch less).  Many columns
     // (COCO's 81): a pass-2 CTA would spend longer on its image's gates than the separate
     // class_gate launch costs, measured in the step graph (profiles/), so that one stays.
-    pl.gate_hist = pl.converter != SSD_CONVERT_IDENTITY && pl.nblk < 65536 && pl.C <= 32;
-    { const char* e = getenv("SSD_GATE"); if (e) pl.gate_hist = e[0] == 'h' && pl.converter != SSD_CONVERT_IDENTITY; }
     gate_range(pl.converter, p->score_threshold, pl.bin_lo, pl.bin_scale);
     pl.off_rowstat = take(BA * sizeof(float2));
-    pl.off_blockmax = take(pl.gate_hist ? 0 : (size_t)pl.B * pl.nblk * pl.C * sizeof(float));
+    pl.off_blockmax = take((size_t)pl.B * pl.nblk * pl.C * sizeof(float));
     pl.off_gate = take((size_t)pl.B * pl.C * sizeof(float));
     pl.off_cand = take((size_t)pl.B * pl.Cf * pl.cand_cap * sizeof(uint2));
     pl.off_kept_count = take((size_t)pl.B * pl.Cf * sizeof(int));
     pl.off_kept = take((size_t)pl.B * pl.Cf * pl.K * kKeptCols * sizeof(float));
     pl.off_anchor_tmp = take((size_t)pl.B * (pl.det_cap > 0 ? pl.det_cap : 1) * sizeof(int));
     pl.zero_begin = off;
-    pl.off_bhist = take(pl.gate_hist ? (size_t)pl.B * pl.C * kGateWords * sizeof(uint32_t) : 0);
+    pl.off_bhist = 0;
     pl.off_cand_count = take((size_t)pl.B * pl.Cf * sizeof(int));
     pl.off_status = take(4 * sizeof(int));
     pl.off_score_hist = take((size_t)pl.B * kScoreBins * sizeof(int));
@@ -195,8 +199,8 @@ __device__ __forceinline__ float gate_bin_edge(int bin, GateBins gb) {
 template <int Q, int NREG, int CMIN, int CONV>
 __global__ void __launch_bounds__(kStreamThreads)
 score_pass1_kernel(const float* __restrict__ scores, ScoreGrid g, float2* __restrict__ rowstat,
-                   float* __restrict__ blockmax, uint32_t* __restrict__ bhist, GateBins gbins,
-                   uint32_t* __restrict__ loss_keys) {
+                   float* __restrict__ blockmax, uint32_t* __restrict__ loss_keys, uint4* __restrict__ zero_ptr,
+                   unsigned zero_n16) {
     extern __shared__ __align__(128) unsigned char smem[];
     KernelTrace trace_(TR_PASS1);
     stream_init(smem);
@@ -205,6 +209,11 @@ score_pass1_kernel(const float* __restrict__ scores, ScoreGrid g, float2* __rest
         producer_loop(smem, g, scores, nullptr, policy_evict_last());      // pass 2 re-reads the same bytes
         return;
     }
+    // counters / histograms of the launches that FOLLOW (candidate counts, score histograms, tickets): zeroed
+    // here, so the call needs no memset or zeroing launch in front of it.  Nothing this kernel accumulates
+    // into needs a zero start: the block maxima are plain stores.
+    for (unsigned i = blockIdx.x * (kConsumerWarps * 32) + threadIdx.x; i < zero_n16; i += gridDim.x * (kConsumerWarps * 32))
+        zero_ptr[i] = make_uint4(0u, 0u, 0u, 0u);
     const RowLanes<Q> ln;
     const RowShape<Q, NREG, CMIN> shape(ln.sub, g.C);
     const int rows_per_warp = g.tile_rows / kConsumerWarps;
@@ -256,13 +265,9 @@ score_pass1_kernel(const float* __restrict__ scores, ScoreGrid g, float2* __rest
                     const float r = warp_max(cmax[i]);
                     if (lane_id() == i) mine = r;
                 }
-                if (lane_id() < g.C) {
-                    if (bhist != nullptr)
-                        bump_gate_bin(bhist + ((size_t)cur.image(g) * g.C + lane_id()) * kGateWords, mine, gbins);
-                    else
-                        blockmax[((size_t)cur.image(g) * g.nblk + (size_t)cur.group(g) * kConsumerWarps + warp_id()) * g.C +
-                                 lane_id()] = mine;
-                }
+                if (lane_id() < g.C)
+                    blockmax[((size_t)cur.image(g) * g.nblk + (size_t)cur.group(g) * kConsumerWarps + warp_id()) * g.C +
+                             lane_id()] = mine;
             } else {
                 // merge the row slots of the warp down to `split` blocks, then one vector per block
 #pragma unroll
@@ -279,12 +284,7 @@ score_pass1_kernel(const float* __restrict__ scores, ScoreGrid g, float2* __rest
 #pragma unroll
                     for (int i = 0; i < NREG; ++i) {
                         const int col = ln.sub + i * Q;
-                        if (col < g.C) {
-                            if (bhist != nullptr)
-                                bump_gate_bin(bhist + ((size_t)cur.image(g) * g.C + col) * kGateWords, cmax[i], gbins);
-                            else
-                                dst[col] = cmax[i];
-                        }
+                        if (col < g.C) dst[col] = cmax[i];
                     }
                 }
             }
@@ -455,22 +455,63 @@ struct CandQueue {
 // the gate is the lower edge of the highest bin whose suffix count reaches K -- a lower bound of
 // the K-th largest block maximum, hence of the K-th largest score of the class.
 struct GateHist {
-    const uint32_t* bhist;      // nullptr: gates are read from the `gate` array (class_gate_kernel)
+    const float* blockmax;      // nullptr: gates are read from the `gate` array (class_gate_kernel)
+    int nblk;
     int K, converter;
     float score_thr;
     GateBins bins;
 };
 constexpr int kGateBatch = 4;
-__device__ __forceinline__ void image_gates(const GateHist& gh, const ScoreGrid& g, int img, float* __restrict__ sgate) {
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory"); }
+__device__ __forceinline__ void image_gates(const GateHist& gh, const ScoreGrid& g, int img, float* __restrict__ sgate,
+                                            uint32_t* __restrict__ shist) {
     const int lane = lane_id();
     static_assert(kGateWords == 32 * 4, "four words per lane");
-    const uint4* base = reinterpret_cast<const uint4*>(gh.bhist + (size_t)img * g.C * kGateWords) + lane;
+    // histogram of the image's block maxima per column, built in shared memory (pass 1 stores the maxima,
+    // [nblk, C] per image, 23 KB for SSD300: no global atomics and no zeroed scratch on that side).
+    // Column stride kGateStride = kGateWords + 1 words: neighbouring lanes hold neighbouring COLUMNS of one
+    // block whose maxima fall into similar bins -- with a stride of 128 words they would all hit one bank.
+    for (int i = threadIdx.x; i < g.C * kGateStride; i += kConsumerWarps * 32) shist[i] = 0u;
+    consumer_barrier();
+    {
+        const float* bm = gh.blockmax + (size_t)img * gh.nblk * g.C;
+        const int total = gh.nblk * g.C;
+        // nblk is a multiple of 8, so an image's maxima are a whole number of 16-byte vectors: every thread's
+        // loads (six LDG.128 for SSD300) are in flight together -- one L2 round trip
+        const float4* bm4 = reinterpret_cast<const float4*>(bm);
+        const int total4 = total >> 2;
+        constexpr int kDeep = 8;
+        for (int i0 = threadIdx.x; i0 < total4; i0 += kDeep * kConsumerWarps * 32) {
+            float4 v[kDeep];
+#pragma unroll
+            for (int u = 0; u < kDeep; ++u) {
+                const int i = i0 + u * kConsumerWarps * 32;
+                v[u] = i < total4 ? __ldcg(bm4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < kDeep; ++u) {
+                const int i = i0 + u * kConsumerWarps * 32;
+                if (i < total4) {
+                    int col = (4 * i) % g.C;
+                    const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        bump_gate_bin(shist + (size_t)col * kGateStride, e[j], gh.bins);
+                        col = col + 1 == g.C ? 0 : col + 1;
+                    }
+                }
+            }
+        }
+    }
+    consumer_barrier();
+    const uint32_t* base = shist + 4 * lane;
     for (int col0 = g.first_fg + warp_id(); col0 < g.C; col0 += kConsumerWarps * kGateBatch) {
         uint4 h[kGateBatch];
 #pragma unroll
         for (int u = 0; u < kGateBatch; ++u) {
             const int col = col0 + u * kConsumerWarps;
-            h[u] = col < g.C ? base[(size_t)col * (kGateWords / 4)] : make_uint4(0, 0, 0, 0);
+            const uint32_t* src = base + (size_t)col * kGateStride;
+            h[u] = col < g.C ? make_uint4(src[0], src[1], src[2], src[3]) : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
         for (int u = 0; u < kGateBatch; ++u) {
@@ -503,7 +544,6 @@ __device__ __forceinline__ void image_gates(const GateHist& gh, const ScoreGrid&
     }
     for (int c = threadIdx.x; c < g.first_fg; c += kConsumerWarps * 32) sgate[c] = INFINITY;
 }
-__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory"); }
 
 template <int Q, int NREG, int CMIN, int CONV>
 __global__ void __launch_bounds__(kStreamThreads)
@@ -530,6 +570,8 @@ score_pass2_kernel(const float* __restrict__ scores, ScoreGrid g, const float2* 
         q.seg = base; q.anchor = base + kQueueCap; q.val = base + 2 * kQueueCap; q.n = 0;
     }
     float* sgate = reinterpret_cast<float*>(smem + stream_smem_bytes_dev(g) + kQueueBytes);      // [C]
+    uint32_t* shist = reinterpret_cast<uint32_t*>(smem + stream_smem_bytes_dev(g) + kQueueBytes +
+                                                  round_up((size_t)g.C * sizeof(float), 16));     // [C, kGateWords]
     const unsigned lt_mask = (1u << lane_id()) - 1u;
 
     float gv[NREG];
@@ -543,9 +585,9 @@ score_pass2_kernel(const float* __restrict__ scores, ScoreGrid g, const float2* 
         if (img != cur_image) {                 // per-lane slice of this image's gates
             cur_image = img;
             const float* gsrc = gate + (size_t)img * g.C;
-            if (gh.bhist != nullptr) {
+            if (gh.blockmax != nullptr) {
                 consumer_barrier();             // everybody is done with the previous image's gates
-                image_gates(gh, g, img, sgate);
+                image_gates(gh, g, img, sgate, shist);
                 consumer_barrier();
                 gsrc = sgate;
             }
@@ -1462,22 +1504,23 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
     const ScoreGrid& g = pl.g;
     const int grid = pl.grid;
     const size_t stream_smem = stream_smem_bytes(g);
-    const size_t pass2_smem = stream_smem + kQueueBytes + round_up((size_t)pl.C * sizeof(float), 16);
-    uint32_t* bhist = pl.gate_hist ? (uint32_t*)(ws + pl.off_bhist) : nullptr;
+    const size_t pass2_smem = stream_smem + kQueueBytes + round_up((size_t)pl.C * sizeof(float), 16) +
+                              (pl.gate_hist ? (size_t)pl.C * kGateStride * sizeof(uint32_t) : 0);
     GateBins gbins;
     gbins.lo = pl.bin_lo; gbins.scale = pl.bin_scale;
 
     if (stages & kStagePass1) {
-    // counters, histograms and the status words start at zero
-    SSD_CUDA(zero_async(ws + pl.zero_begin, pl.zero_bytes, st));
+    // (the counters, histograms and status words of the later launches are zeroed by pass 1 itself)
+    uint4* zero_ptr = (uint4*)(ws + pl.zero_begin);
+    const unsigned zero_n16 = (unsigned)(pl.zero_bytes / 16);
 
 #define SSD_LAUNCH_PASS1(QQ, NN, CM)                                                                                     \
     do {                                                                                                               \
         auto launch = [&](auto kern) -> int {                                                                          \
             SSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem));    \
             LaunchTimer lt_("pass1", st);                                                            \
-            SSD_CUDA(launch_pdl(kern, dim3(grid), dim3(kStreamThreads), stream_smem, st, scores, g, rowstat, blockmax, \
-                                bhist, gbins, loss_keys));                                                      \
+            SSD_CUDA(launch_pdl(kern, dim3(pl.grid1), dim3(kStreamThreads), stream_smem, st, scores, g, rowstat, blockmax, \
+                                loss_keys, zero_ptr, zero_n16));                                                \
             return SSD_OK;                                                                                             \
         };                                                                                                             \
         int rc;                                                                                                        \
@@ -1505,7 +1548,7 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
     }
 
     GateHist gh;
-    gh.bhist = bhist; gh.K = pl.K; gh.converter = pl.converter; gh.score_thr = p->score_threshold;
+    gh.blockmax = pl.gate_hist ? (const float*)blockmax : nullptr; gh.nblk = pl.nblk; gh.K = pl.K; gh.converter = pl.converter; gh.score_thr = p->score_threshold;
     gh.bins = gbins;
 #define SSD_LAUNCH_PASS2(QQ, NN, CM)                                                                                     \
     do {                                                                                                               \

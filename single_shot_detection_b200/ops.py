@@ -44,14 +44,26 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 _workspaces: Dict[Tuple[int, str], torch.Tensor] = {}
+_retired: list = []          # outgrown buffers: CUDA graphs captured earlier still hold their addresses
 
 
 def workspace(nbytes: int, device: torch.device, tag: str = "default") -> torch.Tensor:
-    """A cached, 256-byte aligned scratch buffer on ``device`` (grown on demand, never shrunk)."""
+    """A cached, 256-byte aligned scratch buffer on ``device`` (grown on demand, never shrunk).
+
+    Growth is geometric and an outgrown buffer is kept alive: a step graph captured while it was current
+    keeps replaying with its address (torch.cuda.graph() empties the allocator cache when a capture begins,
+    which would unmap a freed one)."""
     key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        size = max(int(nbytes), 256)
+        if buf is not None:
+            size = max(size, 2 * buf.numel())
+            _retired.append(buf)
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError(f"the '{tag}' workspace would have to grow to {size} bytes inside a CUDA graph capture; "
+                               "run the step once eagerly with the largest shapes first")
+        buf = torch.empty(size, dtype=torch.uint8, device=device)
         _workspaces[key] = buf
     return buf
 
@@ -126,7 +138,10 @@ def _assign_targets(anchors: torch.Tensor, gt_rows: torch.Tensor, gt_offsets: to
     stats = torch.empty((batch, 4), dtype=torch.int32, device=dev)
     gt_cols = gt_rows.shape[1] if gt_rows.dim() == 2 else 6
     with torch.cuda.device(dev):
-        ws_bytes = N.lib().ssd_assign_workspace_bytes(batch, max_gt)
+        cap = 64                                        # scratch sized for a bucket of boxes per image, not for
+        while cap < max_gt:                             # this batch's maximum: its address stays put across batches
+            cap *= 2
+        ws_bytes = N.lib().ssd_assign_workspace_bytes(batch, cap)
         ws = workspace(ws_bytes, dev, "assign")
         N.check(N.lib().ssd_assign_targets(_ptr(anchors), _ptr(gt_rows) if gt_rows.numel() else None, gt_cols,
                                            _ptr(gt_offsets), max_gt, batch, num_anchors, matched_threshold,

@@ -58,7 +58,9 @@ class AnchorPipeline:
             {"max_per_class": cfg["max_per_class"], "overlap_threshold": cfg["overlap_threshold"]},
             score_converter=cfg["converter"], max_total=cfg["max_total"])
         self.fuse_encode = False       # True: one pass for to_centroids+encode (same rounding)
-        self.share_logit_pass = True   # eval step: mining criterion out of the post-processor's first pass
+        # eval step: mining criterion out of the post-processor's first pass (SSD_SHARE_PASS=0: separate kernels)
+        import os
+        self.share_logit_pass = os.environ.get("SSD_SHARE_PASS", "1") != "0"
         self._graph = None
         self._side = None
         self._copy = None
