@@ -117,6 +117,18 @@ SSD_API int ssd_assign_targets(const float* anchors, const float* gt_rows, int g
                        float matched_threshold, float unmatched_threshold, int force_match,
                        float* target_out, int32_t* match_out, int32_t* stats_out, void* workspace,
                        size_t workspace_bytes, void* stream);
+/* The same launch with the box columns written ALREADY passed through the loss route's box coding:
+ * box_utils.to_centroids(inplace=True) + BoxCoder.encode_box(inplace=True), detection/losses/
+ * multibox_loss.py:81-82, applied to every row as the reference does (its only consumer of the target
+ * tensor does exactly that right away).  Bit-identical to ssd_assign_targets followed by
+ * ssd_box_transform(SSD_BOX_CENTROIDS_ENCODE_INPLACE); match_out is required.  The NaN statistic still
+ * refers to the corner boxes (target_assigner.py:60-61). */
+SSD_API int ssd_assign_targets_encoded(const float* anchors, const float* gt_rows, int gt_cols,
+                               const int32_t* gt_offsets, int max_gt, int batch, int num_anchors,
+                               float matched_threshold, float unmatched_threshold, int force_match,
+                               float xy_scale, float wh_scale, float eps, float* target_out,
+                               int32_t* match_out, int32_t* stats_out, void* workspace,
+                               size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * a1/a6/a7  box format + coding, bf/utils/box_utils.py:16-36 and detection/box_coder.py:13-57.

@@ -70,6 +70,9 @@ _SIGNATURES = {
     "ssd_assign_workspace_bytes": (c_size_t, [c_int, c_int]),
     "ssd_assign_targets": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_float, c_int,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ssd_assign_targets_encoded": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_float,
+                                           c_int, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                                           c_size_t, c_void_p]),
     "ssd_box_transform": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_float,
                                   c_float, c_float, c_void_p]),
     "ssd_generalized_iou": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),

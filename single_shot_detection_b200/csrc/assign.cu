@@ -66,11 +66,24 @@ __device__ __forceinline__ void row_class_counts(float cls, float4 bx, int& pos,
     nan = p && (bx.x != bx.x || bx.y != bx.y || bx.z != bx.z || bx.w != bx.w);
 }
 
+// coding.on: the box columns of the target rows are written ALREADY passed through the loss route's
+// to_centroids(inplace) + encode_box(inplace) (multibox_loss.py:81-82) -- the only consumer of the target
+// does exactly that to every row right away, so the two box passes over [B, A, 4] disappear.
+struct BoxCoding {
+    int on;
+    float xy, wh, eps;
+};
+__device__ __forceinline__ float4 coded_box(float4 corners, float4 prior, const BoxCoding& c) {
+    const Box e = encode_inplace(to_centroids_inplace(Box{corners.x, corners.y, corners.z, corners.w}), prior, c.xy, c.wh, c.eps);
+    return make_float4(e.a, e.b, e.c, e.d);
+}
+
 __global__ void __launch_bounds__(kAssignThreads)
 assign_targets_kernel(const float4* __restrict__ anchors, const float* __restrict__ gt_rows, int gt_cols,
                       const int32_t* __restrict__ gt_offsets, int A, int max_gt, float matched_thr,
                       float unmatched_thr, int force_match, float* __restrict__ target, int32_t* __restrict__ match_out,
-                      int32_t* __restrict__ stats, int* __restrict__ counters, unsigned long long* __restrict__ gbest) {
+                      int32_t* __restrict__ stats, int* __restrict__ counters, unsigned long long* __restrict__ gbest,
+                      BoxCoding coding) {
     KernelTrace trace_(TR_ASSIGN);
     griddep_wait();
     const int img = blockIdx.y;
@@ -85,13 +98,14 @@ assign_targets_kernel(const float4* __restrict__ anchors, const float* __restric
     unsigned long long* best = reinterpret_cast<unsigned long long*>(gbox + Gcap);      // later: int anchor[G]
     float2* gcs = reinterpret_cast<float2*>(best + Gcap);
     float* garea = reinterpret_cast<float*>(gcs + Gcap);
-    __shared__ int match[kAssignTile];
+    int* gslow = reinterpret_cast<int*>(garea + Gcap);            // box with a non-finite coordinate: no quick reject
     __shared__ int s_last;
 
     // the anchors do not depend on the ground truth: their loads go out before the staging barrier
     float4 ab[kAssignPerThread];
     float aarea[kAssignPerThread];
     bool valid[kAssignPerThread];
+    bool aslow[kAssignPerThread];          // zero / NaN area or a non-finite coordinate: never quick-rejected
 #pragma unroll
     for (int j = 0; j < kAssignPerThread; ++j) {
         const int la = threadIdx.x + j * kAssignThreads;
@@ -102,6 +116,7 @@ assign_targets_kernel(const float4* __restrict__ anchors, const float* __restric
             ab[j] = corners_of(anchors[a_begin + la]);
             aarea[j] = clamped_area(ab[j].x, ab[j].y, ab[j].z, ab[j].w);
         }
+        aslow[j] = !(aarea[j] > 0.f) || !(isfinite(ab[j].x) && isfinite(ab[j].y) && isfinite(ab[j].z) && isfinite(ab[j].w));
     }
 
     for (int g = threadIdx.x; g < G; g += blockDim.x) {
@@ -109,12 +124,14 @@ assign_targets_kernel(const float4* __restrict__ anchors, const float* __restric
         const float4 bx = make_float4(row[0], row[1], row[2], row[3]);
         gbox[g] = bx;
         garea[g] = clamped_area(bx.x, bx.y, bx.z, bx.w);
+        gslow[g] = !(isfinite(bx.x) && isfinite(bx.y) && isfinite(bx.z) && isfinite(bx.w));
         gcs[g] = make_float2(row[SSD_CLASS_COL], row[SSD_SCORE_COL]);
         best[g] = 0ull;                   // nothing overlapping seen: stands for (IoU 0, anchor 0)
     }
     __syncthreads();
     trace_.mark(0);
 
+    int n_pos = 0, n_ign = 0, n_nan = 0;
     // ---- phase 1: per-anchor best GT, per-GT best anchor of this CTA ----
     {
         // IoU 0 against every box so far: the state torch.max would be in after a row of zeros
@@ -126,31 +143,36 @@ assign_targets_kernel(const float4* __restrict__ anchors, const float* __restric
         for (int g = 0; g < G; ++g) {
             const float4 gb = gbox[g];
             const float ga = garea[g];
-            float inter[kAssignPerThread];
-            bool live[kAssignPerThread];
-            bool any_live = false;
+            // Quick reject, four compares per pair: if the boxes do not overlap with positive extent on both
+            // axes, one clamped side of the intersection is exactly 0 and (finite inputs) so is `inter` -- the
+            // pair is disjoint, IoU +0: it can neither raise the anchor's running maximum nor beat the
+            // (0, anchor 0) entry every GT starts with.  ~90 % of the pairs end here.  Non-finite boxes and
+            // zero-area anchors (0/0 -> NaN) always take the full path.
+            const bool gs = gslow[g] != 0;
+            bool ov[kAssignPerThread];
+            bool any_ov = false;
 #pragma unroll
             for (int j = 0; j < kAssignPerThread; ++j) {
-                const float iw = fmaxf(fsub(fminf(gb.z, ab[j].z), fmaxf(gb.x, ab[j].x)), 0.f);
-                const float ih = fmaxf(fsub(fminf(gb.w, ab[j].w), fmaxf(gb.y, ab[j].y)), 0.f);
-                inter[j] = fmul(iw, ih);
-                // Disjoint pairs have IoU +0 exactly: they can neither raise the anchor's running
-                // maximum nor beat the (0, anchor 0) entry every GT starts with, so the divide and
-                // both argmax updates are skipped unless some lane of the warp overlaps this box.
-                // (0/0 -> NaN needs both areas to be zero / NaN; NaN inter is not == 0.)
-                live[j] = valid[j] && !(inter[j] == 0.f);
-                if (valid[j] && !(aarea[j] > 0.f)) live[j] = live[j] || !(ga > 0.f);
-                any_live = any_live || live[j];
+                ov[j] = valid[j] && (gs || aslow[j] ||
+                                     (gb.z > ab[j].x && ab[j].z > gb.x && gb.w > ab[j].y && ab[j].w > gb.y));
+                any_ov = any_ov || ov[j];
             }
-            if (!__any_sync(FULL, any_live)) continue;
+            if (!__any_sync(FULL, any_ov)) continue;
             // this thread's best (key, anchor) for the box: j ascending = anchor ascending, strict > keeps the lower
             uint32_t kbest = 0u;
             uint32_t abest = 0xFFFFFFFFu;
 #pragma unroll
             for (int j = 0; j < kAssignPerThread; ++j) {
-                if (!live[j]) continue;
-                const float uni = fsub(fadd(ga, aarea[j]), inter[j]);
-                const float v = (inter[j] == 0.f && uni > 0.f) ? 0.f : fdiv(inter[j], uni);
+                if (!ov[j]) continue;
+                const float iw = fmaxf(fsub(fminf(gb.z, ab[j].z), fmaxf(gb.x, ab[j].x)), 0.f);
+                const float ih = fmaxf(fsub(fminf(gb.w, ab[j].w), fmaxf(gb.y, ab[j].y)), 0.f);
+                const float inter = fmul(iw, ih);
+                // (0/0 -> NaN needs both areas to be zero / NaN; NaN inter is not == 0.)
+                bool live = !(inter == 0.f);
+                if (!(aarea[j] > 0.f)) live = live || !(ga > 0.f);
+                if (!live) continue;
+                const float uni = fsub(fadd(ga, aarea[j]), inter);
+                const float v = (inter == 0.f && uni > 0.f) ? 0.f : fdiv(inter, uni);
                 // torch.max(dim=0): first maximum wins, NaN propagates and sticks
                 if (!(v <= best_iou[j]) && !(best_iou[j] != best_iou[j])) { best_iou[j] = v; best_g[j] = g; }
                 uint32_t key = ordered_key(v);
@@ -167,21 +189,45 @@ assign_targets_kernel(const float4* __restrict__ anchors, const float* __restric
                 }
             }
         }
+        // ---- phase 3 (same registers): thresholds (matcher.py:49-50) and the target rows.  Each thread writes
+        //      its four rows as three float2 stores per row (rows are 24 bytes: 8-byte aligned); the three
+        //      store instructions of a warp cover the same six 128-byte lines. ----
+        float2* out = reinterpret_cast<float2*>(target + ((size_t)img * A + a_begin) * SSD_TARGET_COLS);
 #pragma unroll
         for (int j = 0; j < kAssignPerThread; ++j) {
+            if (!valid[j]) continue;
+            const int la = threadIdx.x + j * kAssignThreads;
             int m = SSD_NOT_MATCHED;
             if (G > 0) {
                 m = best_g[j];
                 if (best_iou[j] < unmatched_thr) m = SSD_NOT_MATCHED;              // matcher.py:49
                 else if (best_iou[j] < matched_thr) m = SSD_IGNORE;                // matcher.py:50
             }
-            match[threadIdx.x + j * kAssignThreads] = m;
+            float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);                  // target_assigner.py:38: rows start as zeros
+            float2 cs;
+            if (m >= 0) {
+                bx = gbox[m];
+                cs = gcs[m];
+                int p_, i_, n_;
+                row_class_counts(cs.x, bx, p_, i_, n_);
+                n_pos += p_; n_ign += i_; n_nan += n_;
+            } else if (m == SSD_IGNORE) {
+                cs = make_float2((float)SSD_IGNORE_CLASS, (float)SSD_IGNORE_CLASS);
+                n_ign += 1;
+            } else {
+                cs = make_float2((float)SSD_NEGATIVE_CLASS, 1.f);
+            }
+            if (coding.on) bx = coded_box(bx, anchors[a_begin + la], coding);
+            out[la * 3 + 0] = make_float2(bx.x, bx.y);
+            out[la * 3 + 1] = make_float2(bx.z, bx.w);
+            out[la * 3 + 2] = cs;
+            if (match_out != nullptr) match_out[(size_t)img * A + a_begin + la] = m;
         }
     }
-    __syncthreads();
     trace_.mark(1);
     // dependents may be scheduled from here on (not earlier: an early dependent only squats on the SMs)
     griddep_launch_dependents();
+    __syncthreads();                       // every warp is done with best[] (phase 1 atomics)
 
     // ---- phase 2: publish this CTA's per-GT winners ----
     if (force_match) {
@@ -189,35 +235,6 @@ assign_targets_kernel(const float4* __restrict__ anchors, const float* __restric
             const unsigned long long w = best[g];
             if (w != 0ull) atomicMax(&gbest[(size_t)img * max_gt + g], w);
         }
-    }
-
-    // ---- phase 3: target rows, flat coalesced float2 stores over this CTA's [n_local, 6] slab ----
-    float2* out = reinterpret_cast<float2*>(target + ((size_t)img * A + a_begin) * SSD_TARGET_COLS);
-    int n_pos = 0, n_ign = 0, n_nan = 0;
-    for (int p = threadIdx.x; p < n_local * 3; p += blockDim.x) {
-        const int la = p / 3;
-        const int part = p - la * 3;
-        const int m = match[la];
-        float2 v;
-        if (m >= 0) {
-            const float4 bx = gbox[m];
-            const float2 cs = gcs[m];
-            v = part == 0 ? make_float2(bx.x, bx.y) : part == 1 ? make_float2(bx.z, bx.w) : cs;
-            if (part == 2) {
-                int p_, i_, n_;
-                row_class_counts(cs.x, bx, p_, i_, n_);
-                n_pos += p_; n_ign += i_; n_nan += n_;
-            }
-        } else if (m == SSD_IGNORE) {
-            v = part == 2 ? make_float2((float)SSD_IGNORE_CLASS, (float)SSD_IGNORE_CLASS) : make_float2(0.f, 0.f);
-            n_ign += part == 2;
-        } else {
-            v = part == 2 ? make_float2((float)SSD_NEGATIVE_CLASS, 1.f) : make_float2(0.f, 0.f);
-        }
-        out[p] = v;
-    }
-    if (match_out != nullptr) {
-        for (int la = threadIdx.x; la < n_local; la += blockDim.x) match_out[(size_t)img * A + a_begin + la] = match[la];
     }
     int* cnt = counters + (size_t)img * kAssignCounters;
     n_pos = __reduce_add_sync(FULL, n_pos);
@@ -241,6 +258,16 @@ assign_targets_kernel(const float4* __restrict__ anchors, const float* __restric
     trace_.mark(3);
     if (!s_last) return;
     __threadfence();
+    // The tail is a chain of dependent global round trips on ONE CTA per image while the rest of the GPU
+    // waits for the kernel to end, so independent loads are issued together: the other CTAs' totals (all
+    // published before their tickets) go out with the per-GT winners, and the forced-match deltas are
+    // added in shared memory instead of bouncing off the global counters again.
+    __shared__ int s_delta[3];
+    int base_pos = 0, base_ign = 0, base_nan = 0;
+    if (threadIdx.x == 0) {
+        base_pos = __ldcg(cnt + 1); base_ign = __ldcg(cnt + 2); base_nan = __ldcg(cnt + 3);
+        s_delta[0] = 0; s_delta[1] = 0; s_delta[2] = 0;
+    }
     if (force_match && G > 0) {
         int* ganchor = reinterpret_cast<int*>(best);                   // [G] (the 64-bit table is done with)
         for (int g0_ = 0; g0_ < G; g0_ += blockDim.x) {
@@ -260,28 +287,36 @@ assign_targets_kernel(const float4* __restrict__ anchors, const float* __restric
             const float2 o0 = __ldcg(reinterpret_cast<const float2*>(row));
             const float2 o1 = __ldcg(reinterpret_cast<const float2*>(row) + 1);
             const float2 o2 = __ldcg(reinterpret_cast<const float2*>(row) + 2);
+            int m_old = 0;
+            float4 prior = make_float4(0.f, 0.f, 1.f, 1.f);
+            if (coding.on) {                                           // the row holds coded values: its corner box
+                m_old = __ldcg(match_out + (size_t)img * A + a);       // comes from its previous match
+                prior = anchors[a];
+            }
             int p_, i_, n_;
-            row_class_counts(o2.x, make_float4(o0.x, o0.y, o1.x, o1.y), p_, i_, n_);
+            float4 old = make_float4(o0.x, o0.y, o1.x, o1.y);
+            if (coding.on) old = m_old >= 0 ? gbox[m_old] : make_float4(0.f, 0.f, 0.f, 0.f);
+            row_class_counts(o2.x, old, p_, i_, n_);
             d_pos -= p_; d_ign -= i_; d_nan -= n_;
             const float4 bx = gbox[g];
             const float2 cs = gcs[g];
             row_class_counts(cs.x, bx, p_, i_, n_);
             d_pos += p_; d_ign += i_; d_nan += n_;
-            reinterpret_cast<float2*>(row)[0] = make_float2(bx.x, bx.y);
-            reinterpret_cast<float2*>(row)[1] = make_float2(bx.z, bx.w);
+            const float4 wr = coding.on ? coded_box(bx, prior, coding) : bx;
+            reinterpret_cast<float2*>(row)[0] = make_float2(wr.x, wr.y);
+            reinterpret_cast<float2*>(row)[1] = make_float2(wr.z, wr.w);
             reinterpret_cast<float2*>(row)[2] = cs;
             if (match_out != nullptr) match_out[(size_t)img * A + a] = g;
         }
-        if (d_pos) atomicAdd(cnt + 1, d_pos);
-        if (d_ign) atomicAdd(cnt + 2, d_ign);
-        if (d_nan) atomicAdd(cnt + 3, d_nan);
-        __threadfence();
+        if (d_pos) atomicAdd(&s_delta[0], d_pos);
+        if (d_ign) atomicAdd(&s_delta[1], d_ign);
+        if (d_nan) atomicAdd(&s_delta[2], d_nan);
         __syncthreads();
     }
     if (stats != nullptr && threadIdx.x == 0) {
-        stats[img * 4 + 0] = atomicAdd(cnt + 1, 0);
-        stats[img * 4 + 1] = atomicAdd(cnt + 2, 0);
-        stats[img * 4 + 2] = atomicAdd(cnt + 3, 0);
+        stats[img * 4 + 0] = base_pos + s_delta[0];
+        stats[img * 4 + 1] = base_ign + s_delta[1];
+        stats[img * 4 + 2] = base_nan + s_delta[2];
         stats[img * 4 + 3] = G;
     }
 }
@@ -434,10 +469,10 @@ extern "C" size_t ssd_assign_workspace_bytes(int batch, int max_gt) {
            round_up((size_t)batch * max_gt * sizeof(unsigned long long), 256);
 }
 
-extern "C" int ssd_assign_targets(const float* anchors, const float* gt_rows, int gt_cols, const int32_t* gt_offsets,
-                                  int max_gt, int batch, int num_anchors, float matched_threshold,
-                                  float unmatched_threshold, int force_match, float* target_out, int32_t* match_out,
-                                  int32_t* stats_out, void* workspace, size_t workspace_bytes, void* stream) {
+static int assign_impl(const float* anchors, const float* gt_rows, int gt_cols, const int32_t* gt_offsets,
+                       int max_gt, int batch, int num_anchors, float matched_threshold,
+                       float unmatched_threshold, int force_match, float* target_out, int32_t* match_out,
+                       int32_t* stats_out, void* workspace, size_t workspace_bytes, void* stream, BoxCoding coding) {
     SSD_REQUIRE(batch >= 0 && num_anchors >= 0 && max_gt >= 0, SSD_ERR_INVALID_ARGUMENT,
                 "ssd_assign_targets: negative shape");
     if (batch == 0 || num_anchors == 0) return SSD_OK;
@@ -462,7 +497,7 @@ extern "C" int ssd_assign_targets(const float* anchors, const float* gt_rows, in
     unsigned long long* gbest = (unsigned long long*)((unsigned char*)workspace +
                                                       round_up((size_t)batch * kAssignCounters * sizeof(int), 256));
     const int gcap = max_gt > 0 ? max_gt : 1;
-    const size_t smem = (size_t)gcap * (sizeof(float4) + sizeof(unsigned long long) + sizeof(float2) + sizeof(float));
+    const size_t smem = (size_t)gcap * (sizeof(float4) + sizeof(unsigned long long) + sizeof(float2) + sizeof(float) + sizeof(int));
     SSD_REQUIRE(smem <= 200 * 1024, SSD_ERR_UNSUPPORTED, "ssd_assign_targets: %zu bytes of shared memory needed (boxes %d)",
                 smem, max_gt);
     SSD_CUDA(cudaFuncSetAttribute(assign_targets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -470,9 +505,35 @@ extern "C" int ssd_assign_targets(const float* anchors, const float* gt_rows, in
     LaunchTimer lt_("assign", st);
     SSD_CUDA(launch_pdl(assign_targets_kernel, grid, dim3(kAssignThreads), smem, st, (const float4*)anchors, gt_rows,
                         gt_cols, gt_offsets, num_anchors, gcap, matched_threshold, unmatched_threshold, force_match,
-                        target_out, match_out, stats_out, counters, gbest));
+                        target_out, match_out, stats_out, counters, gbest, coding));
     count_launch();
     return SSD_OK;
+}
+
+extern "C" int ssd_assign_targets(const float* anchors, const float* gt_rows, int gt_cols, const int32_t* gt_offsets,
+                                  int max_gt, int batch, int num_anchors, float matched_threshold,
+                                  float unmatched_threshold, int force_match, float* target_out, int32_t* match_out,
+                                  int32_t* stats_out, void* workspace, size_t workspace_bytes, void* stream) {
+    BoxCoding coding;
+    coding.on = 0; coding.xy = 1.f; coding.wh = 1.f; coding.eps = 0.f;
+    return assign_impl(anchors, gt_rows, gt_cols, gt_offsets, max_gt, batch, num_anchors, matched_threshold,
+                       unmatched_threshold, force_match, target_out, match_out, stats_out, workspace, workspace_bytes,
+                       stream, coding);
+}
+
+extern "C" int ssd_assign_targets_encoded(const float* anchors, const float* gt_rows, int gt_cols,
+                                          const int32_t* gt_offsets, int max_gt, int batch, int num_anchors,
+                                          float matched_threshold, float unmatched_threshold, int force_match,
+                                          float xy_scale, float wh_scale, float eps, float* target_out,
+                                          int32_t* match_out, int32_t* stats_out, void* workspace,
+                                          size_t workspace_bytes, void* stream) {
+    SSD_REQUIRE(match_out != nullptr || batch == 0 || num_anchors == 0, SSD_ERR_INVALID_ARGUMENT,
+                "ssd_assign_targets_encoded: match_out is required");
+    BoxCoding coding;
+    coding.on = 1; coding.xy = xy_scale; coding.wh = wh_scale; coding.eps = eps;
+    return assign_impl(anchors, gt_rows, gt_cols, gt_offsets, max_gt, batch, num_anchors, matched_threshold,
+                       unmatched_threshold, force_match, target_out, match_out, stats_out, workspace, workspace_bytes,
+                       stream, coding);
 }
 
 SSD_DEFINE_TRACE_SETTER(set_trace_assign)

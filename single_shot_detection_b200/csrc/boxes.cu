@@ -7,8 +7,6 @@
 
 namespace ssd {
 
-struct Box { float a, b, c, d; };
-
 template <bool VEC4>
 __device__ __forceinline__ Box load_box(const float* p) {
     if (VEC4) {
@@ -36,17 +34,9 @@ __device__ __forceinline__ Box to_corners(Box c) {                       // box_
 __device__ __forceinline__ Box to_centroids(Box m) {                     // box_utils.py:36
     return {fmul(fadd(m.c, m.a), 0.5f), fmul(fadd(m.d, m.b), 0.5f), fsub(m.c, m.a), fsub(m.d, m.b)};
 }
-__device__ __forceinline__ Box to_centroids_inplace(Box m) {             // box_utils.py:33-34
-    const float w = fsub(m.c, m.a), h = fsub(m.d, m.b);
-    return {fadd(m.a, fmul(w, 0.5f)), fadd(m.b, fmul(h, 0.5f)), w, h};
-}
 __device__ __forceinline__ Box encode(Box b, float4 p, float xy, float wh, float eps) {   // box_coder.py:32-34
     return {fmul(fdiv(fsub(b.a, p.x), p.z), xy), fmul(fdiv(fsub(b.b, p.y), p.w), xy),
             fmul(logf(fdiv(fadd(b.c, eps), p.z)), wh), fmul(logf(fdiv(fadd(b.d, eps), p.w)), wh)};
-}
-__device__ __forceinline__ Box encode_inplace(Box b, float4 p, float xy, float wh, float eps) {  // :22-29
-    return {fmul(fdiv(fsub(b.a, p.x), p.z), xy), fmul(fdiv(fsub(b.b, p.y), p.w), xy),
-            fmul(logf(fadd(fdiv(b.c, p.z), eps)), wh), fmul(logf(fadd(fdiv(b.d, p.w), eps)), wh)};
 }
 __device__ __forceinline__ Box decode(Box l, float4 p, float xy, float wh) {              // box_coder.py:55-57
     return {fadd(p.x, fdiv(fmul(p.z, l.a), xy)), fadd(p.y, fdiv(fmul(p.w, l.b), xy)),

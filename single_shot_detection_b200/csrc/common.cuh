@@ -53,6 +53,18 @@ __device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b)
 __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
 
+// The loss route's box coding (shared by boxes.cu and the fused assignment): box_utils.to_centroids(inplace=True)
+// followed by BoxCoder.encode_box(inplace=True), in the reference's in-place operation order.
+struct Box { float a, b, c, d; };
+__device__ __forceinline__ Box to_centroids_inplace(Box m) {             // bf/utils/box_utils.py:33-34
+    const float w = fsub(m.c, m.a), h = fsub(m.d, m.b);
+    return {fadd(m.a, fmul(w, 0.5f)), fadd(m.b, fmul(h, 0.5f)), w, h};
+}
+__device__ __forceinline__ Box encode_inplace(Box b, float4 p, float xy, float wh, float eps) {  // detection/box_coder.py:22-29
+    return {fmul(fdiv(fsub(b.a, p.x), p.z), xy), fmul(fdiv(fsub(b.b, p.y), p.w), xy),
+            fmul(logf(fadd(fdiv(b.c, p.z), eps)), wh), fmul(logf(fadd(fdiv(b.d, p.w), eps)), wh)};
+}
+
 // Monotone map float -> uint32 (a < b  <=>  key(a) < key(b) for non-NaN), NaN -> top.
 // Keys of real values lie in [0x007FFFFF (-inf), 0xFF800000 (+inf)].
 __device__ __forceinline__ uint32_t ordered_key(float v) {

@@ -20,7 +20,8 @@ _LIB.define("generalized_iou(Tensor a, Tensor b, bool cartesian) -> Tensor")
 _LIB.define("match_per_prediction(Tensor weights, float matched_threshold, float unmatched_threshold, "
             "bool force_match) -> Tensor")
 _LIB.define("assign_targets(Tensor anchors, Tensor gt_rows, Tensor gt_offsets, int max_gt, "
-            "float matched_threshold, float unmatched_threshold, bool force_match) -> (Tensor, Tensor, Tensor)")
+            "float matched_threshold, float unmatched_threshold, bool force_match, float[]? box_coding=None) "
+            "-> (Tensor, Tensor, Tensor)")
 _LIB.define("box_transform(Tensor src, Tensor? priors, int op, float xy_scale, float wh_scale, float eps) -> Tensor")
 _LIB.define("box_transform_(Tensor(a!) boxes, Tensor? priors, int op, float xy_scale, float wh_scale, float eps) -> ()")
 _LIB.define("positive_mask(Tensor target_classes) -> Tensor")
@@ -128,7 +129,9 @@ def _match_per_prediction(weights: torch.Tensor, matched_threshold: float, unmat
 
 
 def _assign_targets(anchors: torch.Tensor, gt_rows: torch.Tensor, gt_offsets: torch.Tensor, max_gt: int,
-                    matched_threshold: float, unmatched_threshold: float, force_match: bool):
+                    matched_threshold: float, unmatched_threshold: float, force_match: bool, box_coding=None):
+    """``box_coding`` = (xy_scale, wh_scale, eps): the box columns come out already passed through the loss
+    route's to_centroids + encode_box (ssd_assign_targets_encoded)."""
     N.require_device()
     batch = gt_offsets.numel() - 1
     num_anchors = anchors.shape[0]
@@ -143,10 +146,17 @@ def _assign_targets(anchors: torch.Tensor, gt_rows: torch.Tensor, gt_offsets: to
             cap *= 2
         ws_bytes = N.lib().ssd_assign_workspace_bytes(batch, cap)
         ws = workspace(ws_bytes, dev, "assign")
-        N.check(N.lib().ssd_assign_targets(_ptr(anchors), _ptr(gt_rows) if gt_rows.numel() else None, gt_cols,
-                                           _ptr(gt_offsets), max_gt, batch, num_anchors, matched_threshold,
-                                           unmatched_threshold, int(force_match), _ptr(target), _ptr(match),
-                                           _ptr(stats), _ptr(ws), ws.numel(), _stream()))
+        if box_coding is not None:
+            xy, wh, eps = (float(x) for x in box_coding)
+            N.check(N.lib().ssd_assign_targets_encoded(_ptr(anchors), _ptr(gt_rows) if gt_rows.numel() else None, gt_cols,
+                                                       _ptr(gt_offsets), max_gt, batch, num_anchors, matched_threshold,
+                                                       unmatched_threshold, int(force_match), xy, wh, eps, _ptr(target),
+                                                       _ptr(match), _ptr(stats), _ptr(ws), ws.numel(), _stream()))
+        else:
+            N.check(N.lib().ssd_assign_targets(_ptr(anchors), _ptr(gt_rows) if gt_rows.numel() else None, gt_cols,
+                                               _ptr(gt_offsets), max_gt, batch, num_anchors, matched_threshold,
+                                               unmatched_threshold, int(force_match), _ptr(target), _ptr(match),
+                                               _ptr(stats), _ptr(ws), ws.numel(), _stream()))
     return target, match, stats
 
 

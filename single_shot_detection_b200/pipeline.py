@@ -16,6 +16,7 @@ a CUDA graph (launch-bound configs: ~10 kernels of a few microseconds each).
 from __future__ import annotations
 
 import functools
+import os
 from typing import Dict, NamedTuple, Optional
 
 import torch
@@ -58,8 +59,10 @@ class AnchorPipeline:
             {"max_per_class": cfg["max_per_class"], "overlap_threshold": cfg["overlap_threshold"]},
             score_converter=cfg["converter"], max_total=cfg["max_total"])
         self.fuse_encode = False       # True: one pass for to_centroids+encode (same rounding)
+        # the assignment writes the box columns already coded for the loss (same bits as the two box passes of
+        # multibox_loss.py:81-82, which then disappear from the step); SSD_FUSE_ASSIGN_ENCODE=0 switches it off
+        self.fuse_assign_encode = os.environ.get("SSD_FUSE_ASSIGN_ENCODE", "1") != "0"
         # eval step: mining criterion out of the post-processor's first pass (SSD_SHARE_PASS=0: separate kernels)
-        import os
         self.share_logit_pass = os.environ.get("SSD_SHARE_PASS", "1") != "0"
         self._graph = None
         self._side = None
@@ -235,8 +238,9 @@ class AnchorPipeline:
         # captured graph started ~10 us after its dependency had finished, a same-stream successor starts at
         # once.  So the train-side chain stays on ONE side stream -- assign -> to_centroids -> encode_box ->
         # selection -- and only the selection has a second (event) dependency, on the post-processor's pass 1.
+        coder = self.box_coder if self.fuse_assign_encode else None
         with torch.cuda.stream(side):
-            target = self.target_assigner.encode_packed(packed, anchors_dev)
+            target = self.target_assigner.encode_packed(packed, anchors_dev, box_coder=coder)
             if not share:
                 classes = target[..., CLASS_INDEX].long()                      # multibox_loss.py:49 (before the boxes change)
             else:
@@ -246,7 +250,8 @@ class AnchorPipeline:
             keyed = torch.cuda.Event()
             keyed.record(main)
         with torch.cuda.stream(side):
-            self._encode_target_boxes(target, anchors_dev)                     # touches columns 0-3 only
+            if coder is None:
+                self._encode_target_boxes(target, anchors_dev)                 # touches columns 0-3 only
             if share:
                 side.wait_event(keyed)
                 mask = _sampler.hard_negative_mining_from_keys(flight.loss_keys, target, self.cfg.get("ratio"),

@@ -109,11 +109,17 @@ class TargetAssigner(object):
             event.synchronize()
             assert int(stats_host[:, 2].sum()) == 0, "NaN in the target box of a positive anchor"
 
-    def encode_packed(self, packed: PackedGroundTruth, anchors: torch.Tensor) -> torch.Tensor:
-        """Device-resident entry point: no host packing, no sync."""
+    def encode_packed(self, packed: PackedGroundTruth, anchors: torch.Tensor, box_coder=None) -> torch.Tensor:
+        """Device-resident entry point: no host packing, no sync.
+
+        ``box_coder``: write the box columns already coded for the loss -- what
+        ``to_centroids(target_locs, inplace=True); box_coder.encode_box(target_locs, anchors, inplace=True)``
+        (multibox_loss.py:81-82) would turn them into, bit for bit -- in the same launch."""
         assert self.matched_threshold >= self.unmatched_threshold           # matcher.py:43
+        coding = None if box_coder is None else [float(box_coder.xy_scale), float(box_coder.wh_scale), float(box_coder.eps)]
         target, match, stats = OPS.assign_targets(anchors, packed.rows, packed.offsets, packed.max_gt,
-                                                  float(self.matched_threshold), float(self.unmatched_threshold), True)
+                                                  float(self.matched_threshold), float(self.unmatched_threshold), True,
+                                                  coding)
         self.last_match, self.last_stats = match, stats
         return target
 

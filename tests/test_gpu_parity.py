@@ -723,3 +723,32 @@ def test_shared_logit_pass_equals_separate_calls(dev, name, batch):
     assert torch.equal(mask, b.mask) and torch.equal(target, b.target)
     for i, d in enumerate(dets):
         assert torch.equal(d, b.dets[i, : int(b.counts[i])])
+
+
+@pytest.mark.parametrize("name,batch", [("ssd300_voc_b8", 8), ("edge", 0), ("ssd_mb2_coco_b64", 12), ("retina500_coco_b32", 3)])
+def test_assignment_with_coded_boxes_equals_the_two_box_passes(dev, name, batch):
+    """ssd_assign_targets_encoded == ssd_assign_targets + to_centroids(inplace) + encode_box(inplace), bit for bit,
+    including the rows the forced matches rewrite and the statistics."""
+    ta, _, bc, _, _, box_utils = _modules()
+    if name == "edge":
+        case = gio.PipelineCase("edge_tiny")
+        w, anchors, gt = case.w, case.anchors, case.gt
+    else:
+        w = wl.WORKLOADS[name]
+        anchors = wl.build_anchors(w)
+        gen = torch.Generator().manual_seed(3)
+        gt = wl.make_ground_truth(batch, w.img, w.num_fg, w.max_gt, gen, mixup=0.3)
+        gt[1] = torch.zeros((0, 6))
+        gt[2] = torch.cat([gt[2], gt[2][:1]])                    # duplicate box: colliding forced matches
+    coder = bc.BoxCoder(w.xy_scale, w.wh_scale, w.eps)
+    from single_shot_detection_b200.target_assigner import pack_ground_truth
+    anchors_d = anchors.to(dev)
+    a1 = ta.TargetAssigner(w.matched_threshold, w.unmatched_threshold, nan_check="off")
+    t1 = a1.encode_packed(pack_ground_truth(gt, dev), anchors_d)
+    tl = t1[..., 0:4]
+    box_utils.to_centroids(tl, inplace=True)
+    coder.encode_box(tl, anchors_d, inplace=True)
+    a2 = ta.TargetAssigner(w.matched_threshold, w.unmatched_threshold, nan_check="off")
+    t2 = a2.encode_packed(pack_ground_truth(gt, dev), anchors_d, box_coder=coder)
+    assert torch.equal(t1.view(torch.int32), t2.view(torch.int32))
+    assert torch.equal(a1.last_match, a2.last_match) and torch.equal(a1.last_stats, a2.last_stats)
