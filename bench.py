@@ -418,11 +418,11 @@ def roofline_probe(w, dev_sets, anchors_dev, pipe, B, A, C, nsets, iters: int = 
     us = timed(pass1)
     achieved = algo_p1 / (us * 1e-6) / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` capture per workload
-    # (profiles/r01_ncu_full.md); None for a workload that has no committed capture
+    # (profiles/r01c_ncu_full.md); None for a workload that has no committed capture
     traffic = NCU_TRAFFIC.get(w.name)
     return {"bound": "hbm", "kernel": "score_pass1_kernel (ssd_postprocess_pass1)", "achieved": achieved, "peak": peak,
             "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-            "traffic_source": "profiles/r01_ncu_full.md" if traffic else None,
+            "traffic_source": "profiles/r01c_ncu_full.md" if traffic else None,
             "algorithmic_bytes_per_launch": algo_p1, "us_per_launch": us, "other_streaming_kernels": other,
             "note": "the streaming kernel of the step: one read of the logits yields the row statistics, the gate "
                     "bookkeeping and the sampler's criterion (4C read + 12 written bytes per anchor); the call is timed "
@@ -430,8 +430,8 @@ def roofline_probe(w, dev_sets, anchors_dev, pipe, B, A, C, nsets, iters: int = 
                     "than L2; the largest kernel of the step, segment_nms_kernel, is ALU bound and reported under 'nms'"}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel (profiles/r01_ncu_full.md)
-NCU_TRAFFIC = {}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel (profiles/r01c_ncu_full.md)
+NCU_TRAFFIC = {"ssd300_voc_b32": 23524608, "ssd512_coco_b32": 254768384 + 15038208}
 
 
 def main():
