@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample-images", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--in-flight", type=int, default=2,
+                    help="step graphs in flight on as many streams (1 = strictly one step after the other)")
     return ap.parse_args()
 
 
@@ -205,8 +207,10 @@ def run_ours(args):
     # one pipeline (and one CUDA graph) per input set
     pipes, outs = [], []
     launches0 = N.lib().ssd_b200_launch_count()
-    for packed, scores_d, locs_d in dev_sets:
-        pipe = AnchorPipeline(w.cfg())
+    in_flight = max(1, min(args.in_flight, nsets))
+    for k, (packed, scores_d, locs_d) in enumerate(dev_sets):
+        # steps of different slots may run concurrently: each slot has its own scratch buffers
+        pipe = AnchorPipeline(w.cfg(), workspace_slot=k % in_flight)
         pipes.append(pipe)
     # kernels per step, counted on one eager step
     launches_before = N.lib().ssd_b200_launch_count()
@@ -223,23 +227,61 @@ def run_ours(args):
     # asynchronously: the all-gather of step i overlaps the kernels of step i+1
     gather = sharding.OverlappedGather(B * world, w.max_total) if world > 1 else None
 
-    def device_step(i):
+    # Throughput mode: `in_flight` consecutive steps run concurrently, each replayed on its own stream (input
+    # set k always on stream k % in_flight, with that slot's scratch buffers).  A step alone leaves most of the
+    # GPU idle (its longest kernel, the NMS, runs 640 small CTAs at ~35 % issue utilisation), so the next
+    # batch's streaming kernels fill the gaps.  --in-flight 1 is the strictly serial number (reported beside it).
+    streams = [torch.cuda.Stream() for _ in range(in_flight)]
+
+    def device_step(i, serial=False):
         k = i % nsets
-        pipes[k].replay()
-        if world > 1:
-            if outs[k].gathered is not None:          # the all-gather is a node of the step graph
-                return outs[k].gathered
-            return gather.submit(outs[k].shard)
+        if serial or in_flight == 1:
+            pipes[k].replay()
+            if world > 1:
+                return gather.submit(outs[k].shard)
+            return outs[k].dets, outs[k].counts, outs[k].assign_stats
+        with torch.cuda.stream(streams[k % in_flight]):
+            pipes[k].replay()
+            if world > 1:
+                return gather.submit(outs[k].shard)
         return outs[k].dets, outs[k].counts, outs[k].assign_stats
+
+    def fork():
+        main = torch.cuda.current_stream()
+        for s_ in streams:
+            s_.wait_stream(main)
+
+    def join():
+        main = torch.cuda.current_stream()
+        for s_ in streams:
+            main.wait_stream(s_)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- serial reference: one step after the other on one stream ----
+    for i in range(args.warmup):
+        device_step(i, serial=True)
+    if world > 1:
+        gather.flush()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        device_step(i, serial=True)
+    if world > 1:
+        gather.flush()
+    e1.record()
+    barrier()
+    serial_ms = e0.elapsed_time(e1)
+
     # ---- value: device-resident, CUDA events ----
+    fork()
     for i in range(args.warmup):
         device_step(i)
+    join()
     if world > 1:
         gather.flush()
     clocks = ClockSampler(local)
@@ -248,8 +290,10 @@ def run_ours(args):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    fork()
     for i in range(args.steps):
         device_step(i)
+    join()
     if world > 1:
         gather.flush()                    # the last step's exchange completes inside the timed region
     e1.record()
@@ -311,10 +355,10 @@ def run_ours(args):
                 "note": "K(K-1)/2 IoU tests per (image, class) at K = max_per_class; bound by the ALU pipe, not HBM"}
 
     # max over ranks
-    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, e2e_s, serial_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_s = float(t[0]), float(t[1])
+    dev_ms, e2e_s, serial_ms = float(t[0]), float(t[1]), float(t[2])
 
     if rank == 0:
         ms_per_step = dev_ms / args.steps
@@ -329,13 +373,18 @@ def run_ours(args):
                        "region": "encode_ground_truth + sampler + to_centroids/encode_box + postprocess"
                                  + (" + all_gather(dets,stats)" if world > 1 else ""),
                        "l2": f"inputs rotate over {nsets} sets = {nsets * per_set / 2**20:.0f} MiB > 126 MiB L2",
-                       "device_path": "CUDA graph replay per step" + (
+                       "steps_in_flight": in_flight,
+                       "device_path": (f"CUDA graph replay per step, {in_flight} consecutive steps in flight on "
+                                       f"{in_flight} streams (own scratch buffers per slot)" if in_flight > 1
+                                       else "CUDA graph replay per step, one step after the other") + (
                            "" if world == 1 else (", all-gather captured in the graph" if outs[0].gathered is not None
                                                   else ", all-gather of step i overlapping step i+1"))},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
                     "path": "AnchorPipeline.stream(batches of (list of GT, pinned host scores, locs), CPU anchors) -> "
                             "(target, mask, list of host detections) per batch; H2D of batch i+1 overlaps batch i"},
+            "serial": {"ms_per_step": serial_ms / args.steps, "value": B * world / (serial_ms / args.steps * 1e-3),
+                       "note": "the same K steps strictly one after the other on one stream (--in-flight 1)"},
             "gpu_launches": launches_per_step * args.steps,
             "launches_per_step": launches_per_step,
             "clocks": clock_info,

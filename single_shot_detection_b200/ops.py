@@ -45,6 +45,26 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 _workspaces: Dict[Tuple[int, str], torch.Tensor] = {}
+_slot = 0                    # see workspace_slot()
+
+
+class workspace_slot:
+    """``with workspace_slot(k):`` -- the scratch buffers handed out inside belong to slot ``k``.  Steps that
+    may run CONCURRENTLY (two step graphs in flight on two streams) must use different slots; steps that
+    serialise on one stream can share one."""
+
+    def __init__(self, slot: int):
+        self.slot, self.prev = int(slot), 0
+
+    def __enter__(self):
+        global _slot
+        self.prev, _slot = _slot, self.slot
+        return self
+
+    def __exit__(self, *exc):
+        global _slot
+        _slot = self.prev
+        return False
 _retired: list = []          # outgrown buffers: CUDA graphs captured earlier still hold their addresses
 
 
@@ -54,7 +74,7 @@ def workspace(nbytes: int, device: torch.device, tag: str = "default") -> torch.
     Growth is geometric and an outgrown buffer is kept alive: a step graph captured while it was current
     keeps replaying with its address (torch.cuda.graph() empties the allocator cache when a capture begins,
     which would unmap a freed one)."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+    key = (device.index if device.index is not None else torch.cuda.current_device(), f"{tag}#{_slot}" if _slot else tag)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
         size = max(int(nbytes), 256)

@@ -42,11 +42,14 @@ class StepOutput(NamedTuple):
 
 
 class AnchorPipeline:
-    def __init__(self, cfg: Dict):
-        """``cfg`` carries the reference's config dict entries (samples/*.py): matched_threshold,
+    def __init__(self, cfg: Dict, workspace_slot: int = 0):
+        """``workspace_slot``: pipelines whose steps may run concurrently (two step graphs in flight on two
+        streams) need different slots -- the kernels' scratch buffers are cached per slot (ops.workspace_slot).
+        ``cfg`` carries the reference's config dict entries (samples/*.py): matched_threshold,
         unmatched_threshold, sampler, ratio, min_neg, xy_scale, wh_scale, eps, score_threshold,
         overlap_threshold, max_per_class, max_total, converter."""
         self.cfg = dict(cfg)
+        self.workspace_slot = int(workspace_slot)
         self.target_assigner = TargetAssigner(cfg["matched_threshold"], cfg["unmatched_threshold"])
         self.box_coder = BoxCoder(cfg["xy_scale"], cfg["wh_scale"], cfg.get("eps", 1e-8))
         fn = getattr(_sampler, cfg["sampler"])               # detection/init.py:90-92
@@ -221,6 +224,12 @@ class AnchorPipeline:
     # -- device-resident, sync-free -------------------------------------------------------------
     def step_device(self, packed: PackedGroundTruth, anchors_dev, scores_dev, locs_dev,
                     shard_capacity: Optional[int] = None, gather: bool = False) -> "StepOutput":
+        from . import ops
+        with ops.workspace_slot(self.workspace_slot):
+            return self._step_device(packed, anchors_dev, scores_dev, locs_dev, shard_capacity, gather)
+
+    def _step_device(self, packed: PackedGroundTruth, anchors_dev, scores_dev, locs_dev,
+                     shard_capacity: Optional[int] = None, gather: bool = False) -> "StepOutput":
         """``shard_capacity``: also pack (dets, counts, stats) into the one-buffer layout
         ``sharding.all_gather_detections`` exchanges (so the packing is part of the graph).
         ``gather``: also run that exchange -- one NCCL all-gather over all ranks -- as the last

@@ -752,3 +752,42 @@ def test_assignment_with_coded_boxes_equals_the_two_box_passes(dev, name, batch)
     t2 = a2.encode_packed(pack_ground_truth(gt, dev), anchors_d, box_coder=coder)
     assert torch.equal(t1.view(torch.int32), t2.view(torch.int32))
     assert torch.equal(a1.last_match, a2.last_match) and torch.equal(a1.last_stats, a2.last_stats)
+
+
+def test_two_step_graphs_in_flight_equal_serial_steps(dev):
+    """bench.py's throughput mode: consecutive steps replayed concurrently on two streams, each slot with its own
+    scratch buffers (ops.workspace_slot) -- every step's outputs equal the same step run alone."""
+    from single_shot_detection_b200.pipeline import AnchorPipeline
+    from single_shot_detection_b200.target_assigner import pack_ground_truth
+    w = wl.WORKLOADS["ssd300_voc_b8"]
+    anchors = wl.build_anchors(w).to(dev)
+    sets, want = [], []
+    for k in range(4):
+        _, gt, scores, locs = wl.make_inputs(w, seed=40 + k, batch=6)
+        packed = pack_ground_truth(gt, dev)
+        packed.rows, packed.offsets = packed.rows.clone(), packed.offsets.clone()
+        sets.append((packed, scores.to(dev), locs.to(dev)))
+        out = AnchorPipeline(w.cfg()).step_device(packed, anchors, sets[-1][1], sets[-1][2])
+        torch.cuda.synchronize()
+        want.append([t.clone() for t in (out.target, out.mask, out.dets, out.counts)])
+    pipes, outs = [], []
+    for k, (packed, scores, locs) in enumerate(sets):
+        pipe = AnchorPipeline(w.cfg(), workspace_slot=k % 2)
+        outs.append(pipe.capture(packed, anchors, scores, locs))
+        pipes.append(pipe)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    for rep in range(25):
+        for k, pipe in enumerate(pipes):
+            with torch.cuda.stream(streams[k % 2]):
+                pipe.replay()
+    torch.cuda.synchronize()
+    for k, out in enumerate(outs):
+        got = (out.target, out.mask, out.dets, out.counts)
+        for g, r in zip(got, want[k]):
+            if g is out.dets:
+                for i in range(g.shape[0]):
+                    n = int(out.counts[i])
+                    assert torch.equal(g[i, :n], r[i, :n]), k
+            else:
+                assert torch.equal(g, r), k
