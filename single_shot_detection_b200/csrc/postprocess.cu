@@ -560,6 +560,24 @@ __device__ __forceinline__ void image_gates(const GateHist& gh, const ScoreGrid&
     for (int c = threadIdx.x; c < g.first_fg; c += kConsumerWarps * 32) sgate[c] = INFINITY;
 }
 
+// The same gates once per image in a launch of their own (SSD_GATE_KERNEL, default for C <= 32): one CTA per image
+// instead of every pass-2 CTA repeating its image's histogram (~9 CTAs per image at SSD300 b32, 1.6 M warp
+// instructions per step) -- one more launch in the chain, a quarter less work in pass 2; with two steps in
+// flight the saved issue slots are what counts.
+__global__ void __launch_bounds__(kConsumerWarps * 32)
+hist_gate_kernel(GateHist gh, ScoreGrid g, float* __restrict__ gate) {
+    extern __shared__ __align__(16) unsigned char gsm[];
+    KernelTrace trace_(TR_GATE);
+    griddep_wait();
+    float* sgate = reinterpret_cast<float*>(gsm);
+    uint32_t* shist = reinterpret_cast<uint32_t*>(gsm + round_up((size_t)g.C * sizeof(float), 16));
+    const int img = blockIdx.x;
+    image_gates(gh, g, img, sgate, shist);
+    consumer_barrier();
+    griddep_launch_dependents();
+    for (int c = threadIdx.x; c < g.C; c += kConsumerWarps * 32) gate[(size_t)img * g.C + c] = sgate[c];
+}
+
 template <int Q, int NREG, int CMIN, int CONV>
 __global__ void __launch_bounds__(kStreamThreads)
 score_pass2_kernel(const float* __restrict__ scores, ScoreGrid g, const float2* __restrict__ rowstat,
@@ -1565,6 +1583,16 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
     GateHist gh;
     gh.blockmax = pl.gate_hist ? (const float*)blockmax : nullptr; gh.nblk = pl.nblk; gh.K = pl.K; gh.converter = pl.converter; gh.score_thr = p->score_threshold;
     gh.bins = gbins;
+    bool gate_in_pass2 = pl.gate_hist;
+    { const char* e = getenv("SSD_GATE_KERNEL"); if (pl.gate_hist && !(e && e[0] == '0')) gate_in_pass2 = false; }
+    if (pl.gate_hist && !gate_in_pass2) {
+        LaunchTimer lt_("gate", st);
+        const size_t gsmem = round_up((size_t)pl.C * sizeof(float), 16) + (size_t)pl.C * kGateStride * sizeof(uint32_t);
+        SSD_CUDA(cudaFuncSetAttribute(hist_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+        SSD_CUDA(launch_pdl(hist_gate_kernel, dim3(pl.B), dim3(kConsumerWarps * 32), gsmem, st, gh, g, gate));
+        count_launch();
+        gh.blockmax = nullptr;                    // pass 2 reads the gate array
+    }
 #define SSD_LAUNCH_PASS2(QQ, NN, CM)                                                                                     \
     do {                                                                                                               \
         auto launch = [&](auto kern) -> int {                                                                          \
