@@ -193,6 +193,7 @@ assign_targets_kernel(const float4* __restrict__ anchors, const float* __restric
         //      its four rows as three float2 stores per row (rows are 24 bytes: 8-byte aligned); the three
         //      store instructions of a warp cover the same six 128-byte lines. ----
         float2* out = reinterpret_cast<float2*>(target + ((size_t)img * A + a_begin) * SSD_TARGET_COLS);
+        const float zero_wh = fmul(logf(fadd(0.f, coding.eps)), coding.wh);
 #pragma unroll
         for (int j = 0; j < kAssignPerThread; ++j) {
             if (!valid[j]) continue;
@@ -217,7 +218,18 @@ assign_targets_kernel(const float4* __restrict__ anchors, const float* __restric
             } else {
                 cs = make_float2((float)SSD_NEGATIVE_CLASS, 1.f);
             }
-            if (coding.on) bx = coded_box(bx, anchors[a_begin + la], coding);
+            if (coding.on) {
+                const float4 pr = anchors[a_begin + la];
+                if (m < 0 && pr.z > 0.f && pr.w > 0.f) {
+                    // an all-zero box (97 % of the rows): w / p_w = +0 exactly, so both size terms are the constant
+                    // log(0 + eps) * wh_scale -- the same operations the full path would execute, minus two divides
+                    // and two logarithms per row
+                    bx = make_float4(fmul(fdiv(fsub(0.f, pr.x), pr.z), coding.xy), fmul(fdiv(fsub(0.f, pr.y), pr.w), coding.xy),
+                                     zero_wh, zero_wh);
+                } else {
+                    bx = coded_box(bx, pr, coding);
+                }
+            }
             out[la * 3 + 0] = make_float2(bx.x, bx.y);
             out[la * 3 + 1] = make_float2(bx.z, bx.w);
             out[la * 3 + 2] = cs;
