@@ -1193,6 +1193,10 @@ __device__ int nms_segment(const KernelTrace& tr, const NmsArgs& a, unsigned cha
     float* sarea = reinterpret_cast<float*>(fbox + a.K);
     uint32_t* mask = reinterpret_cast<uint32_t*>(sarea + a.K);
     int* keep = reinterpret_cast<int*>(mask + (size_t)a.K * kwords);
+    // 32-bit score words of the rank sort [kRankSortMax + 4]: the rank sort touches only the first kRankSortMax of the
+    // >= 1024 key slots, the words live behind them
+    static_assert(kRankSortMax <= 512, "hk sits at key slot 512");
+    uint32_t* hk = reinterpret_cast<uint32_t*>(keys + 512);
 
     const bool overflow = n_raw > a.cand_cap;
     if (threadIdx.x == 0) s_valid = 0;
@@ -1242,20 +1246,56 @@ __device__ int nms_segment(const KernelTrace& tr, const NmsArgs& a, unsigned cha
 
     // ---- order: (score desc, anchor asc) ----
     if (by_rank) {
-        // keys are unique, so the rank of a key is the number of larger keys; no barrier in the loop
-        const ulonglong2* k2 = reinterpret_cast<const ulonglong2*>(keys);
-        for (int t = threadIdx.x; t < n_raw; t += blockDim.x) {
+        // Keys are unique, so the rank of a key is the number of larger keys.  Fast path on the 32-bit SCORE
+        // word alone: three instructions per key, four keys per LDS.128, two independent counters (the 64-bit
+        // compare-and-add it replaces was 18 % of the kernel's instructions).  Two candidates
+        // with the SAME score word (rare: equal fp32 scores) get the same rank; the collision is detected when
+        // a key does not find itself in its slot, and the exact 64-bit ranking (ties: lower anchor first) runs.
+        const int fill4 = (n_raw + 3) & ~3;
+        for (int t = threadIdx.x; t < fill4; t += blockDim.x) hk[t] = t < n_raw ? (uint32_t)(keys[t] >> 32) : 0u;
+        __syncthreads();
+        const uint4* h4 = reinterpret_cast<const uint4*>(hk);
+        constexpr int kPerThread = (kRankSortMax + kNmsThreads - 1) / kNmsThreads;
+        int myrank[kPerThread];
+#pragma unroll
+        for (int u = 0; u < kPerThread; ++u) {
+            const int t = threadIdx.x + u * kNmsThreads;
+            myrank[u] = -1;
+            if (t >= n_raw) continue;
             const unsigned long long me = keys[t];
             if (me == 0ull) continue;
-            int rank = 0;
+            const uint32_t mine = (uint32_t)(me >> 32);
+            uint32_t rank = 0u, rank_b = 0u;
 #pragma unroll 4
-            for (int j = 0; j < (fill >> 1); ++j) {
-                const ulonglong2 o = k2[j];
-                rank += (o.x > me) + (o.y > me);
+            for (int j = 0; j < (fill4 >> 2); ++j) {
+                const uint4 o = h4[j];
+                rank += (o.x > mine) + (o.z > mine);
+                rank_b += (o.y > mine) + (o.w > mine);
             }
-            if (rank < n) sorted[rank] = me;
+            rank += rank_b;
+            if ((int)rank < n) { sorted[rank] = me; myrank[u] = (int)rank; }
         }
         __syncthreads();
+        bool bad = false;
+#pragma unroll
+        for (int u = 0; u < kPerThread; ++u)          // a key that is not in its own slot lost it to a tied score word
+            if (myrank[u] >= 0) bad = bad || sorted[myrank[u]] != keys[threadIdx.x + u * kNmsThreads];
+        if (__syncthreads_or(bad)) {
+            // exact ranking on the full 64-bit keys
+            const ulonglong2* k2 = reinterpret_cast<const ulonglong2*>(keys);
+            for (int t = threadIdx.x; t < n_raw; t += blockDim.x) {
+                const unsigned long long me = keys[t];
+                if (me == 0ull) continue;
+                int rank = 0;
+#pragma unroll 4
+                for (int j = 0; j < (fill >> 1); ++j) {
+                    const ulonglong2 o = k2[j];
+                    rank += (o.x > me) + (o.y > me);
+                }
+                if (rank < n) sorted[rank] = me;
+            }
+            __syncthreads();
+        }
     } else {
         bitonic_sort_desc(keys, n2);                 // starts and ends with a barrier
         for (int t = threadIdx.x; t < n; t += blockDim.x) sorted[t] = keys[t];
