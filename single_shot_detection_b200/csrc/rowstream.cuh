@@ -62,12 +62,15 @@ struct ScoreGrid {
 
 struct TileCursor {
     int item, item_end, img, grp, tile, tile_end;
-    // contiguous: CTA c owns the item range [c * n / grid, (c + 1) * n / grid) -- at most two images
+    // contiguous: CTA c owns q or q + 1 consecutive items (q = n / grid) -- at most two images
     // per CTA unless an image has fewer items than a CTA's share; otherwise items are dealt round-robin.
     __device__ __forceinline__ void start(const ScoreGrid& g) {
         if (g.contiguous) {
-            item = (int)(((int64_t)blockIdx.x * g.num_items) / gridDim.x);
-            item_end = (int)(((int64_t)(blockIdx.x + 1) * g.num_items) / gridDim.x);
+            // balanced contiguous ranges without 64-bit divisions: the first r CTAs take q + 1 items
+            const unsigned n = (unsigned)g.num_items, nc = gridDim.x, c = blockIdx.x;
+            const unsigned q = n / nc, r = n - q * nc;
+            item = (int)(c * q + min(c, r));
+            item_end = item + (int)q + (c < r ? 1 : 0);
         } else {
             item = blockIdx.x;
             item_end = g.num_items;
