@@ -225,7 +225,7 @@ def run_ours(args):
 
     # the one exchange step of the path (detections + counts + stats, one collective per step) runs
     # asynchronously: the all-gather of step i overlaps the kernels of step i+1
-    gather = sharding.OverlappedGather(B * world, w.max_total) if world > 1 else None
+    gather = sharding.OverlappedGather(B * world, w.max_total, ring=max(3, nsets + 1)) if world > 1 else None
 
     # Throughput mode: `in_flight` consecutive steps run concurrently, each replayed on its own stream (input
     # set k always on stream k % in_flight, with that slot's scratch buffers).  A step alone leaves most of the
@@ -243,7 +243,7 @@ def run_ours(args):
         with torch.cuda.stream(streams[k % in_flight]):
             pipes[k].replay()
             if world > 1:
-                return gather.submit(outs[k].shard)
+                return gather.submit_nowait(outs[k].shard)
         return outs[k].dets, outs[k].counts, outs[k].assign_stats
 
     def fork():

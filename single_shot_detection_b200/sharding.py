@@ -111,6 +111,8 @@ class OverlappedGather:
         self._pending = None
         self._ring = [None] * ring
         self._next = 0
+        self._loose = []
+        self._last = None
 
     def unpack(self, gathered: torch.Tensor):
         return unpack_gathered(gathered, self.batch, self.world, self.max_rows)
@@ -121,6 +123,25 @@ class OverlappedGather:
         work, out = self._pending
         self._pending = None
         work.wait()                       # orders the current stream after the collective; no host sync on NCCL
+        return out
+
+    def submit_nowait(self, shard: torch.Tensor):
+        """Throughput mode (several steps in flight on several streams): enqueue the exchange behind the work
+        already on the CURRENT stream and return at once; nothing is ordered after it until :meth:`flush`, which
+        waits for every exchange submitted this way (NCCL runs them in submission order on its own stream, so a
+        ring buffer is rewritten only after the exchange that used it before)."""
+        k = self._next
+        self._next = (k + 1) % len(self._ring)
+        out = self._ring[k]
+        shape = (self.world * shard.shape[0], shard.shape[1])
+        if out is None or tuple(out.shape) != shape or out.device != shard.device:
+            out = torch.empty(shape, dtype=shard.dtype, device=shard.device)
+            self._ring[k] = out
+        work = dist.all_gather_into_tensor(out, shard, group=self.group, async_op=True)
+        self._loose.append(work)
+        if len(self._loose) > 4 * len(self._ring):
+            self._loose.pop(0).wait()
+        self._last = out
         return out
 
     def submit(self, shard: torch.Tensor):
@@ -137,4 +158,9 @@ class OverlappedGather:
         return previous
 
     def flush(self):
+        if self._loose:
+            for work in self._loose:
+                work.wait()
+            self._loose = []
+            return self._last
         return self._finish()

@@ -56,6 +56,15 @@ def _worker(rank, world, port, batch, max_rows, failures):
         for got3, want in ((second, (dets, counts, stats)), (third, (dets_b, counts_b, stats_b))):
             if not all(torch.equal(a.to(b.dtype), b) for a, b in zip(og.unpack(got3), want)):
                 failures.put((rank, "OverlappedGather differs"))
+        # throughput mode: several exchanges enqueued without waiting, one flush at the end
+        og2 = sharding.OverlappedGather(batch, max_rows, ring=4)
+        bufs = [og2.submit_nowait(m) for m in (mine, mine_b, mine)]
+        last = og2.flush()
+        if last is not bufs[-1]:
+            failures.put((rank, "submit_nowait: flush must return the last buffer"))
+        for got4, want in zip(bufs, ((dets, counts, stats), (dets_b, counts_b, stats_b), (dets, counts, stats))):
+            if not all(torch.equal(a.to(b.dtype), b) for a, b in zip(og2.unpack(got4), want)):
+                failures.put((rank, "submit_nowait differs"))
     except Exception as e:  # noqa: BLE001
         failures.put((rank, repr(e)))
     finally:
