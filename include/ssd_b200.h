@@ -218,6 +218,15 @@ SSD_API int ssd_multibox_loss(const float* logits, const float* locs, const floa
                       float gamma, float alpha, float class_weight, float loc_weight,
                       float* grad_logits, float* grad_locs, float* loss_out, void* workspace,
                       size_t workspace_bytes, void* stream);
+/* The same with bf/modules/losses.py:109-114 GeneralizedIoULoss as the localisation term
+ * (multibox_loss.py:77-79): `target` rows hold the CORNER boxes (no coding), locs are decoded against
+ * `priors` [A,4] (cx,cy,w,h) with BoxCoder.decode_box + to_corners, loc_loss = sum over the positives of
+ * 1 - generalized_iou; grad_locs is d loss / d locs through GIoU, to_corners and the decoding. */
+SSD_API int ssd_multibox_loss_giou(const float* logits, const float* locs, const float* target, const float* priors,
+                           const uint8_t* sampled_mask, int batch, int num_anchors, int num_cols, int kind,
+                           float gamma, float alpha, float class_weight, float loc_weight, float xy_scale,
+                           float wh_scale, float* grad_logits, float* grad_locs, float* loss_out, void* workspace,
+                           size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * a7+a8+a9  detection/postprocessor.py:24-78  Postprocessor.postprocess, including

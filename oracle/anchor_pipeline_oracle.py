@@ -572,6 +572,20 @@ def multibox_loss_focal_smoothl1(scores: torch.Tensor, locs: torch.Tensor, targe
     return class_loss + loc_loss, class_loss, loc_loss
 
 
+def giou_localization_loss(locs: torch.Tensor, priors: torch.Tensor, target: torch.Tensor, xy_scale: float,
+                           wh_scale: float, loc_weight: float = 1.0):
+    """The IOU_LOSS branch of MultiboxLoss.forward (multibox_loss.py:77-79, 84-90) with GeneralizedIoULoss
+    (bf/modules/losses.py:109-114, reduction='sum' -- `reduction` IS in its constructor's signature, so
+    filter_kwargs keeps it): the predictions are decoded and turned into corner boxes, the target stays a
+    corner box; sum over the positives of 1 - giou, times the weight, over max(#positives, 1).
+    ``locs`` may require grad (torch autograd gives the reference's gradient)."""
+    b, a = target.shape[:2]
+    pos = positives_mask(target[..., CLS_COL].long())
+    corners = corners_from_centroids(decode_boxes(locs.view(b, a, 4), priors, xy_scale, wh_scale))
+    loss = (1.0 - generalized_iou(corners[pos].view(-1, 4), target[..., :4][pos].view(-1, 4), cartesian=False)).sum()
+    return loss * loc_weight / pos.sum().clamp(min=1).float()
+
+
 # --------------------------------------------------------------------------------------
 # whole timed region (SURVEY.md §8 d) as the reference executes it on the CPU
 # --------------------------------------------------------------------------------------

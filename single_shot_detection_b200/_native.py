@@ -88,6 +88,9 @@ _SIGNATURES = {
     "ssd_multibox_loss_workspace_bytes": (c_size_t, [c_int, c_int]),
     "ssd_multibox_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float,
                                   c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ssd_multibox_loss_giou": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
+                                       c_float, c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_size_t, c_void_p]),
     "ssd_map_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "ssd_map_append": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "ssd_mean_average_precision": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float,

@@ -28,7 +28,52 @@ struct LossArgs {
     int A, C, kind;                 // kind: SSD_LOSS_SOFTMAX_CE / SSD_LOSS_SIGMOID_FOCAL
     float gamma, alpha, class_weight, loc_weight;
     int64_t rows;                   // B * A
+    // localisation term: SmoothL1 on coded boxes (priors == nullptr) or GeneralizedIoULoss on decoded corner
+    // boxes against the CORNER target rows (multibox_loss.py:77-79, bf/modules/losses.py:109-114)
+    const float4* priors;
+    float xy_scale, wh_scale;
 };
+
+// derivative of min(a, b) / max(a, b) with respect to a, torch's convention at ties (half each)
+__device__ __forceinline__ float dmin_da(float a, float b) { return a < b ? 1.f : (a == b ? 0.5f : 0.f); }
+__device__ __forceinline__ float dmax_da(float a, float b) { return a > b ? 1.f : (a == b ? 0.5f : 0.f); }
+
+// 1 - generalized_iou(decode -> to_corners (locs), target corners) of one anchor and d/d locs.
+//   decode (out of place, box_coder.py:55-57): c = p_xy + (p_wh * l_xy) / xy_scale, s = p_wh * exp(l_wh / wh_scale)
+//   giou = I / U - (E - U) / E  (box_utils.py:104-143; clamped areas), loss = 1 - giou
+__device__ __forceinline__ float giou_loss_term(float4 l, float4 p, float4 t, float xs, float ws, float (&g)[4]) {
+    const float cx = p.x + (p.z * l.x) / xs, cy = p.y + (p.w * l.y) / xs;
+    const float w = p.z * expf(l.z / ws), h = p.w * expf(l.w / ws);
+    const float x1 = cx - w * 0.5f, y1 = cy - h * 0.5f, x2 = cx + w * 0.5f, y2 = cy + h * 0.5f;
+    const float aw = fmaxf(x2 - x1, 0.f), ah = fmaxf(y2 - y1, 0.f);
+    const float area_a = aw * ah;
+    const float area_b = fmaxf(t.z - t.x, 0.f) * fmaxf(t.w - t.y, 0.f);
+    const float ix1 = fmaxf(x1, t.x), iy1 = fmaxf(y1, t.y), ix2 = fminf(x2, t.z), iy2 = fminf(y2, t.w);
+    const float iw = fmaxf(ix2 - ix1, 0.f), ih = fmaxf(iy2 - iy1, 0.f);
+    const float I = iw * ih;
+    const float U = area_a + area_b - I;
+    const float ex1 = fminf(x1, t.x), ey1 = fminf(y1, t.y), ex2 = fmaxf(x2, t.z), ey2 = fmaxf(y2, t.w);
+    const float ew = fmaxf(ex2 - ex1, 0.f), eh = fmaxf(ey2 - ey1, 0.f);
+    const float E = ew * eh;
+    const float giou = I / U - (E - U) / E;
+    // d loss: giou = I/U - 1 + U/E
+    const float GA = I / (U * U) - 1.f / E;                  // d loss / d area_a  (through U)
+    const float GI = -1.f / U - GA;                          // d loss / d I       (direct and through U)
+    const float GE = U / (E * E);                            // d loss / d E
+    // clamp(min = 0) passes the gradient where its input is >= 0 (torch)
+    const float m_aw = (x2 - x1) >= 0.f, m_ah = (y2 - y1) >= 0.f;
+    const float m_iw = (ix2 - ix1) >= 0.f, m_ih = (iy2 - iy1) >= 0.f;
+    const float m_ew = (ex2 - ex1) >= 0.f, m_eh = (ey2 - ey1) >= 0.f;
+    const float gx2 = GA * m_aw * ah + GI * ih * m_iw * dmin_da(x2, t.z) + GE * eh * m_ew * dmax_da(x2, t.z);
+    const float gx1 = -GA * m_aw * ah - GI * ih * m_iw * dmax_da(x1, t.x) - GE * eh * m_ew * dmin_da(x1, t.x);
+    const float gy2 = GA * m_ah * aw + GI * iw * m_ih * dmin_da(y2, t.w) + GE * ew * m_eh * dmax_da(y2, t.w);
+    const float gy1 = -GA * m_ah * aw - GI * iw * m_ih * dmax_da(y1, t.y) - GE * ew * m_eh * dmin_da(y1, t.y);
+    g[0] = (gx1 + gx2) * p.z / xs;
+    g[1] = (gy1 + gy2) * p.w / xs;
+    g[2] = (gx2 - gx1) * 0.5f * w / ws;
+    g[3] = (gy2 - gy1) * 0.5f * h / ws;
+    return 1.f - giou;
+}
 
 __device__ __forceinline__ bool is_positive_class(float c) {
     return c != (float)SSD_NEGATIVE_CLASS && c != (float)SSD_IGNORE_CLASS;
@@ -100,14 +145,18 @@ loss_rows_kernel(LossArgs a, const float* __restrict__ logits, const float* __re
             const float4 p = *reinterpret_cast<const float4*>(locs + r * 4);
             const float2 t0 = *reinterpret_cast<const float2*>(target + r * SSD_TARGET_COLS);
             const float2 t1 = *reinterpret_cast<const float2*>(target + r * SSD_TARGET_COLS + 2);
-            const float d[4] = {p.x - t0.x, p.y - t0.y, p.z - t1.x, p.w - t1.y};
             float gd[4];
             float l = 0.f;
+            if (a.priors != nullptr) {
+                l = giou_loss_term(p, a.priors[r % a.A], make_float4(t0.x, t0.y, t1.x, t1.y), a.xy_scale, a.wh_scale, gd);
+            } else {
+                const float d[4] = {p.x - t0.x, p.y - t0.y, p.z - t1.x, p.w - t1.y};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float ad = fabsf(d[k]);
-                l += ad < 1.f ? 0.5f * d[k] * d[k] : ad - 0.5f;
-                gd[k] = ad < 1.f ? d[k] : (d[k] > 0.f ? 1.f : -1.f);
+                for (int k = 0; k < 4; ++k) {
+                    const float ad = fabsf(d[k]);
+                    l += ad < 1.f ? 0.5f * d[k] * d[k] : ad - 0.5f;
+                    gd[k] = ad < 1.f ? d[k] : (d[k] > 0.f ? 1.f : -1.f);
+                }
             }
             loc_sum += (double)l;
             g = make_float4(gd[0] * lscale, gd[1] * lscale, gd[2] * lscale, gd[3] * lscale);
@@ -222,10 +271,11 @@ extern "C" size_t ssd_multibox_loss_workspace_bytes(int batch, int num_anchors) 
     return 256 + round_up((size_t)loss_ctas((int64_t)batch * num_anchors) * 2 * sizeof(double), 256);
 }
 
-extern "C" int ssd_multibox_loss(const float* logits, const float* locs, const float* target, const uint8_t* sampled_mask,
-                                 int batch, int num_anchors, int num_cols, int kind, float gamma, float alpha,
-                                 float class_weight, float loc_weight, float* grad_logits, float* grad_locs,
-                                 float* loss_out, void* workspace, size_t workspace_bytes, void* stream) {
+static int multibox_loss_impl(const float* logits, const float* locs, const float* target, const uint8_t* sampled_mask,
+                              int batch, int num_anchors, int num_cols, int kind, float gamma, float alpha,
+                              float class_weight, float loc_weight, float* grad_logits, float* grad_locs,
+                              float* loss_out, void* workspace, size_t workspace_bytes, void* stream,
+                              const float* priors, float xy_scale, float wh_scale) {
     SSD_REQUIRE(batch >= 0 && num_anchors >= 0 && num_cols >= 1, SSD_ERR_INVALID_ARGUMENT, "ssd_multibox_loss: bad shape");
     SSD_REQUIRE(kind == SSD_LOSS_SOFTMAX_CE || kind == SSD_LOSS_SIGMOID_FOCAL, SSD_ERR_INVALID_ARGUMENT,
                 "ssd_multibox_loss: unknown classification loss %d", kind);
@@ -255,6 +305,7 @@ extern "C" int ssd_multibox_loss(const float* logits, const float* locs, const f
     LossArgs a;
     a.A = num_anchors; a.C = num_cols; a.kind = kind; a.gamma = gamma; a.alpha = alpha;
     a.class_weight = class_weight; a.loc_weight = loc_weight; a.rows = rows;
+    a.priors = reinterpret_cast<const float4*>(priors); a.xy_scale = xy_scale; a.wh_scale = wh_scale;
     const int ctas = loss_ctas(rows);
     {
         LaunchTimer lt_("loss_rows", st);
@@ -269,6 +320,27 @@ extern "C" int ssd_multibox_loss(const float* logits, const float* locs, const f
         count_launch();
     }
     return SSD_OK;
+}
+
+extern "C" int ssd_multibox_loss(const float* logits, const float* locs, const float* target, const uint8_t* sampled_mask,
+                                 int batch, int num_anchors, int num_cols, int kind, float gamma, float alpha,
+                                 float class_weight, float loc_weight, float* grad_logits, float* grad_locs,
+                                 float* loss_out, void* workspace, size_t workspace_bytes, void* stream) {
+    return multibox_loss_impl(logits, locs, target, sampled_mask, batch, num_anchors, num_cols, kind, gamma, alpha,
+                              class_weight, loc_weight, grad_logits, grad_locs, loss_out, workspace, workspace_bytes,
+                              stream, nullptr, 1.f, 1.f);
+}
+
+extern "C" int ssd_multibox_loss_giou(const float* logits, const float* locs, const float* target, const float* priors,
+                                      const uint8_t* sampled_mask, int batch, int num_anchors, int num_cols, int kind,
+                                      float gamma, float alpha, float class_weight, float loc_weight, float xy_scale,
+                                      float wh_scale, float* grad_logits, float* grad_locs, float* loss_out,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+    SSD_REQUIRE(priors != nullptr && aligned(priors, 16), SSD_ERR_INVALID_ARGUMENT,
+                "ssd_multibox_loss_giou: priors must be a 16-byte aligned device pointer");
+    return multibox_loss_impl(logits, locs, target, sampled_mask, batch, num_anchors, num_cols, kind, gamma, alpha,
+                              class_weight, loc_weight, grad_logits, grad_locs, loss_out, workspace, workspace_bytes,
+                              stream, priors, xy_scale, wh_scale);
 }
 
 SSD_DEFINE_TRACE_SETTER(set_trace_loss)

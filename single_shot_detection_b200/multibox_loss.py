@@ -11,9 +11,11 @@ the loss modules and lets autograd scatter the gradients back.  Here one fused p
 (csrc/loss.cu, ``ssd_multibox_loss``) produces the three loss values AND the dense gradients
 w.r.t. ``scores`` and ``locs``; ``torch.autograd`` only sees one custom Function.
 
-Supported configurations = what the samples use (samples/*.py): ``CrossEntropyLoss`` or
-``SigmoidFocalLoss`` for classification, ``SmoothL1Loss`` for localisation.  Anything else
-(``GeneralizedIoULoss``, the soft-target losses) raises: there is no silent fallback.
+Supported configurations: ``CrossEntropyLoss`` or ``SigmoidFocalLoss`` for classification (what the
+samples use), ``SmoothL1Loss`` or ``GeneralizedIoULoss`` for localisation -- with the latter the
+target boxes stay corner boxes and the predictions are decoded instead (multibox_loss.py:77-79), the
+gradient flows through GIoU, ``to_corners`` and the decoding inside the same kernel.  The soft-target
+classification losses raise: there is no silent fallback.
 """
 import torch
 import torch.nn as nn
@@ -26,10 +28,12 @@ from .target_assigner import LOC_INDEX_START, LOC_INDEX_END, CLASS_INDEX  # noqa
 
 class _FusedMultiboxLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, scores, locs, target, sampled_mask, kind, gamma, alpha, class_weight, loc_weight):
+    def forward(ctx, scores, locs, target, sampled_mask, kind, gamma, alpha, class_weight, loc_weight,
+                giou_priors=None, xy_scale=1.0, wh_scale=1.0):
         need_grad = scores.requires_grad or locs.requires_grad
         loss3, grad_scores, grad_locs = OPS.multibox_loss(scores, locs, target, sampled_mask, kind, gamma, alpha,
-                                                          class_weight, loc_weight, need_grad)
+                                                          class_weight, loc_weight, need_grad, giou_priors,
+                                                          xy_scale, wh_scale)
         ctx.save_for_backward(grad_scores, grad_locs)
         ctx.dtypes = (scores.dtype, locs.dtype)
         return loss3
@@ -43,7 +47,7 @@ class _FusedMultiboxLoss(torch.autograd.Function):
             gs = (grad_scores * (g[0] + g[1])).to(ctx.dtypes[0])
         if ctx.needs_input_grad[1]:
             gl = (grad_locs * (g[0] + g[2])).to(ctx.dtypes[1])
-        return gs, gl, None, None, None, None, None, None, None
+        return gs, gl, None, None, None, None, None, None, None, None, None, None
 
 
 class MultiboxLoss(nn.Module):
@@ -78,9 +82,10 @@ class MultiboxLoss(nn.Module):
         self.soft_target = False
 
         loc_cfg = dict(localization_loss)
-        if loc_cfg.pop('name') != 'SmoothL1Loss' or loc_cfg:
+        loc_name = loc_cfg.pop('name')
+        if loc_name not in ('SmoothL1Loss', 'GeneralizedIoULoss') or loc_cfg:
             raise NotImplementedError(f'localization loss {localization_loss!r} is not part of the accelerated path')
-        self.iou_loss = False
+        self.iou_loss = loc_name == 'GeneralizedIoULoss'               # bf/modules/losses.py:110 IOU_LOSS
 
         self.classification_weight = classification_weight
         self.localization_weight = localization_weight
@@ -104,6 +109,15 @@ class MultiboxLoss(nn.Module):
         num_priors = target.size(1)
 
         sampled_mask = self.sampler(scores.view(batch_size, num_priors, -1), target_classes)
+
+        if self.iou_loss:
+            # multibox_loss.py:77-79: the predictions are decoded (inside the kernel), the target stays as it is
+            from . import _devcache
+            priors = _devcache.device_copy(anchors, target.device)
+            loss3 = _FusedMultiboxLoss.apply(scores, locs, target, sampled_mask, self.kind, self.gamma, self.alpha,
+                                             float(self.classification_weight), float(self.localization_weight),
+                                             priors, float(self.box_coder.xy_scale), float(self.box_coder.wh_scale))
+            return loss3[0], loss3[1], loss3[2]
 
         box_utils.to_centroids(target_locs, inplace=True)
         self.box_coder.encode_box(target_locs, anchors, inplace=True)

@@ -33,7 +33,8 @@ _LIB.define("postprocess(Tensor scores, Tensor boxes, Tensor? priors, int conver
 _LIB.define("nms(Tensor boxes, Tensor scores, int max_per_class, float overlap_threshold) -> (Tensor, Tensor)")
 _LIB.define("soft_nms(Tensor boxes, Tensor scores, int max_per_class, float score_threshold, float sigma) -> (Tensor, Tensor)")
 _LIB.define("multibox_loss(Tensor scores, Tensor locs, Tensor target, Tensor sampled_mask, int kind, float gamma, "
-            "float alpha, float class_weight, float loc_weight, bool need_grad) -> (Tensor, Tensor, Tensor)")
+            "float alpha, float class_weight, float loc_weight, bool need_grad, Tensor? giou_priors=None, "
+            "float xy_scale=1.0, float wh_scale=1.0) -> (Tensor, Tensor, Tensor)")
 
 
 def _stream() -> int:
@@ -384,7 +385,8 @@ def _soft_nms(boxes: torch.Tensor, scores: torch.Tensor, max_per_class: int, sco
 
 
 def _multibox_loss(scores: torch.Tensor, locs: torch.Tensor, target: torch.Tensor, sampled_mask: torch.Tensor,
-                   kind: int, gamma: float, alpha: float, class_weight: float, loc_weight: float, need_grad: bool):
+                   kind: int, gamma: float, alpha: float, class_weight: float, loc_weight: float, need_grad: bool,
+                   giou_priors: Optional[torch.Tensor] = None, xy_scale: float = 1.0, wh_scale: float = 1.0):
     """(loss3 [3], grad_scores like scores, grad_locs like locs); the gradients are empty tensors when
     ``need_grad`` is false.  ``target`` rows hold the ENCODED boxes (after to_centroids + encode_box)."""
     N.require_device()
@@ -402,11 +404,20 @@ def _multibox_loss(scores: torch.Tensor, locs: torch.Tensor, target: torch.Tenso
     with torch.cuda.device(dev):
         nbytes = N.lib().ssd_multibox_loss_workspace_bytes(batch, num_anchors)
         ws = workspace(nbytes, dev, "loss")
-        N.check(N.lib().ssd_multibox_loss(_ptr(scores_c), _ptr(locs_c), _ptr(target_c), _ptr(mask), batch, num_anchors,
-                                          num_cols, kind, gamma, alpha, class_weight, loc_weight,
-                                          _ptr(grad_scores) if need_grad else None,
-                                          _ptr(grad_locs) if need_grad else None, _ptr(loss3), _ptr(ws), ws.numel(),
-                                          _stream()))
+        if giou_priors is not None:
+            priors_c = _f32c(giou_priors)
+            N.check(N.lib().ssd_multibox_loss_giou(_ptr(scores_c), _ptr(locs_c), _ptr(target_c), _ptr(priors_c), _ptr(mask),
+                                                   batch, num_anchors, num_cols, kind, gamma, alpha, class_weight,
+                                                   loc_weight, xy_scale, wh_scale,
+                                                   _ptr(grad_scores) if need_grad else None,
+                                                   _ptr(grad_locs) if need_grad else None, _ptr(loss3), _ptr(ws),
+                                                   ws.numel(), _stream()))
+        else:
+            N.check(N.lib().ssd_multibox_loss(_ptr(scores_c), _ptr(locs_c), _ptr(target_c), _ptr(mask), batch, num_anchors,
+                                              num_cols, kind, gamma, alpha, class_weight, loc_weight,
+                                              _ptr(grad_scores) if need_grad else None,
+                                              _ptr(grad_locs) if need_grad else None, _ptr(loss3), _ptr(ws), ws.numel(),
+                                              _stream()))
     return loss3, grad_scores, grad_locs
 
 

@@ -21,6 +21,9 @@ sys.path.insert(0, ROOT)
 from bf.utils import box_utils as ref_box_utils  # noqa: E402
 from detection.box_coder import BoxCoder as RefBoxCoder  # noqa: E402
 from detection.postprocessor import Postprocessor as RefPostprocessor  # noqa: E402
+from detection import sampler as ref_sampler  # noqa: E402
+from detection.losses.multibox_loss import MultiboxLoss as RefMultiboxLoss  # noqa: E402
+from detection.target_assigner import TargetAssigner as RefTargetAssigner  # noqa: E402
 
 from single_shot_detection_b200 import workloads as wl  # noqa: E402
 
@@ -82,6 +85,37 @@ def main():
     blob["giou_a"], blob["giou_b"] = a.numpy(), b.numpy()
     blob["giou_cartesian"] = ref_box_utils.generalized_iou(a, b).numpy()
     blob["giou_elementwise"] = ref_box_utils.generalized_iou(a, b[:37], cartesian=False).numpy()
+    # ---- MultiboxLoss with GeneralizedIoULoss as the localisation term: values and gradients (autograd) ----
+    import functools
+    g = 0
+    for name, batch in [("tiny_voc_b3", 3), ("tiny_sigmoid_b2", 2)]:
+        w = wl.WORKLOADS[name]
+        anchors, gt, scores, locs = wl.make_inputs(w, seed=51 + g, batch=batch)
+        locs = locs * 3.0                                                        # decoded boxes that really move
+        coder = RefBoxCoder(w.xy_scale, w.wh_scale)
+        target = RefTargetAssigner(w.matched_threshold, w.unmatched_threshold).encode_ground_truth(gt, anchors)
+        if w.converter == "SOFTMAX":
+            smp = functools.partial(ref_sampler.hard_negative_mining, negative_per_positive_ratio=w.ratio,
+                                    min_negative_per_image=w.min_neg)
+            crit = RefMultiboxLoss(smp, coder, {"name": "CrossEntropyLoss"}, {"name": "GeneralizedIoULoss"},
+                                   localization_weight=2.0)
+        else:
+            crit = RefMultiboxLoss(ref_sampler.naive_sampler, coder, {"name": "SigmoidFocalLoss", "gamma": 2.0, "alpha": 0.25},
+                                   {"name": "GeneralizedIoULoss"}, localization_weight=2.0)
+        s_in = scores.clone().requires_grad_(True)
+        l_in = locs.clone().requires_grad_(True)
+        loss, class_loss, loc_loss = crit((s_in, l_in), anchors, target.clone())
+        loss.backward()
+        blob[f"giou_loss_workload_{g}"] = np.array(name)
+        blob[f"giou_loss_scores_{g}"] = scores.numpy()
+        blob[f"giou_loss_locs_{g}"] = locs.numpy()
+        blob[f"giou_loss_target_{g}"] = target.numpy()
+        blob[f"giou_loss_values_{g}"] = np.array([float(x.detach()) for x in (loss, class_loss, loc_loss)], dtype=np.float64)
+        blob[f"giou_loss_grad_locs_{g}"] = l_in.grad.numpy()
+        blob[f"giou_loss_grad_scores_{g}"] = s_in.grad.numpy()
+        print("giou loss", g, name, float(loss.detach()), float(loc_loss.detach()), float(l_in.grad.abs().max()))
+        g += 1
+    blob["num_giou_loss"] = np.array(g)
     np.savez_compressed(os.path.join(HERE, "corners.npz"), **blob)
 
 

@@ -98,3 +98,57 @@ def test_numpy_route_of_box_utils(dev):
     sc = np.linspace(0.2, 0.9, a.shape[0]).astype(np.float32)
     subset = np.arange(a.shape[0] - 20, a.shape[0])                              # the 20 best (scores increase)
     assert np.array_equal(keep, subset[ora.greedy_nms(a[subset], sc[subset], .45)])
+
+
+def _giou_module(w):
+    import functools
+    from single_shot_detection_b200 import box_coder, multibox_loss, sampler
+    coder = box_coder.BoxCoder(w.xy_scale, w.wh_scale, w.eps)
+    if w.converter == "SOFTMAX":
+        smp = functools.partial(sampler.hard_negative_mining, negative_per_positive_ratio=w.ratio,
+                                min_negative_per_image=w.min_neg)
+        return multibox_loss.MultiboxLoss(smp, coder, {"name": "CrossEntropyLoss"}, {"name": "GeneralizedIoULoss"},
+                                          localization_weight=2.0)
+    return multibox_loss.MultiboxLoss(sampler.naive_sampler, coder, {"name": "SigmoidFocalLoss", "gamma": 2.0, "alpha": 0.25},
+                                      {"name": "GeneralizedIoULoss"}, localization_weight=2.0)
+
+
+def test_multibox_loss_with_giou_matches_reference_values_and_gradients(dev):
+    """MultiboxLoss(localization_loss=GeneralizedIoULoss): (loss, class_loss, loc_loss) and d loss / d locs,
+    d loss / d scores against the reference + autograd (tests/golden/corners.npz), 1e-5 relative."""
+    z = gio.load("corners.npz")
+    for g in range(int(z["num_giou_loss"])):
+        w = wl.WORKLOADS[str(z[f"giou_loss_workload_{g}"])]
+        anchors = wl.build_anchors(w)
+        scores = torch.from_numpy(z[f"giou_loss_scores_{g}"]).to(dev).requires_grad_(True)
+        locs = torch.from_numpy(z[f"giou_loss_locs_{g}"]).to(dev).requires_grad_(True)
+        target = torch.from_numpy(z[f"giou_loss_target_{g}"]).to(dev)
+        before = target.clone()
+        loss, class_loss, loc_loss = _giou_module(w)((scores, locs), anchors, target)
+        loss.backward()
+        assert torch.equal(target, before)                    # the IOU_LOSS branch leaves the target alone (:77-79)
+        np.testing.assert_allclose([float(x.detach()) for x in (loss, class_loss, loc_loss)], z[f"giou_loss_values_{g}"], rtol=REL)
+        np.testing.assert_allclose(locs.grad.cpu().numpy(), z[f"giou_loss_grad_locs_{g}"], rtol=1e-4, atol=1e-7)
+        np.testing.assert_allclose(scores.grad.cpu().numpy(), z[f"giou_loss_grad_scores_{g}"], rtol=1e-4, atol=1e-7)
+
+
+def test_giou_loss_gradient_random_vs_oracle_autograd(dev):
+    from single_shot_detection_b200 import _devcache  # noqa: F401
+    from single_shot_detection_b200.ops import OPS
+    from single_shot_detection_b200 import _native as N
+    gen = torch.Generator().manual_seed(17)
+    for name, batch in [("ssd300_voc_b8", 4), ("ssd_mb2_coco_b64", 5)]:
+        w = wl.WORKLOADS[name]
+        anchors, gt, scores, locs = wl.make_inputs(w, seed=61, batch=batch)
+        locs = (locs * 4.0)
+        target = ora.assign_targets(gt, anchors, w.matched_threshold, w.unmatched_threshold)
+        ref_locs = locs.clone().requires_grad_(True)
+        ref = ora.giou_localization_loss(ref_locs, anchors, target, w.xy_scale, w.wh_scale, loc_weight=1.5)
+        ref.backward()
+        mask = torch.zeros(target.shape[:2], dtype=torch.bool)
+        loss3, _, grad_locs = OPS.multibox_loss(scores.to(dev), locs.to(dev), target.to(dev), mask.to(dev),
+                                                N.LOSS_SOFTMAX_CE, 0.0, 0.0, 1.0, 1.5, True, anchors.to(dev),
+                                                float(w.xy_scale), float(w.wh_scale))
+        np.testing.assert_allclose(float(loss3[2]), float(ref), rtol=REL)
+        np.testing.assert_allclose(grad_locs.cpu().numpy().reshape(batch, -1), ref_locs.grad.numpy().reshape(batch, -1),
+                                   rtol=1e-4, atol=1e-7)

@@ -239,3 +239,17 @@ def test_generalized_iou_oracle_matches_reference():
     assert np.array_equal(ora.generalized_iou(a, b).numpy(), z["giou_cartesian"])
     assert np.array_equal(ora.generalized_iou(a, b[:37], cartesian=False).numpy(), z["giou_elementwise"])
     assert z["giou_cartesian"][3, 5] == 1.0
+
+
+def test_giou_localization_loss_oracle_matches_reference_autograd():
+    """Value and gradient of the GIoU localisation term against the reference's MultiboxLoss + autograd."""
+    z = gio.load("corners.npz")
+    for g in range(int(z["num_giou_loss"])):
+        w = wl.WORKLOADS[str(z[f"giou_loss_workload_{g}"])]
+        anchors = wl.build_anchors(w)
+        locs = torch.from_numpy(z[f"giou_loss_locs_{g}"]).clone().requires_grad_(True)
+        target = torch.from_numpy(z[f"giou_loss_target_{g}"])
+        loc_loss = ora.giou_localization_loss(locs, anchors, target, w.xy_scale, w.wh_scale, loc_weight=2.0)
+        loc_loss.backward()
+        np.testing.assert_allclose(float(loc_loss), z[f"giou_loss_values_{g}"][2], rtol=1e-6)
+        np.testing.assert_allclose(locs.grad.numpy(), z[f"giou_loss_grad_locs_{g}"], rtol=1e-5, atol=1e-8)
