@@ -169,7 +169,7 @@ __device__ __forceinline__ void block_sum4(SelShared& sh, int (&c)[4]) {
     __syncthreads();          // sh.total may be overwritten by the next call
 }
 
-__global__ void __launch_bounds__(kSelThreads)
+__global__ void __launch_bounds__(kSelThreads, 2)
 mining_select_kernel(const uint32_t* __restrict__ keys, const void* __restrict__ cls, int cls_stride, int A, double ratio,
                      int ratio_is_integer, double min_negatives, uint8_t* __restrict__ mask,
                      int32_t* __restrict__ stats) {
