@@ -218,14 +218,32 @@ def run_ours(args):
     torch.cuda.synchronize()
     launches_per_step = int(N.lib().ssd_b200_launch_count() - launches_before)
     cap = B if world > 1 else None
-    for pipe, (packed, scores_d, locs_d) in zip(pipes, dev_sets):
-        # (the all-gather stays outside the graph: capturing the NCCL collective hung on this stack)
-        outs.append(pipe.capture(packed, anchors_dev, scores_d, locs_d, shard_capacity=cap))
+    # The exchange step: by default the last kernel of every step graph packs the shard and writes it into every
+    # rank's gathered buffer over NVLink peer memory (sharding.PeerExchange, csrc/exchange.cu); SSD_EXCHANGE=nccl
+    # packs locally and calls NCCL's all-gather after every replay instead (capturing the NCCL collective into the
+    # graph hung on this stack).
+    px = None
+    if world > 1 and os.environ.get("SSD_EXCHANGE", "peer") != "nccl":
+        px = sharding.PeerExchange(B * world, w.max_total, slots=nsets)
+    for k, (pipe, (packed, scores_d, locs_d)) in enumerate(zip(pipes, dev_sets)):
+        if px is not None:
+            outs.append(pipe.capture(packed, anchors_dev, scores_d, locs_d, exchange=(px, k)))
+        else:
+            outs.append(pipe.capture(packed, anchors_dev, scores_d, locs_d, shard_capacity=cap))
     torch.cuda.synchronize()
 
     # the one exchange step of the path (detections + counts + stats, one collective per step) runs
     # asynchronously: the all-gather of step i overlaps the kernels of step i+1
-    gather = sharding.OverlappedGather(B * world, w.max_total, ring=max(3, nsets + 1)) if world > 1 else None
+    gather = sharding.OverlappedGather(B * world, w.max_total, ring=max(3, nsets + 1)) if world > 1 and px is None else None
+
+    class _PeerFlush:                      # same surface as OverlappedGather for the loops below
+        def flush(self):
+            for k in range(nsets):
+                px.wait(k)
+            return px.gathered(0)
+
+    if px is not None:
+        gather = _PeerFlush()
 
     # Throughput mode: `in_flight` consecutive steps run concurrently, each replayed on its own stream (input
     # set k always on stream k % in_flight, with that slot's scratch buffers).  A step alone leaves most of the
@@ -237,12 +255,12 @@ def run_ours(args):
         k = i % nsets
         if serial or in_flight == 1:
             pipes[k].replay()
-            if world > 1:
+            if world > 1 and px is None:
                 return gather.submit(outs[k].shard)
             return outs[k].dets, outs[k].counts, outs[k].assign_stats
         with torch.cuda.stream(streams[k % in_flight]):
             pipes[k].replay()
-            if world > 1:
+            if world > 1 and px is None and not os.environ.get("SSD_BENCH_NO_GATHER"):   # (diagnostics)
                 return gather.submit_nowait(outs[k].shard)
         return outs[k].dets, outs[k].counts, outs[k].assign_stats
 
@@ -377,8 +395,9 @@ def run_ours(args):
                        "device_path": (f"CUDA graph replay per step, {in_flight} consecutive steps in flight on "
                                        f"{in_flight} streams (own scratch buffers per slot)" if in_flight > 1
                                        else "CUDA graph replay per step, one step after the other") + (
-                           "" if world == 1 else (", all-gather captured in the graph" if outs[0].gathered is not None
-                                                  else ", all-gather of step i overlapping step i+1"))},
+                           "" if world == 1 else (", shard packed and written into every rank's gathered buffer over NVLink "
+                                                  "peer memory by the last kernel of the step graph" if px is not None
+                                                  else ", NCCL all-gather of step i overlapping step i+1"))},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
                     "path": "AnchorPipeline.stream(batches of (list of GT, pinned host scores, locs), CPU anchors) -> "

@@ -353,6 +353,24 @@ SSD_API int ssd_pack_shard(const float* dets, const int32_t* counts, const int32
                    const int32_t* mining_stats, int batch, int max_total, int capacity, float* shard_out,
                    int32_t* stats_out, void* stream);
 
+/* The same packing FUSED with the exchange over NVLink peer memory: every CTA writes its row into slot `rank` of
+ * every peer's gathered buffer, no NCCL call (csrc/exchange.cu has the protocol).  `peer_arenas` is a HOST array
+ * of `world` device pointers: the arena of every rank as mapped into this process (CUDA IPC; entry `rank` is the
+ * own arena).  An arena is ssd_exchange_arena_bytes(...) bytes, 256-byte aligned, ZERO-filled once when it is
+ * created; gathered slot `slot` of the own arena starts at ssd_exchange_slot_offset(...) and holds
+ * [world, capacity, T*6 + 5] words once ssd_exchange_wait(slot) has completed on the stream.  One slot per step
+ * graph / stream: launches that use the same slot must be serialised.  A peer that stops answering turns into
+ * a non-zero first header word (int64) after 4 s, never into a hang. */
+#define SSD_EXCHANGE_MAX_WORLD 8
+#define SSD_EXCHANGE_MAX_SLOTS 16
+SSD_API int ssd_exchange_enable_peer(int device, int peer_device);   /* cudaDeviceEnablePeerAccess, idempotent */
+SSD_API size_t ssd_exchange_arena_bytes(int world, int slots, int capacity, int max_total);
+SSD_API size_t ssd_exchange_slot_offset(int world, int slot, int capacity, int max_total);
+SSD_API int ssd_pack_exchange(const float* dets, const int32_t* counts, const int32_t* assign_stats,
+                      const int32_t* mining_stats, int batch, int max_total, int capacity,
+                      void* const* peer_arenas, int world, int rank, int slot, int32_t* stats_out, void* stream);
+SSD_API int ssd_exchange_wait(void* own_arena, int world, int slot, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -97,6 +97,12 @@ _SIGNATURES = {
                                            c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                            c_void_p]),
     "ssd_pack_shard": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "ssd_exchange_enable_peer": (c_int, [c_int, c_int]),
+    "ssd_exchange_arena_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "ssd_exchange_slot_offset": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "ssd_pack_exchange": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, POINTER(c_void_p), c_int,
+                                  c_int, c_int, c_void_p, c_void_p]),
+    "ssd_exchange_wait": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "ssd_generate_anchors": (c_int, [POINTER(AnchorLevel), c_int, c_void_p, c_int64, c_void_p]),
     "ssd_postprocess_workspace_bytes": (c_size_t, [POINTER(PostprocessParams)]),
     "ssd_postprocess": (c_int, [POINTER(PostprocessParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

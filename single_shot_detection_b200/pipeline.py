@@ -223,13 +223,15 @@ class AnchorPipeline:
 
     # -- device-resident, sync-free -------------------------------------------------------------
     def step_device(self, packed: PackedGroundTruth, anchors_dev, scores_dev, locs_dev,
-                    shard_capacity: Optional[int] = None, gather: bool = False) -> "StepOutput":
+                    shard_capacity: Optional[int] = None, gather: bool = False, exchange=None) -> "StepOutput":
+        """``exchange`` = (sharding.PeerExchange, slot): pack the shard and write it into every rank's gathered
+        buffer over NVLink peer memory as the last kernel of the step (no NCCL call; capturable)."""
         from . import ops
         with ops.workspace_slot(self.workspace_slot):
-            return self._step_device(packed, anchors_dev, scores_dev, locs_dev, shard_capacity, gather)
+            return self._step_device(packed, anchors_dev, scores_dev, locs_dev, shard_capacity, gather, exchange)
 
     def _step_device(self, packed: PackedGroundTruth, anchors_dev, scores_dev, locs_dev,
-                     shard_capacity: Optional[int] = None, gather: bool = False) -> "StepOutput":
+                     shard_capacity: Optional[int] = None, gather: bool = False, exchange=None) -> "StepOutput":
         """``shard_capacity``: also pack (dets, counts, stats) into the one-buffer layout
         ``sharding.all_gather_detections`` exchanges (so the packing is part of the graph).
         ``gather``: also run that exchange -- one NCCL all-gather over all ranks -- as the last
@@ -275,7 +277,11 @@ class AnchorPipeline:
         main.wait_stream(side)
         mining = _sampler.hard_negative_mining.last_stats if self.cfg["sampler"] == "hard_negative_mining" else None
         stats, shard = None, None
-        if shard_capacity is not None:
+        if exchange is not None:
+            px, slot = exchange
+            stats = px.pack_exchange(dets, counts, self.target_assigner.last_stats, mining, slot)
+            shard = px.gathered(slot)
+        elif shard_capacity is not None:
             from . import sharding
             shard, stats = sharding.pack_shard_device(dets, counts, self.target_assigner.last_stats, mining, shard_capacity)
         gathered = None
@@ -292,14 +298,14 @@ class AnchorPipeline:
         return self._side
 
     def capture(self, packed: PackedGroundTruth, anchors_dev, scores_dev, locs_dev, warmup: int = 2,
-                shard_capacity: Optional[int] = None, gather: bool = False) -> "StepOutput":
+                shard_capacity: Optional[int] = None, gather: bool = False, exchange=None) -> "StepOutput":
         """Record ``step_device`` on these (static) buffers into a CUDA graph; returns the outputs
         the replays will keep overwriting."""
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                out = self.step_device(packed, anchors_dev, scores_dev, locs_dev, shard_capacity, gather)
+                out = self.step_device(packed, anchors_dev, scores_dev, locs_dev, shard_capacity, gather, exchange)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
@@ -310,7 +316,7 @@ class AnchorPipeline:
         import os
         prio = os.environ.get("SSD_GRAPH_PRIORITY", "1") != "0"
         with torch.cuda.graph(graph, stream=torch.cuda.Stream(priority=-1) if prio else None):
-            out = self.step_device(packed, anchors_dev, scores_dev, locs_dev, shard_capacity, gather)
+            out = self.step_device(packed, anchors_dev, scores_dev, locs_dev, shard_capacity, gather, exchange)
         self._graph = graph
         return out
 

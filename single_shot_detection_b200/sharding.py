@@ -58,6 +58,90 @@ def pack_shard_device(dets: torch.Tensor, counts: torch.Tensor, assign_stats: Op
     return shard, stats
 
 
+class PeerExchange:
+    """The exchange step WITHOUT a collective library: every rank owns one arena of gathered buffers, maps the
+    arenas of its peers through CUDA IPC (all ranks sit on one NVSwitch box) and ``pack_exchange`` -- one kernel,
+    capturable into the step graph -- packs the local shard and writes it straight into every peer's buffer over
+    NVLink (csrc/exchange.cu).  ``torch.distributed`` is used once, to hand the IPC handles around.
+
+    One ``slot`` per concurrently usable step graph; launches on the same slot must be serialised (same stream).
+    ``gathered(slot)`` is complete once ``wait(slot)`` has run on the stream, and stays valid until the slot's
+    graph is launched again."""
+
+    def __init__(self, batch: int, max_rows: int, slots: int, group: Optional[dist.ProcessGroup] = None,
+                 device: Optional[torch.device] = None):
+        import ctypes
+        from torch.multiprocessing.reductions import reduce_tensor
+        from . import _native as N
+        N.require_device()
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.batch, self.max_rows, self.slots = batch, max_rows, slots
+        self.capacity = shard_capacity(batch, self.world)
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self._N = N
+        nbytes = N.lib().ssd_exchange_arena_bytes(self.world, slots, self.capacity, max_rows)
+        if nbytes == 0:
+            raise ValueError(f"PeerExchange: world {self.world} / slots {slots} outside the supported range")
+        self.arena = torch.zeros((nbytes,), dtype=torch.uint8, device=self.device)          # zero-filled once
+        torch.cuda.synchronize(self.device)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, reduce_tensor(self.arena), group=group)
+        self._peers = []                                   # keep the mappings alive
+        ptrs = (ctypes.c_void_p * self.world)()
+        for r, (rebuild, args) in enumerate(handles):
+            if r == self.rank:
+                t = self.arena
+            else:
+                # torch would open the IPC handle under the EXPORTER's device index; the kernels that use the
+                # mapping run on THIS device, so it is opened here (cudaIpcOpenMemHandle then enables peer access
+                # between this device and the exporter's lazily) -- argument 6 of rebuild_cuda_tensor is the device
+                peer_device = int(args[6])
+                args = list(args)
+                args[6] = self.device.index
+                N.check(N.lib().ssd_exchange_enable_peer(self.device.index, peer_device))
+                t = rebuild(*args)
+            self._peers.append(t)
+            ptrs[r] = t.data_ptr()
+        self._ptrs = ptrs
+        dist.barrier(group=group)                          # every rank has mapped every arena
+
+    def pack_exchange(self, dets: torch.Tensor, counts: torch.Tensor, assign_stats: Optional[torch.Tensor],
+                      mining_stats: Optional[torch.Tensor], slot: int):
+        """-> stats [B_local, 4] int32; the packed shard lands in slot ``slot`` of every rank's arena."""
+        n, t = int(dets.shape[0]), int(dets.shape[1])
+        assert t == self.max_rows and n <= self.capacity and 0 <= slot < self.slots
+        stats = torch.empty((n, 4), dtype=torch.int32, device=dets.device)
+        N = self._N
+        with torch.cuda.device(self.device):
+            N.check(N.lib().ssd_pack_exchange(dets.data_ptr(), counts.data_ptr(),
+                                              None if assign_stats is None else assign_stats.data_ptr(),
+                                              None if mining_stats is None else mining_stats.data_ptr(), n, t,
+                                              self.capacity, self._ptrs, self.world, self.rank, slot, stats.data_ptr(),
+                                              torch.cuda.current_stream().cuda_stream))
+        return stats
+
+    def wait(self, slot: int) -> None:
+        N = self._N
+        with torch.cuda.device(self.device):
+            N.check(N.lib().ssd_exchange_wait(self.arena.data_ptr(), self.world, slot,
+                                              torch.cuda.current_stream().cuda_stream))
+
+    def gathered(self, slot: int) -> torch.Tensor:
+        """[world * capacity, T*6 + 5] fp32 view of the slot (the layout ``unpack_gathered`` reads)."""
+        words = self.max_rows * 6 + 5
+        off = self._N.lib().ssd_exchange_slot_offset(self.world, slot, self.capacity, self.max_rows)
+        n = self.world * self.capacity * words
+        return self.arena[off: off + 4 * n].view(torch.float32).view(self.world * self.capacity, words)
+
+    def unpack(self, slot: int):
+        return unpack_gathered(self.gathered(slot), self.batch, self.world, self.max_rows)
+
+    def error(self) -> int:
+        """Non-zero after a peer failed to answer within the kernel's time-out (one host sync)."""
+        return int(self.arena[:8].view(torch.int64)[0].item())
+
+
 def unpack_gathered(gathered: torch.Tensor, batch: int, world: int, max_rows: int):
     """Inverse of pack_shard over the concatenation of all ranks' buffers."""
     capacity = gathered.shape[0] // world

@@ -791,3 +791,33 @@ def test_two_step_graphs_in_flight_equal_serial_steps(dev):
                     assert torch.equal(g[i, :n], r[i, :n]), k
             else:
                 assert torch.equal(g, r), k
+
+
+def test_peer_exchange_single_rank_equals_tensor_op_packing(dev):
+    """sharding.PeerExchange with a world of one (the multi-GPU check is tools/exchange_check.py under torchrun):
+    slots, launch counters, the wait kernel and the gathered layout."""
+    import torch.distributed as dist
+    from single_shot_detection_b200 import sharding
+    from single_shot_detection_b200.pipeline import matched_stats
+    import socket
+    with socket.socket() as s_:
+        s_.bind(("127.0.0.1", 0))
+        port = s_.getsockname()[1]
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
+    try:
+        px = sharding.PeerExchange(6, 20, slots=2, device=dev)
+        gen = torch.Generator().manual_seed(2)
+        for rnd in range(3):
+            for k in range(2):
+                dets = torch.rand((6, 20, 6), generator=gen)
+                counts = torch.randint(0, 21, (6,), generator=gen, dtype=torch.int32)
+                a_stats = torch.randint(0, 9, (6, 4), generator=gen, dtype=torch.int32)
+                stats = px.pack_exchange(dets.to(dev), counts.to(dev), a_stats.to(dev), None, k)
+                px.wait(k)
+                want_stats = matched_stats(a_stats, None, counts)
+                want = sharding.pack_shard(dets, counts, want_stats, 6)
+                assert torch.equal(px.gathered(k).cpu().view(torch.int32), want.view(torch.int32)), (rnd, k)
+                assert torch.equal(stats.cpu(), want_stats)
+        assert px.error() == 0
+    finally:
+        dist.destroy_process_group()
