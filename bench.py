@@ -224,7 +224,15 @@ def run_ours(args):
     # graph hung on this stack).
     px = None
     if world > 1 and os.environ.get("SSD_EXCHANGE", "peer") != "nccl":
-        px = sharding.PeerExchange(B * world, w.max_total, slots=nsets)
+        try:
+            px = sharding.PeerExchange(B * world, w.max_total, slots=nsets)
+            ok = torch.tensor([1], device=dev)
+        except Exception as e:  # noqa: BLE001  (no peer access / IPC on this box: every rank must take the same route)
+            print(f"[bench] peer exchange unavailable on rank {rank}: {e!r}", file=sys.stderr)
+            px, ok = None, torch.tensor([0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok) == 0:
+            px = None
     for k, (pipe, (packed, scores_d, locs_d)) in enumerate(zip(pipes, dev_sets)):
         if px is not None:
             outs.append(pipe.capture(packed, anchors_dev, scores_d, locs_d, exchange=(px, k)))
