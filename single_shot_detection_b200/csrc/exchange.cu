@@ -84,14 +84,12 @@ __device__ __forceinline__ void st_release_sys(long long* p, long long v) {
     asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// spin until every flag[k][r] (r < world, LOCAL memory) has reached `need`; false on time-out
-__device__ __forceinline__ bool wait_flags(long long* hdr, int k, int world, long long need) {
+// spin until flag[k][r] (LOCAL memory, written by rank r) has reached `need`; false on time-out
+__device__ __forceinline__ bool wait_flag(long long* hdr, int k, int r, long long need) {
     const unsigned long long t0 = global_ns();
-    for (int r = 0; r < world; ++r) {
-        while (ld_acquire_sys(hdr + hdr_flag(k, r)) < need) {
-            if (global_ns() - t0 > kSpinLimitNs) { hdr[0] = 1; return false; }
-            __nanosleep(100);
-        }
+    while (ld_acquire_sys(hdr + hdr_flag(k, r)) < need) {
+        if (global_ns() - t0 > kSpinLimitNs) { hdr[0] = 1; return false; }
+        __nanosleep(100);
     }
     return true;
 }
@@ -107,10 +105,10 @@ pack_exchange_kernel(const float* __restrict__ dets, const int32_t* __restrict__
     __shared__ long long s_n;
     __shared__ int s_last;
     long long* hdr = reinterpret_cast<long long*>(peers.base[rank]);
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < world) {                             // one thread per peer: the polls run in parallel
         const long long n = hdr[hdr_count(slot)];          // only the last CTA of the previous launch wrote it
-        wait_flags(hdr, slot, world, n);                   // every peer has finished its launch n of this slot
-        s_n = n;
+        wait_flag(hdr, slot, threadIdx.x, n);              // that peer has finished its launch n of this slot
+        if (threadIdx.x == 0) s_n = n;
     }
     __syncthreads();
     const int words = max_total * 6 + 5;
@@ -149,7 +147,7 @@ pack_exchange_kernel(const float* __restrict__ dets, const int32_t* __restrict__
 __global__ void exchange_wait_kernel(long long* hdr, int world, int slot) {
     griddep_wait();
     griddep_launch_dependents();
-    if (threadIdx.x == 0 && blockIdx.x == 0) wait_flags(hdr, slot, world, hdr[hdr_count(slot)]);
+    if (threadIdx.x < world && blockIdx.x == 0) wait_flag(hdr, slot, threadIdx.x, hdr[hdr_count(slot)]);
 }
 
 }  // namespace ssd
