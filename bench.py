@@ -430,6 +430,8 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.cuda.synchronize()
+        if px is not None:
+            px.close()
         dist.barrier()
         dist.destroy_process_group()
 

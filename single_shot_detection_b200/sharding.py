@@ -86,13 +86,15 @@ class PeerExchange:
         self.arena = torch.zeros((nbytes,), dtype=torch.uint8, device=self.device)          # zero-filled once
         torch.cuda.synchronize(self.device)
         handles = [None] * self.world
-        dist.all_gather_object(handles, reduce_tensor(self.arena), group=group)
+        if self.world > 1:
+            dist.all_gather_object(handles, reduce_tensor(self.arena), group=group)
         self._peers = []                                   # keep the mappings alive
         ptrs = (ctypes.c_void_p * self.world)()
-        for r, (rebuild, args) in enumerate(handles):
+        for r, handle in enumerate(handles):
             if r == self.rank:
                 t = self.arena
             else:
+                rebuild, args = handle
                 # torch would open the IPC handle under the EXPORTER's device index; the kernels that use the
                 # mapping run on THIS device, so it is opened here (cudaIpcOpenMemHandle then enables peer access
                 # between this device and the exporter's lazily) -- argument 6 of rebuild_cuda_tensor is the device
@@ -104,7 +106,18 @@ class PeerExchange:
             self._peers.append(t)
             ptrs[r] = t.data_ptr()
         self._ptrs = ptrs
-        dist.barrier(group=group)                          # every rank has mapped every arena
+        if self.world > 1:
+            dist.barrier(group=group)                      # every rank has mapped every arena
+
+    def close(self) -> None:
+        """Drop the mappings of the peers' arenas (collective: every rank calls it before it exits, so that no
+        exporter goes away while its memory is still mapped elsewhere)."""
+        import gc
+        torch.cuda.synchronize(self.device)
+        self._peers = [t for r, t in enumerate(self._peers) if r == self.rank]
+        gc.collect()
+        if self.world > 1:
+            dist.barrier(group=self.group)
 
     def pack_exchange(self, dets: torch.Tensor, counts: torch.Tensor, assign_stats: Optional[torch.Tensor],
                       mining_stats: Optional[torch.Tensor], slot: int):

@@ -47,6 +47,7 @@ def main():
                     print(f"rank {rank} round {rnd} slot {k}: gathered buffer differs", flush=True)
         dist.barrier()
     err = px.error()
+    px.close()
     flag = torch.tensor([0 if ok and err == 0 else 1], device=dev)
     dist.all_reduce(flag)
     if rank == 0:
