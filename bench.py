@@ -1,18 +1,21 @@
 #!/usr/bin/env python
 """Benchmark of the anchor pipeline (BASELINE.json metric: images/sec target-assign+NMS, SSD300 b32).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference] [--in-flight F]
 
 A step = one pass of the hot path over one batch of synthetic input:
-    encode_ground_truth -> sampler (+ .long()) -> to_centroids + encode_box (in place) -> postprocess.
+    encode_ground_truth -> sampler -> to_centroids + encode_box (in place) -> postprocess
+    [-> exchange of detections + statistics between the ranks, N > 1].
 
-ours:       `value`  = device-resident inputs, the step replayed from a CUDA graph, timed with CUDA
-                       events on the launching stream (max over ranks);
+ours:       `value`  = device-resident inputs, every step replayed from a CUDA graph, F consecutive steps in
+                       flight on F streams (default 4), timed with CUDA events (max over ranks);
+            `serial` = the same K steps strictly one after the other on one stream;
             `e2e`    = the same step through the reference-shaped Python API with HOST buffers:
                        pinned scores/locs and the ground-truth list are copied H2D and the padded
                        detections + counts + statistics are read back D2H inside the timed region;
-            `roofline` = the dominant kernel (score_pass1 / mining_loss, picked from the launch list
-                       in profiles/) timed alone with CUDA events against MEASURED_PEAKS.json;
+            `roofline` = the logit-streaming kernel of the step (score_pass1, with the sampler's
+                       criterion output) timed alone with CUDA events against MEASURED_PEAKS.json,
+                       the sampler's own streaming kernel beside it;
             `cpu_baseline` = the CPU oracle (same torch CPU ops as the reference) on a bounded sample.
 reference:  the reference's CPU algorithm (oracle port, torch CPU ops + torchvision NMS) on the
             host cores, same metric / config.
