@@ -191,7 +191,7 @@ def run_ours(args):
     A, C = int(anchors.shape[0]), w.num_score_cols
     per_set = B * A * (C + 4) * 4
     nsets = max(2, -(-int(1.5 * L2_BYTES) // per_set))
-    nsets = min(nsets, 16)
+    nsets = min(max(nsets, args.in_flight), 16)          # one input set per step in flight (HBM is not the limit)
 
     # synthetic inputs, one seed per (rank, set)
     host_sets = []
