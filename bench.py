@@ -236,11 +236,21 @@ def run_ours(args):
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if int(ok) == 0:
             px = None
+    conc = in_flight > 1
     for k, (pipe, (packed, scores_d, locs_d)) in enumerate(zip(pipes, dev_sets)):
         if px is not None:
-            outs.append(pipe.capture(packed, anchors_dev, scores_d, locs_d, exchange=(px, k)))
+            outs.append(pipe.capture(packed, anchors_dev, scores_d, locs_d, exchange=(px, k), concurrent=conc))
         else:
-            outs.append(pipe.capture(packed, anchors_dev, scores_d, locs_d, shard_capacity=cap))
+            outs.append(pipe.capture(packed, anchors_dev, scores_d, locs_d, shard_capacity=cap, concurrent=conc))
+    # the strictly serial number uses graphs captured for a step that runs alone (single GPU; with several ranks the
+    # serial loop replays the in-flight graphs)
+    pipes_serial = pipes
+    if conc and world == 1:
+        pipes_serial = []
+        for packed, scores_d, locs_d in dev_sets:
+            ps = AnchorPipeline(w.cfg())
+            ps.capture(packed, anchors_dev, scores_d, locs_d)
+            pipes_serial.append(ps)
     torch.cuda.synchronize()
 
     # the one exchange step of the path (detections + counts + stats, one collective per step) runs
@@ -265,7 +275,7 @@ def run_ours(args):
     def device_step(i, serial=False):
         k = i % nsets
         if serial or in_flight == 1:
-            pipes[k].replay()
+            pipes_serial[k].replay()
             if world > 1 and px is None:
                 return gather.submit(outs[k].shard)
             return outs[k].dets, outs[k].counts, outs[k].assign_stats

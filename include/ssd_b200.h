@@ -74,6 +74,10 @@ SSD_API size_t ssd_b200_timing_report(char* buf, size_t capacity);
  * uint64 in device memory (initialise every pair to {UINT64_MAX, 0}); every kernel of the library
  * then records min(start) / max(end) of %globaltimer in its slot -- also inside a replayed CUDA
  * graph.  Pass NULL to switch the trace off (the default). */
+/* Resident CTAs per SM of the logit-streaming kernels (process-wide, read when a launch is issued or captured):
+ * 0 = automatic (fill the shared memory: fastest for a step that runs alone); 1 leaves room for the kernels of
+ * other steps when several step graphs are in flight. */
+SSD_API int ssd_b200_set_stream_ctas_per_sm(int ctas);
 SSD_API int ssd_b200_trace_enable(unsigned long long* device_slots);
 SSD_API int ssd_b200_trace_slots(void);
 

@@ -78,6 +78,7 @@ _SIGNATURES = {
     "ssd_generalized_iou": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "ssd_positive_mask": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "ssd_b200_launch_count": (ctypes.c_ulonglong, []),
+    "ssd_b200_set_stream_ctas_per_sm": (c_int, [c_int]),
     "ssd_mining_keys": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ssd_hard_negative_workspace_bytes": (c_size_t, [c_int, c_int]),
     "ssd_hard_negative_mask": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_int, c_double,

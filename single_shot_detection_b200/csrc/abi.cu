@@ -34,6 +34,19 @@ int sm_count() {
     return cached[dev];
 }
 
+// Resident CTAs per SM of the logit-streaming kernels: 0 = as many as shared memory allows (best for a step that
+// runs alone), 1 = one per SM, which leaves shared memory for the NMS / selection CTAs of OTHER steps when
+// several step graphs are in flight (bench.py: 34.6 -> 32.2 us per step with four in flight, 64 -> 68 us alone).
+// Read when a launch is issued or captured.
+static int g_stream_ctas = -1;
+int stream_ctas_override() {
+    if (g_stream_ctas < 0) {
+        const char* e = getenv("SSD_CTAS_PER_SM");
+        g_stream_ctas = (e && e[0]) ? atoi(e) : 0;
+    }
+    return g_stream_ctas;
+}
+
 __global__ void probe_kernel(int* out) { *out = 100; }
 
 // Scratch zeroing as a KERNEL node: inside a captured step graph a memset node in front of a branch was
@@ -167,3 +180,9 @@ extern "C" size_t ssd_b200_timing_report(char* buf, size_t capacity) {
 }
 
 SSD_DEFINE_TRACE_SETTER(set_trace_abi)
+
+extern "C" int ssd_b200_set_stream_ctas_per_sm(int ctas) {
+    SSD_REQUIRE(ctas >= 0 && ctas <= 8, SSD_ERR_INVALID_ARGUMENT, "ssd_b200_set_stream_ctas_per_sm: %d outside 0..8", ctas);
+    ssd::g_stream_ctas = ctas;
+    return SSD_OK;
+}

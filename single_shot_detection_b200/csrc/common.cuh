@@ -33,6 +33,7 @@ int cuda_fail(cudaError_t e, const char* what);
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 __host__ __device__ inline size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 int sm_count();
+int stream_ctas_override();        // 0 = automatic (ssd_b200_set_stream_ctas_per_sm / SSD_CTAS_PER_SM)
 cudaError_t zero_async(void* p, size_t bytes, cudaStream_t st);   // scratch zeroing as a kernel node (abi.cu)
 void count_launch(int n = 1);      // bumps the library-wide kernel launch counter (ssd_b200_launch_count)
 // diagnostics: per-launch CUDA-event timing when enabled through ssd_b200_timing_enable()

@@ -351,7 +351,7 @@ __device__ __forceinline__ size_t stream_smem_bytes_dev(const ScoreGrid& g) { re
 inline int stream_grid(ScoreGrid& g, size_t extra_smem = 0) {
     int per_sm = (int)((size_t)(224 * 1024) / (stream_smem_bytes(g) + extra_smem + 1024));
     if (per_sm > 4) per_sm = 4;
-    per_sm = env_int("SSD_CTAS_PER_SM", per_sm);                                // tuning knob
+    if (stream_ctas_override() > 0) per_sm = stream_ctas_override();            // see abi.cu
     if (per_sm < 1) per_sm = 1;
     int grid = per_sm * sm_count();
     if (grid > g.num_items) grid = g.num_items;

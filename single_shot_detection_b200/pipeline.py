@@ -298,9 +298,24 @@ class AnchorPipeline:
         return self._side
 
     def capture(self, packed: PackedGroundTruth, anchors_dev, scores_dev, locs_dev, warmup: int = 2,
-                shard_capacity: Optional[int] = None, gather: bool = False, exchange=None) -> "StepOutput":
+                shard_capacity: Optional[int] = None, gather: bool = False, exchange=None,
+                concurrent: bool = False) -> "StepOutput":
         """Record ``step_device`` on these (static) buffers into a CUDA graph; returns the outputs
-        the replays will keep overwriting."""
+        the replays will keep overwriting.
+
+        ``concurrent``: the graph will be replayed while other step graphs are in flight on other streams: the
+        logit-streaming kernels are captured with ONE resident CTA per SM, which leaves shared memory for the
+        NMS / selection CTAs of the other steps (slower for a step that runs alone, faster in aggregate)."""
+        from . import _native as N
+        if concurrent:
+            N.check(N.lib().ssd_b200_set_stream_ctas_per_sm(1))
+        try:
+            return self._capture(packed, anchors_dev, scores_dev, locs_dev, warmup, shard_capacity, gather, exchange)
+        finally:
+            if concurrent:
+                N.check(N.lib().ssd_b200_set_stream_ctas_per_sm(0))
+
+    def _capture(self, packed, anchors_dev, scores_dev, locs_dev, warmup, shard_capacity, gather, exchange):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
