@@ -152,3 +152,18 @@ def test_giou_loss_gradient_random_vs_oracle_autograd(dev):
         np.testing.assert_allclose(float(loss3[2]), float(ref), rtol=REL)
         np.testing.assert_allclose(grad_locs.cpu().numpy().reshape(batch, -1), ref_locs.grad.numpy().reshape(batch, -1),
                                    rtol=1e-4, atol=1e-7)
+
+
+def test_match_bipartite_vs_oracle(dev):
+    """detection/matcher.py:7-31 (dead code in the reference, kept importable): greedy one-to-one matching."""
+    from single_shot_detection_b200 import matcher
+    gen = torch.Generator().manual_seed(8)
+    for g, a in [(1, 7), (5, 40), (12, 300)]:
+        w = torch.rand((g, a), generator=gen)
+        w[torch.rand((g, a), generator=gen) < 0.3] = 0.0
+        w[:, 0] += 0.01                                        # every box keeps a positive weight
+        ref_box, ref_anchor = ora.greedy_bipartite_match(w.clone())
+        box, anchor = matcher.match_bipartite(w.to(dev))
+        assert torch.equal(box.cpu(), ref_box) and torch.equal(anchor.cpu(), ref_anchor), (g, a)
+    with pytest.raises(AssertionError):
+        matcher.match_bipartite(torch.zeros((2, 5), device=dev))
