@@ -178,9 +178,10 @@ SSD_API int ssd_positive_mask(const int64_t* target_classes, int64_t count, uint
  * ---------------------------------------------------------------------------------------- */
 SSD_API size_t ssd_hard_negative_workspace_bytes(int batch, int num_anchors);
 /* First half only: the streamed mining criterion folded with the class id into one sortable
- * uint32 key per anchor (0 = ignored, 0xFFFFFFFF = positive, else ordered(-log_softmax[0])), plus
- * the per-image loss histograms the selection reads (kept inside the workspace, same size query).
- * This is the HBM-bound kernel of the sampler; exported so it can be timed / profiled alone. */
+ * uint32 key per anchor (0 = ignored, 0xFFFFFFFF = positive, else ordered(-log_softmax[0])).  One launch,
+ * no atomics, no memset (the selection builds its loss histogram itself); the workspace argument is kept
+ * for ABI stability and not touched.  This is the HBM-bound kernel of the sampler; exported so it can be
+ * timed / profiled alone. */
 SSD_API int ssd_mining_keys(const float* logits, const int64_t* target_classes, int batch, int num_anchors,
                     int num_cols, uint32_t* keys_out, void* workspace, size_t workspace_bytes, void* stream);
 SSD_API int ssd_hard_negative_mask(const float* logits, const int64_t* target_classes,
