@@ -460,12 +460,13 @@ def detections_from_scores(fg_probs: torch.Tensor, corner_boxes: torch.Tensor,
         for c in range(num_fg):
             col = probs[:, c]
             above = col > score_threshold                               # :62 (fp32 compare)
-            cand = torch.nonzero(above).view(-1)
             (b_keep, s_keep), keep, subset = class_nms(boxes[above], col[above], overlap_threshold,
                                                        max_per_class, canonical, use_torchvision,
                                                        None if soft_sigma is None else (score_threshold, soft_sigma))
-            src = cand if subset is None else cand[subset]
-            per_class.append(src[keep])
+            if return_keep:             # bookkeeping the reference does not do: only when asked for
+                cand = torch.nonzero(above).view(-1)
+                src = cand if subset is None else cand[subset]
+                per_class.append(src[keep])
             cls = torch.full((s_keep.shape[0], 1), float(c + 1))        # :66
             rows.append(torch.cat((b_keep, cls, s_keep.unsqueeze(1)), dim=-1))
         picked = torch.cat(rows, dim=0)
@@ -590,32 +591,46 @@ def giou_localization_loss(locs: torch.Tensor, priors: torch.Tensor, target: tor
 # whole timed region (SURVEY.md §8 d) as the reference executes it on the CPU
 # --------------------------------------------------------------------------------------
 def run_step(gt_per_image, anchors, scores, locs, cfg, *, canonical: bool = False,
-             use_torchvision: bool = True):
+             use_torchvision: bool = True, stage_seconds: Optional[dict] = None):
     """assign -> sampler -> to_centroids+encode (in place) -> postprocess, CPU.
 
     ``cfg`` keys: matched_threshold, unmatched_threshold, sampler ('hard_negative_mining' |
     'naive_sampler'), ratio, min_neg, xy_scale, wh_scale, eps, score_threshold,
     overlap_threshold, max_per_class, max_total, converter.
     With the defaults (reference tie behaviour, torchvision NMS) this executes the same torch
-    CPU ops in the same order as the reference and is what ``bench.py`` times as the CPU arm.
+    CPU ops in the same order as the reference -- including the NaN assertion that closes
+    target_assigner.py:60-61 -- and is what ``bench.py`` times as the CPU arm.  ``stage_seconds``
+    (a dict) accumulates the wall time of the four stages of SURVEY.md 8(d).
     """
+    import time
+    clock = time.perf_counter
     b = len(gt_per_image)
     a = anchors.shape[0]
+    t0 = clock()
     target = assign_targets(gt_per_image, anchors, cfg["matched_threshold"],
                             cfg["unmatched_threshold"])
-    cls = target[..., CLS_COL].long()
+    assert not positive_rows_have_nan(target)                            # target_assigner.py:60-61
+    t1 = clock()
+    cls = target[..., CLS_COL].long()                                    # multibox_loss.py:49
     logits = scores.view(b, a, -1)
     if cfg["sampler"] == "hard_negative_mining":
         mask = mine_hard_negatives(logits, cls, cfg["ratio"], cfg["min_neg"], canonical=canonical)
     else:
         mask = positives_mask(cls)
+    t2 = clock()
     tl = target[..., LOC_LO:LOC_HI]
     centroids_from_corners(tl, inplace=True)
     encode_boxes(tl, anchors, cfg["xy_scale"], cfg["wh_scale"], cfg.get("eps", 1e-8), inplace=True)
+    t3 = clock()
     dets = postprocess(scores, locs, anchors, xy_scale=cfg["xy_scale"], wh_scale=cfg["wh_scale"],
                        score_threshold=cfg["score_threshold"],
                        overlap_threshold=cfg["overlap_threshold"],
                        max_per_class=cfg["max_per_class"], max_total=cfg["max_total"],
                        converter=cfg["converter"], canonical=canonical,
                        use_torchvision=use_torchvision)
+    t4 = clock()
+    if stage_seconds is not None:
+        for key, dt in (("encode_ground_truth", t1 - t0), ("sampler", t2 - t1), ("to_centroids+encode_box", t3 - t2),
+                        ("postprocess", t4 - t3)):
+            stage_seconds[key] = stage_seconds.get(key, 0.0) + dt
     return target, mask, dets

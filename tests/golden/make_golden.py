@@ -160,6 +160,99 @@ def run_pipeline_case(name: str, w: wl.Workload, gt, anchors, scores, locs, out_
     print(f"  pipeline_{name}: B={b} A={a} C={c} dets={[int(d.shape[0]) for d in dets]}")
 
 
+# BASELINE.json configs at their full anchor / class shapes (B = 2 images each).  The inputs are NOT stored --
+# random head outputs do not compress (16 MB for SSD512) -- they are regenerated by
+# ``workloads.make_inputs(w, seed, batch)`` and pinned by SHA-256; only the reference's compact outputs
+# are kept: matched indices (int16), targets (mostly zero rows), bit-packed masks, detections, the anchor of
+# every kept row, the coded boxes of the matched rows + a sample of the others, the loss triple.
+CONFIG_CASES = [("ssd300_voc_b32", 2, 23), ("ssd512_coco_b32", 2, 23), ("retina500_coco_b32", 2, 23),
+                ("m2det512_coco_b256", 2, 23)]
+
+
+def _sha(t: torch.Tensor) -> str:
+    import hashlib
+    return hashlib.sha256(t.contiguous().numpy().tobytes()).hexdigest()
+
+
+def run_config_case(name: str, batch: int, seed: int, out_dir: str):
+    w = wl.WORKLOADS[name]
+    anchors, gt, scores, locs = wl.make_inputs(w, seed=seed, batch=batch)
+    ref_anchors = reference_anchors(w)
+    assert torch.equal(ref_anchors, anchors), name          # the package's table IS the reference's (anchors.npz)
+    b, a, c = batch, anchors.shape[0], w.num_score_cols
+    assigner = RefTargetAssigner(w.matched_threshold, w.unmatched_threshold)
+    target = assigner.encode_ground_truth(gt, anchors)
+    corner_anchors = ref_box_utils.to_corners(anchors)
+    match_idx = torch.full((b, a), ref_matcher.NOT_MATCHED, dtype=torch.long)
+    for i, g in enumerate(gt):
+        if len(g):
+            match_idx[i] = ref_matcher.match_per_prediction(ref_box_utils.iou(g[:, :4], corner_anchors),
+                                                            w.matched_threshold, w.unmatched_threshold)
+    cls = target[..., 4].long()
+    logits = scores.view(b, a, c)
+    # detection/init.py:90-92 builds the sampler from the config; the reference function is called directly here
+    hnm_mask = ref_sampler.hard_negative_mining(logits, cls, w.ratio, w.min_neg)
+    naive_mask = ref_sampler.naive_sampler(logits, cls)
+
+    coder = RefBoxCoder(w.xy_scale, w.wh_scale, w.eps)
+    enc = target.clone()
+    tl = enc[..., 0:4]
+    ref_box_utils.to_centroids(tl, inplace=True)                       # multibox_loss.py:81
+    coder.encode_box(tl, anchors, inplace=True)                        # multibox_loss.py:82
+    flat_cls = target[..., 4].reshape(-1)
+    rows = torch.nonzero(flat_cls != 0).flatten()
+    sample = torch.arange(0, b * a, 37)
+    enc_rows = torch.unique(torch.cat([rows, sample]))
+    enc_vals = tl.reshape(-1, 4)[enc_rows]
+
+    nms_cfg = {"max_per_class": w.max_per_class, "overlap_threshold": w.overlap_threshold}
+    post = RefPostprocessor(coder, w.score_threshold, nms_cfg, score_converter=w.converter, max_total=w.max_total)
+    dets = post.postprocess((scores, locs), anchors)
+    post_all = RefPostprocessor(coder, w.score_threshold, nms_cfg, score_converter=w.converter, max_total=None)
+    dets_all = post_all.postprocess((scores, locs), anchors)
+
+    # the anchor behind every kept row, from the reference's own intermediates (postprocessor.py:44-55)
+    probs = post.score_converter_fn(logits)
+    fg = probs[..., 1:] if w.converter == "SOFTMAX" else probs
+    corners = ref_box_utils.to_corners(coder.decode_box(locs.view(b, a, 4), anchors, inplace=torch.tensor(0)))
+    det_anchor = []
+    for i, d in enumerate(dets_all):
+        out = torch.empty((d.shape[0],), dtype=torch.int32)
+        for r in range(d.shape[0]):
+            col = int(d[r, 4]) - 1
+            hit = torch.nonzero((fg[i, :, col] == d[r, 5]) & (corners[i] == d[r, :4]).all(dim=1)).flatten()
+            assert hit.numel() >= 1, (name, i, r)
+            out[r] = int(hit[0])
+        det_anchor.append(out)
+
+    if w.converter == "SOFTMAX":
+        sampler = functools.partial(ref_sampler.hard_negative_mining,
+                                    negative_per_positive_ratio=w.ratio, min_negative_per_image=w.min_neg)
+        crit = RefMultiboxLoss(sampler, coder, {"name": "CrossEntropyLoss"}, {"name": "SmoothL1Loss"})
+    else:
+        crit = RefMultiboxLoss(ref_sampler.naive_sampler, coder,
+                               {"name": "SigmoidFocalLoss", "gamma": 2.0, "alpha": 0.25}, {"name": "SmoothL1Loss"})
+    loss3 = [float(x) for x in crit((scores, locs), anchors, target.clone())]
+
+    gt_flat, gt_off = ragged(gt)
+    det_flat, det_off = ragged(dets)
+    det_all_flat, det_all_off = ragged(dets_all)
+    assert int(match_idx.max()) < 32767
+    blob = dict(
+        workload=np.array(w.name), regen_seed=np.array(seed), regen_batch=np.array(batch),
+        sha_scores=np.array(_sha(scores)), sha_locs=np.array(_sha(locs)), sha_anchors=np.array(_sha(anchors)),
+        gt_flat=gt_flat, gt_off=gt_off, gt_cols=np.array(6),
+        thresholds=np.array([w.matched_threshold, w.unmatched_threshold], dtype=np.float64),
+        target=target.numpy(), match_idx=match_idx.numpy().astype(np.int16),
+        hnm_mask=np.packbits(hnm_mask.numpy(), axis=1), naive_mask=np.packbits(naive_mask.numpy(), axis=1),
+        enc_rows=enc_rows.numpy().astype(np.int32), enc_vals=enc_vals.numpy(),
+        det_flat=det_flat, det_off=det_off, det_all_flat=det_all_flat, det_all_off=det_all_off,
+        det_all_anchor=torch.cat(det_anchor).numpy(), loss3=np.array(loss3, dtype=np.float64))
+    np.savez_compressed(os.path.join(out_dir, f"pipeline_{name}.npz"), **blob)
+    print(f"  pipeline_{name}: B={b} A={a} C={c} dets={[int(d.shape[0]) for d in dets]} "
+          f"kept={[int(d.shape[0]) for d in dets_all]} positives={int((hnm_mask & naive_mask).sum())}")
+
+
 def edge_case_inputs(w: wl.Workload, anchors: torch.Tensor, gen: torch.Generator):
     """Hand-made ground truth exercising the matcher's tie rules and the API edge cases."""
     img = float(w.img)
@@ -234,6 +327,11 @@ def main():
     out_dir = HERE
     torch.manual_seed(23)
     torch.set_num_threads(1)
+    if "--configs-only" in sys.argv:
+        print("BASELINE config cases")
+        for name, batch, seed in CONFIG_CASES:
+            run_config_case(name, batch, seed, out_dir)
+        return
 
     print("anchor tables")
     blob = {}
@@ -273,6 +371,10 @@ def main():
 
     print("nms cases")
     np.savez_compressed(os.path.join(out_dir, "nms.npz"), **nms_cases(gen))
+
+    print("BASELINE config cases")
+    for name, batch, seed in CONFIG_CASES:
+        run_config_case(name, batch, seed, out_dir)
 
     meta = {"torch": torch.__version__, "torchvision": torchvision.__version__,
             "numpy": np.__version__, "reference_root": REF, "seed": 23}

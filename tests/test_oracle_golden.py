@@ -70,8 +70,8 @@ def test_box_coding(case):
     if case.full:
         assert torch.equal(tl, case.t("centroids_inplace"))
     ora.encode_boxes(tl, case.anchors, case.w.xy_scale, case.w.wh_scale, case.w.eps, inplace=True)
-    torch.testing.assert_close(tl, case.enc_inplace, rtol=1e-6, atol=1e-6, equal_nan=True)
-    assert torch.equal(tl[..., :2], case.enc_inplace[..., :2])          # xy has no transcendental
+    torch.testing.assert_close(case.enc_view(tl), case.enc_inplace, rtol=1e-6, atol=1e-6, equal_nan=True)
+    assert torch.equal(case.enc_view(tl)[..., :2], case.enc_inplace[..., :2])          # xy has no transcendental
     if not case.full:
         return
     cen = ora.centroids_from_corners(case.target[..., 0:4])
@@ -124,6 +124,24 @@ def test_postprocess_end_to_end(case, max_total):
             ms = m[torch.argsort(m[:, 5], descending=True, stable=True)]
             assert len(torch.unique(r[:, 5])) < r.shape[0] or torch.allclose(ms, r, rtol=1e-6, atol=1e-6)
         torch.testing.assert_close(torch.sort(m[:, 5])[0], torch.sort(r[:, 5])[0], rtol=1e-6, atol=1e-6)
+
+
+def test_keep_anchors_of_config_cases(case):
+    """BASELINE-config fixtures: the oracle keeps the same anchors, class by class and in the same order, as the
+    reference did (the anchor of every kept row was recovered from the reference's own intermediates)."""
+    if case.det_all_anchor is None:
+        pytest.skip("no kept-anchor list in this fixture")
+    w = case.w
+    fg = ora.convert_scores(case.scores.view(case.B, case.A, case.C), w.converter)      # foreground columns
+    if bool(ora.class_topk_boundary_tie(fg, w.score_threshold, w.max_per_class).any()):
+        pytest.skip("score tie at a top-k boundary: the reference answer is not unique")
+    corners = ora.corners_from_centroids(ora.decode_boxes(case.locs.view(case.B, case.A, 4), case.anchors,
+                                                          w.xy_scale, w.wh_scale))
+    dets, keep = ora.detections_from_scores(fg, corners, w.score_threshold, w.overlap_threshold, w.max_per_class,
+                                            None, canonical=True, use_torchvision=False, return_keep=True)
+    for i in range(case.B):
+        assert torch.cat(keep[i]).tolist() == case.det_all_anchor[i].tolist(), i
+        torch.testing.assert_close(dets[i], case.dets_all[i], rtol=1e-6, atol=1e-6)
 
 
 def test_postprocess_stage_exact(case):
