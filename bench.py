@@ -1,24 +1,33 @@
 #!/usr/bin/env python
 """Benchmark of the anchor pipeline (BASELINE.json metric: images/sec target-assign+NMS, SSD300 b32).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference] [--in-flight F]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+                    [--in-flight F] [--scaling weak|strong] [--no-config5] [--no-cpu-baseline]
 
 A step = one pass of the hot path over one batch of synthetic input:
     encode_ground_truth -> sampler -> to_centroids + encode_box (in place) -> postprocess
-    [-> exchange of detections + statistics between the ranks, N > 1].
+    -> exchange of detections + statistics between the ranks (the same kernels also run at N = 1).
 
 ours:       `value`  = device-resident inputs, every step replayed from a CUDA graph, F consecutive steps in
-                       flight on F streams (default 4), timed with CUDA events (max over ranks);
-            `serial` = the same K steps strictly one after the other on one stream;
+                       flight on F streams (default 4), timed with CUDA events (max over ranks).  The timed region
+                       is K steps repeated until it lasts >= 50 ms (`timed_steps`);
+            `serial` = the same steps strictly one after the other on one stream;
             `e2e`    = the same step through the reference-shaped Python API with HOST buffers:
                        pinned scores/locs and the ground-truth list are copied H2D and the padded
                        detections + counts + statistics are read back D2H inside the timed region;
             `roofline` = the logit-streaming kernel of the step (score_pass1, with the sampler's
-                       criterion output) timed alone with CUDA events against MEASURED_PEAKS.json,
-                       the sampler's own streaming kernel beside it;
-            `cpu_baseline` = the CPU oracle (same torch CPU ops as the reference) on a bounded sample.
+                       criterion output) timed alone with CUDA events against MEASURED_PEAKS.json, the
+                       sampler's own streaming kernel beside it, and `roofline.step`: SURVEY.md §8(d)'s
+                       algorithmic bytes per batch / step time / peak for the whole step;
+            `cpu_baseline` = the CPU oracle (same torch CPU ops as the reference) on a bounded sample, with all
+                       host threads, with one thread, and per stage;
+            `config5_strong` = BASELINE configs[4] as north_star states it: M2Det-512 b256 sharded by image over the
+                       N ranks (256 / N images per GPU), with a check that the gathered buffer of every rank equals a
+                       single-GPU run of the same global batch bit for bit (`gather_parity`).
 reference:  the reference's CPU algorithm (oracle port, torch CPU ops + torchvision NMS) on the
             host cores, same metric / config.
+
+--scaling weak (default): every rank owns a full batch of the workload; strong: the workload's batch is sharded.
 
 Inputs rotate over several independent input sets whose total size exceeds the 126 MB L2, so a
 timed iteration never finds its logits in cache.
@@ -26,7 +35,9 @@ timed iteration never finds its logits in cache.
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -43,6 +54,9 @@ import torch  # noqa: E402
 from single_shot_detection_b200 import workloads as wl  # noqa: E402
 
 L2_BYTES = 126 * 1024 * 1024
+MIN_TIMED_MS = 50.0
+METRIC = "images/sec target-assign+NMS"
+REGION = "encode_ground_truth + sampler + to_centroids/encode_box + postprocess + exchange(dets,stats)"
 
 
 def parse_args():
@@ -52,8 +66,11 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--workload", default=wl.HEADLINE)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--cpu-sample-images", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config5", action="store_true", help="skip the M2Det b256 strong-scaling leg")
+    ap.add_argument("--no-e2e", action="store_true", help="(diagnostics) skip the host-buffer leg")
     ap.add_argument("--in-flight", type=int, default=4,
                     help="step graphs in flight on as many streams (1 = strictly one step after the other)")
     return ap.parse_args()
@@ -65,6 +82,15 @@ def measured_peaks():
         with open(path) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def config_block(w: wl.Workload, anchors: int, images_per_gpu: int, world: int, extra=None):
+    """The `config` object: the same keys in both arms."""
+    cfg = {"workload": w.name, "anchors": anchors, "score_cols": w.num_score_cols, "images_per_gpu": images_per_gpu,
+           "global_batch": images_per_gpu * world, "converter": w.converter, "sampler": w.sampler, "region": REGION}
+    if extra:
+        cfg.update(extra)
+    return cfg
 
 
 # --------------------------------------------------------------------------------------------
@@ -122,18 +148,37 @@ class ClockSampler:
 # CPU arm: the reference's algorithm on the host cores (oracle port)
 # --------------------------------------------------------------------------------------------
 def time_cpu_oracle(w: wl.Workload, images: int, steps: int, warmup: int, threads: int):
+    """-> (best images/s, mean images/s, per-stage ms of the best step)"""
     from oracle import anchor_pipeline_oracle as ora
     torch.set_num_threads(threads)
     anchors, gt, scores, locs = wl.make_inputs(w, seed=23, batch=images)
     cfg = w.cfg()
     for _ in range(warmup):
         ora.run_step(gt, anchors, scores, locs, cfg, canonical=False, use_torchvision=True)
-    times = []
+    times, stages = [], []
     for _ in range(steps):
+        st = {}
         t0 = time.perf_counter()
-        ora.run_step(gt, anchors, scores, locs, cfg, canonical=False, use_torchvision=True)
+        ora.run_step(gt, anchors, scores, locs, cfg, canonical=False, use_torchvision=True, stage_seconds=st)
         times.append(time.perf_counter() - t0)
-    return images / min(times), images / (sum(times) / len(times)), sum(times)
+        stages.append(st)
+    best = min(range(len(times)), key=times.__getitem__)
+    return images / times[best], images / (sum(times) / len(times)), {k: 1e3 * v for k, v in stages[best].items()}
+
+
+def cpu_baseline_block(w: wl.Workload, images: int, steps: int, warm: int):
+    cores = os.cpu_count() or 1
+    best, mean, stage_ms = time_cpu_oracle(w, images, steps, warm, cores)
+    best1, mean1, stage_ms1 = time_cpu_oracle(w, images, max(1, min(steps, 2)), 1, 1)
+    torch.set_num_threads(cores)
+    sample = (f"{images} of {w.batch} images per step, {steps} steps + {warm} warm-up, oracle port of the reference "
+              f"(the reference's torch CPU op sequence + torchvision.ops.nms), {cores} torch threads")
+    return {"value": mean, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample, "best": best,
+            "stage_ms_per_sample": stage_ms,
+            "one_thread": {"value": mean1, "best": best1, "cores": 1, "stage_ms_per_sample": stage_ms1},
+            "port_vs_reference": "tools/cpu_arm_check.py (build container, where /root/reference exists): the port "
+                                 "runs at 0.8-1.2x the reference's own modules on the same inputs (timer noise of "
+                                 "a shared host; same ops)"}
 
 
 def run_reference(args):
@@ -142,23 +187,20 @@ def run_reference(args):
     if rank != 0:
         return
     w = wl.WORKLOADS[args.workload]
-    cores = os.cpu_count() or 1
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     images = min(args.cpu_sample_images, w.batch)
     steps = max(1, min(args.steps, 5))
     warm = max(1, min(args.warmup, 1))
-    best, mean, total = time_cpu_oracle(w, images, steps, warm, cores)
+    cb = cpu_baseline_block(w, images, steps, warm)
     anchors = wl.build_anchors(w)
-    sample = (f"{images} of {w.batch} images per step, {steps} steps + {warm} warm-up, oracle port of the reference "
-              f"(torch CPU ops + torchvision.ops.nms), {cores} torch threads")
+    per_gpu = w.batch if args.scaling == "weak" else w.batch // max(world, 1)
     line = {
-        "impl": "reference", "metric": "images/sec target-assign+NMS", "value": mean, "unit": "images/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * images / mean,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w.name, "anchors": int(anchors.shape[0]), "score_cols": w.num_score_cols,
-                   "batch": w.batch, "sample_images": images},
-        "cpu_baseline": {"value": mean, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample,
-                         "best": best},
-        "e2e": {"value": mean, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "images/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * images / cb["value"],
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_block(w, int(anchors.shape[0]), per_gpu, max(world, 1), {"sample_images": images}),
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -167,13 +209,150 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------
+class DeviceRunner:
+    """Device-resident steps of one workload: one captured step graph per input set (its last kernel packs the
+    shard and writes it into every rank's gathered buffer), replayed with `in_flight` consecutive steps on as many
+    streams, or strictly one after the other."""
+
+    def __init__(self, w, dev_sets, anchors_dev, in_flight, dist_world):
+        from single_shot_detection_b200 import sharding
+        from single_shot_detection_b200.pipeline import AnchorPipeline
+        self.w, self.dev_sets, self.anchors_dev = w, dev_sets, anchors_dev
+        self.nsets = len(dev_sets)
+        self.in_flight = max(1, min(in_flight, self.nsets))
+        self.world = dist_world
+        batch_local = dev_sets[0][0].batch
+        rows = dev_sets[0][3]
+        conc = self.in_flight > 1
+        self.px = sharding.PeerExchange(batch_local * dist_world, rows, slots=self.nsets)
+        self.pipes, self.outs = [], []
+        for k, (packed, scores_d, locs_d, _) in enumerate(dev_sets):
+            pipe = AnchorPipeline(w.cfg(), workspace_slot=k % self.in_flight)      # own scratch per concurrent slot
+            self.outs.append(pipe.capture(packed, anchors_dev, scores_d, locs_d, exchange=(self.px, k), concurrent=conc))
+            self.pipes.append(pipe)
+        # the strictly serial number uses graphs captured for a step that runs alone (full streaming grids)
+        self.px_serial, self.pipes_serial = self.px, self.pipes
+        if conc:
+            self.px_serial = sharding.PeerExchange(batch_local * dist_world, rows, slots=self.nsets)
+            self.pipes_serial = []
+            for k, (packed, scores_d, locs_d, _) in enumerate(dev_sets):
+                ps = AnchorPipeline(w.cfg())
+                ps.capture(packed, anchors_dev, scores_d, locs_d, exchange=(self.px_serial, k))
+                self.pipes_serial.append(ps)
+        torch.cuda.synchronize()
+        self.streams = [torch.cuda.Stream() for _ in range(self.in_flight)]
+
+    def _issue(self, steps, serial):
+        if serial or self.in_flight == 1:
+            for i in range(steps):
+                self.pipes_serial[i % self.nsets].replay()
+            return
+        main = torch.cuda.current_stream()
+        for s_ in self.streams:
+            s_.wait_stream(main)
+        for i in range(steps):
+            k = i % self.nsets
+            with torch.cuda.stream(self.streams[k % self.in_flight]):
+                self.pipes[k].replay()
+        for s_ in self.streams:
+            main.wait_stream(s_)
+
+    def flush(self, serial):
+        px = self.px_serial if serial else self.px
+        for k in range(self.nsets):
+            px.wait(k)                      # the exchange of every slot's last step has completed on this rank
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, steps, warmup, serial, clocks=None):
+        """-> (ms per step, steps timed): `steps` steps repeated until the region lasts >= MIN_TIMED_MS."""
+        self._issue(max(warmup, 1), serial)
+        self.flush(serial)
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        self._issue(steps, serial)          # estimate (also warm-up)
+        self.flush(serial)
+        e1.record()
+        self.barrier()
+        est = max(e0.elapsed_time(e1), 1e-3)
+        repeats = max(1, int(math.ceil(MIN_TIMED_MS / est)))
+        if self.world > 1:                  # the same number of steps on every rank
+            import torch.distributed as dist
+            t = torch.tensor([repeats], device=self.anchors_dev.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            repeats = int(t)
+        if clocks is not None:
+            clocks.start()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        self._issue(steps * repeats, serial)
+        self.flush(serial)                  # the last steps' exchanges complete inside the timed region
+        e1.record()
+        self.barrier()
+        (self.px_serial if serial else self.px).check()
+        return e0.elapsed_time(e1) / (steps * repeats), steps * repeats
+
+    def close(self):
+        torch.cuda.synchronize()
+        if self.px_serial is not self.px:
+            self.px_serial.close()
+        self.px.close()
+
+
+def make_device_sets(w, batch_local, nsets, rank, dev, first_image=None):
+    """[(packed GT, scores, locs, rows per image)], plus the host copies (None when generated on the device).
+
+    first_image is None: one seed per (rank, set), generated on the host (also feeds the e2e leg).
+    Otherwise (sharded global batch): image i of the global batch is generated on the DEVICE from seed 5000 + i, so
+    that every sharding of the batch sees the same images."""
+    from single_shot_detection_b200.ops import det_capacity
+    from single_shot_detection_b200.target_assigner import pack_ground_truth
+    anchors = wl.build_anchors(w)
+    a, c = int(anchors.shape[0]), w.num_score_cols
+    rows = det_capacity(w.num_fg, w.max_per_class, w.max_total or 0)
+    host_sets, dev_sets = [], []
+    for s in range(nsets):
+        if first_image is None:
+            _, gt, scores, locs = wl.make_inputs(w, seed=23 + 1000 * rank + s, batch=batch_local)
+            scores, locs = scores.pin_memory(), locs.pin_memory()
+            host_sets.append((gt, scores, locs))
+            scores_d, locs_d = scores.to(dev), locs.to(dev)
+        else:
+            gt = []
+            scores_d = torch.empty((batch_local, a * c), dtype=torch.float32, device=dev)
+            locs_d = torch.empty((batch_local, a * 4), dtype=torch.float32, device=dev)
+            for j in range(batch_local):
+                i = first_image + j
+                gen = torch.Generator().manual_seed(5000 + i + 100000 * s)
+                gt.extend(wl.make_ground_truth(1, w.img, w.num_fg, w.max_gt, gen))
+                dgen = torch.Generator(device=dev).manual_seed(5000 + i + 100000 * s)
+                scores_d[j] = torch.randn((a * c,), generator=dgen, device=dev) + w.logit_mean
+                locs_d[j] = torch.randn((a * 4,), generator=dgen, device=dev) * 0.1
+        packed = pack_ground_truth(gt, dev)
+        packed.rows = packed.rows.clone()
+        packed.offsets = packed.offsets.clone()
+        dev_sets.append((packed, scores_d, locs_d, rows))
+    torch.cuda.synchronize()
+    return anchors, host_sets, dev_sets
+
+
+def sets_for(w, batch_local, in_flight):
+    a = int(wl.build_anchors(w).shape[0])
+    per_set = batch_local * a * (w.num_score_cols + 4) * 4
+    nsets = max(2, -(-int(1.5 * L2_BYTES) // per_set))
+    return min(max(nsets, in_flight), 16), per_set
+
+
 def run_ours(args):
     import torch.distributed as dist
     from single_shot_detection_b200 import _native as N
-    from single_shot_detection_b200 import sharding
-    from single_shot_detection_b200.pipeline import AnchorPipeline, matched_stats
-    from single_shot_detection_b200.target_assigner import pack_ground_truth
-    from single_shot_detection_b200 import sampler as S
+    from single_shot_detection_b200.pipeline import AnchorPipeline
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -184,168 +363,39 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     N.require_device()
+    pin_to_numa_node(local)
 
     w = wl.WORKLOADS[args.workload]
-    B = w.batch                       # images per GPU (weak scaling: every rank has its own batch)
-    anchors = wl.build_anchors(w)
+    if args.scaling == "strong":
+        assert w.batch % world == 0, "strong scaling: the workload's batch must divide by the number of ranks"
+        B = w.batch // world
+    else:
+        B = w.batch                   # weak scaling: every rank has its own batch
+    nsets, per_set = sets_for(w, B, args.in_flight)
+    anchors, host_sets, dev_sets = make_device_sets(w, B, nsets, rank, dev)
     A, C = int(anchors.shape[0]), w.num_score_cols
-    per_set = B * A * (C + 4) * 4
-    nsets = max(2, -(-int(1.5 * L2_BYTES) // per_set))
-    nsets = min(max(nsets, args.in_flight), 16)          # one input set per step in flight (HBM is not the limit)
-
-    # synthetic inputs, one seed per (rank, set)
-    host_sets = []
-    for s in range(nsets):
-        a_, gt, scores, locs = wl.make_inputs(w, seed=23 + 1000 * rank + s)
-        host_sets.append((gt, scores.pin_memory(), locs.pin_memory()))
     anchors_dev = anchors.to(dev)
-    dev_sets = []
-    for gt, scores, locs in host_sets:
-        packed = pack_ground_truth(gt, dev)
-        packed.rows = packed.rows.clone()
-        packed.offsets = packed.offsets.clone()
-        dev_sets.append((packed, scores.to(dev), locs.to(dev)))
-    torch.cuda.synchronize()
-
-    # one pipeline (and one CUDA graph) per input set
-    pipes, outs = [], []
-    launches0 = N.lib().ssd_b200_launch_count()
-    in_flight = max(1, min(args.in_flight, nsets))
-    for k, (packed, scores_d, locs_d) in enumerate(dev_sets):
-        # steps of different slots may run concurrently: each slot has its own scratch buffers
-        pipe = AnchorPipeline(w.cfg(), workspace_slot=k % in_flight)
-        pipes.append(pipe)
-    # kernels per step, counted on one eager step
-    launches_before = N.lib().ssd_b200_launch_count()
-    pipes[0].step_device(dev_sets[0][0], anchors_dev, dev_sets[0][1], dev_sets[0][2])
-    torch.cuda.synchronize()
-    launches_per_step = int(N.lib().ssd_b200_launch_count() - launches_before)
-    cap = B if world > 1 else None
-    # The exchange step: by default the last kernel of every step graph packs the shard and writes it into every
-    # rank's gathered buffer over NVLink peer memory (sharding.PeerExchange, csrc/exchange.cu); SSD_EXCHANGE=nccl
-    # packs locally and calls NCCL's all-gather after every replay instead (capturing the NCCL collective into the
-    # graph hung on this stack).
-    px = None
-    if world > 1 and os.environ.get("SSD_EXCHANGE", "peer") != "nccl":
-        try:
-            px = sharding.PeerExchange(B * world, w.max_total, slots=nsets)
-            ok = torch.tensor([1], device=dev)
-        except Exception as e:  # noqa: BLE001  (no peer access / IPC on this box: every rank must take the same route)
-            print(f"[bench] peer exchange unavailable on rank {rank}: {e!r}", file=sys.stderr)
-            px, ok = None, torch.tensor([0], device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if int(ok) == 0:
-            px = None
-    conc = in_flight > 1
-    for k, (pipe, (packed, scores_d, locs_d)) in enumerate(zip(pipes, dev_sets)):
-        if px is not None:
-            outs.append(pipe.capture(packed, anchors_dev, scores_d, locs_d, exchange=(px, k), concurrent=conc))
-        else:
-            outs.append(pipe.capture(packed, anchors_dev, scores_d, locs_d, shard_capacity=cap, concurrent=conc))
-    # the strictly serial number uses graphs captured for a step that runs alone (single GPU; with several ranks the
-    # serial loop replays the in-flight graphs)
-    pipes_serial = pipes
-    if conc and world == 1:
-        pipes_serial = []
-        for packed, scores_d, locs_d in dev_sets:
-            ps = AnchorPipeline(w.cfg())
-            ps.capture(packed, anchors_dev, scores_d, locs_d)
-            pipes_serial.append(ps)
-    torch.cuda.synchronize()
-
-    # the one exchange step of the path (detections + counts + stats, one collective per step) runs
-    # asynchronously: the all-gather of step i overlaps the kernels of step i+1
-    gather = sharding.OverlappedGather(B * world, w.max_total, ring=max(3, nsets + 1)) if world > 1 and px is None else None
-
-    class _PeerFlush:                      # same surface as OverlappedGather for the loops below
-        def flush(self):
-            for k in range(nsets):
-                px.wait(k)
-            return px.gathered(0)
-
-    if px is not None:
-        gather = _PeerFlush()
-
-    # Throughput mode: `in_flight` consecutive steps run concurrently, each replayed on its own stream (input
-    # set k always on stream k % in_flight, with that slot's scratch buffers).  A step alone leaves most of the
-    # GPU idle (its longest kernel, the NMS, runs 640 small CTAs at ~35 % issue utilisation), so the next
-    # batch's streaming kernels fill the gaps.  --in-flight 1 is the strictly serial number (reported beside it).
-    streams = [torch.cuda.Stream() for _ in range(in_flight)]
-
-    def device_step(i, serial=False):
-        k = i % nsets
-        if serial or in_flight == 1:
-            pipes_serial[k].replay()
-            if world > 1 and px is None:
-                return gather.submit(outs[k].shard)
-            return outs[k].dets, outs[k].counts, outs[k].assign_stats
-        with torch.cuda.stream(streams[k % in_flight]):
-            pipes[k].replay()
-            if world > 1 and px is None and not os.environ.get("SSD_BENCH_NO_GATHER"):   # (diagnostics)
-                return gather.submit_nowait(outs[k].shard)
-        return outs[k].dets, outs[k].counts, outs[k].assign_stats
-
-    def fork():
-        main = torch.cuda.current_stream()
-        for s_ in streams:
-            s_.wait_stream(main)
-
-    def join():
-        main = torch.cuda.current_stream()
-        for s_ in streams:
-            main.wait_stream(s_)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- serial reference: one step after the other on one stream ----
-    for i in range(args.warmup):
-        device_step(i, serial=True)
     if world > 1:
-        gather.flush()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        device_step(i, serial=True)
-    if world > 1:
-        gather.flush()
-    e1.record()
-    barrier()
-    serial_ms = e0.elapsed_time(e1)
+        dist.barrier()                # captures (which run the exchange kernels) start together on every rank
 
-    # ---- value: device-resident, CUDA events ----
-    fork()
-    for i in range(args.warmup):
-        device_step(i)
-    join()
-    if world > 1:
-        gather.flush()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    fork()
-    for i in range(args.steps):
-        device_step(i)
-    join()
-    if world > 1:
-        gather.flush()                    # the last step's exchange completes inside the timed region
-    e1.record()
-    barrier()
-    dev_ms = e0.elapsed_time(e1)
+    launches0 = int(N.lib().ssd_b200_launch_count())
+    runner = DeviceRunner(w, dev_sets, anchors_dev, args.in_flight, world)
+    in_flight = runner.in_flight
+    # kernels per step: every capture ran 2 eager warm-up steps + 1 captured one
+    captures = nsets * (2 if in_flight > 1 else 1)
+    launches_per_step = (int(N.lib().ssd_b200_launch_count()) - launches0) // (3 * captures)
+
+    clocks = ClockSampler(local) if rank == 0 else None
+    serial_ms, serial_steps = runner.timed(args.steps, args.warmup, serial=True)
+    dev_ms, timed_steps = runner.timed(args.steps, args.warmup, serial=False, clocks=clocks)
 
     # ---- e2e: reference-shaped API, host buffers, H2D + D2H inside the timed region ----
     pipe_e = AnchorPipeline(w.cfg())
-    T = w.max_total
+    T = dev_sets[0][3]
 
     # AnchorPipeline.stream: the reference-shaped step over a sequence of host batches, the H2D copies
     # of batch i+1 overlapping the kernels of batch i; every batch's detections, counts and statistics
-    # are read back to pinned host memory before it is yielded (under torchrun: after the all-gather).
+    # are read back to pinned host memory before it is yielded (under torchrun: after the exchange).
     def e2e_run(n):
         seen = 0
         batches = (host_sets[i % nsets] for i in range(n))
@@ -354,34 +404,182 @@ def run_ours(args):
         assert seen == n * B * world
         torch.cuda.current_stream().synchronize()
 
-    e2e_steps = max(3, min(args.steps, 50))
-    e2e_run(max(3, min(args.warmup, 5)))
-    barrier()
-    t0 = time.perf_counter()
-    e2e_run(e2e_steps)
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    e2e_steps, e2e_s = 0, float("nan")
+    if not args.no_e2e:
+        e2e_steps = max(3, min(args.steps, 50))
+        e2e_run(max(3, min(args.warmup, 5)))
+        runner.barrier()
+        t0 = time.perf_counter()
+        e2e_run(e2e_steps)
+        runner.barrier()
+        e2e_s = time.perf_counter() - t0
+        pipe_e.close()
     clock_info = clocks.stop() if rank == 0 else None
 
     gt0 = host_sets[0][0]
     gt_bytes = sum(g.numel() * 4 for g in gt0) + (B + 1) * 4
     h2d = B * A * C * 4 + B * A * 16 + gt_bytes
-    d2h = B * world * (T * 6 * 4 + 5 * 4) + B * 4 + 16 + B * 16
+    from single_shot_detection_b200 import sharding
+    d2h = B * world * sharding.row_words(T) * 4
 
-    # ---- roofline: the dominant kernel alone, CUDA events, rotating (cold-L2) inputs ----
-    roof = roofline_probe(w, dev_sets, anchors_dev, pipes[0], B, A, C, nsets)
+    roof, kernels_us, nms_info = None, None, None
+    if rank == 0:
+        # ---- roofline: the dominant kernel alone, CUDA events, rotating (cold-L2) inputs ----
+        roof = roofline_probe(w, dev_sets, anchors_dev, runner.pipes[0], B, A, C, nsets)
+        kernels_us, nms_info = kernel_times(w, dev_sets, anchors_dev, runner.pipes[0], B, C, nsets)
+    runner.close()
 
-    # ---- per-kernel times in context (library event timers around every launch of an eager step) ----
+    # ---- BASELINE configs[4] as stated: M2Det-512 b256 sharded over the ranks, gathered == single GPU ----
+    config5 = None
+    if not args.no_config5 and w.name == wl.HEADLINE and args.scaling == "weak":
+        config5 = config5_strong(rank, world, dev, args)
+
+    # max over ranks
+    t = torch.tensor([dev_ms, e2e_s if e2e_steps else 0.0, serial_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_s, serial_ms = float(t[0]), float(t[1]), float(t[2])
+
+    if rank == 0:
+        peak, _ = measured_peaks()
+        value = B * world / (dev_ms * 1e-3)
+        step_bytes = wl.algorithmic_bytes_per_image(w, A, B) * B
+        roof["step"] = {
+            "algorithmic_bytes_per_batch": step_bytes,
+            "definition": "SURVEY.md 8(d): every input of the four API calls read once, every output written once "
+                          "(2 x 4AC logit reads for a softmax + hard-negative-mining config), per GPU",
+            "in_flight": {"ms_per_step": dev_ms, "achieved": step_bytes / (dev_ms * 1e-3) / 1e9,
+                          "frac": step_bytes / (dev_ms * 1e-3) / 1e9 / peak},
+            "serial": {"ms_per_step": serial_ms, "achieved": step_bytes / (serial_ms * 1e-3) / 1e9,
+                       "frac": step_bytes / (serial_ms * 1e-3) / 1e9 / peak}}
+        line = {
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "timed_steps": timed_steps, "timed_ms": dev_ms * timed_steps,
+            "config": config_block(w, A, B, world, {
+                "l2": f"inputs rotate over {nsets} sets = {nsets * per_set / 2**20:.0f} MiB > 126 MiB L2",
+                "steps_in_flight": in_flight,
+                "device_path": (f"CUDA graph replay per step, {in_flight} consecutive steps in flight on "
+                                f"{in_flight} streams (own scratch buffers per slot)" if in_flight > 1
+                                else "CUDA graph replay per step, one step after the other") +
+                               "; the last kernel of every step graph packs the shard and writes it into every rank's "
+                               "gathered buffer (NVLink peer memory when N > 1; the same kernels run at N = 1)"}),
+            "e2e": {"value": B * world * e2e_steps / e2e_s if e2e_steps else None, "unit": "images/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps if e2e_steps else None,
+                    "path": "AnchorPipeline.stream(batches of (list of GT, pinned host scores, locs), CPU anchors) -> "
+                            "(target, mask, list of host detections) per batch; H2D of batch i+1 overlaps batch i"},
+            "serial": {"ms_per_step": serial_ms, "value": B * world / (serial_ms * 1e-3), "timed_steps": serial_steps,
+                       "note": "the same steps strictly one after the other on one stream (--in-flight 1)"},
+            "gpu_launches": launches_per_step * timed_steps,
+            "launches_per_step": launches_per_step,
+            "clocks": clock_info,
+            "roofline": roof,
+            "kernels_us": kernels_us,
+            "nms": nms_info,
+        }
+        if config5 is not None:
+            line["config5_strong"] = config5
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_block(w, min(args.cpu_sample_images, B), 3, 1)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def pin_to_numa_node(local_rank: int) -> None:
+    """Every rank pulls ~28 MB per step out of host memory in the e2e leg: keep its host threads (and with them its
+    pinned allocations, first touch) on the NUMA node of its GPU when the box has more than one."""
+    try:
+        import re
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20)
+        ids = set()
+        for ln in out.stdout.splitlines():
+            fields = [re.sub(r"\x1b\[[0-9;]*m", "", f).strip() for f in ln.split("\t")]
+            if not fields or fields[0] != f"GPU{local_rank}":
+                continue
+            for f in fields[1:]:
+                if re.fullmatch(r"\d+(-\d+)?(,\d+(-\d+)?)*", f) and ("-" in f or "," in f):     # the CPU affinity column
+                    for part in f.split(","):
+                        lo, _, hi = part.partition("-")
+                        ids.update(range(int(lo), int(hi or lo) + 1))
+                    break
+        ids &= os.sched_getaffinity(0)
+        if ids:
+            os.sched_setaffinity(0, ids)
+    except Exception:  # noqa: BLE001  (best effort: an unknown topology leaves the affinity alone)
+        pass
+
+
+def config5_strong(rank, world, dev, args):
+    """M2Det-512-VGG16 COCO, global batch 256 sharded by image over the ranks (BASELINE configs[4]):
+    rank r runs images [r * 256 / N, (r + 1) * 256 / N) and the last kernel of its step writes its packed shard into
+    every rank's gathered buffer.  gather_parity: the gathered buffer of EVERY rank is compared, bit for bit, with a
+    single-GPU run of the whole 256-image batch on that rank."""
+    import torch.distributed as dist
+    from single_shot_detection_b200 import sharding
+    from single_shot_detection_b200.pipeline import AnchorPipeline
+    w = wl.WORKLOADS["m2det512_coco_b256"]
+    if w.batch % world:
+        return {"skipped": f"256 images do not divide over {world} ranks"}
+    b_local = w.batch // world
+    lo, _ = sharding.image_shard(w.batch, rank, world)
+    anchors, _, dev_sets = make_device_sets(w, b_local, 1, rank, dev, first_image=lo)
+    anchors_dev = anchors.to(dev)
+    if world > 1:
+        dist.barrier()
+    runner = DeviceRunner(w, dev_sets, anchors_dev, 1, world)          # one 2 GB input set >> L2; strictly serial steps
+    steps = max(3, min(args.steps, 20))
+    ms, timed = runner.timed(steps, 3, serial=True)
+    runner.flush(True)
+    torch.cuda.synchronize()
+    gathered = runner.px.gathered(0).clone()
+    runner.close()
+    # the same global batch on this GPU alone
+    parity = "ok"
+    if world > 1:
+        del dev_sets
+        _, _, full_sets = make_device_sets(w, w.batch, 1, rank, dev, first_image=0)
+        pipe = AnchorPipeline(w.cfg())
+        packed, scores_d, locs_d, rows = full_sets[0]
+        out = pipe.step_device(packed, anchors_dev, scores_d, locs_d, shard_capacity=w.batch)
+        torch.cuda.synchronize()
+        same = torch.equal(out.shard.view(torch.int32), gathered.view(torch.int32))
+        flag = torch.tensor([0 if same else 1], device=dev)
+        dist.all_reduce(flag)
+        parity = "ok" if int(flag) == 0 else f"FAILED on {int(flag)} rank(s)"
+        del full_sets, out
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    peak, _ = measured_peaks()
+    a = int(anchors.shape[0])
+    step_bytes = wl.algorithmic_bytes_per_image(w, a, b_local) * b_local
+    torch.cuda.empty_cache()
+    return {"workload": w.name, "scaling": "strong", "global_batch": w.batch, "images_per_gpu": b_local, "n_gpus": world,
+            "value": w.batch / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms, "timed_steps": timed,
+            "steps_in_flight": 1, "gather_parity": parity if world > 1 else "n/a (one rank)",
+            "roofline_step_frac": step_bytes / (ms * 1e-3) / 1e9 / peak,
+            "data": "synthetic, image i of the global batch generated on the device from seed 5000 + i on whichever rank owns it"}
+
+
+def kernel_times(w, dev_sets, anchors_dev, pipe, B, C, nsets):
+    """Per-kernel times in context (library event timers around every launch of an eager step)."""
     import ctypes
+    from single_shot_detection_b200 import _native as N
     lib = N.lib()
     for i in range(3):
         k = i % nsets
-        pipes[0].step_device(dev_sets[k][0], anchors_dev, dev_sets[k][1], dev_sets[k][2])
+        pipe.step_device(dev_sets[k][0], anchors_dev, dev_sets[k][1], dev_sets[k][2])
     torch.cuda.synchronize()
     lib.ssd_b200_timing_enable(1)
     for i in range(20):
         k = i % nsets
-        pipes[0].step_device(dev_sets[k][0], anchors_dev, dev_sets[k][1], dev_sets[k][2])
+        pipe.step_device(dev_sets[k][0], anchors_dev, dev_sets[k][1], dev_sets[k][2])
     buf = ctypes.create_string_buffer(4096)
     lib.ssd_b200_timing_report(buf, 4096)
     lib.ssd_b200_timing_enable(0)
@@ -392,64 +590,34 @@ def run_ours(args):
                 "pair_tests_per_launch": pair_tests,
                 "pair_tests_per_s": pair_tests / (kernels_us["nms"] * 1e-6) if kernels_us.get("nms") else None,
                 "note": "K(K-1)/2 IoU tests per (image, class) at K = max_per_class; bound by the ALU pipe, not HBM"}
-
-    # max over ranks
-    t = torch.tensor([dev_ms, e2e_s, serial_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_s, serial_ms = float(t[0]), float(t[1]), float(t[2])
-
-    if rank == 0:
-        ms_per_step = dev_ms / args.steps
-        value = B * world / (ms_per_step * 1e-3)
-        e2e_value = B * world * e2e_steps / e2e_s
-        line = {
-            "metric": "images/sec target-assign+NMS", "value": value, "unit": "images/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w.name, "anchors": A, "score_cols": C, "images_per_gpu": B,
-                       "global_batch": B * world, "converter": w.converter, "sampler": w.sampler,
-                       "region": "encode_ground_truth + sampler + to_centroids/encode_box + postprocess"
-                                 + (" + all_gather(dets,stats)" if world > 1 else ""),
-                       "l2": f"inputs rotate over {nsets} sets = {nsets * per_set / 2**20:.0f} MiB > 126 MiB L2",
-                       "steps_in_flight": in_flight,
-                       "device_path": (f"CUDA graph replay per step, {in_flight} consecutive steps in flight on "
-                                       f"{in_flight} streams (own scratch buffers per slot)" if in_flight > 1
-                                       else "CUDA graph replay per step, one step after the other") + (
-                           "" if world == 1 else (", shard packed and written into every rank's gathered buffer over NVLink "
-                                                  "peer memory by the last kernel of the step graph" if px is not None
-                                                  else ", NCCL all-gather of step i overlapping step i+1"))},
-            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
-                    "path": "AnchorPipeline.stream(batches of (list of GT, pinned host scores, locs), CPU anchors) -> "
-                            "(target, mask, list of host detections) per batch; H2D of batch i+1 overlaps batch i"},
-            "serial": {"ms_per_step": serial_ms / args.steps, "value": B * world / (serial_ms / args.steps * 1e-3),
-                       "note": "the same K steps strictly one after the other on one stream (--in-flight 1)"},
-            "gpu_launches": launches_per_step * args.steps,
-            "launches_per_step": launches_per_step,
-            "clocks": clock_info,
-            "roofline": roof,
-            "kernels_us": kernels_us,
-            "nms": nms_info,
-        }
-        if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            images = min(args.cpu_sample_images, B)
-            best, mean, total = time_cpu_oracle(w, images, 3, 1, cores)
-            line["cpu_baseline"] = {
-                "value": mean, "unit": "images/s", "cores": cores, "kind": "port", "best": best,
-                "sample": f"{images} of {B} images per step, 3 steps + 1 warm-up, oracle port of the reference "
-                          f"(torch CPU ops + torchvision.ops.nms), {cores} torch threads"}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        torch.cuda.synchronize()
-        if px is not None:
-            px.close()
-        dist.barrier()
-        dist.destroy_process_group()
+    return kernels_us, nms_info
 
 
-def roofline_probe(w, dev_sets, anchors_dev, pipe, B, A, C, nsets, iters: int = 50):
+def source_digest():
+    """SHA-256 over the CUDA sources of the streaming kernels: an ncu capture is only quoted for the code it saw."""
+    h = hashlib.sha256()
+    for name in ("postprocess.cu", "rowstream.cuh", "common.cuh"):
+        with open(os.path.join(ROOT, "single_shot_detection_b200", "csrc", name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_traffic(workload: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel from the committed
+    `ncu --set full` capture (profiles/ncu_traffic.json, written by tools/ncu_traffic.py) -- or None when the
+    kernel sources have changed since that capture."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None, None
+    with open(path) as f:
+        table = json.load(f)
+    entry = table.get(workload)
+    if not entry or entry.get("source_digest") != source_digest():
+        return None, None
+    return entry["traffic_bytes"], entry.get("source")
+
+
+def roofline_probe(w, dev_sets, anchors_dev, pipe, B, A, C, nsets, iters: int = 200):
     """Time the logit-streaming kernels alone (CUDA events on the launching stream, launches back to back,
     inputs rotating over sets larger than L2).  The roofline entry is the one that runs in the step: the
     post-processor's first pass (row statistics + gate bookkeeping + the sampler's criterion); the sampler's
@@ -495,7 +663,6 @@ def roofline_probe(w, dev_sets, anchors_dev, pipe, B, A, C, nsets, iters: int = 
     else:
         want_keys = True
         algo_p1 = B * A * (4 * C + 8 + 4)          # logits read, (max, sum) float2 + uint32 criterion key written
-    post = pipe.postprocessor
     conv, first_fg = {"SOFTMAX": (N.CONVERT_SOFTMAX, 1), "SIGMOID": (N.CONVERT_SIGMOID, 0)}[w.converter]
     p = ops._post_params(dev_sets[0][1], dev_sets[0][2], conv, first_fg, N.BOXES_ENCODED, float(w.xy_scale),
                          float(w.wh_scale), float(w.score_threshold), int(w.max_per_class), float(w.overlap_threshold),
@@ -508,21 +675,16 @@ def roofline_probe(w, dev_sets, anchors_dev, pipe, B, A, C, nsets, iters: int = 
 
     us = timed(pass1)
     achieved = algo_p1 / (us * 1e-6) / 1e9
-    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` capture per workload
-    # (profiles/r01c_ncu_full.md); None for a workload that has no committed capture
-    traffic = NCU_TRAFFIC.get(w.name)
+    traffic, traffic_src = ncu_traffic(w.name)
     return {"bound": "hbm", "kernel": "score_pass1_kernel (ssd_postprocess_pass1)", "achieved": achieved, "peak": peak,
             "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-            "traffic_source": "profiles/r01c_ncu_full.md" if traffic else None,
+            "traffic_source": traffic_src,
             "algorithmic_bytes_per_launch": algo_p1, "us_per_launch": us, "other_streaming_kernels": other,
             "note": "the streaming kernel of the step: one read of the logits yields the row statistics, the gate "
-                    "bookkeeping and the sampler's criterion (4C read + 12 written bytes per anchor); the call is timed "
-                    "back to back on one stream INCLUDING its scratch-zeroing kernel, inputs rotating over sets larger "
-                    "than L2; the largest kernel of the step, segment_nms_kernel, is ALU bound and reported under 'nms'"}
-
-
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel (profiles/r01c_ncu_full.md)
-NCU_TRAFFIC = {"ssd300_voc_b32": 23524608, "ssd512_coco_b32": 254768384 + 15038208}
+                    "bookkeeping and the sampler's criterion (4C read + 12 written bytes per anchor); timed back to back "
+                    "on one stream, inputs rotating over sets larger than L2; `traffic` is quoted only while the kernel "
+                    "sources still hash to what the committed ncu capture saw; the largest kernel of the step, "
+                    "segment_nms_kernel, is ALU bound and reported under 'nms'"}
 
 
 def main():

@@ -347,9 +347,9 @@ SSD_API int ssd_generate_anchors(const SsdAnchorLevel* levels, int num_levels, f
 
 /* ------------------------------------------------------------------------------------------
  * e   the exchange step (no reference equivalent): pack the local images' padded
- *     detections [B,T,6], counts [B] and statistics into shard_out [capacity, T*6 + 5] fp32 words:
- *     T*6 detection words, then int32 {count, positives, hard negatives selected, ignored,
- *     detections}; rows >= batch are padding with count = -1.  assign_stats = stats_out of
+ *     detections [B,T,6], counts [B] and statistics into shard_out [capacity, ssd_shard_row_words(T)] fp32
+ *     words: T*6 detection words, then int32 {count, positives, hard negatives selected, ignored,
+ *     detections}, then zero padding to a 16-byte multiple; rows >= batch are padding with count = -1.  assign_stats = stats_out of
  *     ssd_assign_targets, mining_stats = stats_out of ssd_hard_negative_mask (either may be NULL).
  *     stats_out [B,4] int32 (optional) receives the four statistics.  The buffer is what ONE
  *     all-gather (NCCL over NVLink) moves.
@@ -358,23 +358,36 @@ SSD_API int ssd_pack_shard(const float* dets, const int32_t* counts, const int32
                    const int32_t* mining_stats, int batch, int max_total, int capacity, float* shard_out,
                    int32_t* stats_out, void* stream);
 
-/* The same packing FUSED with the exchange over NVLink peer memory: every CTA writes its row into slot `rank` of
- * every peer's gathered buffer, no NCCL call (csrc/exchange.cu has the protocol).  `peer_arenas` is a HOST array
- * of `world` device pointers: the arena of every rank as mapped into this process (CUDA IPC; entry `rank` is the
- * own arena).  An arena is ssd_exchange_arena_bytes(...) bytes, 256-byte aligned, ZERO-filled once when it is
- * created; gathered slot `slot` of the own arena starts at ssd_exchange_slot_offset(...) and holds
- * [world, capacity, T*6 + 5] words once ssd_exchange_wait(slot) has completed on the stream.  One slot per step
- * graph / stream: launches that use the same slot must be serialised.  A peer that stops answering turns into
- * a non-zero first header word (int64) after 4 s, never into a hang. */
+/* Words per packed row: T*6 detections + count + 4 statistics, rounded up to a multiple of four (16-byte rows). */
+SSD_API int ssd_shard_row_words(int max_total);
+
+/* The same packing FUSED with the exchange over NVLink peer memory: every CTA reads its image's row once and stores
+ * it (16-byte stores) into slot `rank` of EVERY rank's gathered buffer, no NCCL call (csrc/exchange.cu has the
+ * protocol).  `peer_arenas` is a HOST array of `world` device pointers: the arena of every rank as mapped into this
+ * process (entry `rank` is the own arena).  An arena is ssd_exchange_arena_bytes(...) bytes of ZERO-filled device
+ * memory (ssd_exchange_arena_alloc also returns its 64-byte CUDA IPC handle; a peer maps it with
+ * ssd_exchange_peer_open).  Gathered slot `slot` of the own arena starts at ssd_exchange_slot_offset(...) and holds
+ * [world, capacity, ssd_shard_row_words(T)] words once ssd_exchange_wait(slot) has completed on the stream.
+ * One slot per step graph / stream: launches that use the same slot must be serialised, and every launch is
+ *     ssd_exchange_open(slot)  ...the step...  ssd_pack_exchange(slot)  [ssd_exchange_wait(slot), readers]
+ * -- the open call releases the slot's previous contents on every rank (a writer never overwrites rows a peer may
+ * still be reading: it waits until every rank has opened the same launch).  A peer that stops answering turns into a
+ * non-zero first header word (int64) after 10 s, never into a hang. */
 #define SSD_EXCHANGE_MAX_WORLD 8
 #define SSD_EXCHANGE_MAX_SLOTS 16
+#define SSD_EXCHANGE_MAX_ROWS 512            /* images per rank and slot */
 SSD_API int ssd_exchange_enable_peer(int device, int peer_device);   /* cudaDeviceEnablePeerAccess, idempotent */
 SSD_API size_t ssd_exchange_arena_bytes(int world, int slots, int capacity, int max_total);
 SSD_API size_t ssd_exchange_slot_offset(int world, int slot, int capacity, int max_total);
+SSD_API int ssd_exchange_arena_alloc(size_t bytes, void** arena_out, void* ipc_handle_out64);
+SSD_API int ssd_exchange_arena_free(void* arena);
+SSD_API int ssd_exchange_peer_open(const void* ipc_handle64, void** mapped_out);
+SSD_API int ssd_exchange_peer_close(void* mapped);
+SSD_API int ssd_exchange_open(void* const* peer_arenas, int world, int rank, int slot, void* stream);
 SSD_API int ssd_pack_exchange(const float* dets, const int32_t* counts, const int32_t* assign_stats,
                       const int32_t* mining_stats, int batch, int max_total, int capacity,
                       void* const* peer_arenas, int world, int rank, int slot, int32_t* stats_out, void* stream);
-SSD_API int ssd_exchange_wait(void* own_arena, int world, int slot, void* stream);
+SSD_API int ssd_exchange_wait(void* own_arena, int world, int capacity, int slot, void* stream);
 
 #ifdef __cplusplus
 }

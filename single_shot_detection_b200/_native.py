@@ -103,7 +103,13 @@ _SIGNATURES = {
     "ssd_exchange_slot_offset": (c_size_t, [c_int, c_int, c_int, c_int]),
     "ssd_pack_exchange": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, POINTER(c_void_p), c_int,
                                   c_int, c_int, c_void_p, c_void_p]),
-    "ssd_exchange_wait": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "ssd_exchange_wait": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
+    "ssd_exchange_open": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_void_p]),
+    "ssd_exchange_arena_alloc": (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),
+    "ssd_exchange_arena_free": (c_int, [c_void_p]),
+    "ssd_exchange_peer_open": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "ssd_exchange_peer_close": (c_int, [c_void_p]),
+    "ssd_shard_row_words": (c_int, [c_int]),
     "ssd_generate_anchors": (c_int, [POINTER(AnchorLevel), c_int, c_void_p, c_int64, c_void_p]),
     "ssd_postprocess_workspace_bytes": (c_size_t, [POINTER(PostprocessParams)]),
     "ssd_postprocess": (c_int, [POINTER(PostprocessParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -71,6 +71,7 @@ class AnchorPipeline:
         self._side = None
         self._copy = None
         self._stream_slots = None
+        self._px = None                # sharding.PeerExchange of stream(gather_batch=...)
         self.last_host_stats = None    # [B, 5] int32 host: count, positives, hard negatives, ignored, detections
 
     # -- the reference-facing call -------------------------------------------------------------
@@ -152,6 +153,20 @@ class AnchorPipeline:
             cols = min([int(g.shape[1]) for g in ground_truth if g.dim() == 2 and g.shape[0]] or [6])
             compute.synchronize()
             del slots[:]
+            # under torch.distributed the exchange is the peer-memory one (sharding.PeerExchange: the last kernel of
+            # every slot's step graph writes the packed shard into every rank's gathered buffer -- no collective
+            # call and no allocation per step); it is rebuilt with the slots (collective: every rank sees the same
+            # sequence of batch shapes)
+            if self._px is not None:
+                self._px.close()
+                self._px = None
+            px = None
+            if gather_batch is not None:
+                from .ops import det_capacity
+                num_cols = scores.numel() // (batch * anchors_dev.shape[0])
+                num_fg = num_cols - (1 if self.cfg["converter"] == "SOFTMAX" else 0)
+                rows_per_image = det_capacity(num_fg, int(self.cfg["max_per_class"]), int(self.cfg["max_total"] or 0))
+                px = self._px = sharding.PeerExchange(gather_batch, rows_per_image, slots=depth + 1)
             for _ in range(depth + 1):
                 packed = PackedGroundTruth(torch.zeros((batch * cap, cols), dtype=torch.float32, device=device),
                                            torch.zeros((batch + 1,), dtype=torch.int32, device=device), cap, batch)
@@ -161,11 +176,14 @@ class AnchorPipeline:
                 locs_d = locs.to(device=device, dtype=torch.float32).contiguous()
                 pack_ground_truth(ground_truth, device, out=packed)
                 runner = AnchorPipeline(self.cfg)
-                out = runner.capture(packed, anchors_dev, scores_d, locs_d, shard_capacity=batch)
+                if px is not None:
+                    out = runner.capture(packed, anchors_dev, scores_d, locs_d, exchange=(px, len(slots)))
+                else:
+                    out = runner.capture(packed, anchors_dev, scores_d, locs_d, shard_capacity=batch)
                 rows = gather_batch if gather_batch is not None else batch
                 host = torch.empty((rows, out.shard.shape[1]), dtype=torch.float32).pin_memory()
                 slots.append({"packed": packed, "scores": scores_d, "locs": locs_d, "runner": runner, "out": out,
-                              "host": host, "ready": torch.cuda.Event(), "done": torch.cuda.Event(),
+                              "host": host, "ready": torch.cuda.Event(), "done": torch.cuda.Event(), "index": len(slots),
                               "key": (tuple(scores.shape), tuple(locs.shape), batch, cols, gather_batch)})
 
         def batch_key(ground_truth, scores, locs):
@@ -190,12 +208,10 @@ class AnchorPipeline:
             slot["runner"].replay()
             shard = slot["out"].shard
             if gather_batch is not None:
-                world = torch.distributed.get_world_size()
-                gathered = torch.empty((world * shard.shape[0], shard.shape[1]), dtype=shard.dtype, device=device)
-                torch.distributed.all_gather_into_tensor(gathered, shard)
-                shard = gathered
-                if gathered.shape[0] != gather_batch:
-                    dets, counts, stats = sharding.unpack_gathered(gathered, gather_batch, world, slot["out"].dets.shape[1])
+                px = self._px
+                px.wait(slot["index"])                 # every rank's rows of this step have landed in the own arena
+                if shard.shape[0] != gather_batch:     # uneven shards: drop the padding rows
+                    dets, counts, stats = sharding.unpack_gathered(shard, gather_batch, px.world, slot["out"].dets.shape[1])
                     shard = sharding.pack_shard(dets, counts, stats, gather_batch)
             slot["host"].copy_(shard, non_blocking=True)
             slot["done"].record(compute)
@@ -206,7 +222,7 @@ class AnchorPipeline:
             host = slot["host"]
             t = slot["out"].dets.shape[1]
             ints = host.view(torch.int32)
-            self.last_host_stats = ints[:, t * 6:]
+            self.last_host_stats = ints[:, t * 6: t * 6 + 5]
             dets = host[:, : t * 6].view(host.shape[0], t, 6)
             return slot["out"].target, slot["out"].mask, [dets[i, :n] for i, n in enumerate(ints[:, t * 6].tolist())]
 
@@ -220,6 +236,14 @@ class AnchorPipeline:
                 yield finish(queue.popleft())
         while queue:
             yield finish(queue.popleft())
+
+    def close(self) -> None:
+        """Release what :meth:`stream` set up for the multi-GPU exchange (collective under torch.distributed)."""
+        if self._px is not None:
+            torch.cuda.synchronize()
+            self._stream_slots = None
+            self._px.close()
+            self._px = None
 
     # -- device-resident, sync-free -------------------------------------------------------------
     def step_device(self, packed: PackedGroundTruth, anchors_dev, scores_dev, locs_dev,
@@ -251,6 +275,8 @@ class AnchorPipeline:
         # selection -- and only the selection has a second (event) dependency, on the post-processor's pass 1.
         coder = self.box_coder if self.fuse_assign_encode else None
         with torch.cuda.stream(side):
+            if exchange is not None:
+                exchange[0].open(exchange[1])          # a new launch of the slot: its previous contents are released
             target = self.target_assigner.encode_packed(packed, anchors_dev, box_coder=coder)
             if not share:
                 classes = target[..., CLASS_INDEX].long()                      # multibox_loss.py:49 (before the boxes change)

@@ -26,29 +26,34 @@ def shard_capacity(batch: int, world: int) -> int:
     return (batch + world - 1) // world
 
 
+def row_words(max_rows: int) -> int:
+    """Words per packed row: T*6 detections, count, 4 statistics, zero padding to a 16-byte multiple
+    (``ssd_shard_row_words`` of the C ABI)."""
+    return (max_rows * 6 + 5 + 3) & ~3
+
+
 def pack_shard(dets: torch.Tensor, counts: torch.Tensor, stats: torch.Tensor, capacity: int) -> torch.Tensor:
-    """[capacity, T*6 + 1 + 4] fp32 words: detections, then count and stats bit-cast from int32.
+    """[capacity, row_words(T)] fp32 words: detections, then count and stats bit-cast from int32, then padding.
     Rows beyond the local image count have count = -1."""
     n, t = dets.shape[0], dets.shape[1]
-    words = t * 6 + 5
-    buf = torch.zeros((capacity, words), dtype=torch.float32, device=dets.device)
+    buf = torch.zeros((capacity, row_words(t)), dtype=torch.float32, device=dets.device)
     ints = buf.view(torch.int32)
     ints[:, t * 6] = -1
     if n:
         buf[:n, : t * 6] = dets.reshape(n, t * 6)
         ints[:n, t * 6] = counts.to(torch.int32)
-        ints[:n, t * 6 + 1:] = stats.to(torch.int32)
+        ints[:n, t * 6 + 1: t * 6 + 5] = stats.to(torch.int32)
     return buf
 
 
 def pack_shard_device(dets: torch.Tensor, counts: torch.Tensor, assign_stats: Optional[torch.Tensor],
                       mining_stats: Optional[torch.Tensor], capacity: int):
     """:func:`pack_shard` + ``pipeline.matched_stats`` for CUDA tensors in ONE launch (csrc/exchange.cu):
-    -> (shard [capacity, T*6 + 5], stats [B, 4] int32)."""
+    -> (shard [capacity, row_words(T)], stats [B, 4] int32)."""
     from . import _native as N
     N.require_device()
     n, t = int(dets.shape[0]), int(dets.shape[1])
-    shard = torch.empty((capacity, t * 6 + 5), dtype=torch.float32, device=dets.device)
+    shard = torch.empty((capacity, row_words(t)), dtype=torch.float32, device=dets.device)
     stats = torch.empty((n, 4), dtype=torch.int32, device=dets.device)
     with torch.cuda.device(dets.device):
         N.check(N.lib().ssd_pack_shard(dets.data_ptr(), counts.data_ptr(),
@@ -58,91 +63,125 @@ def pack_shard_device(dets: torch.Tensor, counts: torch.Tensor, assign_stats: Op
     return shard, stats
 
 
+class _DeviceBytes:
+    """``__cuda_array_interface__`` over raw device memory, so that torch can alias it (torch.as_tensor)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2,
+                                         "strides": None}
+
+
 class PeerExchange:
     """The exchange step WITHOUT a collective library: every rank owns one arena of gathered buffers, maps the
     arenas of its peers through CUDA IPC (all ranks sit on one NVSwitch box) and ``pack_exchange`` -- one kernel,
-    capturable into the step graph -- packs the local shard and writes it straight into every peer's buffer over
-    NVLink (csrc/exchange.cu).  ``torch.distributed`` is used once, to hand the IPC handles around.
+    capturable into the step graph -- packs the local shard and writes it straight into every rank's buffer over
+    NVLink (csrc/exchange.cu).  ``torch.distributed`` is used once, to hand the 64-byte IPC handles around; with a
+    world of one (or without a process group) the same kernels run on the own arena alone.
 
-    One ``slot`` per concurrently usable step graph; launches on the same slot must be serialised (same stream).
-    ``gathered(slot)`` is complete once ``wait(slot)`` has run on the stream, and stays valid until the slot's
-    graph is launched again."""
+    One ``slot`` per concurrently usable step graph; launches on the same slot must be serialised (same stream)
+    and every launch is ``open(slot)`` ... ``pack_exchange(slot)``: ``open`` tells every rank that this one has
+    finished with the slot's previous contents, and a writer waits until every rank has opened the same launch, so
+    a rank that runs ahead never overwrites rows a slower peer is still reading.  ``gathered(slot)`` is complete
+    once ``wait(slot)`` has run on the stream, and stays valid until the slot is opened again."""
 
     def __init__(self, batch: int, max_rows: int, slots: int, group: Optional[dist.ProcessGroup] = None,
                  device: Optional[torch.device] = None):
         import ctypes
-        from torch.multiprocessing.reductions import reduce_tensor
         from . import _native as N
         N.require_device()
         self.group = group
-        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        distributed = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if distributed else 1
+        self.rank = dist.get_rank(group) if distributed else 0
         self.batch, self.max_rows, self.slots = batch, max_rows, slots
         self.capacity = shard_capacity(batch, self.world)
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self._N = N
-        nbytes = N.lib().ssd_exchange_arena_bytes(self.world, slots, self.capacity, max_rows)
+        self._closed = False
+        lib = N.lib()
+        nbytes = lib.ssd_exchange_arena_bytes(self.world, slots, self.capacity, max_rows)
         if nbytes == 0:
-            raise ValueError(f"PeerExchange: world {self.world} / slots {slots} outside the supported range")
-        self.arena = torch.zeros((nbytes,), dtype=torch.uint8, device=self.device)          # zero-filled once
-        torch.cuda.synchronize(self.device)
+            raise ValueError(f"PeerExchange: world {self.world} / slots {slots} / {self.capacity} images per rank "
+                             "outside the supported range")
+        self._nbytes = nbytes
+        handle = ctypes.create_string_buffer(64)
+        own = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            N.check(lib.ssd_exchange_arena_alloc(nbytes, ctypes.byref(own), handle))     # zero-filled, synchronised
+        self._own = own.value
         handles = [None] * self.world
         if self.world > 1:
-            dist.all_gather_object(handles, reduce_tensor(self.arena), group=group)
-        self._peers = []                                   # keep the mappings alive
+            dist.all_gather_object(handles, (bytes(handle.raw), int(self.device.index)), group=group)
+        self._mapped = []                                   # peers' arenas as mapped here: closed in close()
         ptrs = (ctypes.c_void_p * self.world)()
-        for r, handle in enumerate(handles):
-            if r == self.rank:
-                t = self.arena
-            else:
-                rebuild, args = handle
-                # torch would open the IPC handle under the EXPORTER's device index; the kernels that use the
-                # mapping run on THIS device, so it is opened here (cudaIpcOpenMemHandle then enables peer access
-                # between this device and the exporter's lazily) -- argument 6 of rebuild_cuda_tensor is the device
-                peer_device = int(args[6])
-                args = list(args)
-                args[6] = self.device.index
-                N.check(N.lib().ssd_exchange_enable_peer(self.device.index, peer_device))
-                t = rebuild(*args)
-            self._peers.append(t)
-            ptrs[r] = t.data_ptr()
+        with torch.cuda.device(self.device):
+            for r in range(self.world):
+                if r == self.rank:
+                    ptrs[r] = self._own
+                    continue
+                raw, peer_device = handles[r]
+                # the kernels that use the mapping run on THIS device: the handle is opened with this device
+                # current (cudaIpcOpenMemHandle enables peer access to the exporter's device lazily)
+                N.check(lib.ssd_exchange_enable_peer(self.device.index, peer_device))
+                mapped = ctypes.c_void_p()
+                N.check(lib.ssd_exchange_peer_open(ctypes.create_string_buffer(raw, 64), ctypes.byref(mapped)))
+                self._mapped.append(mapped.value)
+                ptrs[r] = mapped.value
         self._ptrs = ptrs
+        self.arena = torch.as_tensor(_DeviceBytes(self._own, nbytes), device=self.device)   # aliases the arena
         if self.world > 1:
             dist.barrier(group=group)                      # every rank has mapped every arena
 
     def close(self) -> None:
-        """Drop the mappings of the peers' arenas (collective: every rank calls it before it exits, so that no
-        exporter goes away while its memory is still mapped elsewhere)."""
-        import gc
+        """Unmap the peers' arenas and free the own one (collective: every rank calls it before it exits, so that
+        no exporter frees memory that is still mapped elsewhere)."""
+        if self._closed:
+            return
+        self._closed = True
+        lib = self._N.lib()
         torch.cuda.synchronize(self.device)
-        self._peers = [t for r, t in enumerate(self._peers) if r == self.rank]
-        gc.collect()
-        if self.world > 1:
-            dist.barrier(group=self.group)
+        with torch.cuda.device(self.device):
+            for mapped in self._mapped:
+                self._N.check(lib.ssd_exchange_peer_close(mapped))
+            self._mapped = []
+            if self.world > 1:
+                dist.barrier(group=self.group)             # nobody maps this rank's arena any more
+            self.arena = None
+            self._N.check(lib.ssd_exchange_arena_free(self._own))
+            self._own = None
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream().cuda_stream
+
+    def open(self, slot: int) -> None:
+        """First operation of a launch of ``slot`` (see the class docstring); capturable."""
+        assert 0 <= slot < self.slots
+        with torch.cuda.device(self.device):
+            self._N.check(self._N.lib().ssd_exchange_open(self._ptrs, self.world, self.rank, slot, self._stream()))
 
     def pack_exchange(self, dets: torch.Tensor, counts: torch.Tensor, assign_stats: Optional[torch.Tensor],
                       mining_stats: Optional[torch.Tensor], slot: int):
         """-> stats [B_local, 4] int32; the packed shard lands in slot ``slot`` of every rank's arena."""
         n, t = int(dets.shape[0]), int(dets.shape[1])
         assert t == self.max_rows and n <= self.capacity and 0 <= slot < self.slots
-        stats = torch.empty((n, 4), dtype=torch.int32, device=dets.device)
+        stats = torch.empty((max(n, 1), 4), dtype=torch.int32, device=dets.device)[:n]
         N = self._N
         with torch.cuda.device(self.device):
             N.check(N.lib().ssd_pack_exchange(dets.data_ptr(), counts.data_ptr(),
                                               None if assign_stats is None else assign_stats.data_ptr(),
                                               None if mining_stats is None else mining_stats.data_ptr(), n, t,
                                               self.capacity, self._ptrs, self.world, self.rank, slot, stats.data_ptr(),
-                                              torch.cuda.current_stream().cuda_stream))
+                                              self._stream()))
         return stats
 
     def wait(self, slot: int) -> None:
         N = self._N
         with torch.cuda.device(self.device):
-            N.check(N.lib().ssd_exchange_wait(self.arena.data_ptr(), self.world, slot,
-                                              torch.cuda.current_stream().cuda_stream))
+            N.check(N.lib().ssd_exchange_wait(self._own, self.world, self.capacity, slot, self._stream()))
 
     def gathered(self, slot: int) -> torch.Tensor:
-        """[world * capacity, T*6 + 5] fp32 view of the slot (the layout ``unpack_gathered`` reads)."""
-        words = self.max_rows * 6 + 5
+        """[world * capacity, row_words(T)] fp32 view of the slot (the layout ``unpack_gathered`` reads)."""
+        words = row_words(self.max_rows)
         off = self._N.lib().ssd_exchange_slot_offset(self.world, slot, self.capacity, self.max_rows)
         n = self.world * self.capacity * words
         return self.arena[off: off + 4 * n].view(torch.float32).view(self.world * self.capacity, words)
@@ -154,6 +193,10 @@ class PeerExchange:
         """Non-zero after a peer failed to answer within the kernel's time-out (one host sync)."""
         return int(self.arena[:8].view(torch.int64)[0].item())
 
+    def check(self) -> None:
+        if self.error():
+            raise RuntimeError("PeerExchange: a rank stopped answering (time-out word set by the exchange kernels)")
+
 
 def unpack_gathered(gathered: torch.Tensor, batch: int, world: int, max_rows: int):
     """Inverse of pack_shard over the concatenation of all ranks' buffers."""
@@ -161,7 +204,7 @@ def unpack_gathered(gathered: torch.Tensor, batch: int, world: int, max_rows: in
     ints = gathered.view(torch.int32)
     if batch == world * capacity:                       # even shards: pure views, no kernel
         dets = gathered[:, : max_rows * 6].reshape(batch, max_rows, 6)
-        return dets, ints[:, max_rows * 6], ints[:, max_rows * 6 + 1:]
+        return dets, ints[:, max_rows * 6], ints[:, max_rows * 6 + 1: max_rows * 6 + 5]
     keep = []
     for r in range(world):
         lo, hi = image_shard(batch, r, world)
@@ -171,7 +214,7 @@ def unpack_gathered(gathered: torch.Tensor, batch: int, world: int, max_rows: in
     irows = ints.index_select(0, idx)
     dets = rows[:, : max_rows * 6].reshape(batch, max_rows, 6)
     counts = irows[:, max_rows * 6].contiguous()
-    stats = irows[:, max_rows * 6 + 1:].contiguous()
+    stats = irows[:, max_rows * 6 + 1: max_rows * 6 + 5].contiguous()
     return dets, counts, stats
 
 

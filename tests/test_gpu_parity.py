@@ -815,29 +815,48 @@ def test_two_step_graphs_in_flight_equal_serial_steps(dev):
 
 def test_peer_exchange_single_rank_equals_tensor_op_packing(dev):
     """sharding.PeerExchange with a world of one (the multi-GPU check is tools/exchange_check.py under torchrun):
-    slots, launch counters, the wait kernel and the gathered layout."""
-    import torch.distributed as dist
+    slots, launch counters, row flags, the wait kernel and the gathered layout; no process group needed."""
     from single_shot_detection_b200 import sharding
     from single_shot_detection_b200.pipeline import matched_stats
-    import socket
-    with socket.socket() as s_:
-        s_.bind(("127.0.0.1", 0))
-        port = s_.getsockname()[1]
-    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
-    try:
-        px = sharding.PeerExchange(6, 20, slots=2, device=dev)
+    for n, t in [(6, 20), (3, 200), (1, 7)]:
+        px = sharding.PeerExchange(n, t, slots=2, device=dev)
+        assert px.world == 1 and px.gathered(0).shape == (n, sharding.row_words(t)) and sharding.row_words(t) % 4 == 0
         gen = torch.Generator().manual_seed(2)
         for rnd in range(3):
             for k in range(2):
-                dets = torch.rand((6, 20, 6), generator=gen)
-                counts = torch.randint(0, 21, (6,), generator=gen, dtype=torch.int32)
-                a_stats = torch.randint(0, 9, (6, 4), generator=gen, dtype=torch.int32)
+                dets = torch.rand((n, t, 6), generator=gen)
+                counts = torch.randint(0, t + 1, (n,), generator=gen, dtype=torch.int32)
+                a_stats = torch.randint(0, 9, (n, 4), generator=gen, dtype=torch.int32)
+                px.open(k)
                 stats = px.pack_exchange(dets.to(dev), counts.to(dev), a_stats.to(dev), None, k)
                 px.wait(k)
                 want_stats = matched_stats(a_stats, None, counts)
-                want = sharding.pack_shard(dets, counts, want_stats, 6)
+                want = sharding.pack_shard(dets, counts, want_stats, n)
                 assert torch.equal(px.gathered(k).cpu().view(torch.int32), want.view(torch.int32)), (rnd, k)
                 assert torch.equal(stats.cpu(), want_stats)
         assert px.error() == 0
-    finally:
-        dist.destroy_process_group()
+        px.close()
+
+
+def test_peer_exchange_in_step_graph_single_rank(dev):
+    """The exchange as the last kernel of a captured step graph (what bench.py replays, also at N = 1): the gathered
+    slot holds the step's detections, counts and statistics after every replay."""
+    from single_shot_detection_b200 import sharding
+    from single_shot_detection_b200.pipeline import AnchorPipeline
+    from single_shot_detection_b200.target_assigner import pack_ground_truth
+    w = wl.WORKLOADS["ssd300_voc_b8"]
+    anchors, gt, scores, locs = wl.make_inputs(w, seed=3, batch=4)
+    px = sharding.PeerExchange(4, w.max_total, slots=1, device=dev)
+    pipe = AnchorPipeline(w.cfg())
+    packed = pack_ground_truth(gt, dev)
+    out = pipe.capture(packed, anchors.to(dev), scores.to(dev), locs.to(dev), exchange=(px, 0))
+    for _ in range(3):
+        pipe.replay()
+    px.wait(0)
+    torch.cuda.synchronize()
+    dets, counts, stats = px.unpack(0)
+    assert torch.equal(counts.cpu(), out.counts.cpu())
+    assert torch.equal(dets.cpu(), out.dets.cpu())
+    assert torch.equal(stats.cpu()[:, 0], out.assign_stats.cpu()[:, 0]) and torch.equal(stats.cpu()[:, 3], out.counts.cpu())
+    assert px.error() == 0
+    px.close()

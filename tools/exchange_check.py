@@ -2,7 +2,10 @@
 """Multi-GPU check of the peer-memory exchange (run under torchrun, one rank per GPU):
 `python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/exchange_check.py`
 Every rank packs random shards into several slots for several rounds with sharding.PeerExchange and compares each
-gathered slot, bit for bit, with NCCL's all-gather of the tensor-op packing (sharding.all_gather_detections)."""
+gathered slot, bit for bit, with NCCL's all-gather of the tensor-op packing (sharding.all_gather_detections).
+A second phase skews the ranks: one rank per round stalls its stream between wait() and its read of the gathered
+slots while the others run ahead into the next rounds -- the slot must still hold the round it waited for (the
+writers wait for every rank's open() of the next launch before they overwrite)."""
 import os
 import sys
 
@@ -34,6 +37,7 @@ def main():
             counts = torch.randint(0, T + 1, (batch_local,), generator=gen, dtype=torch.int32).to(dev)
             a_stats = torch.randint(0, 99, (batch_local, 4), generator=gen, dtype=torch.int32).to(dev)
             m_stats = torch.randint(0, 99, (batch_local, 4), generator=gen, dtype=torch.int32).to(dev)
+            px.open(k)
             px.pack_exchange(dets, counts, a_stats, m_stats, k)
             want.append(sharding.all_gather_detections(dets, counts, matched_stats(a_stats, m_stats, counts), batch))
         for k in range(slots):
@@ -46,6 +50,32 @@ def main():
                     ok = False
                     print(f"rank {rank} round {rnd} slot {k}: gathered buffer differs", flush=True)
         dist.barrier()
+    # ---- skewed ranks: the reader of round r is slow, the writers of round r + 1 must wait for it ----
+    snaps, wants = [], []
+    for rnd in range(8):
+        want = []
+        for k in range(slots):
+            dets = torch.rand((batch_local, T, 6), generator=gen).to(dev)
+            counts = torch.randint(0, T + 1, (batch_local,), generator=gen, dtype=torch.int32).to(dev)
+            a_stats = torch.randint(0, 99, (batch_local, 4), generator=gen, dtype=torch.int32).to(dev)
+            px.open(k)
+            px.pack_exchange(dets, counts, a_stats, None, k)
+            want.append(sharding.all_gather_detections(dets, counts, matched_stats(a_stats, None, counts), batch))
+        for k in range(slots):
+            px.wait(k)
+        if rnd % world == rank:
+            torch.cuda._sleep(40_000_000)                  # ~20 ms: the peers are rounds ahead by now
+        snaps.append([px.gathered(k).clone() for k in range(slots)])
+        wants.append(want)
+    torch.cuda.synchronize()
+    for rnd, (snap, want) in enumerate(zip(snaps, wants)):
+        for k in range(slots):
+            got = sharding.unpack_gathered(snap[k], batch, world, T)
+            for g, r in zip(got, want[k]):
+                if not torch.equal(g.to(r.dtype), r):
+                    ok = False
+                    print(f"rank {rank} skewed round {rnd} slot {k}: slot overwritten while it was being read", flush=True)
+    dist.barrier()
     err = px.error()
     px.close()
     flag = torch.tensor([0 if ok and err == 0 else 1], device=dev)
