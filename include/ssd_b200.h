@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SSD_B200_ABI_VERSION 1
+#define SSD_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define SSD_API __attribute__((visibility("default")))
@@ -78,6 +78,10 @@ SSD_API size_t ssd_b200_timing_report(char* buf, size_t capacity);
  * 0 = automatic (fill the shared memory: fastest for a step that runs alone); 1 leaves room for the kernels of
  * other steps when several step graphs are in flight. */
 SSD_API int ssd_b200_set_stream_ctas_per_sm(int ctas);
+/* Candidate selection of the post-processor: -1 = automatic (one thread-block cluster per image when the image's
+ * logits fit the cluster's shared memory -- one launch instead of pass 1 / gates / pass 2), 0 = always the streaming
+ * two-pass path, 1/2/4/8 = that cluster size when it fits.  Both paths produce identical detections. */
+SSD_API int ssd_b200_set_fused_select(int mode);
 SSD_API int ssd_b200_trace_enable(unsigned long long* device_slots);
 SSD_API int ssd_b200_trace_slots(void);
 
@@ -192,9 +196,11 @@ SSD_API int ssd_hard_negative_mask(const float* logits, const int64_t* target_cl
 
 /* The selection alone, on the RAW criterion keys ssd_postprocess_pass1 emits (ordered_key(-log_softmax[0]),
  * class-agnostic) + the classes: int64 [B,A] (class_stride == 0) or the class column of fp32 target rows
- * (`classes` = &target[0][0][4], class_stride = 6 floats).  No workspace. */
+ * (`classes` = &target[0][0][4], class_stride = 6 floats).  `match` (optional) is match_out of the ssd_assign_targets
+ * call that wrote those rows: an unmatched / ignored anchor's class (0 / -1) is then taken from it (a coalesced read)
+ * and only the few matched anchors read the strided class column.  No workspace. */
 SSD_API int ssd_hard_negative_mask_from_keys(const uint32_t* loss_keys, const void* classes, int class_stride,
-                                     int batch, int num_anchors, double ratio, int ratio_is_integer,
+                                     const int32_t* match, int batch, int num_anchors, double ratio, int ratio_is_integer,
                                      double min_negatives, uint8_t* mask_out, int32_t* stats_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -47,6 +47,19 @@ int stream_ctas_override() {
     return g_stream_ctas;
 }
 
+// Fused candidate selection of the post-processor (postprocess.cu: fused_select_kernel): 0 = off (the streaming
+// two-pass path; the default: measured on B200 the cluster kernel is not faster), -1 = automatic (images
+// that fit the shared memory of one thread-block cluster, all clusters resident at once), 1/2/4/8 = this cluster size
+// when it fits.  SSD_FUSED_SELECT presets it; read when a launch is planned.
+static int g_fused_select = -2;
+int fused_select_mode() {
+    if (g_fused_select == -2) {
+        const char* e = getenv("SSD_FUSED_SELECT");
+        g_fused_select = (e && e[0]) ? atoi(e) : 0;
+    }
+    return g_fused_select;
+}
+
 __global__ void probe_kernel(int* out) { *out = 100; }
 
 // Scratch zeroing as a KERNEL node: inside a captured step graph a memset node in front of a branch was
@@ -180,6 +193,13 @@ extern "C" size_t ssd_b200_timing_report(char* buf, size_t capacity) {
 }
 
 SSD_DEFINE_TRACE_SETTER(set_trace_abi)
+
+extern "C" int ssd_b200_set_fused_select(int mode) {
+    SSD_REQUIRE(mode == -1 || mode == 0 || mode == 1 || mode == 2 || mode == 4 || mode == 8, SSD_ERR_INVALID_ARGUMENT,
+                "ssd_b200_set_fused_select: %d is not one of -1, 0, 1, 2, 4, 8", mode);
+    ssd::g_fused_select = mode;
+    return SSD_OK;
+}
 
 extern "C" int ssd_b200_set_stream_ctas_per_sm(int ctas) {
     SSD_REQUIRE(ctas >= 0 && ctas <= 8, SSD_ERR_INVALID_ARGUMENT, "ssd_b200_set_stream_ctas_per_sm: %d outside 0..8", ctas);

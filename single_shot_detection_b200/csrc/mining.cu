@@ -124,10 +124,21 @@ struct KeySource {
     const uint32_t* keys;
     const void* cls;
     int stride;
+    const int32_t* match;        // matcher output per anchor (optional): spares the strided class read for unmatched anchors
     __device__ __forceinline__ uint32_t key(int a) const {
         const uint32_t k = keys[a];
         if (cls == nullptr) return k;
-        const long long c = stride ? (long long)reinterpret_cast<const float*>(cls)[(size_t)a * stride]
+        long long c;
+        if (match != nullptr) {
+            // target_assigner.py:38-58: an unmatched anchor keeps class 0, an ignored one gets -1; only a MATCHED anchor
+            // (a few percent) carries its box's class, which is read from the row
+            const int m = match[a];
+            c = m == SSD_NOT_MATCHED ? (long long)SSD_NEGATIVE_CLASS
+                                     : (m == SSD_IGNORE ? (long long)SSD_IGNORE_CLASS
+                                                        : (stride ? (long long)reinterpret_cast<const float*>(cls)[(size_t)a * stride]
+                                                                  : reinterpret_cast<const long long*>(cls)[a]));
+        } else
+        c = stride ? (long long)reinterpret_cast<const float*>(cls)[(size_t)a * stride]
                                    : reinterpret_cast<const long long*>(cls)[a];
         if (c == SSD_NEGATIVE_CLASS) return k == 0u ? 1u : (k == kKeyPositive ? kKeyPositive - 1u : k);
         return c == SSD_IGNORE_CLASS ? kKeyIgnored : kKeyPositive;
@@ -170,7 +181,8 @@ __device__ __forceinline__ void block_sum4(SelShared& sh, int (&c)[4]) {
 }
 
 __global__ void __launch_bounds__(kSelThreads, 2)
-mining_select_kernel(const uint32_t* __restrict__ keys, const void* __restrict__ cls, int cls_stride, int A, double ratio,
+mining_select_kernel(const uint32_t* __restrict__ keys, const void* __restrict__ cls, int cls_stride,
+                     const int32_t* __restrict__ match, int A, double ratio,
                      int ratio_is_integer, double min_negatives, uint8_t* __restrict__ mask,
                      int32_t* __restrict__ stats) {
     __shared__ SelShared sh;
@@ -184,7 +196,7 @@ mining_select_kernel(const uint32_t* __restrict__ keys, const void* __restrict__
     // class column of float target rows `cls_stride` floats apart.
     const KeySource src{gk, cls == nullptr ? nullptr : (cls_stride ? (const void*)(reinterpret_cast<const float*>(cls) + (size_t)b * A * cls_stride)
                                                                   : (const void*)(reinterpret_cast<const long long*>(cls) + (size_t)b * A)),
-                        cls_stride};
+                        cls_stride, match == nullptr ? nullptr : match + (size_t)b * A};
     uint8_t* gm = mask + (size_t)b * A;
     const int tid = threadIdx.x;
     static_assert(kLossBins == 4 * kSelThreads, "four bins per thread");
@@ -459,13 +471,13 @@ extern "C" int ssd_hard_negative_mask(const float* logits, const int64_t* target
 
     LaunchTimer lt_("mining_select", st);
     SSD_CUDA(launch_pdl(mining_select_kernel, dim3(batch), dim3(kSelThreads), 0, st, (const uint32_t*)keys,
-                        (const void*)nullptr, 0, num_anchors, ratio, ratio_is_integer, min_negatives, mask_out, stats_out));
+                        (const void*)nullptr, 0, (const int32_t*)nullptr, num_anchors, ratio, ratio_is_integer, min_negatives, mask_out, stats_out));
     count_launch();
     return SSD_OK;
 }
 
 extern "C" int ssd_hard_negative_mask_from_keys(const uint32_t* loss_keys, const void* classes, int class_stride,
-                                                int batch, int num_anchors, double ratio, int ratio_is_integer,
+                                                const int32_t* match, int batch, int num_anchors, double ratio, int ratio_is_integer,
                                                 double min_negatives, uint8_t* mask_out, int32_t* stats_out,
                                                 void* stream) {
     SSD_REQUIRE(batch >= 0 && num_anchors >= 0 && class_stride >= 0, SSD_ERR_INVALID_ARGUMENT,
@@ -474,7 +486,7 @@ extern "C" int ssd_hard_negative_mask_from_keys(const uint32_t* loss_keys, const
     SSD_REQUIRE(loss_keys && classes && mask_out, SSD_ERR_INVALID_ARGUMENT, "ssd_hard_negative_mask_from_keys: null pointer");
     LaunchTimer lt_("mining_select", (cudaStream_t)stream);
     SSD_CUDA(launch_pdl(mining_select_kernel, dim3(batch), dim3(kSelThreads), 0, (cudaStream_t)stream, loss_keys, classes,
-                        class_stride, num_anchors, ratio, ratio_is_integer, min_negatives, mask_out, stats_out));
+                        class_stride, match, num_anchors, ratio, ratio_is_integer, min_negatives, mask_out, stats_out));
     count_launch();
     return SSD_OK;
 }

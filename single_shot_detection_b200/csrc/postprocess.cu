@@ -29,10 +29,13 @@
 // exact scores, the exact threshold compare, the ordering and the NMS overlap test are evaluated
 // in step 4 with separately rounded fp32 ops in the reference's order; the NMS overlap compare
 // is float-vs-double as in torchvision's CPU kernel.
+#include <cooperative_groups.h>
 #include <float.h>
 #include <math.h>
 
 #include "rowstream.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace ssd {
 
@@ -54,7 +57,12 @@ struct PostPlan {
     float bin_lo, bin_scale;
     float soft_thr;
     size_t total_bytes;
+    // fused candidate selection (fused_select_kernel): one thread-block cluster per image, 0 = not used
+    int fused_cluster, fused_rows_per_cta, fused_merge, fused_split, fused_chunk_floats;
+    unsigned fused_off_slab, fused_off_trow, fused_off_hist, fused_off_gate, fused_off_stage;
+    size_t fused_smem;
 };
+static void plan_fused(PostPlan& pl);
 
 constexpr int kKeptCols = 6;          // x1,y1,x2,y2,score,anchor(bits)
 constexpr int kScoreBins = 2048;      // per-image histogram of the kept scores (final top-k)
@@ -146,6 +154,7 @@ static int make_plan(const ssd_postprocess_params* p, PostPlan& pl) {
     int cap = 512;                        // power of two (the segment sort pads to one), >= 8K
     while (cap < 8 * pl.K && cap < 4096) cap <<= 1;
     pl.cand_cap = cap;
+    plan_fused(pl);
 
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += round_up(bytes, 256); return o; };
@@ -675,6 +684,422 @@ score_pass2_kernel(const float* __restrict__ scores, ScoreGrid g, const float2* 
     }
     griddep_launch_dependents();       // late: see the note at launch_pdl
     q.flush(cand_count, cand, cand_cap);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// 1-3 fused: candidate selection of an image that FITS THE SHARED MEMORY OF ONE THREAD-BLOCK CLUSTER
+//     (SSD300-VOC: 733 KB per image, SSD-MobileNetV2-COCO: 735 KB -- the launch-bound configurations).
+//     One cluster of cs <= 8 CTAs per image; CTA r keeps rows [r R, (r+1) R) of the image's logits in ITS shared
+//     memory (TMA bulk copies, a few chunks with one mbarrier each), so the logits leave HBM once and are never
+//     re-read through L2, and the three launches of the streaming path (pass 1 -> gates -> pass 2) with their two
+//     kernel boundaries become three phases of one kernel separated by cluster barriers:
+//       P1  row statistics (max, sum exp) -> rowstat / criterion keys as score_pass1_kernel writes them, the
+//           row's log-normaliser kept in shared memory; every lane keeps the running column maxima of the rows
+//           IT sees over `merge` steps (a "block" of the row partition) and bumps the CTA's shared-memory
+//           histogram of block maxima per column -- no cross-lane reduction, no block-maximum array at all;
+//       P2  cluster barrier; column c belongs to one warp of CTA c % cs, which sums the cs histograms of the
+//           column through distributed shared memory, finds the bin where the suffix count reaches K (the same
+//           lower bound of the K-th largest score as in the streaming path) and stores the gate into every CTA's
+//           shared memory; cluster barrier;
+//       P3  the slab is walked again out of shared memory, survivors go to the candidate lists.
+//     The NMS launch that follows is unchanged.
+// ---------------------------------------------------------------------------------------------
+constexpr int kFusedWarps = 16;
+constexpr int kFusedThreads = kFusedWarps * 32;
+constexpr int kFusedChunks = 8;
+constexpr size_t kFusedQueueBytes = (size_t)kFusedWarps * kQueueCap * 3 * sizeof(uint32_t);
+constexpr int kFusedStageBlocks = 8;           // blocks of the row partition per warp (at most)
+constexpr size_t kFusedSmemLimit = 226 * 1024;        // 227 KB opt-in maximum per CTA on sm_100
+
+int fused_select_mode();      // abi.cu: -1 automatic, 0 off, 1/2/4/8 forced cluster size
+static int fused_max_clusters(int C, bool softmax, int cs, size_t smem);   // co-resident clusters of the launch (cached)
+
+static void plan_fused(PostPlan& pl) {
+    pl.fused_cluster = 0;
+    const int mode = fused_select_mode();
+    if (mode == 0 || pl.converter == SSD_CONVERT_IDENTITY || pl.A < 1 || pl.B < 1) return;
+    const int q = lanes_per_row(pl.C, true);
+    const int rps = 32 / q;                                   // rows per warp step
+    const size_t hist_bytes = (size_t)pl.C * kGateStride * sizeof(uint32_t);
+    // (+ the staging rows of the block maxima: up to 32 / q blocks per warp, see the end of P1)
+    const size_t tail = round_up(hist_bytes > kFusedQueueBytes ? hist_bytes : kFusedQueueBytes, 16) +
+                        round_up((size_t)pl.C * 3 * sizeof(float), 16) +       // gates, per-class counts and bases
+                        round_up((size_t)kFusedWarps * kFusedStageBlocks * (pl.C | 1) * sizeof(float), 16);
+    auto smem_for = [&](int cs, int& rows_per_cta) {
+        rows_per_cta = (pl.A + cs - 1) / cs;
+        rows_per_cta = (rows_per_cta + rps - 1) / rps * rps;
+        const size_t slab = round_up(((size_t)rows_per_cta * pl.C + 8 + (size_t)(slots_per_row(pl.C) - pl.C)) * sizeof(float), 128);
+        return (size_t)128 + slab + round_up((size_t)rows_per_cta * sizeof(float), 16) + tail;
+    };
+    int cs = 0, rows = 0;
+    for (int c = 1; c <= 8; c <<= 1) {
+        int r;
+        if (smem_for(c, r) <= kFusedSmemLimit) { cs = c; rows = r; break; }
+    }
+    if (cs == 0) return;                                      // the image does not fit a cluster: streaming path
+    if (mode > 0) {
+        int r;
+        if (mode < cs || smem_for(mode, r) > kFusedSmemLimit) return;
+        cs = mode; rows = r;
+    } else {
+        // few images: more (smaller) CTAs per image while the grid stays within one wave of SMs
+        while (cs < 8 && (long long)pl.B * cs * 2 <= sm_count()) {
+            int r;
+            smem_for(cs * 2, r);
+            if (r < rps * 2) break;
+            cs *= 2; rows = r;
+        }
+    }
+    // Blocks of the row partition (any partition works: the K-th largest block maximum bounds the K-th largest
+    // score from below).  A lane keeps the column maxima of ALL the rows it sees (steps_per_warp of them); at the
+    // end of P1 the 32 / Q row slots of a warp are merged down to `split` blocks of ~A / 2K rows (at most ~32), so
+    // that >= ~2K block maxima exist per column.
+    const int steps = rows / rps;
+    const int steps_per_warp = (steps + kFusedWarps - 1) / kFusedWarps;
+    int want_rows = pl.A / (2 * pl.K);
+    if (want_rows > 32) want_rows = 32;
+    if (want_rows < 1) want_rows = 1;
+    int split = 1;
+    while (split < rps && split < kFusedStageBlocks && (long long)steps_per_warp * (rps / split) > want_rows) split <<= 1;
+    const int merge = steps_per_warp;
+    const long long blocks = (long long)cs * kFusedWarps * split;
+    if (blocks >= 65536) return;                              // 16-bit histogram counters
+    int r2;
+    pl.fused_smem = smem_for(cs, r2);
+    // automatic mode: only when every image's cluster is resident at once -- a second wave of clusters costs more than
+    // the two kernel boundaries of the streaming path save
+    if (mode < 0 && pl.B > fused_max_clusters(pl.C, pl.converter == SSD_CONVERT_SOFTMAX, cs, pl.fused_smem)) return;
+    pl.fused_cluster = cs; pl.fused_rows_per_cta = rows; pl.fused_merge = merge; pl.fused_split = split;
+    const size_t slab = round_up(((size_t)rows * pl.C + 8 + (size_t)(slots_per_row(pl.C) - pl.C)) * sizeof(float), 128);
+    pl.fused_off_slab = 128;
+    pl.fused_off_trow = (unsigned)(128 + slab);
+    pl.fused_off_hist = (unsigned)(pl.fused_off_trow + round_up((size_t)rows * sizeof(float), 16));
+    pl.fused_off_gate = (unsigned)(pl.fused_off_hist + round_up(hist_bytes > kFusedQueueBytes ? hist_bytes : kFusedQueueBytes, 16));
+    pl.fused_off_stage = (unsigned)(pl.fused_off_gate + round_up((size_t)pl.C * 3 * sizeof(float), 16));
+    int chunk = 1024;                                         // floats per bulk copy: a power of two (chunk of a float = a shift)
+    while ((size_t)chunk * kFusedChunks < (size_t)rows * pl.C + 4) chunk <<= 1;
+    pl.fused_chunk_floats = chunk;
+}
+
+// histogram bump in the shared memory of CTA `rank` of the cluster: red.shared::cluster, nothing comes back (a generic
+// atomicAdd on the mapped address was observed to cost a blocking round trip per bump)
+__device__ __forceinline__ void bump_gate_bin_remote(const uint32_t* words, int rank, float gval, GateBins gb) {
+    const int b = gate_bin(gval, gb);
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(words + (b >> 1))), "r"(rank));
+    asm volatile("red.relaxed.cluster.shared::cluster.add.u32 [%0], %1;" ::"r"(remote), "r"((b & 1) ? 0x10000u : 1u) : "memory");
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+struct FusedArgs {
+    int A, C, first_fg, K, converter, cand_cap;
+    int rows_per_cta, merge, split, chunk_floats, chunk_shift, queue_cap;
+    float score_thr;
+    GateBins bins;
+    long long total_floats;
+    unsigned off_slab, off_trow, off_hist, off_gate, off_stage;
+};
+
+template <int Q, int NREG, int CMIN, int CONV>
+__global__ void __launch_bounds__(kFusedThreads, 1)
+fused_select_kernel(const float* __restrict__ scores, FusedArgs fa, float2* __restrict__ rowstat,
+                    uint32_t* __restrict__ loss_keys, int* __restrict__ cand_count, uint2* __restrict__ cand,
+                    int* __restrict__ score_hist, int* __restrict__ image_done, int* __restrict__ status) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    KernelTrace trace_(TR_PASS1);
+    cg::cluster_group cluster = cg::this_cluster();
+    const int cs = (int)cluster.num_blocks();
+    const int crank = (int)cluster.block_rank();
+    const int img = blockIdx.x / cs;
+    const int Cf = fa.C - fa.first_fg;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);                          // [kFusedChunks]
+    float* slab = reinterpret_cast<float*>(smem + fa.off_slab);
+    float* trow = reinterpret_cast<float*>(smem + fa.off_trow);
+    uint32_t* shist = reinterpret_cast<uint32_t*>(smem + fa.off_hist);           // [C, kGateStride]; later: the queues
+    float* sgate = reinterpret_cast<float*>(smem + fa.off_gate);                 // [C]
+    int* s_cnt = reinterpret_cast<int*>(sgate + fa.C);                           // [C] candidates of this CTA per class
+    int* s_base = s_cnt + fa.C;                                                  // [C] their first slot in the global list
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int c = 0; c < kFusedChunks; ++c) mbar_init(bars + c, 1);
+        mbar_fence_init();
+    }
+    griddep_wait();
+
+    // ---- P0: this CTA's rows -> shared memory ----
+    const int row0 = crank * fa.rows_per_cta;
+    const int rows = max(0, min(fa.rows_per_cta, fa.A - row0));
+    const long long f0 = ((long long)img * fa.A + row0) * fa.C;
+    const long long f1 = f0 + (long long)rows * fa.C;
+    const long long fal = f0 & ~3ll;                           // 16-byte aligned superset (rows are 4 C bytes)
+    const int head = (int)(f0 - fal);
+    if (threadIdx.x == 0) {
+        long long fe = (f1 + 3) & ~3ll;
+        const long long n4 = fa.total_floats & ~3ll;
+        if (fe > n4) fe = n4 > fal ? n4 : fal;
+        for (long long f = fe; f < f1; ++f) slab[f - fal] = __ldg(scores + f);     // <= 3 floats, array tail only
+        const uint64_t policy = policy_evict_first();                             // read once
+#pragma unroll 1
+        for (int c = 0; c < kFusedChunks; ++c) {
+            const long long lo = fal + (long long)c * fa.chunk_floats;
+            long long hi = lo + fa.chunk_floats;
+            if (hi > fe) hi = fe;
+            if (hi > lo) {
+                const uint32_t bytes = (uint32_t)((hi - lo) * 4);
+                mbar_expect_tx(bars + c, bytes);
+                bulk_g2s(slab + (lo - fal), scores + lo, bytes, bars + c, policy);
+            } else {
+                mbar_arrive(bars + c);
+            }
+        }
+    }
+    trace_.mark(0);
+    // (while the copies fly) this CTA's histogram -- the OWNED columns receive the whole cluster's bumps -- and counters
+    for (int i = threadIdx.x; i < fa.C * kGateStride; i += kFusedThreads) shist[i] = 0u;
+    for (int i = threadIdx.x; i < fa.C; i += kFusedThreads) s_cnt[i] = 0;
+    __syncthreads();
+    cluster_arrive();                      // "my histogram is zeroed"; waited for right before the first remote bump
+    // counters / histograms the LATER launches accumulate into, and this image's candidate counts (P3)
+    if (crank == 0) {
+        for (int i = threadIdx.x; i < Cf; i += kFusedThreads) cand_count[(size_t)img * Cf + i] = 0;
+        int4* sh4 = reinterpret_cast<int4*>(score_hist + (size_t)img * kScoreBins);
+        for (int i = threadIdx.x; i < kScoreBins / 4; i += kFusedThreads) sh4[i] = make_int4(0, 0, 0, 0);
+        if (threadIdx.x == 0) image_done[img] = 0;
+        if (blockIdx.x == 0 && threadIdx.x < 4) status[threadIdx.x] = 0;
+    }
+
+    const RowLanes<Q> ln;
+    const RowShape<Q, NREG, CMIN> shape(ln.sub, fa.C);
+    constexpr int RPS = RowLanes<Q>::kRowsPerWarpStep;
+    const int steps = (rows + RPS - 1) / RPS;
+    const float* base = slab + head;
+
+    // ---- P1: row statistics, criterion keys, histogram of the block maxima ----
+    {
+        float cmax[NREG];
+#pragma unroll
+        for (int i = 0; i < NREG; ++i) cmax[i] = -INFINITY;
+        int ready = 0;
+        for (int s = warp_id(); s < steps; s += kFusedWarps) {
+            const int last_row = min((s + 1) * RPS, rows);
+            const int need = (head + last_row * fa.C - 1) >> fa.chunk_shift;      // chunk holding the step's last float
+            while (ready <= need) { mbar_wait(bars + ready, 0); ++ready; }
+            const int lr = s * RPS + ln.rl;
+            const bool valid = lr < rows;
+            float v[NREG];
+            shape.load(v, base + (size_t)lr * fa.C, ln.sub);
+            if (CONV == SSD_CONVERT_SOFTMAX) {
+                float m, sum;
+                row_max_sum<Q, NREG>(v, m, sum);
+                const float t = valid ? __fadd_rn(m, fast_log(sum)) : INFINITY;  // see score_pass1_kernel
+                if (valid && ln.sub == 0) {
+                    const size_t gr = (size_t)img * fa.A + row0 + lr;
+                    rowstat[gr] = make_float2(m, sum);
+                    trow[lr] = t;
+                    if (loss_keys != nullptr) {
+                        const uint32_t lk = ordered_key(__fsub_rn(t, v[0]));
+                        loss_keys[gr] = lk == 0u ? 1u : lk;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < NREG; ++i) cmax[i] = fmaxf(cmax[i], __fsub_rn(v[i], t));
+            } else {
+#pragma unroll
+                for (int i = 0; i < NREG; ++i) cmax[i] = fmaxf(cmax[i], valid ? v[i] : -INFINITY);
+            }
+        }
+        // The warp's row slots are merged down to `split` blocks and ONE lane per (block, column) bumps the histogram
+        // (lanes that all bumped their own maxima would pile onto the same few bins of a column: 32-way serialised
+        // shared-memory atomics).  Warps without a step contribute nothing.
+        // End of P1 for this warp.  Its row slots are merged down to `split` <= 8 blocks (shuffles), the block maxima
+        // are transposed through a small staging array so that lane c holds COLUMN c of every block, and that lane
+        // bumps the histogram of the column -- in the shared memory of the column's OWNER, CTA (c - first_fg) % cs
+        // (red.shared::cluster, nothing comes back), so that P2 reads local memory only.  (Every lane bumping its own
+        // 21 maxima cost ~900 instructions per warp -- as much as four row steps.)
+        trace_.mark(6);
+        cluster_wait();                    // every CTA of the cluster has zeroed its histogram
+        if (warp_id() < steps) {
+            const int cpad = fa.C | 1;
+            float* stage = reinterpret_cast<float*>(smem + fa.off_stage) + (size_t)warp_id() * kFusedStageBlocks * cpad;
+#pragma unroll
+            for (int i = 0; i < NREG; ++i) {
+                float x = cmax[i];
+#pragma unroll
+                for (int o = Q; o < 32; o <<= 1)
+                    if (o >= Q * fa.split) x = fmaxf(x, __shfl_xor_sync(FULL, x, o));
+                const int col = ln.sub + i * Q;
+                if (ln.rl < fa.split && col < fa.C) stage[ln.rl * cpad + col] = x;
+            }
+            __syncwarp();
+            trace_.mark(7);
+            for (int col = fa.first_fg + lane_id(); col < fa.C; col += 32) {
+                const uint32_t* words = shist + (size_t)col * kGateStride;
+                const int owner = (col - fa.first_fg) % cs;
+                for (int b = 0; b < fa.split; ++b) bump_gate_bin_remote(words, owner, stage[b * cpad + col], fa.bins);
+            }
+        }
+    }
+    trace_.mark(1);
+    cluster.sync();
+    trace_.mark(2);
+
+    // ---- P2: gates of the OWNED columns (CTA (c - first_fg) % cs, warp ((c - first_fg) / cs) % kFusedWarps) from the
+    //          local histogram, stored into every CTA's gate array ----
+    {
+        const int lane = lane_id();
+        for (int j = crank + cs * warp_id(); j < Cf; j += cs * kFusedWarps) {
+            const int col = fa.first_fg + j;
+            int cnt[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) cnt[u] = 0;
+            {
+                const uint32_t* rh = shist + (size_t)col * kGateStride + 4 * lane;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t w = rh[u];
+                    cnt[2 * u] = (int)(w & 0xFFFFu);
+                    cnt[2 * u + 1] = (int)(w >> 16);
+                }
+            }
+            int own = 0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) own += cnt[u];
+            int incl = own;                               // suffix sum towards higher lanes (= higher bins)
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_down_sync(FULL, incl, o);
+                if (lane + o < 32) incl += t;
+            }
+            int above = incl - own;
+            int bin = -1;
+            if (above < fa.K && incl >= fa.K) {
+#pragma unroll
+                for (int u = 7; u >= 0; --u) {
+                    if (bin < 0 && above + cnt[u] >= fa.K) bin = 8 * lane + u;
+                    above += cnt[u];
+                }
+            }
+            const float found = bin >= 0 ? gate_from_kth(fa.converter, fa.score_thr, gate_bin_edge(bin, fa.bins)) : -INFINITY;
+            const unsigned who = __ballot_sync(FULL, bin >= 0);
+            float gate = __shfl_sync(FULL, found, who ? __ffs(who) - 1 : 0);
+            if (who == 0u) gate = gate_from_kth(fa.converter, fa.score_thr, -INFINITY);
+            if (lane < cs) cluster.map_shared_rank(sgate, lane)[col] = gate;
+        }
+        for (int c = threadIdx.x; c < fa.first_fg; c += kFusedThreads) sgate[c] = INFINITY;
+    }
+    trace_.mark(3);
+    cluster.sync();
+    trace_.mark(4);
+
+    // ---- P3: candidates (nobody touches this CTA's histogram any more: the queues take its place).  A survivor takes
+    //          a CTA-local slot of its class (shared-memory atomic) and is parked in the warp's queue; then ONE global
+    //          atomic per (CTA, class) reserves the range in the candidate list -- 2000 same-address returning atomics
+    //          per image would serialise at L2 -- and the queues are written out. ----
+    {
+        CandQueue q;
+        uint32_t* qbase = shist + (size_t)warp_id() * fa.queue_cap * 3;
+        q.seg = qbase; q.anchor = qbase + fa.queue_cap; q.val = qbase + 2 * fa.queue_cap; q.n = 0;
+        const unsigned lt_mask = (1u << lane_id()) - 1u;
+        float gv[NREG];
+#pragma unroll
+        for (int i = 0; i < NREG; ++i) {
+            const int col = ln.sub + i * Q;
+            gv[i] = col < fa.C ? sgate[col] : INFINITY;
+        }
+        for (int s = warp_id(); s < steps; s += kFusedWarps) {
+            const int lr = s * RPS + ln.rl;
+            const bool valid = lr < rows;
+            float v[NREG];
+            shape.load(v, base + (size_t)lr * fa.C, ln.sub);
+            const float t = (CONV == SSD_CONVERT_SOFTMAX && valid) ? trow[lr] : 0.f;
+            unsigned hit = 0u;
+#pragma unroll
+            for (int i = 0; i < NREG; ++i) {
+                const float x = CONV == SSD_CONVERT_SOFTMAX ? __fsub_rn(v[i], t) : v[i];
+                hit |= (x > gv[i]) ? (1u << i) : 0u;            // -inf padding and gv = +inf never pass
+            }
+            if (!valid) hit = 0u;
+            unsigned bal = __ballot_sync(FULL, hit != 0u);
+            while (bal) {
+                const int add = __popc(bal);
+                const bool direct = q.n + add > fa.queue_cap;   // queue full (heavily tied scores): straight to the list
+                if (hit) {
+                    const int i = __ffs(hit) - 1;
+                    hit &= hit - 1;
+                    const int col = ln.sub + i * Q;
+                    const uint32_t seg = (uint32_t)(img * Cf + (col - fa.first_fg));
+                    const uint32_t raw = __float_as_uint(base[(size_t)lr * fa.C + col]);   // (a dynamic register pick costs NREG selects)
+                    if (direct) {
+                        const int slot = atomicAdd(&cand_count[seg], 1);
+                        if (slot < fa.cand_cap) cand[(size_t)seg * fa.cand_cap + slot] = make_uint2((uint32_t)(row0 + lr), raw);
+                    } else {
+                        const int pos = q.n + __popc(bal & lt_mask);
+                        const int local = atomicAdd(&s_cnt[col], 1);
+                        q.seg[pos] = ((uint32_t)col << 20) | (uint32_t)local;          // class column, CTA-local slot
+                        q.anchor[pos] = (uint32_t)(row0 + lr);
+                        q.val[pos] = raw;
+                    }
+                }
+                if (!direct) q.n += add;
+                bal = __ballot_sync(FULL, hit != 0u);
+            }
+        }
+        griddep_launch_dependents();       // late: see the note at launch_pdl
+        __syncthreads();
+        for (int c = fa.first_fg + threadIdx.x; c < fa.C; c += kFusedThreads) {
+            const int n = s_cnt[c];
+            s_base[c] = n ? atomicAdd(&cand_count[(size_t)img * Cf + (c - fa.first_fg)], n) : 0;
+        }
+        __syncthreads();
+        for (int e = lane_id(); e < q.n; e += 32) {
+            const uint32_t w = q.seg[e];
+            const int col = (int)(w >> 20);
+            const int slot = s_base[col] + (int)(w & 0xFFFFFu);
+            if (slot < fa.cand_cap)
+                cand[((size_t)img * Cf + (col - fa.first_fg)) * fa.cand_cap + slot] = make_uint2(q.anchor[e], q.val[e]);
+        }
+    }
+    trace_.mark(5);
+}
+
+
+static int fused_max_clusters(int C, bool softmax, int cs, size_t smem) {
+    struct Entry { int C, softmax, cs; size_t smem; int dev, n; };
+    static Entry cache[32];
+    static int used = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return 0; }   // no device: planning only
+    for (int i = 0; i < used; ++i)
+        if (cache[i].C == C && cache[i].softmax == (int)softmax && cache[i].cs == cs && cache[i].smem == smem && cache[i].dev == dev)
+            return cache[i].n;
+    int n = 0;
+#define SSD_QUERY_FUSED(QQ, NN, CM)                                                                              \
+    do {                                                                                                        \
+        auto query = [&](auto kern) {                                                                           \
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { \
+                (void)cudaGetLastError();                                                                       \
+                return;                                                                                         \
+            }                                                                                                   \
+            cudaLaunchConfig_t cfg = {};                                                                        \
+            cfg.gridDim = dim3((unsigned)(cs * 1024));                                                          \
+            cfg.blockDim = dim3(kFusedThreads);                                                                 \
+            cfg.dynamicSmemBytes = smem;                                                                        \
+            cudaLaunchAttribute attr[1];                                                                        \
+            attr[0].id = cudaLaunchAttributeClusterDimension;                                                   \
+            attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1; \
+            cfg.attrs = attr;                                                                                   \
+            cfg.numAttrs = 1;                                                                                   \
+            if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { (void)cudaGetLastError(); n = 0; } \
+        };                                                                                                      \
+        if (softmax) query(fused_select_kernel<QQ, NN, CM, SSD_CONVERT_SOFTMAX>);                               \
+        else query(fused_select_kernel<QQ, NN, CM, SSD_CONVERT_IDENTITY>);                                      \
+    } while (0)
+    SSD_DISPATCH_ROW_SHAPE_PASS1(C, SSD_QUERY_FUSED);
+#undef SSD_QUERY_FUSED
+    if (used < 32) cache[used++] = Entry{C, (int)softmax, cs, smem, dev, n};
+    return n;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1582,7 +2007,52 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
     GateBins gbins;
     gbins.lo = pl.bin_lo; gbins.scale = pl.bin_scale;
 
-    if (stages & kStagePass1) {
+    if ((stages & kStagePass1) && pl.fused_cluster > 0) {
+        // one cluster per image: row statistics, gates and candidates in one launch (fused_select_kernel)
+        FusedArgs fa;
+        fa.A = pl.A; fa.C = pl.C; fa.first_fg = pl.first_fg; fa.K = pl.K; fa.converter = pl.converter; fa.cand_cap = pl.cand_cap;
+        fa.rows_per_cta = pl.fused_rows_per_cta; fa.merge = pl.fused_merge; fa.split = pl.fused_split; fa.chunk_floats = pl.fused_chunk_floats;
+        fa.chunk_shift = 0;
+        while ((1 << fa.chunk_shift) < fa.chunk_floats) ++fa.chunk_shift;
+        {   // the queues take the place of the histogram: whatever that region holds
+            const size_t hist_bytes = (size_t)pl.C * kGateStride * sizeof(uint32_t);
+            const size_t region = hist_bytes > kFusedQueueBytes ? hist_bytes : kFusedQueueBytes;
+            fa.queue_cap = (int)(region / (kFusedWarps * 3 * sizeof(uint32_t)));
+        }
+        fa.score_thr = p->score_threshold; fa.bins = gbins; fa.total_floats = (long long)pl.B * pl.A * pl.C;
+        fa.off_slab = pl.fused_off_slab; fa.off_trow = pl.fused_off_trow; fa.off_hist = pl.fused_off_hist; fa.off_gate = pl.fused_off_gate; fa.off_stage = pl.fused_off_stage;
+#define SSD_LAUNCH_FUSED(QQ, NN, CM)                                                                                     \
+    do {                                                                                                               \
+        auto launch = [&](auto kern) -> int {                                                                          \
+            SSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.fused_smem));    \
+            prefer_max_shared(kern);                                                                                   \
+            cudaLaunchConfig_t cfg = {};                                                                               \
+            cfg.gridDim = dim3((unsigned)(pl.B * pl.fused_cluster));                                                   \
+            cfg.blockDim = dim3(kFusedThreads);                                                                        \
+            cfg.dynamicSmemBytes = pl.fused_smem;                                                                      \
+            cfg.stream = st;                                                                                           \
+            cudaLaunchAttribute attr[2];                                                                               \
+            attr[0].id = cudaLaunchAttributeClusterDimension;                                                          \
+            attr[0].val.clusterDim.x = (unsigned)pl.fused_cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1; \
+            attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                           \
+            attr[1].val.programmaticStreamSerializationAllowed = 1;                                                    \
+            cfg.attrs = attr;                                                                                          \
+            cfg.numAttrs = 2;                                                                                          \
+            LaunchTimer lt_("fused_select", st);                                                                       \
+            SSD_CUDA(cudaLaunchKernelEx(&cfg, kern, scores, fa, rowstat, loss_keys, cand_count, cand, score_hist,     \
+                                        image_done, status));                                                          \
+            return SSD_OK;                                                                                             \
+        };                                                                                                             \
+        int rc;                                                                                                        \
+        if (pl.converter == SSD_CONVERT_SOFTMAX) rc = launch(fused_select_kernel<QQ, NN, CM, SSD_CONVERT_SOFTMAX>);     \
+        else rc = launch(fused_select_kernel<QQ, NN, CM, SSD_CONVERT_IDENTITY>);                                        \
+        if (rc != SSD_OK) return rc;                                                                                   \
+    } while (0)
+        SSD_DISPATCH_ROW_SHAPE_PASS1(pl.C, SSD_LAUNCH_FUSED);
+#undef SSD_LAUNCH_FUSED
+        SSD_CUDA(cudaGetLastError());
+        count_launch();
+    } else if (stages & kStagePass1) {
     // (the counters, histograms and status words of the later launches are zeroed by pass 1 itself)
     uint4* zero_ptr = (uint4*)(ws + pl.zero_begin);
     const unsigned zero_n16 = (unsigned)(pl.zero_bytes / 16);
@@ -1608,6 +2078,7 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
     }
     if (!(stages & kStageRest)) return SSD_OK;
 
+    if (pl.fused_cluster == 0) {             // streaming path: gates + second pass
     if (!pl.gate_hist) {
         LaunchTimer lt_("gate", st);
         const int merge = (pl.nblk + 32 * kGateKeysPerLane - 1) / (32 * kGateKeysPerLane);
@@ -1651,6 +2122,7 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
 #undef SSD_LAUNCH_PASS2
     SSD_CUDA(cudaGetLastError());
     count_launch();
+    }   // streaming path
 
     {
         NmsArgs a;

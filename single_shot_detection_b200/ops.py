@@ -333,9 +333,11 @@ def postprocess_begin(scores: torch.Tensor, boxes: torch.Tensor, priors: Optiona
 
 
 def hard_negative_mask_from_keys(loss_keys: torch.Tensor, target: torch.Tensor, ratio: float, ratio_is_integer: bool,
-                                 min_negatives: float):
+                                 min_negatives: float, match: Optional[torch.Tensor] = None):
     """Selection on the raw criterion keys of :func:`postprocess_begin`; the classes are read straight from
-    the class column of ``target`` [B, A, 6] fp32 (no ``.long()`` copy) or from an int64 [B, A] tensor."""
+    the class column of ``target`` [B, A, 6] fp32 (no ``.long()`` copy) or from an int64 [B, A] tensor.  ``match``:
+    the int32 [B, A] matcher output of the assignment that wrote ``target`` (TargetAssigner.last_match) -- unmatched
+    and ignored anchors then take their class from it and only matched anchors touch the strided class column."""
     N.require_device()
     batch, num_anchors = loss_keys.shape
     dev = loss_keys.device
@@ -348,7 +350,9 @@ def hard_negative_mask_from_keys(loss_keys: torch.Tensor, target: torch.Tensor, 
     mask = torch.empty((batch, num_anchors), dtype=torch.bool, device=dev)
     stats = torch.empty((batch, 4), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
-        N.check(N.lib().ssd_hard_negative_mask_from_keys(loss_keys.data_ptr(), cls_ptr, stride, batch, num_anchors,
+        if match is not None:
+            assert match.dtype == torch.int32 and match.is_contiguous() and tuple(match.shape) == (batch, num_anchors)
+        N.check(N.lib().ssd_hard_negative_mask_from_keys(loss_keys.data_ptr(), cls_ptr, stride, _ptr(match), batch, num_anchors,
                                                          float(ratio), int(ratio_is_integer), float(min_negatives),
                                                          _ptr(mask), _ptr(stats), _stream()))
     return mask, stats

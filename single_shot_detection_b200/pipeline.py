@@ -67,6 +67,9 @@ class AnchorPipeline:
         self.fuse_assign_encode = os.environ.get("SSD_FUSE_ASSIGN_ENCODE", "1") != "0"
         # eval step: mining criterion out of the post-processor's first pass (SSD_SHARE_PASS=0: separate kernels)
         self.share_logit_pass = os.environ.get("SSD_SHARE_PASS", "1") != "0"
+        # opt-in: the assignment branch starts behind the post-processor's first pass (see _step_device; a single
+        # replayed graph gets shorter, 66 -> 59 us on the device timeline, but back-to-back replays measured slower)
+        self.assign_after_pass1 = os.environ.get("SSD_ASSIGN_AFTER_PASS1", "0") != "0"
         self._graph = None
         self._side = None
         self._copy = None
@@ -85,7 +88,7 @@ class AnchorPipeline:
         if self._shares_logit_pass():
             flight = self.postprocessor.begin_padded((scores, locs), anchors, want_loss_keys=True)
             mask = _sampler.hard_negative_mining_from_keys(flight.loss_keys, target, self.cfg.get("ratio"),
-                                                           self.cfg.get("min_neg"))
+                                                           self.cfg.get("min_neg"), self.target_assigner.last_match)
             self._encode_target_boxes(target, anchors)
             dets = self.postprocessor.to_list(*flight.finish())
         else:
@@ -274,6 +277,15 @@ class AnchorPipeline:
         # once.  So the train-side chain stays on ONE side stream -- assign -> to_centroids -> encode_box ->
         # selection -- and only the selection has a second (event) dependency, on the post-processor's pass 1.
         coder = self.box_coder if self.fuse_assign_encode else None
+        # The assignment shares the SMs with pass 1 when both start together and stretches it from ~11 to ~17 us
+        # (tools/graph_timeline.py); `assign_after_pass1` starts its branch behind pass 1 instead (off by default).
+        late_assign = share and self.assign_after_pass1
+        flight = keyed = None
+        if share and late_assign:
+            flight = self.postprocessor.begin_padded((scores_dev, locs_dev), anchors_dev, want_loss_keys=True)
+            keyed = torch.cuda.Event()
+            keyed.record(main)
+            side.wait_event(keyed)
         with torch.cuda.stream(side):
             if exchange is not None:
                 exchange[0].open(exchange[1])          # a new launch of the slot: its previous contents are released
@@ -282,7 +294,7 @@ class AnchorPipeline:
                 classes = target[..., CLASS_INDEX].long()                      # multibox_loss.py:49 (before the boxes change)
             else:
                 classes = None
-        if share:
+        if share and not late_assign:
             flight = self.postprocessor.begin_padded((scores_dev, locs_dev), anchors_dev, want_loss_keys=True)
             keyed = torch.cuda.Event()
             keyed.record(main)
@@ -292,7 +304,7 @@ class AnchorPipeline:
             if share:
                 side.wait_event(keyed)
                 mask = _sampler.hard_negative_mining_from_keys(flight.loss_keys, target, self.cfg.get("ratio"),
-                                                               self.cfg.get("min_neg"))
+                                                               self.cfg.get("min_neg"), self.target_assigner.last_match)
             else:
                 num_anchors = target.shape[1]
                 mask = self.sampler(scores_dev.view(batch, num_anchors, -1), classes)
@@ -333,11 +345,14 @@ class AnchorPipeline:
         logit-streaming kernels are captured with ONE resident CTA per SM, which leaves shared memory for the
         NMS / selection CTAs of the other steps (slower for a step that runs alone, faster in aggregate)."""
         from . import _native as N
+        late = self.assign_after_pass1
         if concurrent:
             N.check(N.lib().ssd_b200_set_stream_ctas_per_sm(1))
+            self.assign_after_pass1 = False
         try:
             return self._capture(packed, anchors_dev, scores_dev, locs_dev, warmup, shard_capacity, gather, exchange)
         finally:
+            self.assign_after_pass1 = late
             if concurrent:
                 N.check(N.lib().ssd_b200_set_stream_ctas_per_sm(0))
 

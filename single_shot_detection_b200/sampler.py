@@ -40,15 +40,15 @@ def hard_negative_mining_from_loss(loss, target_classes, negative_per_positive_r
     return mask
 
 
-def hard_negative_mining_from_keys(loss_keys, target, negative_per_positive_ratio, min_negative_per_image):
+def hard_negative_mining_from_keys(loss_keys, target, negative_per_positive_ratio, min_negative_per_image, match=None):
     """Selection half on the criterion the post-processor's first pass already produced from the same
     logits (``Postprocessor.begin_padded(..., want_loss_keys=True)``): in an eval step
     (detection/init.py:117-122) the loss and the post-processor see the same prediction, so the logits are
     streamed once for both.  ``target`` is the [B, A, 6] target (its class column is read in place) or the
-    int64 class tensor."""
+    int64 class tensor; ``match`` (optional) the matcher output of the assignment that wrote ``target``."""
     from . import ops
     ratio_is_integer = isinstance(negative_per_positive_ratio, int) and not isinstance(negative_per_positive_ratio, bool)
     mask, stats = ops.hard_negative_mask_from_keys(loss_keys, target, float(negative_per_positive_ratio),
-                                                   ratio_is_integer, float(min_negative_per_image))
+                                                   ratio_is_integer, float(min_negative_per_image), match)
     hard_negative_mining.last_stats = stats
     return mask

@@ -860,3 +860,63 @@ def test_peer_exchange_in_step_graph_single_rank(dev):
     assert torch.equal(stats.cpu()[:, 0], out.assign_stats.cpu()[:, 0]) and torch.equal(stats.cpu()[:, 3], out.counts.cpu())
     assert px.error() == 0
     px.close()
+
+
+# ----------------------------------------------------------------------------------------------
+# candidate selection: one cluster per image (fused_select_kernel) == the streaming two-pass path
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,batch", [("ssd300_voc_b8", 5), ("ssd_mb2_coco_b64", 7), ("tiny_voc_b3", 3),
+                                        ("tiny_sigmoid_b2", 2), ("ssd300_voc_8108_b8", 33)])
+def test_fused_cluster_selection_equals_streaming_path(dev, name, batch):
+    """The two routes to the candidate lists prune with different (both conservative) gates; everything after --
+    exact scores, threshold, top-k, NMS, final top-k -- must come out bit-identical, for every cluster size that
+    fits, and so must the row statistics and the sampler's criterion keys."""
+    from single_shot_detection_b200 import _native as N
+    from single_shot_detection_b200.pipeline import AnchorPipeline
+    w = wl.WORKLOADS[name]
+    anchors, gt, scores, locs = wl.make_inputs(w, seed=9, batch=batch)
+    lib = N.lib()
+
+    def run(mode):
+        N.check(lib.ssd_b200_set_fused_select(mode))
+        try:
+            pipe = AnchorPipeline(w.cfg())
+            target, mask, dets = pipe.step(gt, anchors, scores, locs)
+            torch.cuda.synchronize()
+            return target.cpu(), mask.cpu(), [d.cpu().clone() for d in dets], pipe.postprocessor.last_anchors.cpu().clone()
+        finally:
+            N.check(lib.ssd_b200_set_fused_select(-1))
+
+    ref = run(0)
+    for mode in (-1, 1, 2, 4, 8):
+        got = run(mode)
+        assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1]), (name, mode)
+        assert len(got[2]) == len(ref[2])
+        for i, (g, r) in enumerate(zip(got[2], ref[2])):
+            assert torch.equal(g, r), (name, mode, i)
+            assert torch.equal(got[3][i, :g.shape[0]], ref[3][i, :r.shape[0]]), (name, mode, i)
+
+
+def test_fused_cluster_selection_ties_and_overflow(dev):
+    """Heavily tied scores overflow the candidate lists on either route; the exact fallback must give the same rows."""
+    from single_shot_detection_b200 import _native as N
+    from single_shot_detection_b200.ops import OPS
+    lib = N.lib()
+    gen = torch.Generator().manual_seed(4)
+    b, a, c = 3, 3000, 6
+    logits = torch.randint(-2, 3, (b, a, c), generator=gen).float()          # five distinct values: ties en masse
+    centre = torch.rand((b, a, 2), generator=gen) * 200
+    size = torch.rand((b, a, 2), generator=gen) * 30 + 2
+    corners = torch.cat([centre - size / 2, centre + size / 2], dim=-1)
+    outs = []
+    for mode in (0, -1):
+        N.check(lib.ssd_b200_set_fused_select(mode))
+        try:
+            outs.append([t.cpu() for t in OPS.postprocess(logits.view(b, -1).to(dev), corners.view(b, -1).to(dev), None,
+                                                          N.CONVERT_SOFTMAX, 1, N.BOXES_CORNERS, 1.0, 1.0, 0.01, 100, 0.45, 200)])
+        finally:
+            N.check(lib.ssd_b200_set_fused_select(-1))
+    for i in range(b):
+        n = int(outs[0][1][i])
+        assert n == int(outs[1][1][i])
+        assert torch.equal(outs[0][0][i, :n], outs[1][0][i, :n]) and torch.equal(outs[0][2][i, :n], outs[1][2][i, :n])

@@ -33,6 +33,7 @@ for f, ln, src, s, e in out:
     a = agg.setdefault(k, [src, 0, 0]); a[1] += s; a[2] += e
 ts = sum(a[1] for a in agg.values()) or 1; te = sum(a[2] for a in agg.values()) or 1
 print(f"{first[:80] if first else kern}: samples {ts} warp-inst {te}")
-top = sorted(agg.items(), key=lambda kv: -kv[1][1])[:ntop]
+key_i = 2 if len(sys.argv) > 4 and sys.argv[4] == "inst" else 1
+top = sorted(agg.items(), key=lambda kv: -kv[1][key_i])[:ntop]
 for (f, ln), (src, s, e) in sorted(top):
     print(f"{f}:{ln:<5} {100*s/ts:5.1f}% samp {100*e/te:5.1f}% inst  {src[:105]}")
