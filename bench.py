@@ -9,7 +9,7 @@ A step = one pass of the hot path over one batch of synthetic input (SURVEY.md Â
     -> exchange of detections + statistics between the ranks (the same kernels also run at N = 1).
 
 ours:       `value`  = device-resident inputs, every step replayed from a CUDA graph, F consecutive steps in
-                       flight on F streams (default 4), timed with CUDA events (max over ranks).  The timed region
+                       flight on F streams (default 8), timed with CUDA events (max over ranks).  The timed region
                        is K steps repeated until it lasts >= 50 ms (`timed_steps`);
             `serial` = the same steps strictly one after the other on one stream;
             `e2e`    = the same step through the reference-shaped Python API with HOST buffers:
@@ -71,7 +71,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config5", action="store_true", help="skip the M2Det b256 strong-scaling leg")
     ap.add_argument("--no-e2e", action="store_true", help="(diagnostics) skip the host-buffer leg")
-    ap.add_argument("--in-flight", type=int, default=4,
+    ap.add_argument("--in-flight", type=int, default=8,
                     help="step graphs in flight on as many streams (1 = strictly one step after the other)")
     return ap.parse_args()
 

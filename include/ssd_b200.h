@@ -307,6 +307,19 @@ SSD_API int ssd_soft_nms(const float* corner_boxes, const float* scores, int num
                  float score_threshold, float sigma, int64_t* keep_out, int32_t* count_out, void* workspace,
                  size_t workspace_bytes, void* stream);
 
+/* box_utils.nms without a bound on the boxes that enter the NMS (bf/utils/box_utils.py:165-194 with
+ * max_per_class=None or max_per_class > SSD_MAX_PER_CLASS): global-memory sort (score descending, index ascending),
+ * the first max_keep rows (0 = all), then hard NMS with torchvision's semantics (64 x 64 tiles of the suppression
+ * bit matrix + sweep; keep_out in descending score order) or, soft != 0, the reference's Gaussian soft-NMS loop
+ * (box_utils.py:145-163; keep_out in pick order).  keep_out [min(max_keep or n, n)] int64 INPUT row indices,
+ * count_out [1].  num_boxes <= 2^20; the bit matrix takes k * ceil(k / 64) * 8 workspace bytes.  A corner of the
+ * API no sample configuration reaches: correct for any input, not tuned. */
+#define SSD_MAX_PER_CLASS 512
+SSD_API size_t ssd_nms_large_workspace_bytes(int num_boxes, int max_keep);
+SSD_API int ssd_nms_large(const float* corner_boxes, const float* scores, int num_boxes, int max_keep,
+                  double overlap_threshold, int soft, float soft_threshold, float soft_sigma, int64_t* keep_out,
+                  int32_t* count_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * f2  detection/metrics/mean_average_precision.py:10-116 + the accumulation loop of bf/eval.py:54-70
  *     (the consumer of the post-processor's output).

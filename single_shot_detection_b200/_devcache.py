@@ -11,23 +11,47 @@ from typing import Dict, Tuple
 
 import torch
 
-_const_cache: Dict[Tuple, torch.Tensor] = {}
+_const_cache: Dict[Tuple, Tuple] = {}
 _pinned: Dict[str, torch.Tensor] = {}
 _MAX_CONST = 16
 
 
 def device_copy(t: torch.Tensor, device: torch.device) -> torch.Tensor:
-    """fp32 contiguous copy of a (constant) tensor on ``device``; cached."""
+    """fp32 contiguous copy of a (constant) tensor on ``device``; cached.
+
+    The reference regenerates its CPU anchors every forward (detector.py: generate_anchors -> torch.cat), so the
+    source tensor of one step is freed and its address reused by the next: a cache keyed on the address alone
+    could hand back the copy of a DIFFERENT table of the same shape.  An entry therefore holds a weak reference to
+    its source -- a hit needs the very same tensor object, still alive, at the same version -- and tensors that are
+    new objects with equal CONTENT (the per-step regenerated anchors) are recognised by a digest of their bytes
+    (anchor tables are a few hundred KB: hashing them costs less than the H2D copy it saves)."""
     if t.is_cuda and t.device == device and t.dtype == torch.float32 and t.is_contiguous():
         return t
-    key = (t.data_ptr(), tuple(t.shape), t.dtype, t._version, str(device))
-    hit = _const_cache.get(key)
+    import hashlib
+    import weakref
+    ident = (id(t), t.data_ptr(), tuple(t.shape), t.dtype, t._version, str(device))
+    hit = _const_cache.get(ident)
+    if hit is not None and hit[0]() is t:
+        return hit[1]
+    src = t.detach()
+    if src.is_cuda:                                   # another device / dtype / layout: plain conversion, not cached
+        return src.to(device=device, dtype=torch.float32).contiguous()
+    host = src.contiguous()
+    digest = (hashlib.blake2b(host.numpy().tobytes(), digest_size=16).digest(), tuple(t.shape), t.dtype, str(device))
+    hit = _const_cache.get(digest)
     if hit is None:
-        if len(_const_cache) >= _MAX_CONST:
+        while len(_const_cache) >= _MAX_CONST:
             _const_cache.pop(next(iter(_const_cache)))
-        hit = t.detach().to(device=device, dtype=torch.float32).contiguous()
-        _const_cache[key] = hit
-    return hit
+        hit = (lambda: None, host.to(device=device, dtype=torch.float32).contiguous())
+        _const_cache[digest] = hit
+    # remember this object too, so that the next call with the same (still unmodified) tensor skips the digest
+    while len(_const_cache) >= _MAX_CONST:
+        _const_cache.pop(next(iter(_const_cache)))
+    try:
+        _const_cache[ident] = (weakref.ref(t), hit[1])
+    except TypeError:
+        pass
+    return hit[1]
 
 
 _in_flight = {}

@@ -116,6 +116,9 @@ _SIGNATURES = {
     "ssd_postprocess": (c_int, [POINTER(PostprocessParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ssd_nms_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "ssd_nms_large_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "ssd_nms_large": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_int, c_float, c_float, c_void_p, c_void_p,
+                              c_void_p, c_size_t, c_void_p]),
     "ssd_soft_nms": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_size_t,
                              c_void_p]),
     "ssd_nms": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

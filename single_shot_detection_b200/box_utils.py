@@ -115,8 +115,11 @@ def nms(boxes, scores, overlap_threshold, score_threshold, max_per_class=None, s
         empty = torch.zeros((0,), dtype=torch.long, device=boxes.device)
         return (boxes[empty], scores[empty]), empty
     if k > N.MAX_PER_CLASS:
-        raise NotImplementedError(f"nms over more than {N.MAX_PER_CLASS} boxes: pass max_per_class <= {N.MAX_PER_CLASS}")
-    if soft:            # box_utils.py:145-163 (picked in pick order; the returned scores are the INPUT scores)
+        # more boxes enter the NMS than the batched kernel keeps in shared memory (max_per_class=None on a long list,
+        # or a large max_per_class): the global-memory route, same semantics (csrc/nms_large.cu)
+        keep, count = OPS.nms_large(boxes, scores, 0 if max_per_class is None else int(max_per_class),
+                                    float(overlap_threshold), bool(soft), float(score_threshold), float(sigma))
+    elif soft:            # box_utils.py:145-163 (picked in pick order; the returned scores are the INPUT scores)
         keep, count = OPS.soft_nms(boxes, scores, max(k, 1), float(score_threshold), float(sigma))
     else:
         keep, count = OPS.nms(boxes, scores, max(k, 1), float(overlap_threshold))

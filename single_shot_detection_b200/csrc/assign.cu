@@ -88,7 +88,10 @@ assign_targets_kernel(const float4* __restrict__ anchors, const float* __restric
     griddep_wait();
     const int img = blockIdx.y;
     const int g0 = gt_offsets[img];
-    const int G = gt_offsets[img + 1] - g0;
+    const int G_raw = gt_offsets[img + 1] - g0;
+    // shared memory and the per-GT table are sized for max_gt boxes: an image that (against the contract) has more is
+    // cut there -- never an out-of-bounds access -- and shows as stats[3] > max_gt
+    const int G = G_raw < max_gt ? G_raw : max_gt;
     const int a_begin = blockIdx.x * kAssignTile;
     const int n_local = min(kAssignTile, A - a_begin);
 
@@ -329,7 +332,7 @@ assign_targets_kernel(const float4* __restrict__ anchors, const float* __restric
         stats[img * 4 + 0] = base_pos + s_delta[0];
         stats[img * 4 + 1] = base_ign + s_delta[1];
         stats[img * 4 + 2] = base_nan + s_delta[2];
-        stats[img * 4 + 3] = G;
+        stats[img * 4 + 3] = G_raw;
     }
 }
 
@@ -415,8 +418,9 @@ match_per_prediction_kernel(const float* __restrict__ w, int G, int A, float mat
     }
 }
 
-static unsigned long long* g_match_scratch = nullptr;
-static int g_match_scratch_cap = 0;
+// per-GT winners of ssd_match_per_prediction: one small buffer per DEVICE, allocated on first use (never inside a
+// stream capture) and kept; calls on one device must be serialised by the caller (API convenience path)
+static unsigned long long* g_match_scratch[64] = {nullptr};
 
 }  // namespace ssd
 
@@ -462,14 +466,19 @@ extern "C" int ssd_match_per_prediction(const float* weights, int num_gt, int nu
     SSD_REQUIRE(weights && box_idx_out, SSD_ERR_INVALID_ARGUMENT, "ssd_match_per_prediction: null pointer");
     SSD_REQUIRE(num_gt <= kMaxGtPerImage, SSD_ERR_UNSUPPORTED, "ssd_match_per_prediction: more than %d boxes",
                 kMaxGtPerImage);
-    // small persistent scratch for the per-GT winners (API convenience path, not the batch path)
-    if (g_match_scratch_cap < kMaxGtPerImage) {
-        SSD_CUDA(cudaMalloc(&g_match_scratch, sizeof(unsigned long long) * kMaxGtPerImage));
-        g_match_scratch_cap = kMaxGtPerImage;
+    int dev = 0;
+    SSD_CUDA(cudaGetDevice(&dev));
+    SSD_REQUIRE(dev >= 0 && dev < 64, SSD_ERR_UNSUPPORTED, "ssd_match_per_prediction: device index %d", dev);
+    if (g_match_scratch[dev] == nullptr) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        SSD_CUDA(cudaStreamIsCapturing((cudaStream_t)stream, &cap));
+        SSD_REQUIRE(cap == cudaStreamCaptureStatusNone, SSD_ERR_UNSUPPORTED,
+                    "ssd_match_per_prediction: first call on a device allocates scratch and cannot be captured");
+        SSD_CUDA(cudaMalloc(&g_match_scratch[dev], sizeof(unsigned long long) * kMaxGtPerImage));
     }
     SSD_CUDA(launch_pdl(match_per_prediction_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, weights, num_gt,
                         num_anchors, matched_threshold, unmatched_threshold, force_match, (long long*)box_idx_out,
-                        g_match_scratch));
+                        g_match_scratch[dev]));
     count_launch();
     return SSD_OK;
 }

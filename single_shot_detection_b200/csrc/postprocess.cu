@@ -84,7 +84,7 @@ __device__ __forceinline__ int score_bin(float v) {
     return 1 + (int)s;                 // 1 .. kScoreBins-1 (NaN never reaches here: it fails score > thr)
 }
 constexpr int kMaxPerClass = 512;
-constexpr int kNmsThreads = 128;
+constexpr int kNmsThreadsMax = 256;     // segment_nms_kernel<NT>: NT = 32, 64, 128 or 256 threads per (image, class)
 constexpr int kTopkThreads = 512;
 
 // Bin range of the block-maximum histograms.  SOFTMAX: log-probabilities from just under
@@ -124,7 +124,6 @@ static int make_plan(const ssd_postprocess_params* p, PostPlan& pl) {
     const long long need = (pl.T > 0 && pl.T < all_rows) ? pl.T : all_rows;
     SSD_REQUIRE(pl.det_cap >= need, SSD_ERR_INVALID_ARGUMENT,
                 "ssd_postprocess: det_capacity %d below the %lld rows an image can produce", pl.det_cap, need);
-    SSD_REQUIRE(all_rows <= 26000, SSD_ERR_UNSUPPORTED, "ssd_postprocess: classes*max_per_class = %lld > 26000", all_rows);
 
     const int A1 = pl.A > 0 ? pl.A : 1;
     ScoreGrid& g = pl.g;
@@ -1300,9 +1299,9 @@ __device__ __forceinline__ bool pair_suppressed(const NmsArgs& a, float4 bi, flo
 
 constexpr int kRankSortMax = 256;     // candidate lists up to this size are sorted by ranking
 // 64-bit sort slots at the head of the NMS kernel's shared memory; later reused as the per-warp pair
-// lists of the overlap filter (kNmsThreads / 32 warps x 1024 16-bit codes), hence at least 1024
-__host__ __device__ inline int nms_key_slots(int cand_cap) {
-    const int lo = kMaxPerClass > 256 * (kNmsThreads / 32) ? kMaxPerClass : 256 * (kNmsThreads / 32);
+// lists of the overlap filter (NT / 32 warps x 1024 16-bit codes), hence at least 1024
+__host__ __device__ inline int nms_key_slots(int cand_cap, int nt) {
+    const int lo = kMaxPerClass > 256 * (nt / 32) ? kMaxPerClass : 256 * (nt / 32);
     return cand_cap > lo ? cand_cap : lo;
 }
 
@@ -1595,6 +1594,7 @@ image_topk_kernel(TopkArgs ta) {
 // 4. segment_nms: one CTA per (image, foreground class)
 // ---------------------------------------------------------------------------------------------
 // Returns the number of kept rows of the segment (kept_count[seg] is written by the caller).
+template <int NT>
 __device__ int nms_segment(const KernelTrace& tr, const NmsArgs& a, unsigned char* smem, uint32_t* s_hist, int* s_misc, int& s_valid, int& s_nkeep,
                            const float* __restrict__ scores, const float2* __restrict__ rowstat,
                            const int* __restrict__ cand_count, const uint2* __restrict__ cand,
@@ -1609,7 +1609,7 @@ __device__ int nms_segment(const KernelTrace& tr, const NmsArgs& a, unsigned cha
     int n_raw = cand_count[seg];
     if (n_raw == 0) return 0;
     // carve: keys[key_slots] u64 | sorted[K] u64 | box[K] float4 | fbox[K] float4 | area[K] | mask[K * kwords] | keep[K]
-    const int key_slots = nms_key_slots(a.cand_cap);
+    const int key_slots = nms_key_slots(a.cand_cap, NT);
     const int kwords = (a.K + 31) >> 5;
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem);
     unsigned long long* sorted = keys + key_slots;
@@ -1680,11 +1680,11 @@ __device__ int nms_segment(const KernelTrace& tr, const NmsArgs& a, unsigned cha
         for (int t = threadIdx.x; t < fill4; t += blockDim.x) hk[t] = t < n_raw ? (uint32_t)(keys[t] >> 32) : 0u;
         __syncthreads();
         const uint4* h4 = reinterpret_cast<const uint4*>(hk);
-        constexpr int kPerThread = (kRankSortMax + kNmsThreads - 1) / kNmsThreads;
+        constexpr int kPerThread = (kRankSortMax + NT - 1) / NT;
         int myrank[kPerThread];
 #pragma unroll
         for (int u = 0; u < kPerThread; ++u) {
-            const int t = threadIdx.x + u * kNmsThreads;
+            const int t = threadIdx.x + u * NT;
             myrank[u] = -1;
             if (t >= n_raw) continue;
             const unsigned long long me = keys[t];
@@ -1704,7 +1704,7 @@ __device__ int nms_segment(const KernelTrace& tr, const NmsArgs& a, unsigned cha
         bool bad = false;
 #pragma unroll
         for (int u = 0; u < kPerThread; ++u)          // a key that is not in its own slot lost it to a tied score word
-            if (myrank[u] >= 0) bad = bad || sorted[myrank[u]] != keys[threadIdx.x + u * kNmsThreads];
+            if (myrank[u] >= 0) bad = bad || sorted[myrank[u]] != keys[threadIdx.x + u * NT];
         if (__syncthreads_or(bad)) {
             // exact ranking on the full 64-bit keys
             const ulonglong2* k2 = reinterpret_cast<const ulonglong2*>(keys);
@@ -1933,7 +1933,8 @@ __device__ int nms_segment(const KernelTrace& tr, const NmsArgs& a, unsigned cha
     return nkeep;
 }
 
-__global__ void __launch_bounds__(kNmsThreads)
+template <int NT>
+__global__ void __launch_bounds__(NT)
 segment_nms_kernel(NmsArgs a, TopkArgs ta, const float* __restrict__ scores, const float2* __restrict__ rowstat,
                    const int* __restrict__ cand_count, const uint2* __restrict__ cand,
                    const float4* __restrict__ boxes, const float4* __restrict__ priors, int* __restrict__ kept_count,
@@ -1941,13 +1942,13 @@ segment_nms_kernel(NmsArgs a, TopkArgs ta, const float* __restrict__ scores, con
                    int* __restrict__ image_done) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint32_t s_hist[2048];
-    __shared__ int s_misc[4 + kNmsThreads / 32];
+    __shared__ int s_misc[4 + NT / 32];
     __shared__ int s_valid, s_nkeep, s_ticket;
     KernelTrace trace_(TR_NMS);
     griddep_wait();
     const int seg = blockIdx.x;
     const int img = seg / a.Cf;
-    const int nkeep = nms_segment(trace_, a, smem, s_hist, s_misc, s_valid, s_nkeep, scores, rowstat, cand_count, cand, boxes,
+    const int nkeep = nms_segment<NT>(trace_, a, smem, s_hist, s_misc, s_valid, s_nkeep, scores, rowstat, cand_count, cand, boxes,
                                   priors, kept, status, score_hist);
     griddep_launch_dependents();       // late: see the note at launch_pdl
     if (threadIdx.x == 0) kept_count[seg] = nkeep;
@@ -1961,8 +1962,8 @@ segment_nms_kernel(NmsArgs a, TopkArgs ta, const float* __restrict__ scores, con
     __syncthreads();
     if (s_ticket != a.Cf - 1) return;
     __threadfence();
-    TopkShared<kNmsThreads>& sh = *reinterpret_cast<TopkShared<kNmsThreads>*>(s_hist);
-    image_topk_body<kNmsThreads>(smem, sh, ta, img);
+    TopkShared<NT>& sh = *reinterpret_cast<TopkShared<NT>*>(s_hist);
+    image_topk_body<NT>(smem, sh, ta, img);
 }
 
 __global__ void widen_keep_kernel(const int* __restrict__ src, const int* __restrict__ count, long long* __restrict__ dst,
@@ -1981,6 +1982,15 @@ extern "C" size_t ssd_postprocess_workspace_bytes(const ssd_postprocess_params* 
     PostPlan pl;
     if (make_plan(p, pl) != SSD_OK) return 0;
     return pl.total_bytes;
+}
+
+// threads per (image, class) CTA of the NMS kernel: SSD_NMS_THREADS = 32 / 64 / 128 / 256, read once
+static int nms_threads() {
+    static const int nt = [] {
+        const int v = env_int("SSD_NMS_THREADS", 128);
+        return (v == 32 || v == 64 || v == 256) ? v : 128;
+    }();
+    return nt;
 }
 
 constexpr int kStagePass1 = 1, kStageRest = 2;
@@ -2138,24 +2148,32 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
         ta.Cf = pl.Cf; ta.K = pl.K; ta.T = pl.T; ta.det_cap = pl.det_cap; ta.kept_count = kept_count; ta.kept = kept;
         ta.score_hist = score_hist; ta.dets = dets_out; ta.det_count = count_out; ta.det_anchor = anchor_out;
         const int kwords = (pl.K + 31) / 32;
-        const size_t key_slots = nms_key_slots(pl.cand_cap);
+        const int nt = nms_threads();
+        const size_t key_slots = nms_key_slots(pl.cand_cap, nt);
         const size_t nms_smem = key_slots * 8 + (size_t)(pl.K + 1) * (8 + 16 + 16 + 4 + 4) + (size_t)pl.K * kwords * 4 + 64;
         // The final top-k can run in the last segment CTA of every image (fence + ticket) instead of
         // in its own launch.  Measured on B200 (tools/graph_timeline.py) the 128-thread tail is slower
         // than the launch it saves unless the batch is large, so it is opt-in: SSD_TOPK=fused.
         const size_t topk_smem = topk_smem_bytes(pl.Cf, pl.T);
-        bool fused_topk = false;
-        { const char* e = getenv("SSD_TOPK"); if (e && e[0] == 'f') fused_topk = topk_smem <= nms_smem + 16 * 1024; }
+        static const bool want_fused_topk = [] { const char* e = getenv("SSD_TOPK"); return e && e[0] == 'f'; }();
+        const bool fused_topk = want_fused_topk && topk_smem <= nms_smem + 16 * 1024;
         const size_t smem = fused_topk && topk_smem > nms_smem ? topk_smem : nms_smem;
-        SSD_CUDA(cudaFuncSetAttribute(segment_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        {
+        auto launch_nms = [&](auto kern, int threads) -> int {
+            SSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             LaunchTimer lt_("nms", st);
-            SSD_CUDA(launch_pdl(segment_nms_kernel, dim3(pl.B * pl.Cf), dim3(kNmsThreads), smem, st, a, ta, scores,
+            SSD_CUDA(launch_pdl(kern, dim3(pl.B * pl.Cf), dim3(threads), smem, st, a, ta, scores,
                                 (const float2*)rowstat, (const int*)cand_count, (const uint2*)cand, (const float4*)boxes,
                                 (const float4*)priors, kept_count, kept, status, score_hist,
                                 fused_topk ? image_done : (int*)nullptr));
             count_launch();
-        }
+            return SSD_OK;
+        };
+        int rc_nms;
+        if (nt == 32) rc_nms = launch_nms(segment_nms_kernel<32>, 32);
+        else if (nt == 64) rc_nms = launch_nms(segment_nms_kernel<64>, 64);
+        else if (nt == 256) rc_nms = launch_nms(segment_nms_kernel<256>, 256);
+        else rc_nms = launch_nms(segment_nms_kernel<128>, 128);
+        if (rc_nms != SSD_OK) return rc_nms;
         if (!fused_topk) {
             SSD_REQUIRE(topk_smem <= 224 * 1024, SSD_ERR_UNSUPPORTED,
                         "ssd_postprocess: final top-k needs %zu bytes of shared memory", topk_smem);

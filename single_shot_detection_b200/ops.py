@@ -32,6 +32,8 @@ _LIB.define("postprocess(Tensor scores, Tensor boxes, Tensor? priors, int conver
             "float overlap_threshold, int max_total, float soft_sigma=0.0) -> (Tensor, Tensor, Tensor, Tensor)")
 _LIB.define("nms(Tensor boxes, Tensor scores, int max_per_class, float overlap_threshold) -> (Tensor, Tensor)")
 _LIB.define("soft_nms(Tensor boxes, Tensor scores, int max_per_class, float score_threshold, float sigma) -> (Tensor, Tensor)")
+_LIB.define("nms_large(Tensor boxes, Tensor scores, int max_keep, float overlap_threshold, bool soft, float score_threshold, "
+            "float sigma) -> (Tensor, Tensor)")
 _LIB.define("multibox_loss(Tensor scores, Tensor locs, Tensor target, Tensor sampled_mask, int kind, float gamma, "
             "float alpha, float class_weight, float loc_weight, bool need_grad, Tensor? giou_priors=None, "
             "float xy_scale=1.0, float wh_scale=1.0) -> (Tensor, Tensor, Tensor)")
@@ -154,6 +156,9 @@ def _assign_targets(anchors: torch.Tensor, gt_rows: torch.Tensor, gt_offsets: to
     """``box_coding`` = (xy_scale, wh_scale, eps): the box columns come out already passed through the loss
     route's to_centroids + encode_box (ssd_assign_targets_encoded)."""
     N.require_device()
+    anchors, gt_rows = _f32c(anchors), _f32c(gt_rows)
+    if gt_offsets.dtype != torch.int32 or not gt_offsets.is_contiguous():
+        gt_offsets = gt_offsets.to(torch.int32).contiguous()
     batch = gt_offsets.numel() - 1
     num_anchors = anchors.shape[0]
     dev = anchors.device
@@ -388,6 +393,24 @@ def _soft_nms(boxes: torch.Tensor, scores: torch.Tensor, max_per_class: int, sco
     return keep, count
 
 
+def _nms_large(boxes: torch.Tensor, scores: torch.Tensor, max_keep: int, overlap_threshold: float, soft: bool,
+               score_threshold: float, sigma: float):
+    """box_utils.nms over a long list (ssd_nms_large): keep [k] int64 input rows + count [1] int32."""
+    N.require_device()
+    boxes, scores = _f32c(boxes), _f32c(scores)
+    n = scores.numel()
+    dev = boxes.device
+    k = max_keep if 0 < max_keep < n else n
+    keep = torch.empty((max(k, 1),), dtype=torch.int64, device=dev)
+    count = torch.zeros((1,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        nbytes = N.lib().ssd_nms_large_workspace_bytes(n, max_keep)
+        ws = workspace(max(nbytes, 256), dev, "nms_large")
+        N.check(N.lib().ssd_nms_large(_ptr(boxes), _ptr(scores), n, max_keep, overlap_threshold, int(soft), score_threshold,
+                                      sigma, _ptr(keep), _ptr(count), _ptr(ws), ws.numel(), _stream()))
+    return keep, count
+
+
 def _multibox_loss(scores: torch.Tensor, locs: torch.Tensor, target: torch.Tensor, sampled_mask: torch.Tensor,
                    kind: int, gamma: float, alpha: float, class_weight: float, loc_weight: float, need_grad: bool,
                    giou_priors: Optional[torch.Tensor] = None, xy_scale: float = 1.0, wh_scale: float = 1.0):
@@ -428,7 +451,8 @@ def _multibox_loss(scores: torch.Tensor, locs: torch.Tensor, target: torch.Tenso
 for _name, _fn in [("multibox_loss", _multibox_loss), ("pairwise_iou", _pairwise_iou), ("generalized_iou", _generalized_iou), ("match_per_prediction", _match_per_prediction),
                    ("assign_targets", _assign_targets), ("box_transform", _box_transform),
                    ("box_transform_", _box_transform_), ("positive_mask", _positive_mask),
-                   ("hard_negative_mask", _hard_negative_mask), ("postprocess", _postprocess), ("nms", _nms), ("soft_nms", _soft_nms)]:
+                   ("hard_negative_mask", _hard_negative_mask), ("postprocess", _postprocess), ("nms", _nms), ("soft_nms", _soft_nms),
+                   ("nms_large", _nms_large)]:
     _LIB.impl(_name, _fn, "CUDA")
 
 OPS = torch.ops.ssd_b200

@@ -27,10 +27,12 @@ class Postprocessor(object):
         self.score_converter = score_converter
         if score_converter not in _CONVERTERS:
             raise ValueError(f'Wrong value for score_converter: {score_converter}')
-        if nms.get('max_per_class') is None:
-            raise NotImplementedError('max_per_class=None (NMS over every candidate) is not supported; '
-                                      'every reference sample sets it (100)')
         self._nms_cfg = dict(nms)
+        # The batched kernels keep max_per_class <= 512 boxes per (image, class) in shared memory.  max_per_class=None
+        # (NMS over EVERY box above the threshold) or a larger bound -- no reference sample uses either -- take the
+        # reference's own loop structure over (image, class) with the long-list NMS (csrc/nms_large.cu) inside.
+        k = nms.get('max_per_class')
+        self._unbounded = k is None or int(k) > N.MAX_PER_CLASS
         self.last_status = None
 
     def postprocess_padded(self, prediction, priors):
@@ -39,6 +41,9 @@ class Postprocessor(object):
         device = b_scores.device
         if not b_scores.is_cuda:
             raise TypeError('Postprocessor needs CUDA predictions (no CPU fallback)')
+        if self._unbounded:
+            raise NotImplementedError('postprocess_padded needs max_per_class <= %d; postprocess() handles the rest'
+                                      % N.MAX_PER_CLASS)
         priors_dev = _devcache.device_copy(priors, device)
         converter, first_fg = _CONVERTERS[self.score_converter]
         max_total = int(self.max_total) if self.max_total is not None else 0
@@ -49,6 +54,11 @@ class Postprocessor(object):
                                float(self._nms_cfg.get('sigma', 0.5)) if self._nms_cfg.get('soft', False) else 0.0)
 
     def begin_padded(self, prediction, priors, want_loss_keys=False):
+        if self._unbounded:
+            raise NotImplementedError('begin_padded needs max_per_class <= %d' % N.MAX_PER_CLASS)
+        return self._begin_padded(prediction, priors, want_loss_keys)
+
+    def _begin_padded(self, prediction, priors, want_loss_keys=False):
         """First launch only (row statistics; with ``want_loss_keys`` also the sampler's criterion, see
         ops.postprocess_begin); ``.finish()`` on the result enqueues the rest and returns what
         :meth:`postprocess_padded` returns."""
@@ -76,7 +86,45 @@ class Postprocessor(object):
         Returns:
             processed: list(:len Batch) of torch.tensor(:shape [Boxes_i, 6] ~ {[0-3] - box, [4] - class, [5] - score})
         """
+        if self._unbounded:
+            return self._postprocess_unbounded(prediction, priors)
         return self.to_list(*self.postprocess_padded(prediction, priors))
+
+    def _postprocess_unbounded(self, prediction, priors):
+        """detection/postprocessor.py:36-76 with an unbounded (or > 512) max_per_class: the conversion, decoding
+        and the loop over (image, class) as the reference writes them (device tensor ops + this package's decode
+        kernel), ``box_utils.nms`` -- the long-list kernels -- per class.  One host sync per class, like the
+        reference's boolean indexing; this route exists for completeness, not speed."""
+        b_scores, b_boxes = prediction
+        if not b_scores.is_cuda:
+            raise TypeError('Postprocessor needs CUDA predictions (no CPU fallback)')
+        device = b_scores.device
+        batch_size, num_priors = b_scores.size(0), priors.size(0)
+        priors_dev = _devcache.device_copy(priors, device)
+        b_scores = b_scores.float().view(batch_size, num_priors, -1)
+        b_scores = torch.sigmoid(b_scores) if self.score_converter == 'SIGMOID' else torch.softmax(b_scores, dim=-1)
+        if self.score_converter == 'SOFTMAX':
+            b_scores = b_scores[..., 1:]
+        num_classes = b_scores.size(-1)
+        b_boxes = self.box_coder.decode_box(b_boxes.float().view(batch_size, num_priors, 4), priors_dev,
+                                            inplace=torch.tensor(0))
+        b_boxes = box_utils.to_corners(b_boxes)
+        processed = []
+        for scores, boxes in zip(b_scores, b_boxes):
+            picked = []
+            for class_index in range(num_classes):
+                class_scores = scores[:, class_index].contiguous()
+                mask = class_scores > self.score_threshold
+                (boxes_picked, scores_picked), _ = self.nms(boxes[mask], class_scores[mask])
+                classes_picked = torch.full_like(scores_picked.unsqueeze(1), class_index + 1, dtype=torch.float)
+                picked.append(torch.cat([boxes_picked, classes_picked, scores_picked.unsqueeze(1)], dim=-1))
+            picked = torch.cat(picked, dim=0)
+            if self.max_total is not None and self.max_total < picked.size(0):
+                _, indexes = torch.topk(picked[:, 5], self.max_total, sorted=True, largest=True)
+                picked = picked[indexes]
+            processed.append(picked)
+        self.last_status = [0, 0, 0, 0]
+        return processed
 
     def to_list(self, dets, counts, anchors, status):
         """Padded device output -> the reference's list of ``[n_i, 6]`` views (one host sync: the counts)."""
@@ -85,9 +133,8 @@ class Postprocessor(object):
         host[: counts.numel()].copy_(counts, non_blocking=True)
         host[counts.numel():].copy_(status, non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        # status words (ssd_postprocess): [0] unused (always 0), [1] (image, class) lists that overflowed and were
+        # redone exactly from the score column, [2] lists too long for the rank sort (bitonic path), [3] longest list
         self.last_status = host[counts.numel():].tolist()
-        if self.last_status[0]:
-            raise RuntimeError(f'postprocess: {self.last_status[0]} (image, class) candidate lists overflowed; '
-                               'result would be inexact')
         self.last_anchors = anchors
         return [dets[i, :n] for i, n in enumerate(host[: counts.numel()].tolist())]

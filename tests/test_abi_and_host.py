@@ -133,3 +133,35 @@ def test_anchor_generator_shapes_match_reference_tables():
             assert np.float32(lvl.y_start) == block[0, 0, 0, 1] and np.float32(lvl.y_end) == block[-1, 0, 0, 1], name
             first += n
         assert first == table.shape[0]
+
+
+@pytest.mark.skipif(not os.path.isdir(os.environ.get("SSD_REFERENCE_ROOT", "/root/reference") + "/samples"),
+                    reason="the reference's samples/*.py exist in the build container only")
+def test_every_reference_sample_config_constructs_the_mirrored_classes():
+    """detection/init.py:90-97 builds sampler / BoxCoder / MultiboxLoss / Postprocessor / TargetAssigner from the
+    dicts of a samples/*.py file: every sample the reference ships must construct the mirrored classes as-is
+    (construction is host-only: no device needed)."""
+    import functools
+    import glob
+    import runpy
+    from single_shot_detection_b200 import sampler as samplers
+    from single_shot_detection_b200.box_coder import BoxCoder
+    from single_shot_detection_b200.multibox_loss import MultiboxLoss
+    from single_shot_detection_b200.postprocessor import Postprocessor
+    from single_shot_detection_b200.target_assigner import TargetAssigner
+    root = os.environ.get("SSD_REFERENCE_ROOT", "/root/reference")
+    files = sorted(glob.glob(os.path.join(root, "samples", "*.py")))
+    assert len(files) >= 13
+    for path in files:
+        cfg = runpy.run_path(path)
+        fn = getattr(samplers, cfg["sampler"]["name"])                                     # init.py:90
+        kwargs = {k: v for k, v in cfg["sampler"].items() if k in fn.__code__.co_varnames}  # init.py:91
+        smp = functools.partial(fn, **kwargs)
+        coder = BoxCoder(**cfg["box_coder"])                                               # init.py:94
+        crit = MultiboxLoss(sampler=smp, box_coder=coder, **cfg["loss"])                   # init.py:95
+        post = Postprocessor(coder, **cfg["postprocess"])                                  # init.py:96
+        assigner = TargetAssigner(**cfg["target_assigner"])                                # init.py:97
+        assert post.box_coder is coder and post.score_threshold == cfg["postprocess"]["score_threshold"], path
+        assert post.max_total == cfg["postprocess"].get("max_total"), path
+        assert assigner.matched_threshold == cfg["target_assigner"]["matched_threshold"], path
+        assert crit is not None

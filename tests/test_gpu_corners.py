@@ -167,3 +167,84 @@ def test_match_bipartite_vs_oracle(dev):
         assert torch.equal(box.cpu(), ref_box) and torch.equal(anchor.cpu(), ref_anchor), (g, a)
     with pytest.raises(AssertionError):
         matcher.match_bipartite(torch.zeros((2, 5), device=dev))
+
+
+# ----------------------------------------------------------------------------------------------
+# box_utils.nms / Postprocessor without a bound on the boxes per class (max_per_class=None or > 512):
+# the long-list kernels (csrc/nms_large.cu) against torchvision / the oracle
+# ----------------------------------------------------------------------------------------------
+def _random_boxes(n, gen, span=400.0):
+    c = torch.rand((n, 2), generator=gen) * span
+    s = torch.rand((n, 2), generator=gen) * 60 + 1
+    return torch.cat([c - s / 2, c + s / 2], dim=1)
+
+
+@pytest.mark.parametrize("n,k,thr", [(3000, None, 0.45), (513, None, 0.5), (5000, 600, 0.3), (2049, 2049, 0.6), (4100, None, 0.0)])
+def test_nms_long_lists_vs_torchvision(dev, n, k, thr):
+    import torchvision
+    from single_shot_detection_b200 import box_utils
+    gen = torch.Generator().manual_seed(n)
+    boxes = _random_boxes(n, gen)
+    scores = torch.rand((n,), generator=gen)
+    scores[n // 2:n // 2 + 200] = scores[:200]                     # exact score ties
+    boxes[n // 3:n // 3 + 50] = boxes[:50]                         # duplicate boxes
+    (bk, sk), keep = box_utils.nms(boxes.to(dev), scores.to(dev), thr, 0.01, max_per_class=k)
+    if k is None or k >= n:
+        ref = torchvision.ops.nms(boxes, scores, thr)
+    else:                                                          # bf/utils/box_utils.py:186-188 then :193
+        sub = ora.select_top_scores(scores, k, canonical=True)
+        ref = sub[torchvision.ops.nms(boxes[sub], scores[sub], thr)]
+    assert keep.cpu().tolist() == ref.tolist()
+    assert torch.equal(bk.cpu(), boxes[ref]) and torch.equal(sk.cpu(), scores[ref])
+
+
+def test_soft_nms_long_list_vs_oracle(dev):
+    from single_shot_detection_b200 import box_utils
+    gen = torch.Generator().manual_seed(5)
+    n = 700
+    boxes = _random_boxes(n, gen, span=250.0)
+    scores = torch.rand((n,), generator=gen) * 0.9 + 0.05
+    (bk, sk), keep = box_utils.nms(boxes.to(dev), scores.to(dev), 0.45, 0.3, max_per_class=None, soft=True, sigma=0.5)
+    ref = ora.gaussian_soft_nms(boxes, scores, 0.3, 0.5)
+    assert keep.cpu().tolist() == ref.tolist()
+    assert torch.equal(sk.cpu(), scores[ref])
+
+
+@pytest.mark.parametrize("name,k", [("tiny_voc_b3", None), ("tiny_sigmoid_b2", None), ("ssd300_voc_b8", 600)])
+def test_postprocessor_without_class_bound_vs_oracle(dev, name, k):
+    """Postprocessor(nms={'max_per_class': None | > 512}): detection/postprocessor.py:57-76 over every box above
+    the threshold."""
+    from single_shot_detection_b200.box_coder import BoxCoder
+    from single_shot_detection_b200.postprocessor import Postprocessor
+    w = wl.WORKLOADS[name]
+    anchors, gt, scores, locs = wl.make_inputs(w, seed=31, batch=2)
+    thr = 0.2 if k is None else w.score_threshold
+    post = Postprocessor(BoxCoder(w.xy_scale, w.wh_scale, w.eps), thr,
+                         {"max_per_class": k, "overlap_threshold": w.overlap_threshold},
+                         score_converter=w.converter, max_total=w.max_total)
+    dets = post.postprocess((scores.to(dev), locs.to(dev)), anchors)
+    ref = ora.postprocess(scores, locs, anchors, xy_scale=w.xy_scale, wh_scale=w.wh_scale, score_threshold=thr,
+                          overlap_threshold=w.overlap_threshold, max_per_class=k, max_total=w.max_total,
+                          converter=w.converter, canonical=True, use_torchvision=True)
+    assert len(dets) == len(ref)
+    for d, r in zip(dets, ref):
+        d = d.cpu()
+        assert d.shape == r.shape
+        assert torch.equal(d[:, 4], r[:, 4])
+        torch.testing.assert_close(d[:, 5], r[:, 5], rtol=1e-5, atol=1e-7)
+        torch.testing.assert_close(d[:, :4], r[:, :4], rtol=1e-5, atol=2e-5 * w.img)
+
+
+def test_device_copy_cache_never_serves_a_stale_table(dev):
+    """The reference regenerates its CPU anchors every step: a new tensor may reuse the freed one's address."""
+    from single_shot_detection_b200 import _devcache
+    for _ in range(8):
+        a = torch.rand((300, 4))
+        d = _devcache.device_copy(a, dev)
+        assert torch.equal(d.cpu(), a)
+        assert _devcache.device_copy(a, dev) is d               # same object, unmodified: cached
+        a.mul_(2.0)                                             # modified in place: a new copy
+        assert torch.equal(_devcache.device_copy(a, dev).cpu(), a)
+        b = a.clone()
+        assert _devcache.device_copy(b, dev) is _devcache.device_copy(a, dev)    # equal content: one device copy
+        del a, b
