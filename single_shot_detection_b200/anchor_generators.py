@@ -69,58 +69,65 @@ def _fill_level(level: N.AnchorLevel, img_size, feature_map_size, step, offset, 
     return level
 
 
+def _expand_ratios(aspect_ratios, flip: bool) -> List[float]:
+    """[r, 1/r for every r > 1] in the order the per-cell boxes are laid out (ssd.py:94-99)."""
+    out: List[float] = []
+    for r in aspect_ratios:
+        if flip and r < 1.0:
+            raise AssertionError(f"aspect ratio {r} < 1 cannot be flipped: list ratios >= 1 or pass flip=False")
+        out.append(r)
+        if flip and r > 1.0:
+            out.append(1.0 / r)
+    return out
+
+
 class SsdAnchorGenerator(_AnchorGenerator):
-    """detection/anchor_generators/ssd.py:55-151."""
+    """Per-level SSD boxes: one box per (flipped) aspect ratio at the level's lower size bound plus, when an upper
+    bound is given, the square box at the geometric mean of the two bounds; ``num_branches`` repeats that over a
+    linear subdivision of [lower, upper].  Same constructor as detection/anchor_generators/ssd.py:55-110; the bounds
+    come either as fractions of the image side (``min_scale`` / ``max_scale``) or in pixels (``min_size`` /
+    ``max_size``)."""
 
     def __init__(self, aspect_ratios, min_scale=None, max_scale=None, min_size=None, max_size=None, step=None,
                  offset=[.5, .5], num_branches=1, flip=True, clip=False):
         super(SsdAnchorGenerator, self).__init__()
-        if max_scale is not None and min_scale is None:
-            raise ValueError('"max_scale" should be provided along with "min_scale"')
-        if max_size is not None and min_size is None:
-            raise ValueError('"max_size" should be provided along with "min_size"')
+        for lower, upper, what in ((min_scale, max_scale, "scale"), (min_size, max_size, "size")):
+            if upper is not None and lower is None:
+                raise ValueError(f'"max_{what}" should be provided along with "min_{what}"')
         if min_scale is not None and min_size is not None:
             raise ValueError('Either "min_scale" or "min_size" should be provided')
-        self.min_scale, self.max_scale = min_scale, max_scale
-        self.min_size, self.max_size = min_size, max_size
-        self.num_branches = num_branches
+        self.min_scale, self.max_scale, self.min_size, self.max_size = min_scale, max_scale, min_size, max_size
+        self.step, self.offset, self.num_branches = step, offset, num_branches
         # ssd.py:147-149 clamps `boxes[..., [0, 2]]` -- an advanced-indexing COPY -- so `clip` never
         # changes the reference's table; kept as an attribute, deliberately without effect
         self.clip = clip
-        self.offset = offset
-        self.step = step
-        self.aspect_ratios = []
-        for ar in aspect_ratios:
-            assert ar >= 1.0 or not flip
-            self.aspect_ratios.append(ar)
-            if ar > 1.0 and flip:
-                self.aspect_ratios.append(1.0 / ar)
-        self.num_ratios = len(self.aspect_ratios)
-        if max_scale or max_size:
-            self.num_ratios += 1
+        self.aspect_ratios = _expand_ratios(aspect_ratios, flip)
+        self._has_mean_box = bool(max_scale or max_size)
+        self.num_ratios = len(self.aspect_ratios) + int(self._has_mean_box)
         self.num_boxes = self.num_ratios * num_branches
-        if self.min_size is not None and self.max_size is not None:
-            self.sizes = torch.linspace(self.min_size, self.max_size, self.num_branches + 1).unsqueeze(1).expand(-1, 2)
+        in_pixels = self.min_size is not None and self.max_size is not None
+        lo, hi = (self.min_size, self.max_size) if in_pixels else (self.min_scale, self.max_scale)
+        bounds = torch.linspace(lo, hi, self.num_branches + 1).unsqueeze(1)          # [branches + 1, 1] fp32
+        if in_pixels:
+            self.sizes = bounds.expand(-1, 2)
         else:
-            self.scales = torch.linspace(self.min_scale, self.max_scale, self.num_branches + 1).unsqueeze(1)
+            self.scales = bounds
 
     def _shapes(self, img_size) -> torch.Tensor:
-        """(w, h) per box, fp32 [num_boxes, 2] (ssd.py:121-137, same host arithmetic)."""
-        img_w, img_h = img_size
-        hws = torch.empty((self.num_boxes, 2), dtype=torch.float32)
+        """(w, h) of every box of a cell, fp32 [num_boxes, 2].  The arithmetic keeps the reference's precision steps
+        (ssd.py:121-137): an fp32 bound times / over the fp32-rounded double sqrt(r); the mean box is the double
+        square root of the fp32 product of the two bounds."""
         if self.min_size is not None and self.max_size is not None:
-            sizes = self.sizes
+            bounds = self.sizes
         else:
-            sizes = torch.cat([self.scales * img_w, self.scales * img_h], dim=1)
-        for j in range(self.num_branches):
-            lo, hi = sizes[j], sizes[j + 1]
-            i = -1
-            for i, r in enumerate(self.aspect_ratios):
-                hws[j * self.num_ratios + i][0] = lo[0] * math.sqrt(r)
-                hws[j * self.num_ratios + i][1] = lo[1] / math.sqrt(r)
-            hws[j * self.num_ratios + i + 1][0] = math.sqrt(lo[0] * hi[0])
-            hws[j * self.num_ratios + i + 1][1] = math.sqrt(lo[1] * hi[1])
-        return hws
+            bounds = torch.cat([self.scales * img_size[0], self.scales * img_size[1]], dim=1)   # [branches + 1, (w, h)]
+        lower, upper = bounds[:-1], bounds[1:]                                                  # [branches, 2] each
+        root = torch.tensor([math.sqrt(r) for r in self.aspect_ratios], dtype=torch.float64).to(torch.float32)
+        ratio_boxes = torch.stack([lower[:, 0:1] * root, lower[:, 1:2] / root], dim=-1)         # [branches, ratios, 2]
+        mean_box = torch.sqrt((lower * upper).to(torch.float64)).to(torch.float32).unsqueeze(1)  # [branches, 1, 2]
+        # (an upper bound always exists: without one the bounds' linspace in __init__ has no end point, there as here)
+        per_branch = torch.cat([ratio_boxes, mean_box], dim=1)
+        return per_branch.reshape(self.num_boxes, 2).contiguous()
 
     def _level(self, img_size, feature_map_size) -> N.AnchorLevel:
         return _fill_level(N.AnchorLevel(), img_size, feature_map_size, self.step, self.offset, self._shapes(img_size))
@@ -149,30 +156,25 @@ class RetinaAnchorGenerator(_AnchorGenerator):
 def build_ssd_anchor_generators(num_scales=6, sizes=None, min_scale=None, max_scale=None,
                                 aspect_ratios=[[1.0, 2.0]] + [[1.0, 2.0, 3.0]] * 3 + [[1.0, 2.0]] * 2,
                                 steps=None, offsets=[0.5, 0.5], num_branches=None, **_ignored):
-    """ssd.build_anchor_generators (ssd.py:11-53; unknown keys are dropped as ``filter_kwargs`` does)."""
-    assert sizes is not None or (min_scale is not None and max_scale is not None)
-    if steps is None:
-        steps = [None] * num_scales
+    """One :class:`SsdAnchorGenerator` per feature level, the levels' bounds taken from a linear scale ramp
+    (``min_scale`` .. ``max_scale`` over ``num_scales`` + 1 points) or from explicit pixel ``sizes``
+    (ssd.build_anchor_generators, ssd.py:11-53; unknown keys are dropped as ``filter_kwargs`` does)."""
+    ramp = min_scale is not None and max_scale is not None
+    assert ramp or sizes is not None, "either min_scale + max_scale or sizes"
+    per_level = {"aspect_ratios": aspect_ratios, "steps": steps if steps is not None else [None] * num_scales,
+                 "num_branches": num_branches if num_branches is not None else [1] * num_scales}
+    for name, values in per_level.items():
+        assert len(values) == num_scales, f"{name}: {len(values)} entries for {num_scales} levels"
+    if ramp:
+        edges = torch.linspace(min_scale, max_scale, num_scales + 1)
+        logging.info(f'Detector (Scales: {edges[:-1]})')
+        bound_keys = ("min_scale", "max_scale")
     else:
-        assert len(steps) == num_scales
-    if num_branches is None:
-        num_branches = [1] * num_scales
-    else:
-        assert len(num_branches) == num_scales
-    if min_scale is not None and max_scale is not None:
-        scales = torch.linspace(min_scale, max_scale, num_scales + 1)
-        logging.info(f'Detector (Scales: {scales[:-1]})')
-    else:
-        scales = None
-    assert len(aspect_ratios) == num_scales
-    generators = []
-    for i, (ratios, step, branches) in enumerate(zip(aspect_ratios, steps, num_branches)):
-        if scales is not None:
-            kwargs = {'min_scale': scales[i], 'max_scale': scales[i + 1]}
-        else:
-            kwargs = {'min_size': sizes[i], 'max_size': sizes[i + 1]}
-        generators.append(SsdAnchorGenerator(ratios, step=step, num_branches=branches, **kwargs))
-    return generators
+        edges, bound_keys = sizes, ("min_size", "max_size")
+    return [SsdAnchorGenerator(per_level["aspect_ratios"][i], step=per_level["steps"][i],
+                               num_branches=per_level["num_branches"][i],
+                               **{bound_keys[0]: edges[i], bound_keys[1]: edges[i + 1]})
+            for i in range(num_scales)]
 
 
 def build_retina_anchor_generators(aspect_ratios, min_level, max_level, scale, scales_per_level, **_ignored):

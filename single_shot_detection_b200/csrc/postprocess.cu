@@ -146,7 +146,10 @@ static int make_plan(const ssd_postprocess_params* p, PostPlan& pl) {
     g.nblk = g.groups_per_image * kConsumerWarps * split;
     pl.nblk = g.nblk;
     pl.gate_hist = pl.converter != SSD_CONVERT_IDENTITY && pl.nblk < 65536 && pl.C <= 32;
-    { const char* e = getenv("SSD_GATE"); if (e) pl.gate_hist = e[0] == 'h' && pl.converter != SSD_CONVERT_IDENTITY && pl.C <= 64; }
+    {   // tuning knob, read once
+        static const int gate_knob = [] { const char* e = getenv("SSD_GATE"); return e ? (e[0] == 'h' ? 1 : 0) : -1; }();
+        if (gate_knob >= 0) pl.gate_hist = gate_knob == 1 && pl.converter != SSD_CONVERT_IDENTITY && pl.C <= 64;
+    }
     { ScoreGrid g1 = g; pl.grid1 = stream_grid(g1); }
     pl.grid = stream_grid(g, kQueueBytes + round_up((size_t)pl.C * sizeof(float), 16) +
                                  (pl.gate_hist ? (size_t)pl.C * kGateStride * sizeof(uint32_t) : 0));
@@ -2105,7 +2108,8 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
     gh.blockmax = pl.gate_hist ? (const float*)blockmax : nullptr; gh.nblk = pl.nblk; gh.K = pl.K; gh.converter = pl.converter; gh.score_thr = p->score_threshold;
     gh.bins = gbins;
     bool gate_in_pass2 = pl.gate_hist;
-    { const char* e = getenv("SSD_GATE_KERNEL"); if (pl.gate_hist && !(e && e[0] == '0')) gate_in_pass2 = false; }
+    static const bool gate_kernel_knob = [] { const char* e = getenv("SSD_GATE_KERNEL"); return !(e && e[0] == '0'); }();   // read once
+    if (pl.gate_hist && gate_kernel_knob) gate_in_pass2 = false;
     if (pl.gate_hist && !gate_in_pass2) {
         LaunchTimer lt_("gate", st);
         const size_t gsmem = round_up((size_t)pl.C * sizeof(float), 16) + (size_t)pl.C * kGateStride * sizeof(uint32_t);

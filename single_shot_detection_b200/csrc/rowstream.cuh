@@ -322,7 +322,8 @@ inline int env_int(const char* name, int fallback) {
     return (e && e[0]) ? atoi(e) : fallback;
 }
 inline void plan_tiles(ScoreGrid& g, int images, int A, int C, bool with_side, int target_tile_bytes = 24 * 1024) {
-    target_tile_bytes = env_int("SSD_TILE_BYTES", target_tile_bytes);          // tuning knob (tools/kernel_times.sh)
+    static const int tile_bytes_knob = env_int("SSD_TILE_BYTES", 0);           // tuning knob, read once (tools/kernel_times.sh)
+    if (tile_bytes_knob > 0) target_tile_bytes = tile_bytes_knob;
     const int q_min = lanes_per_row(C) < lanes_per_row(C, true) ? lanes_per_row(C) : lanes_per_row(C, true);
     const int quantum = kConsumerWarps * (32 / q_min);        // a whole number of warp steps for every kernel
     int rows = target_tile_bytes / (C * 4);
@@ -343,7 +344,8 @@ inline void plan_tiles(ScoreGrid& g, int images, int A, int C, bool with_side, i
     g.total_rows = (int64_t)images * A;
     g.first_fg = 0; g.nblk = 0; g.split = 1;
     g.step_img = 0; g.step_grp = 0;
-    { const char* e = getenv("SSD_CURSOR"); g.contiguous = (e && e[0] == 'r') ? 0 : 1; }
+    static const int contiguous_knob = [] { const char* e = getenv("SSD_CURSOR"); return (e && e[0] == 'r') ? 0 : 1; }();   // read once
+    g.contiguous = contiguous_knob;
 }
 inline size_t stream_smem_bytes(const ScoreGrid& g) { return 128 + (size_t)kStreamStages * g.stage_bytes; }
 __device__ __forceinline__ size_t stream_smem_bytes_dev(const ScoreGrid& g) { return 128 + (size_t)kStreamStages * g.stage_bytes; }
