@@ -61,29 +61,31 @@ mining_loss_kernel(const float* __restrict__ logits, const long long* __restrict
     const RowLanes<Q> ln;
     const RowShape<Q, NREG, CMIN> shape(ln.sub, g.C);
     const int rows_per_warp = g.tile_rows / kConsumerWarps;
+    const uint32_t sb = smem_u32(smem);
+    const int wbase = warp_id() * rows_per_warp;
     TileCursor cur;
     cur.start(g);
-    for (int k = 0; cur.valid(g); ++k, cur.next(g)) {
-        const int64_t r0 = cur.first_row(g);
+    for (; cur.valid(g); cur.next(g)) {
+        const unsigned r0 = cur.first_row32(g);
         const int rows = cur.rows(g);
-        const StagedTile tile = consumer_acquire(smem, g, k, r0);
-        const int wbase = warp_id() * rows_per_warp;
-#pragma unroll 2
+        ring_wait_full(sb, cur);
+        const float* tile_logits = ring_logits(smem, g, cur, r0);
+        const unsigned long long* side = ring_side(smem, g, cur, r0);
         for (int step = 0; step < rows_per_warp; step += RowLanes<Q>::kRowsPerWarpStep) {
             if (wbase + step >= rows) break;            // the rest of a partial tile (warp-uniform)
             const int lr = wbase + step + ln.rl;
             float v[NREG];
-            shape.load(v, tile.logits + (size_t)lr * g.C, ln.sub);
+            shape.load(v, tile_logits + lr * g.C, ln.sub);
             float m, sum;
             row_max_sum<Q, NREG>(v, m, sum);
             if (lr < rows && ln.sub == 0) {
                 // v[0] of lane sub == 0 is column 0
                 const float loss = __fsub_rn(__fadd_rn(m, fast_log(sum)), v[0]);
-                const long long c = (long long)tile.side[lr];
+                const long long c = (long long)side[lr];
                 keys[r0 + lr] = mining_key(loss, c);
             }
         }
-        consumer_release(smem, k);
+        ring_release(sb, cur);
     }
     griddep_launch_dependents();       // late: see the note at launch_pdl
 }
@@ -406,6 +408,8 @@ static int launch_mining_keys(const float* logits, const int64_t* target_classes
                 "mining: num_cols %d outside 1..%d", num_cols, kMaxScoreCols);
     SSD_REQUIRE(aligned(logits, 16), SSD_ERR_MISALIGNED, "mining: logits not 16-byte aligned");
     SSD_REQUIRE(aligned(target_classes, 16), SSD_ERR_MISALIGNED, "mining: target_classes not 16-byte aligned");
+    SSD_REQUIRE((long long)batch * num_anchors < 0x7FFFFFFFll, SSD_ERR_UNSUPPORTED,
+                "mining: %d x %d rows exceed the 32-bit row index of the streaming kernel", batch, num_anchors);
     ScoreGrid g;
     plan_tiles(g, batch, num_anchors, num_cols, true);
     const int grid = stream_grid(g);

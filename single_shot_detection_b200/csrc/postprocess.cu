@@ -44,7 +44,8 @@ namespace ssd {
 // ---------------------------------------------------------------------------------------------
 struct PostPlan {
     int B, A, C, Cf, first_fg, K, T, det_cap, converter, box_input;
-    ScoreGrid g;             // tiling of the streaming kernels (shared by both passes)
+    ScoreGrid g;             // tiling of the streaming kernels (pass 2's item split)
+    ScoreGrid g1;            // the same tiling with pass 1's item split (its grid differs)
     int grid;                // CTAs of pass 2
     int grid1;               // CTAs of pass 1 (less shared memory per CTA: one more per SM)
     int nblk;                // row blocks per image
@@ -54,6 +55,7 @@ struct PostPlan {
         off_anchor_tmp, off_score_hist, off_bhist, off_image_done;
     size_t zero_begin, zero_bytes;   // counters and histograms of the LATER launches: zeroed by pass 1 itself
     bool gate_hist;                  // gates from a histogram of the block maxima (SOFTMAX / SIGMOID)
+    bool block_per_step;             // pass 1: a warp step of 32 rows is a block (score_pass1_kernel<.., BPS = true>)
     float bin_lo, bin_scale;
     float soft_thr;
     size_t total_bytes;
@@ -150,7 +152,17 @@ static int make_plan(const ssd_postprocess_params* p, PostPlan& pl) {
         static const int gate_knob = [] { const char* e = getenv("SSD_GATE"); return e ? (e[0] == 'h' ? 1 : 0) : -1; }();
         if (gate_knob >= 0) pl.gate_hist = gate_knob == 1 && pl.converter != SSD_CONVERT_IDENTITY && pl.C <= 64;
     }
-    { ScoreGrid g1 = g; pl.grid1 = stream_grid(g1); }
+    // a warp step of the row-per-lane shape is exactly one block: the block maxima come straight out of the step.
+    // (NaN block maxima -- a column that is NaN in all 32 rows -- are read as -inf by the histogram gate only.)
+    pl.block_per_step = lanes_per_row(pl.C, true) == 1 && pl.gate_hist && split == 1 && gt == 1 && rows_per_warp_tile == 32;
+    {
+        static const int bps_knob = [] { const char* e = getenv("SSD_BPS"); return e ? (e[0] != '0') : 1; }();     // tuning knob, read once
+        if (!bps_knob) pl.block_per_step = false;
+    }
+    SSD_REQUIRE((long long)pl.B * A1 < 0x7FFFFFFFll && (long long)pl.B * pl.nblk * g.bm_stride < 0x7FFFFFFFll, SSD_ERR_UNSUPPORTED,
+                "ssd_postprocess: %d x %d rows exceed the 32-bit row index of the streaming kernels", pl.B, A1);
+    pl.g1 = g;
+    pl.grid1 = stream_grid(pl.g1);
     pl.grid = stream_grid(g, kQueueBytes + round_up((size_t)pl.C * sizeof(float), 16) +
                                  (pl.gate_hist ? (size_t)pl.C * kGateStride * sizeof(uint32_t) : 0));
     int cap = 512;                        // power of two (the segment sort pads to one), >= 8K
@@ -167,7 +179,7 @@ static int make_plan(const ssd_postprocess_params* p, PostPlan& pl) {
     // class_gate launch costs, measured in the step graph (profiles/), so that one stays.
     gate_range(pl.converter, p->score_threshold, pl.bin_lo, pl.bin_scale);
     pl.off_rowstat = take(BA * sizeof(float2));
-    pl.off_blockmax = take((size_t)pl.B * pl.nblk * pl.C * sizeof(float));
+    pl.off_blockmax = take((size_t)pl.B * pl.nblk * pl.g.bm_stride * sizeof(float));
     pl.off_gate = take((size_t)pl.B * pl.C * sizeof(float));
     pl.off_cand = take((size_t)pl.B * pl.Cf * pl.cand_cap * sizeof(uint2));
     pl.off_kept_count = take((size_t)pl.B * pl.Cf * sizeof(int));
@@ -207,7 +219,9 @@ __device__ __forceinline__ float gate_bin_edge(int bin, GateBins gb) {
     return bin <= 0 ? -INFINITY : __fadd_rn(gb.lo, __fdiv_rn((float)bin, gb.scale));
 }
 
-template <int Q, int NREG, int CMIN, int CONV>
+// BPS ("block per step", row-per-lane shapes with one warp step per tile and block): the block maxima are the
+// CREDUX of the step's gate values themselves -- no running per-lane maxima, no resets, no block-end branch.
+template <int Q, int NREG, int CMIN, int CONV, bool BPS>
 __global__ void __launch_bounds__(kStreamThreads)
 score_pass1_kernel(const float* __restrict__ scores, ScoreGrid g, float2* __restrict__ rowstat,
                    float* __restrict__ blockmax, uint32_t* __restrict__ loss_keys, uint4* __restrict__ zero_ptr,
@@ -228,33 +242,77 @@ score_pass1_kernel(const float* __restrict__ scores, ScoreGrid g, float2* __rest
     const RowLanes<Q> ln;
     const RowShape<Q, NREG, CMIN> shape(ln.sub, g.C);
     const int rows_per_warp = g.tile_rows / kConsumerWarps;
+    const uint32_t sb = smem_u32(smem);
+    const int wbase = warp_id() * rows_per_warp;
     float cmax[NREG];
 #pragma unroll
     for (int i = 0; i < NREG; ++i) cmax[i] = -INFINITY;
 
     TileCursor cur;
     cur.start(g);
-    for (int k = 0; cur.valid(g); ++k) {
-        const int64_t r0 = cur.first_row(g);
+    for (; cur.valid(g); cur.next(g)) {
+        const unsigned r0 = cur.first_row32(g);
         const int rows = cur.rows(g);
-        const StagedTile tile = consumer_acquire(smem, g, k, r0);
-        const int wbase = warp_id() * rows_per_warp;
-#pragma unroll 2
+        ring_wait_full(sb, cur);
+        const float* logits = ring_logits(smem, g, cur, r0);
+        if constexpr (BPS) {
+            // Q == 1, rows_per_warp == 32: lane l owns row wbase + l of the tile, the warp's 32 rows are one block
+            static_assert(Q == 1, "block-per-step needs the row-per-lane shape");
+            float4* dst = reinterpret_cast<float4*>(
+                blockmax + (size_t)((unsigned)cur.img * (unsigned)g.nblk + (unsigned)cur.tile * kConsumerWarps + warp_id()) * g.bm_stride);
+            constexpr int NV = (NREG + 3) / 4;
+            if (wbase < rows) {
+                const int lr = wbase + lane_id();
+                const bool valid = lr < rows;
+                float v[NREG];
+                shape.load(v, logits + lr * g.C, 0);
+                float t = 0.f;
+                if (CONV == SSD_CONVERT_SOFTMAX) {
+                    float m, sum;
+                    row_max_sum<Q, NREG>(v, m, sum);
+                    if (valid) rowstat[r0 + lr] = make_float2(m, sum);
+                    // rows past the end of a partial tile: t = +inf turns every gate value into -inf / NaN, both
+                    // of which the warp maximum drops (at least one lane of the warp holds a real row)
+                    t = valid ? __fadd_rn(m, fast_log(sum)) : INFINITY;
+                    // the sampler's criterion -log_softmax(x)[0] = (max + log(sum)) - x0 falls out of the same row
+                    // statistics (mining.cu, same operations): one streamed read of the logits serves both
+                    if (loss_keys != nullptr && valid) {
+                        const uint32_t lk = ordered_key(__fsub_rn(t, v[0]));
+                        loss_keys[r0 + lr] = lk == 0u ? 1u : lk;
+                    }
+                }
+                ring_release(sb, cur);         // the row is in registers: the stage can be refilled during the reductions
+                float r[NV * 4];
+#pragma unroll
+                for (int i = 0; i < NV * 4; ++i) {
+                    if (i < NREG) {
+                        const float x = CONV == SSD_CONVERT_SOFTMAX ? __fsub_rn(v[i], t) : (valid ? v[i] : -INFINITY);
+                        r[i] = warp_max(x);
+                    } else {
+                        r[i] = -INFINITY;
+                    }
+                }
+                if (lane_id() == 0) {
+#pragma unroll
+                    for (int j = 0; j < NV; ++j)
+                        if (4 * j < g.bm_stride) dst[j] = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                }
+            } else {
+                ring_release(sb, cur);
+                if (lane_id() < NV && 4 * lane_id() < g.bm_stride) dst[lane_id()] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            }
+        } else {
         for (int step = 0; step < rows_per_warp; step += RowLanes<Q>::kRowsPerWarpStep) {
             if (wbase + step >= rows) break;            // the rest of a partial tile (warp-uniform)
             const int lr = wbase + step + ln.rl;
             const bool valid = lr < rows;
             float v[NREG];
-            shape.load(v, tile.logits + (size_t)lr * g.C, ln.sub);
+            shape.load(v, logits + lr * g.C, ln.sub);
             if (CONV == SSD_CONVERT_SOFTMAX) {
                 float m, sum;
                 row_max_sum<Q, NREG>(v, m, sum);
                 if (valid && ln.sub == 0) rowstat[r0 + lr] = make_float2(m, sum);
-                // rows past the end of a partial tile: t = +inf turns every gate value into -inf / NaN,
-                // both of which fmaxf drops
-                const float t = valid ? __fadd_rn(m, fast_log(sum)) : INFINITY;
-                // the sampler's criterion -log_softmax(x)[0] = (max + log(sum)) - x0 falls out of the same row
-                // statistics (mining.cu, same operations): one streamed read of the logits serves both
+                const float t = valid ? __fadd_rn(m, fast_log(sum)) : INFINITY;      // see the block-per-step branch
                 if (loss_keys != nullptr && valid && ln.sub == 0) {
                     const uint32_t lk = ordered_key(__fsub_rn(t, v[0]));
                     loss_keys[r0 + lr] = lk == 0u ? 1u : lk;
@@ -266,19 +324,20 @@ score_pass1_kernel(const float* __restrict__ scores, ScoreGrid g, float2* __rest
                 for (int i = 0; i < NREG; ++i) cmax[i] = fmaxf(cmax[i], valid ? v[i] : -INFINITY);
             }
         }
-        consumer_release(smem, k);
+        ring_release(sb, cur);
         if (cur.last_of_item()) {
+            const size_t blk0 = (size_t)cur.image(g) * g.nblk + ((size_t)cur.group(g) * kConsumerWarps + warp_id()) * g.split;
             if (Q == 1 && g.split == 1) {
-                // row-per-lane shape: one CREDUX per column, lane c keeps column c, one coalesced store
-                float mine = -INFINITY;
+                // row-per-lane shape: one CREDUX per column; the results are warp-uniform, lane 0 stores them
+                float r[NREG];
 #pragma unroll
-                for (int i = 0; i < NREG; ++i) {
-                    const float r = warp_max(cmax[i]);
-                    if (lane_id() == i) mine = r;
+                for (int i = 0; i < NREG; ++i) r[i] = warp_max(cmax[i]);
+                if (lane_id() == 0) {
+                    float* dst = blockmax + blk0 * g.bm_stride;
+#pragma unroll
+                    for (int i = 0; i < NREG; ++i)
+                        if (i < g.C) dst[i] = r[i];
                 }
-                if (lane_id() < g.C)
-                    blockmax[((size_t)cur.image(g) * g.nblk + (size_t)cur.group(g) * kConsumerWarps + warp_id()) * g.C +
-                             lane_id()] = mine;
             } else {
                 // merge the row slots of the warp down to `split` blocks, then one vector per block
 #pragma unroll
@@ -290,8 +349,7 @@ score_pass1_kernel(const float* __restrict__ scores, ScoreGrid g, float2* __rest
                     cmax[i] = x;
                 }
                 if (ln.rl < g.split) {
-                    float* dst = blockmax + ((size_t)cur.image(g) * g.nblk +
-                                             ((size_t)cur.group(g) * kConsumerWarps + warp_id()) * g.split + ln.rl) * g.C;
+                    float* dst = blockmax + (blk0 + ln.rl) * g.bm_stride;
 #pragma unroll
                     for (int i = 0; i < NREG; ++i) {
                         const int col = ln.sub + i * Q;
@@ -302,9 +360,17 @@ score_pass1_kernel(const float* __restrict__ scores, ScoreGrid g, float2* __rest
 #pragma unroll
             for (int i = 0; i < NREG; ++i) cmax[i] = -INFINITY;
         }
-        cur.next(g);
+        }   // !BPS
     }
     griddep_launch_dependents();       // late: see the note at launch_pdl
+}
+
+template <int Q, int NREG, int CMIN, int CONV>
+static auto pass1_kernel_ptr(bool block_per_step) {
+    if constexpr (Q == 1) {
+        if (block_per_step) return &score_pass1_kernel<Q, NREG, CMIN, CONV, true>;
+    }
+    return &score_pass1_kernel<Q, NREG, CMIN, CONV, false>;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -361,7 +427,7 @@ constexpr int kGateBits = 20;                // resolved MSBs of the K-th larges
 // a partition) and (b) the bisection stops after kGateBits bits and leaves the low bits zero
 // (a slightly smaller key).  Both only let a few more candidates through.
 __global__ void __launch_bounds__(kGateThreads)
-class_gate_kernel(const float* __restrict__ blockmax, int C, int first_fg, int nblk, int K, int converter,
+class_gate_kernel(const float* __restrict__ blockmax, int C, int bm_stride, int first_fg, int nblk, int K, int converter,
                   float score_thr, float* __restrict__ gate) {
     extern __shared__ __align__(16) uint32_t skey[];          // [merged blocks][kGateCols + 1]
     KernelTrace trace_(TR_GATE);
@@ -372,7 +438,7 @@ class_gate_kernel(const float* __restrict__ blockmax, int C, int first_fg, int n
     const int lane = lane_id();
     const int merge = (nblk + 32 * kGateKeysPerLane - 1) / (32 * kGateKeysPerLane);
     const int nm = (nblk + merge - 1) / merge;                 // merged blocks, <= 512
-    const float* src = blockmax + (size_t)b * nblk * C;
+    const float* src = blockmax + (size_t)b * nblk * bm_stride;
     // coalesced load: 8 consecutive columns of one block row per 8 threads, four rows in flight
     if (merge == 1) {
         const int total = nm * kGateCols;
@@ -382,7 +448,7 @@ class_gate_kernel(const float* __restrict__ blockmax, int C, int first_fg, int n
             for (int u = 0; u < 4; ++u) {
                 const int t = t0 + u * kGateThreads;
                 const int mb = t / kGateCols, cc = t % kGateCols;
-                v[u] = (t < total && c0 + cc < C) ? src[(size_t)mb * C + c0 + cc] : -INFINITY;
+                v[u] = (t < total && c0 + cc < C) ? src[(size_t)mb * bm_stride + c0 + cc] : -INFINITY;
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -405,7 +471,7 @@ class_gate_kernel(const float* __restrict__ blockmax, int C, int first_fg, int n
                     const int t = t0 + u * kGateThreads;
                     const int mb = t / kGateCols, cc = t % kGateCols;
                     const int row = mb * merge + i;
-                    x[u] = (t < total && c0 + cc < C && row < nblk) ? src[(size_t)row * C + c0 + cc] : -INFINITY;
+                    x[u] = (t < total && c0 + cc < C && row < nblk) ? src[(size_t)row * bm_stride + c0 + cc] : -INFINITY;
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -500,10 +566,10 @@ __device__ __forceinline__ void image_gates(const GateHist& gh, const ScoreGrid&
     for (int i = threadIdx.x; i < g.C * kGateStride; i += kConsumerWarps * 32) shist[i] = 0u;
     consumer_barrier();
     {
-        const float* bm = gh.blockmax + (size_t)img * gh.nblk * g.C;
-        const int total = gh.nblk * g.C;
-        // nblk is a multiple of 8, so an image's maxima are a whole number of 16-byte vectors: every thread's
-        // loads (six LDG.128 for SSD300) are in flight together -- one L2 round trip
+        const float* bm = gh.blockmax + (size_t)img * gh.nblk * g.bm_stride;
+        const int total = gh.nblk * g.bm_stride;
+        // a block's maxima are bm_stride floats (C rounded up to a multiple of four: whole 16-byte vectors, the padding
+        // is skipped): every thread's loads (seven LDG.128 for SSD300) are in flight together -- one L2 round trip
         const float4* bm4 = reinterpret_cast<const float4*>(bm);
         const int total4 = total >> 2;
         constexpr int kDeep = 8;
@@ -518,13 +584,11 @@ __device__ __forceinline__ void image_gates(const GateHist& gh, const ScoreGrid&
             for (int u = 0; u < kDeep; ++u) {
                 const int i = i0 + u * kConsumerWarps * 32;
                 if (i < total4) {
-                    int col = (4 * i) % g.C;
+                    const int col = (4 * i) % g.bm_stride;            // a vector never straddles two blocks
                     const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        bump_gate_bin(shist + (size_t)col * kGateStride, e[j], gh.bins);
-                        col = col + 1 == g.C ? 0 : col + 1;
-                    }
+                    for (int j = 0; j < 4; ++j)
+                        if (col + j < g.C) bump_gate_bin(shist + (size_t)(col + j) * kGateStride, e[j], gh.bins);
                 }
             }
         }
@@ -620,10 +684,12 @@ score_pass2_kernel(const float* __restrict__ scores, ScoreGrid g, const float2* 
 
     float gv[NREG];
     int cur_image = -1;
+    const uint32_t sb = smem_u32(smem);
+    const int wbase = warp_id() * rows_per_warp;
     TileCursor cur;
     cur.start(g);
-    for (int k = 0; cur.valid(g); ++k, cur.next(g)) {
-        const int64_t r0 = cur.first_row(g);
+    for (; cur.valid(g); cur.next(g)) {
+        const unsigned r0 = cur.first_row32(g);
         const int rows = cur.rows(g);
         const int img = cur.image(g);
         if (img != cur_image) {                 // per-lane slice of this image's gates
@@ -641,18 +707,19 @@ score_pass2_kernel(const float* __restrict__ scores, ScoreGrid g, const float2* 
                 gv[i] = (col < g.C) ? gsrc[col] : INFINITY;
             }
         }
-        const StagedTile tile = consumer_acquire(smem, g, k, r0);
+        ring_wait_full(sb, cur);
+        const float* logits = ring_logits(smem, g, cur, r0);
+        const float2* side = reinterpret_cast<const float2*>(ring_side(smem, g, cur, r0));
         const int a0 = cur.tile * g.tile_rows;
-        const int wbase = warp_id() * rows_per_warp;
         for (int step = 0; step < rows_per_warp; step += RowLanes<Q>::kRowsPerWarpStep) {
             if (wbase + step >= rows) break;            // the rest of a partial tile (warp-uniform)
             const int lr = wbase + step + ln.rl;
             const bool valid = lr < rows;
             float v[NREG];
-            shape.load(v, tile.logits + (size_t)lr * g.C, ln.sub);
+            shape.load(v, logits + lr * g.C, ln.sub);
             float t = 0.f;
             if (CONV == SSD_CONVERT_SOFTMAX) {
-                const float2 st = reinterpret_cast<const float2*>(tile.side)[lr];
+                const float2 st = side[lr];
                 t = __fadd_rn(st.x, fast_log(st.y));            // bit-identical to pass 1
             }
             unsigned hit = 0u;
@@ -682,7 +749,7 @@ score_pass2_kernel(const float* __restrict__ scores, ScoreGrid g, const float2* 
                 bal = __ballot_sync(FULL, hit != 0u);
             }
         }
-        consumer_release(smem, k);
+        ring_release(sb, cur);
     }
     griddep_launch_dependents();       // late: see the note at launch_pdl
     q.flush(cand_count, cand, cand_cap);
@@ -2075,13 +2142,13 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
         auto launch = [&](auto kern) -> int {                                                                          \
             SSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem));    \
             LaunchTimer lt_("pass1", st);                                                            \
-            SSD_CUDA(launch_pdl(kern, dim3(pl.grid1), dim3(kStreamThreads), stream_smem, st, scores, g, rowstat, blockmax, \
+            SSD_CUDA(launch_pdl(kern, dim3(pl.grid1), dim3(kStreamThreads), stream_smem, st, scores, pl.g1, rowstat, blockmax, \
                                 loss_keys, zero_ptr, zero_n16));                                                \
             return SSD_OK;                                                                                             \
         };                                                                                                             \
         int rc;                                                                                                        \
-        if (pl.converter == SSD_CONVERT_SOFTMAX) rc = launch(score_pass1_kernel<QQ, NN, CM, SSD_CONVERT_SOFTMAX>);         \
-        else rc = launch(score_pass1_kernel<QQ, NN, CM, SSD_CONVERT_IDENTITY>);                                            \
+        if (pl.converter == SSD_CONVERT_SOFTMAX) rc = launch(pass1_kernel_ptr<QQ, NN, CM, SSD_CONVERT_SOFTMAX>(pl.block_per_step)); \
+        else rc = launch(pass1_kernel_ptr<QQ, NN, CM, SSD_CONVERT_IDENTITY>(pl.block_per_step));                        \
         if (rc != SSD_OK) return rc;                                                                                   \
     } while (0)
     SSD_DISPATCH_ROW_SHAPE_PASS1(pl.C, SSD_LAUNCH_PASS1);
@@ -2099,7 +2166,7 @@ static int run_postprocess(const PostPlan& pl, const ssd_postprocess_params* p, 
         const size_t gsmem = (size_t)nm * (kGateCols + 1) * sizeof(uint32_t);
         dim3 ggrid((pl.C + kGateCols - 1) / kGateCols, pl.B);
         SSD_CUDA(launch_pdl(class_gate_kernel, ggrid, dim3(kGateThreads), gsmem, st, (const float*)blockmax, pl.C,
-                            pl.first_fg, pl.nblk, pl.K, pl.converter, p->score_threshold, gate));
+                            pl.g.bm_stride, pl.first_fg, pl.nblk, pl.K, pl.converter, p->score_threshold, gate));
         SSD_CUDA(cudaGetLastError());
         count_launch();
     }

@@ -54,29 +54,34 @@ struct ScoreGrid {
     int stage_bytes;          // bytes per ring stage (logit tile + side array, 16-byte multiples)
     int side_offset;          // byte offset of the side array inside a stage
     int nblk, split;          // post-processor block-max bookkeeping (unused by mining)
+    int bm_stride;            // floats per block-maximum vector: C rounded up to a multiple of four (16-byte rows)
     int step_img, step_grp;   // gridDim.x decomposed as step_img * groups_per_image + step_grp (round-robin)
     int contiguous;           // item dealing, see TileCursor
+    int items_q, items_r;     // contiguous dealing for THIS launch's grid: num_items = grid * items_q + items_r (host)
+    unsigned gpi_magic;       // ceil(2^32 / groups_per_image) when item / groups_per_image == umulhi(item, magic), else 0
     int64_t total_floats;     // B*A*C
     int64_t total_rows;       // B*A
 };
 
 struct TileCursor {
     int item, item_end, img, grp, tile, tile_end;
-    // contiguous: CTA c owns q or q + 1 consecutive items (q = n / grid) -- at most two images
-    // per CTA unless an image has fewer items than a CTA's share; otherwise items are dealt round-robin.
+    int stage;                 // ring stage of the current tile
+    unsigned phase;            // parity of the stage's `full` barrier for the current tile
+    // contiguous: CTA c owns q or q + 1 consecutive items (q = n / grid, split on the host: set_item_split) -- at most
+    // two images per CTA unless an image has fewer items than a CTA's share; otherwise items are dealt round-robin.
     __device__ __forceinline__ void start(const ScoreGrid& g) {
         if (g.contiguous) {
-            // balanced contiguous ranges without 64-bit divisions: the first r CTAs take q + 1 items
-            const unsigned n = (unsigned)g.num_items, nc = gridDim.x, c = blockIdx.x;
-            const unsigned q = n / nc, r = n - q * nc;
-            item = (int)(c * q + min(c, r));
-            item_end = item + (int)q + (c < r ? 1 : 0);
+            const int c = (int)blockIdx.x;
+            item = c * g.items_q + min(c, g.items_r);
+            item_end = item + g.items_q + (c < g.items_r ? 1 : 0);
         } else {
             item = blockIdx.x;
             item_end = g.num_items;
         }
-        img = item / g.groups_per_image;
+        img = g.gpi_magic ? (int)__umulhi((unsigned)item, g.gpi_magic) : item / g.groups_per_image;
         grp = item - img * g.groups_per_image;
+        stage = 0;
+        phase = 0u;
         open(g);
     }
     __device__ __forceinline__ void open(const ScoreGrid& g) {
@@ -88,6 +93,7 @@ struct TileCursor {
     __device__ __forceinline__ int group(const ScoreGrid&) const { return grp; }
     __device__ __forceinline__ bool last_of_item() const { return tile + 1 == tile_end; }
     __device__ __forceinline__ void next(const ScoreGrid& g) {
+        if (++stage == kStreamStages) { stage = 0; phase ^= 1u; }
         if (++tile == tile_end) {
             if (g.contiguous) {
                 ++item;
@@ -105,6 +111,10 @@ struct TileCursor {
     __device__ __forceinline__ int64_t first_row(const ScoreGrid& g) const {
         return (int64_t)img * g.A + (int64_t)tile * g.tile_rows;
     }
+    // the same in 32 bits for the consumers (plan_tiles refuses B * A >= 2^31)
+    __device__ __forceinline__ unsigned first_row32(const ScoreGrid& g) const {
+        return (unsigned)img * (unsigned)g.A + (unsigned)tile * (unsigned)g.tile_rows;
+    }
 };
 
 // shared memory: [0,64) full barriers, [64,128) empty barriers, then the stages
@@ -113,7 +123,7 @@ __device__ __forceinline__ uint64_t* empty_bar(unsigned char* smem, int s) { ret
 __device__ __forceinline__ unsigned char* stage_ptr(unsigned char* smem, const ScoreGrid& g, int s) {
     return smem + 128 + (size_t)s * g.stage_bytes;
 }
-__device__ __forceinline__ int tile_head(int64_t first_row, int C) { return (int)((first_row * C) & 3); }
+__device__ __forceinline__ int tile_head(int64_t first_row, int C) { return (int)(((unsigned)first_row * (unsigned)C) & 3u); }
 __device__ __forceinline__ int side_head(int64_t first_row) { return (int)(first_row & 1); }
 
 __device__ __forceinline__ void stream_init(unsigned char* smem) {
@@ -169,30 +179,49 @@ __device__ __forceinline__ void producer_loop(unsigned char* smem, const ScoreGr
     if (lane_id() != 0) return;
     TileCursor cur;
     cur.start(g);
-    for (int k = 0; cur.valid(g); ++k, cur.next(g)) {
-        const int s = k % kStreamStages;
-        if (k >= kStreamStages) mbar_wait(empty_bar(smem, s), ((k / kStreamStages) - 1) & 1);
+    bool wrapped = false;                       // the ring has been filled once: wait for the consumers from here on
+    for (; cur.valid(g); cur.next(g)) {
+        const int s = cur.stage;
+        if (wrapped) mbar_wait(empty_bar(smem, s), cur.phase ^ 1u);
         produce_tile(stage_ptr(smem, g, s), full_bar(smem, s), g, base, side, cur.first_row(g), cur.rows(g), policy);
+        if (s == kStreamStages - 1) wrapped = true;
     }
 }
 
-// Consumer side of the ring: wait for tile k, hand out its pointers, release it.
+// Consumer side of the ring in shared-space addresses: `sb` = smem_u32(smem), taken ONCE per thread (every
+// cvta of a generic pointer costs S2R + MOV + LEA where it is used: ~25 instructions per tile in the old form).
+__device__ __forceinline__ void ring_wait_full(uint32_t sb, const TileCursor& cur) {
+    mbar_wait(sb + 8u * (unsigned)cur.stage, cur.phase);
+}
+__device__ __forceinline__ void ring_release(uint32_t sb, const TileCursor& cur) {
+    __syncwarp();
+    if (lane_id() == 0) mbar_arrive(sb + 64u + 8u * (unsigned)cur.stage);
+}
+__device__ __forceinline__ const float* ring_logits(unsigned char* smem, const ScoreGrid& g, const TileCursor& cur, unsigned first_row) {
+    return reinterpret_cast<const float*>(smem + 128 + (size_t)(cur.stage * g.stage_bytes)) + ((first_row * (unsigned)g.C) & 3u);
+}
+__device__ __forceinline__ const unsigned long long* ring_side(unsigned char* smem, const ScoreGrid& g, const TileCursor& cur,
+                                                               unsigned first_row) {
+    return reinterpret_cast<const unsigned long long*>(smem + 128 + (size_t)(cur.stage * g.stage_bytes + g.side_offset)) + (first_row & 1u);
+}
+
+// Consumer side of the ring: wait for the cursor's tile, hand out its pointers, release it.
 struct StagedTile {
     const float* logits;                 // first float of the tile's first row
     const unsigned long long* side;      // first side element of the tile (8 bytes per row)
 };
-__device__ __forceinline__ StagedTile consumer_acquire(unsigned char* smem, const ScoreGrid& g, int k, int64_t first_row) {
-    const int s = k % kStreamStages;
-    mbar_wait(full_bar(smem, s), (k / kStreamStages) & 1);
-    unsigned char* st = stage_ptr(smem, g, s);
+__device__ __forceinline__ StagedTile consumer_acquire(unsigned char* smem, const ScoreGrid& g, const TileCursor& cur,
+                                                       int64_t first_row) {
+    mbar_wait(full_bar(smem, cur.stage), cur.phase);
+    unsigned char* st = stage_ptr(smem, g, cur.stage);
     StagedTile t;
     t.logits = reinterpret_cast<const float*>(st) + tile_head(first_row, g.C);
     t.side = reinterpret_cast<const unsigned long long*>(st + g.side_offset) + side_head(first_row);
     return t;
 }
-__device__ __forceinline__ void consumer_release(unsigned char* smem, int k) {
+__device__ __forceinline__ void consumer_release(unsigned char* smem, const TileCursor& cur) {
     __syncwarp();
-    if (lane_id() == 0) mbar_arrive(empty_bar(smem, k % kStreamStages));
+    if (lane_id() == 0) mbar_arrive(empty_bar(smem, cur.stage));
 }
 
 // Lane geometry of the Q-lanes-per-row mapping.
@@ -343,9 +372,20 @@ inline void plan_tiles(ScoreGrid& g, int images, int A, int C, bool with_side, i
     g.total_floats = (int64_t)images * A * C;
     g.total_rows = (int64_t)images * A;
     g.first_fg = 0; g.nblk = 0; g.split = 1;
+    g.bm_stride = (C + 3) & ~3;
     g.step_img = 0; g.step_grp = 0;
+    g.items_q = 0; g.items_r = 0; g.gpi_magic = 0u;
     static const int contiguous_knob = [] { const char* e = getenv("SSD_CURSOR"); return (e && e[0] == 'r') ? 0 : 1; }();   // read once
     g.contiguous = contiguous_knob;
+}
+// contiguous item ranges of a launch with `grid` CTAs (TileCursor::start) and the division-free image index
+inline void set_item_split(ScoreGrid& g, int grid) {
+    if (grid < 1) grid = 1;
+    g.items_q = g.num_items / grid;
+    g.items_r = g.num_items % grid;
+    const unsigned d = (unsigned)g.groups_per_image;
+    // umulhi(n, ceil(2^32 / d)) == n / d for n, d < 2^16 (the error term n * (M d - 2^32) / (d 2^32) stays below 1 / d)
+    g.gpi_magic = (d >= 2u && d < 65536u && g.num_items < 65536) ? (unsigned)((0x100000000ull + d - 1) / d) : 0u;
 }
 inline size_t stream_smem_bytes(const ScoreGrid& g) { return 128 + (size_t)kStreamStages * g.stage_bytes; }
 __device__ __forceinline__ size_t stream_smem_bytes_dev(const ScoreGrid& g) { return 128 + (size_t)kStreamStages * g.stage_bytes; }
@@ -360,6 +400,7 @@ inline int stream_grid(ScoreGrid& g, size_t extra_smem = 0) {
     if (grid < 1) grid = 1;
     g.step_img = grid / g.groups_per_image;
     g.step_grp = grid % g.groups_per_image;
+    set_item_split(g, grid);
     return grid;
 }
 

@@ -1,0 +1,12 @@
+#!/bin/bash
+# Per-kernel device time, executed warp instructions and DRAM bytes of one eager step (ncu: cold cache,
+# serialised launches -- compare SHARES, not absolute times); `full` adds an --set full report with sources.
+# usage: tools/ncu_step.sh <workload> <out-prefix> [full]
+W=${1:-ssd300_voc_b32}; OUT=${2:-gpurun_out/ncu_$W}
+python tools/prof_step.py $W 4 > $OUT.plain.log 2>&1 || { echo "plain run failed"; exit 1; }
+ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,dram__bytes_read.sum,dram__bytes_write.sum \
+    --clock-control none -k regex:_kernel -c 60 --csv --log-file $OUT.launches.csv python tools/prof_step.py $W 4 > $OUT.ncu.log 2>&1
+if [ "$3" = full ]; then
+    ncu --set full --import-source on --clock-control none -k regex:_kernel --launch-skip 20 -c 12 -f -o $OUT \
+        python tools/prof_step.py $W 3 > $OUT.ncufull.log 2>&1
+fi
