@@ -72,7 +72,9 @@ def parse_args():
     ap.add_argument("--no-config5", action="store_true", help="skip the M2Det b256 strong-scaling leg")
     ap.add_argument("--no-e2e", action="store_true", help="(diagnostics) skip the host-buffer leg")
     ap.add_argument("--in-flight", type=int, default=8,
-                    help="step graphs in flight on as many streams (1 = strictly one step after the other)")
+                    help="steps in flight (1 = strictly one step after the other)")
+    ap.add_argument("--group", type=int, default=1,
+                    help="steps per CUDA graph launch (parallel branches of one graph); in-flight / group streams")
     return ap.parse_args()
 
 
@@ -214,22 +216,39 @@ class DeviceRunner:
     shard and writes it into every rank's gathered buffer), replayed with `in_flight` consecutive steps on as many
     streams, or strictly one after the other."""
 
-    def __init__(self, w, dev_sets, anchors_dev, in_flight, dist_world):
+    def __init__(self, w, dev_sets, anchors_dev, in_flight, dist_world, group=1):
         from single_shot_detection_b200 import sharding
-        from single_shot_detection_b200.pipeline import AnchorPipeline
+        from single_shot_detection_b200.pipeline import AnchorPipeline, StepGroup
         self.w, self.dev_sets, self.anchors_dev = w, dev_sets, anchors_dev
         self.nsets = len(dev_sets)
         self.in_flight = max(1, min(in_flight, self.nsets))
+        self.group = max(1, min(group, self.in_flight))
+        while self.nsets % self.group or self.in_flight % self.group:
+            self.group -= 1
         self.world = dist_world
         batch_local = dev_sets[0][0].batch
         rows = dev_sets[0][3]
         conc = self.in_flight > 1
         self.px = sharding.PeerExchange(batch_local * dist_world, rows, slots=self.nsets)
         self.pipes, self.outs = [], []
-        for k, (packed, scores_d, locs_d, _) in enumerate(dev_sets):
-            pipe = AnchorPipeline(w.cfg(), workspace_slot=k % self.in_flight)      # own scratch per concurrent slot
-            self.outs.append(pipe.capture(packed, anchors_dev, scores_d, locs_d, exchange=(self.px, k), concurrent=conc))
-            self.pipes.append(pipe)
+        self.groups = []
+        if self.group > 1:
+            # `group` consecutive steps per graph launch: the host launches in-flight / group graphs round-robin
+            for k0 in range(0, self.nsets, self.group):
+                items = []
+                for k in range(k0, k0 + self.group):
+                    packed, scores_d, locs_d, _ = dev_sets[k]
+                    pipe = AnchorPipeline(w.cfg(), workspace_slot=k % self.in_flight)
+                    items.append((pipe, packed, anchors_dev, scores_d, locs_d, {"exchange": (self.px, k)}))
+                    self.pipes.append(pipe)
+                grp = StepGroup(items, concurrent=True)
+                self.groups.append(grp)
+                self.outs.extend(grp.outs)
+        else:
+            for k, (packed, scores_d, locs_d, _) in enumerate(dev_sets):
+                pipe = AnchorPipeline(w.cfg(), workspace_slot=k % self.in_flight)      # own scratch per concurrent slot
+                self.outs.append(pipe.capture(packed, anchors_dev, scores_d, locs_d, exchange=(self.px, k), concurrent=conc))
+                self.pipes.append(pipe)
         # the strictly serial number uses graphs captured for a step that runs alone (full streaming grids)
         self.px_serial, self.pipes_serial = self.px, self.pipes
         if conc:
@@ -240,22 +259,35 @@ class DeviceRunner:
                 ps.capture(packed, anchors_dev, scores_d, locs_d, exchange=(self.px_serial, k))
                 self.pipes_serial.append(ps)
         torch.cuda.synchronize()
-        self.streams = [torch.cuda.Stream() for _ in range(self.in_flight)]
+        self.streams = [torch.cuda.Stream() for _ in range(self.in_flight // self.group)]
+        self.host_issue_s = 0.0
 
     def _issue(self, steps, serial):
+        """-> steps actually issued (a multiple of the group size)"""
         if serial or self.in_flight == 1:
             for i in range(steps):
                 self.pipes_serial[i % self.nsets].replay()
-            return
+            return steps
         main = torch.cuda.current_stream()
         for s_ in self.streams:
             s_.wait_stream(main)
-        for i in range(steps):
-            k = i % self.nsets
-            with torch.cuda.stream(self.streams[k % self.in_flight]):
-                self.pipes[k].replay()
+        t0 = time.perf_counter()
+        if self.group > 1:
+            launches = -(-steps // self.group)
+            for j in range(launches):
+                g = j % len(self.groups)
+                with torch.cuda.stream(self.streams[g % len(self.streams)]):
+                    self.groups[g].replay()
+            steps = launches * self.group
+        else:
+            for i in range(steps):
+                k = i % self.nsets
+                with torch.cuda.stream(self.streams[k % self.in_flight]):
+                    self.pipes[k].replay()
+        self.host_issue_s = time.perf_counter() - t0
         for s_ in self.streams:
             main.wait_stream(s_)
+        return steps
 
     def flush(self, serial):
         px = self.px_serial if serial else self.px
@@ -291,12 +323,13 @@ class DeviceRunner:
         self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        self._issue(steps * repeats, serial)
+        issued = self._issue(steps * repeats, serial)
         self.flush(serial)                  # the last steps' exchanges complete inside the timed region
         e1.record()
         self.barrier()
         (self.px_serial if serial else self.px).check()
-        return e0.elapsed_time(e1) / (steps * repeats), steps * repeats
+        self.host_issue_ms_per_step = 1e3 * self.host_issue_s / issued
+        return e0.elapsed_time(e1) / issued, issued
 
     def close(self):
         torch.cuda.synchronize()
@@ -379,7 +412,7 @@ def run_ours(args):
         dist.barrier()                # captures (which run the exchange kernels) start together on every rank
 
     launches0 = int(N.lib().ssd_b200_launch_count())
-    runner = DeviceRunner(w, dev_sets, anchors_dev, args.in_flight, world)
+    runner = DeviceRunner(w, dev_sets, anchors_dev, args.in_flight, world, args.group)
     in_flight = runner.in_flight
     # kernels per step: every capture ran 2 eager warm-up steps + 1 captured one
     captures = nsets * (2 if in_flight > 1 else 1)
@@ -460,8 +493,10 @@ def run_ours(args):
             "config": config_block(w, A, B, world, {
                 "l2": f"inputs rotate over {nsets} sets = {nsets * per_set / 2**20:.0f} MiB > 126 MiB L2",
                 "steps_in_flight": in_flight,
-                "device_path": (f"CUDA graph replay per step, {in_flight} consecutive steps in flight on "
-                                f"{in_flight} streams (own scratch buffers per slot)" if in_flight > 1
+                "steps_per_graph_launch": runner.group if in_flight > 1 else 1,
+                "device_path": (f"CUDA graph replay, {runner.group} consecutive step(s) per graph launch (parallel "
+                                f"branches), {in_flight} steps in flight on {len(runner.streams)} streams (own "
+                                f"scratch buffers per slot)" if in_flight > 1
                                 else "CUDA graph replay per step, one step after the other") +
                                "; the last kernel of every step graph packs the shard and writes it into every rank's "
                                "gathered buffer (NVLink peer memory when N > 1; the same kernels run at N = 1)"}),
@@ -472,6 +507,7 @@ def run_ours(args):
                             "(target, mask, list of host detections) per batch; H2D of batch i+1 overlaps batch i"},
             "serial": {"ms_per_step": serial_ms, "value": B * world / (serial_ms * 1e-3), "timed_steps": serial_steps,
                        "note": "the same steps strictly one after the other on one stream (--in-flight 1)"},
+            "host_issue_ms_per_step": getattr(runner, "host_issue_ms_per_step", None),
             "gpu_launches": launches_per_step * timed_steps,
             "launches_per_step": launches_per_step,
             "clocks": clock_info,

@@ -186,8 +186,11 @@ __global__ void __launch_bounds__(kSelThreads, 2)
 mining_select_kernel(const uint32_t* __restrict__ keys, const void* __restrict__ cls, int cls_stride,
                      const int32_t* __restrict__ match, int A, double ratio,
                      int ratio_is_integer, double min_negatives, uint8_t* __restrict__ mask,
-                     int32_t* __restrict__ stats) {
+                     int32_t* __restrict__ stats, int stage_keys) {
     __shared__ SelShared sh;
+    // stage_keys: the image's final keys (class folded in) are kept in shared memory between the two passes, so the
+    // second pass and the boundary ranking never go back to L2 (each src.key() is up to three dependent round trips)
+    extern __shared__ __align__(16) uint32_t skeys[];
     KernelTrace trace_(TR_MINING_SELECT);
     griddep_wait();
     griddep_launch_dependents();
@@ -219,6 +222,7 @@ mining_select_kernel(const uint32_t* __restrict__ keys, const void* __restrict__
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const uint32_t key = kk[u];
+                if (stage_keys && a0 + u * kSelThreads < A) skeys[a0 + u * kSelThreads] = key;
                 if (key == kKeyPositive) ++pos;
                 else if (key != kKeyIgnored) atomicAdd(&sh.hist[key_bin(key)], 1);
             }
@@ -286,13 +290,14 @@ mining_select_kernel(const uint32_t* __restrict__ keys, const void* __restrict__
     const bool rank_bin = partial && need < in_bin;   // otherwise the whole boundary bin is taken
     const bool in_smem = in_bin <= kBoundaryCap;
 
+    auto key_at = [&](int a) -> uint32_t { return stage_keys ? skeys[a] : src.key(a); };
     // ---- one pass over the keys (four loads in flight per thread) ----
     for (int a0 = tid; a0 < A; a0 += 4 * kSelThreads) {
         uint32_t kk[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int a = a0 + u * kSelThreads;
-            kk[u] = a < A ? src.key(a) : kKeyIgnored;
+            kk[u] = a < A ? key_at(a) : kKeyIgnored;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -334,7 +339,7 @@ mining_select_kernel(const uint32_t* __restrict__ keys, const void* __restrict__
                 int d[4] = {0, 0, 0, 0};
                 const uint32_t pre_hi = shift + 2 >= 32 ? 0u : prefix >> (shift + 2);
                 for (int a = tid; a < A; a += kSelThreads) {
-                    const uint32_t key = src.key(a);
+                    const uint32_t key = key_at(a);
                     if (key != kKeyPositive && key != kKeyIgnored && key_bin(key) == cut_bin) {
                         const uint32_t khi = shift + 2 >= 32 ? 0u : key >> (shift + 2);
                         if (khi == pre_hi) d[(key >> shift) & 3u]++;
@@ -355,7 +360,7 @@ mining_select_kernel(const uint32_t* __restrict__ keys, const void* __restrict__
             for (int i = 0; i < rounds; ++i) {
                 const int a = i * kSelThreads + tid;
                 uint32_t key = kKeyIgnored;
-                if (a < A) key = src.key(a);
+                if (a < A) key = key_at(a);
                 const bool member = a < A && key != kKeyPositive && key != kKeyIgnored && key_bin(key) == cut_bin;
                 const bool tie = member && key == thr_key;
                 const unsigned bal = __ballot_sync(FULL, tie);
@@ -381,6 +386,13 @@ mining_select_kernel(const uint32_t* __restrict__ keys, const void* __restrict__
         stats[b * 4 + 2] = (int)k;
         stats[b * 4 + 3] = rank_bin ? (in_smem ? in_bin : num_ties) : 0;
     }
+}
+
+// keys staged in shared memory while an image's keys fit next to the static arrays (A <= 40960), else re-read from L2
+constexpr size_t kSelStageMax = 160 * 1024;
+static size_t select_smem_bytes(int num_anchors) {
+    const size_t need = round_up((size_t)num_anchors * sizeof(uint32_t), 16);
+    return need <= kSelStageMax ? need : 0;
 }
 
 }  // namespace ssd
@@ -474,8 +486,11 @@ extern "C" int ssd_hard_negative_mask(const float* logits, const int64_t* target
     }
 
     LaunchTimer lt_("mining_select", st);
-    SSD_CUDA(launch_pdl(mining_select_kernel, dim3(batch), dim3(kSelThreads), 0, st, (const uint32_t*)keys,
-                        (const void*)nullptr, 0, (const int32_t*)nullptr, num_anchors, ratio, ratio_is_integer, min_negatives, mask_out, stats_out));
+    const size_t sel_smem = select_smem_bytes(num_anchors);
+    SSD_CUDA(cudaFuncSetAttribute(mining_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelStageMax));
+    SSD_CUDA(launch_pdl(mining_select_kernel, dim3(batch), dim3(kSelThreads), sel_smem, st, (const uint32_t*)keys,
+                        (const void*)nullptr, 0, (const int32_t*)nullptr, num_anchors, ratio, ratio_is_integer, min_negatives, mask_out, stats_out,
+                        sel_smem ? 1 : 0));
     count_launch();
     return SSD_OK;
 }
@@ -489,8 +504,11 @@ extern "C" int ssd_hard_negative_mask_from_keys(const uint32_t* loss_keys, const
     if (batch == 0 || num_anchors == 0) return SSD_OK;
     SSD_REQUIRE(loss_keys && classes && mask_out, SSD_ERR_INVALID_ARGUMENT, "ssd_hard_negative_mask_from_keys: null pointer");
     LaunchTimer lt_("mining_select", (cudaStream_t)stream);
-    SSD_CUDA(launch_pdl(mining_select_kernel, dim3(batch), dim3(kSelThreads), 0, (cudaStream_t)stream, loss_keys, classes,
-                        class_stride, match, num_anchors, ratio, ratio_is_integer, min_negatives, mask_out, stats_out));
+    const size_t sel_smem = select_smem_bytes(num_anchors);
+    SSD_CUDA(cudaFuncSetAttribute(mining_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelStageMax));
+    SSD_CUDA(launch_pdl(mining_select_kernel, dim3(batch), dim3(kSelThreads), sel_smem, (cudaStream_t)stream, loss_keys, classes,
+                        class_stride, match, num_anchors, ratio, ratio_is_integer, min_negatives, mask_out, stats_out,
+                        sel_smem ? 1 : 0));
     count_launch();
     return SSD_OK;
 }

@@ -722,13 +722,17 @@ score_pass2_kernel(const float* __restrict__ scores, ScoreGrid g, const float2* 
                 const float2 st = side[lr];
                 t = __fadd_rn(st.x, fast_log(st.y));            // bit-identical to pass 1
             }
+            // bit i of `hit` = sign of gate[i] - x[i], i.e. x[i] > gate[i] (one funnel shift per column collects the sign
+            // bits, most significant = column 0).  A NaN or a signed zero can set a bit the comparison would not: the
+            // gate only PRUNES, the exact score test of the NMS kernel drops such a candidate again.
             unsigned hit = 0u;
 #pragma unroll
             for (int i = 0; i < NREG; ++i) {
                 const float x = CONV == SSD_CONVERT_SOFTMAX ? __fsub_rn(v[i], t) : v[i];
-                hit |= (x > gv[i]) ? (1u << i) : 0u;            // -inf padding and gv = +inf never pass
+                hit = __funnelshift_l(__float_as_uint(__fsub_rn(gv[i], x)), hit, 1);
             }
             if (!valid) hit = 0u;
+            hit = __brev(hit) >> (32 - NREG);                    // bit i = column slot i
             // park the survivors: every round each lane with a pending hit adds one entry
             unsigned bal = __ballot_sync(FULL, hit != 0u);
             while (bal) {
@@ -737,13 +741,11 @@ score_pass2_kernel(const float* __restrict__ scores, ScoreGrid g, const float2* 
                 if (hit) {
                     const int i = __ffs(hit) - 1;
                     hit &= hit - 1;
-                    float x = v[0];
-#pragma unroll
-                    for (int j = 1; j < NREG; ++j) x = (i == j) ? v[j] : x;
+                    const int col = ln.sub + i * Q;
                     const int pos = q.n + __popc(bal & lt_mask);
-                    q.seg[pos] = (uint32_t)(img * Cf + (ln.sub + i * Q - g.first_fg));
+                    q.seg[pos] = (uint32_t)(img * Cf + (col - g.first_fg));
                     q.anchor[pos] = (uint32_t)(a0 + lr);
-                    q.val[pos] = __float_as_uint(x);
+                    q.val[pos] = __float_as_uint(logits[lr * g.C + col]);     // (a dynamic register pick costs NREG selects)
                 }
                 q.n += add;
                 bal = __ballot_sync(FULL, hit != 0u);

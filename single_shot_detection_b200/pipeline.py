@@ -347,7 +347,7 @@ class AnchorPipeline:
         from . import _native as N
         late = self.assign_after_pass1
         if concurrent:
-            N.check(N.lib().ssd_b200_set_stream_ctas_per_sm(1))
+            N.check(N.lib().ssd_b200_set_stream_ctas_per_sm(int(os.environ.get("SSD_CONCURRENT_CTAS", "1"))))
             self.assign_after_pass1 = False
         try:
             return self._capture(packed, anchors_dev, scores_dev, locs_dev, warmup, shard_capacity, gather, exchange)
@@ -378,6 +378,55 @@ class AnchorPipeline:
 
     def replay(self):
         self._graph.replay()
+
+
+class StepGroup:
+    """Several step graphs as the parallel branches of ONE CUDA graph.
+
+    A replay is one ``cudaGraphLaunch`` for ``len(items)`` steps: with ~10 kernel nodes and two branches per step the
+    host needs longer to launch a step graph (~25 us through ``torch.cuda.CUDAGraph.replay`` under a stream context)
+    than the GPU needs to run it when several steps are in flight -- the launches, not the kernels, bound the
+    throughput.  Every member keeps its own buffers and workspace slot (they run concurrently)."""
+
+    def __init__(self, items, warmup: int = 2, concurrent: bool = True):
+        """``items``: [(AnchorPipeline, packed, anchors_dev, scores_dev, locs_dev, kwargs for step_device)]"""
+        from . import _native as N
+        slots = [it[0].workspace_slot for it in items]
+        assert len(set(slots)) == len(slots), "members of a step group run concurrently: one workspace slot each"
+        if concurrent:
+            N.check(N.lib().ssd_b200_set_stream_ctas_per_sm(int(os.environ.get("SSD_CONCURRENT_CTAS", "1"))))
+        late = [it[0].assign_after_pass1 for it in items]
+        try:
+            if concurrent:
+                for it in items:
+                    it[0].assign_after_pass1 = False
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    for pipe, packed, anchors_dev, scores_dev, locs_dev, kw in items:
+                        pipe.step_device(packed, anchors_dev, scores_dev, locs_dev, **kw)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            branches = [torch.cuda.Stream(priority=-1) for _ in items]
+            self.outs = []
+            root = torch.cuda.Stream()
+            with torch.cuda.graph(self.graph, stream=root):
+                for br, (pipe, packed, anchors_dev, scores_dev, locs_dev, kw) in zip(branches, items):
+                    br.wait_stream(root)
+                    with torch.cuda.stream(br):
+                        self.outs.append(pipe.step_device(packed, anchors_dev, scores_dev, locs_dev, **kw))
+                for br in branches:
+                    root.wait_stream(br)
+        finally:
+            for it, l in zip(items, late):
+                it[0].assign_after_pass1 = l
+            if concurrent:
+                N.check(N.lib().ssd_b200_set_stream_ctas_per_sm(0))
+
+    def replay(self):
+        self.graph.replay()
 
 
 def matched_stats(assign_stats: torch.Tensor, mining_stats: Optional[torch.Tensor], counts: torch.Tensor):

@@ -7,6 +7,6 @@ python tools/prof_step.py $W 4 > $OUT.plain.log 2>&1 || { echo "plain run failed
 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,dram__bytes_read.sum,dram__bytes_write.sum \
     --clock-control none -k regex:_kernel -c 60 --csv --log-file $OUT.launches.csv python tools/prof_step.py $W 4 > $OUT.ncu.log 2>&1
 if [ "$3" = full ]; then
-    ncu --set full --import-source on --clock-control none -k regex:_kernel --launch-skip 20 -c 12 -f -o $OUT \
+    ncu --set full --import-source on --clock-control none -k regex:_kernel --launch-skip 16 -c 8 -f -o $OUT \
         python tools/prof_step.py $W 3 > $OUT.ncufull.log 2>&1
 fi
