@@ -1748,8 +1748,12 @@ __device__ int nms_segment(const KernelTrace& tr, const NmsArgs& a, unsigned cha
         // compare-and-add it replaces was 18 % of the kernel's instructions).  Two candidates
         // with the SAME score word (rare: equal fp32 scores) get the same rank; the collision is detected when
         // a key does not find itself in its slot, and the exact 64-bit ranking (ties: lower anchor first) runs.
+        // The words are the top 31 bits of the score key (an invalid entry is 0): both operands below 2^31, so the sign
+        // bit of mine - other says `other > mine` and one shift-and-add (LEA.HI) accumulates it -- two instructions per
+        // key instead of compare + add + select.  Dropping the lowest key bit only makes a collision (adjacent fp32
+        // scores) marginally more likely; collisions are detected below.
         const int fill4 = (n_raw + 3) & ~3;
-        for (int t = threadIdx.x; t < fill4; t += blockDim.x) hk[t] = t < n_raw ? (uint32_t)(keys[t] >> 32) : 0u;
+        for (int t = threadIdx.x; t < fill4; t += blockDim.x) hk[t] = t < n_raw ? (uint32_t)(keys[t] >> 33) : 0u;
         __syncthreads();
         const uint4* h4 = reinterpret_cast<const uint4*>(hk);
         constexpr int kPerThread = (kRankSortMax + NT - 1) / NT;
@@ -1761,13 +1765,15 @@ __device__ int nms_segment(const KernelTrace& tr, const NmsArgs& a, unsigned cha
             if (t >= n_raw) continue;
             const unsigned long long me = keys[t];
             if (me == 0ull) continue;
-            const uint32_t mine = (uint32_t)(me >> 32);
+            const uint32_t mine = (uint32_t)(me >> 33);
             uint32_t rank = 0u, rank_b = 0u;
 #pragma unroll 4
             for (int j = 0; j < (fill4 >> 2); ++j) {
                 const uint4 o = h4[j];
-                rank += (o.x > mine) + (o.z > mine);
-                rank_b += (o.y > mine) + (o.w > mine);
+                rank += (mine - o.x) >> 31;
+                rank_b += (mine - o.y) >> 31;
+                rank += (mine - o.z) >> 31;
+                rank_b += (mine - o.w) >> 31;
             }
             rank += rank_b;
             if ((int)rank < n) { sorted[rank] = me; myrank[u] = (int)rank; }

@@ -20,6 +20,12 @@ def hard_negative_mining(predictions, target_classes, negative_per_positive_rati
     predictions [B, A, C] logits, target_classes [B, A] int64 -> bool [B, A].  Loss values that tie
     exactly across the cut go to the lower anchor index (the reference's unstable argsort leaves
     that case implementation defined).
+
+    Tolerance: the SELECTION is bit-exact on identical fp32 losses (``hard_negative_mining_from_loss``).  From
+    logits, the criterion -log_softmax(x)[0] is evaluated with the hardware ex2 / lg2 approximations (relative
+    error 2^-22, csrc/rowstream.cuh), so anchors whose losses differ by less than that can swap sides of the cut:
+    at most a few anchors per image against the reference (counts per BASELINE configuration:
+    profiles/r02_mining_mismatch.md; the tests bound it by 2 per image).
     """
     ratio_is_integer = isinstance(negative_per_positive_ratio, int) and not isinstance(negative_per_positive_ratio, bool)
     mask, stats = OPS.hard_negative_mask(predictions, target_classes, None, float(negative_per_positive_ratio),
