@@ -29,9 +29,10 @@ for r in rows[2:]:
             return fmt.format(float(g(r, k).replace(",", "")) * scale)
         except ValueError:
             return "?"
-    unit = rows[1][idx["dram__bytes_read.sum"]]
-    sc = {"Mbyte": 1.0, "Kbyte": 1e-3, "byte": 1e-6, "Gbyte": 1e3}.get(unit, 1.0)
+    units = {"Mbyte": 1.0, "Kbyte": 1e-3, "byte": 1e-6, "Gbyte": 1e3}
+    sc = units.get(rows[1][idx["dram__bytes_read.sum"]], 1.0)
+    scw = units.get(rows[1][idx["dram__bytes_write.sum"]], 1.0)
     print(f"| {name} | {f('gpu__time_duration.sum', 1e-3 if rows[1][idx['gpu__time_duration.sum']]=='ns' else 1.0)} | "
           f"{g(r,'launch__grid_size')}x{g(r,'launch__block_size')} | {g(r,'launch__registers_per_thread')} | "
-          f"{f('smsp__inst_executed.sum', 1e-6, '{:.2f}M')} | {f('dram__bytes_read.sum', sc, '{:.2f}')} | {f('dram__bytes_write.sum', sc, '{:.2f}')} | "
+          f"{f('smsp__inst_executed.sum', 1e-6, '{:.2f}M')} | {f('dram__bytes_read.sum', sc, '{:.2f}')} | {f('dram__bytes_write.sum', scw, '{:.2f}')} | "
           f"{f('sm__throughput.avg.pct_of_peak_sustained_elapsed')} | {f('smsp__issue_active.avg.pct_of_peak_sustained_active')} | {tops} |")
