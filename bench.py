@@ -2,7 +2,7 @@
 """Benchmark of the anchor pipeline (BASELINE.json metric: images/sec target-assign+NMS, SSD300 b32).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
-                    [--in-flight F] [--scaling weak|strong] [--no-config5] [--no-cpu-baseline]
+                    [--in-flight F] [--group G] [--scaling weak|strong] [--no-config5] [--no-cpu-baseline]
 
 A step = one pass of the hot path over one batch of synthetic input (SURVEY.md ยง8d):
     encode_ground_truth -> sampler -> to_centroids + encode_box (in place) -> postprocess
@@ -11,7 +11,10 @@ A step = one pass of the hot path over one batch of synthetic input (SURVEY.md ย
 ours:       `value`  = device-resident inputs, every step replayed from a CUDA graph, F consecutive steps in
                        flight on F streams (default 8), timed with CUDA events (max over ranks).  The timed region
                        is K steps repeated until it lasts >= 50 ms (`timed_steps`);
-            `serial` = the same steps strictly one after the other on one stream;
+            `serial` = the same steps strictly one after the other (every step starts when the previous one has
+                       finished; the steps of all input sets are chained in one graph, SSD_SERIAL_CHAIN=0 launches
+                       one graph per step instead);
+            `host_issue_ms_per_step` = host time of the launch loop per step (the host is not the limit);
             `e2e`    = the same step through the reference-shaped Python API with HOST buffers:
                        pinned scores/locs and the ground-truth list are copied H2D and the padded
                        detections + counts + statistics are read back D2H inside the timed region;
@@ -19,13 +22,13 @@ ours:       `value`  = device-resident inputs, every step replayed from a CUDA g
                        criterion output) timed alone with CUDA events against MEASURED_PEAKS.json, the
                        sampler's own streaming kernel beside it, and `roofline.step`: SURVEY.md ยง8(d)'s
                        algorithmic bytes per batch / step time / peak for the whole step;
-            `cpu_baseline` = the CPU oracle (same torch CPU ops as the reference) on a bounded sample, with all
-                       host threads, with one thread, and per stage;
+            `cpu_baseline` = the CPU oracle (same torch CPU ops as the reference) on whole batches of the workload
+                       (20 steps, ~10 s), with all host threads, with one thread, and per stage;
             `config5_strong` = BASELINE configs[4] as north_star states it: M2Det-512 b256 sharded by image over the
                        N ranks (256 / N images per GPU), with a check that the gathered buffer of every rank equals a
                        single-GPU run of the same global batch bit for bit (`gather_parity`).
 reference:  the reference's CPU algorithm (oracle port, torch CPU ops + torchvision NMS) on the
-            host cores, same metric / config.
+            host cores, same metric / config keys, the requested steps (up to 100) over whole batches.
 
 --scaling weak (default): every rank owns a full batch of the workload; strong: the workload's batch is sharded.
 
@@ -55,6 +58,8 @@ from single_shot_detection_b200 import workloads as wl  # noqa: E402
 
 L2_BYTES = 126 * 1024 * 1024
 MIN_TIMED_MS = 50.0
+# the strictly serial leg: all input sets' steps chained in one graph (1) or one graph launch per step (0)
+SERIAL_CHAIN = os.environ.get("SSD_SERIAL_CHAIN", "1") != "0"
 METRIC = "images/sec target-assign+NMS"
 REGION = "encode_ground_truth + sampler + to_centroids/encode_box + postprocess + exchange(dets,stats)"
 
@@ -67,7 +72,8 @@ def parse_args():
     ap.add_argument("--workload", default=wl.HEADLINE)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
-    ap.add_argument("--cpu-sample-images", type=int, default=8)
+    ap.add_argument("--cpu-sample-images", type=int, default=32,
+                    help="images per CPU step (default: the whole batch of the headline workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config5", action="store_true", help="skip the M2Det b256 strong-scaling leg")
     ap.add_argument("--no-e2e", action="store_true", help="(diagnostics) skip the host-buffer leg")
@@ -171,7 +177,7 @@ def time_cpu_oracle(w: wl.Workload, images: int, steps: int, warmup: int, thread
 def cpu_baseline_block(w: wl.Workload, images: int, steps: int, warm: int):
     cores = os.cpu_count() or 1
     best, mean, stage_ms = time_cpu_oracle(w, images, steps, warm, cores)
-    best1, mean1, stage_ms1 = time_cpu_oracle(w, images, max(1, min(steps, 2)), 1, 1)
+    best1, mean1, stage_ms1 = time_cpu_oracle(w, images, max(1, min(steps, 10)), 1, 1)
     torch.set_num_threads(cores)
     sample = (f"{images} of {w.batch} images per step, {steps} steps + {warm} warm-up, oracle port of the reference "
               f"(the reference's torch CPU op sequence + torchvision.ops.nms), {cores} torch threads")
@@ -191,8 +197,9 @@ def run_reference(args):
     w = wl.WORKLOADS[args.workload]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     images = min(args.cpu_sample_images, w.batch)
-    steps = max(1, min(args.steps, 5))
-    warm = max(1, min(args.warmup, 1))
+    # exactly the requested steps / warm-up while that stays within minutes (a step is ~0.25 s at SSD300 b32)
+    steps = max(1, min(args.steps, 100))
+    warm = max(1, min(args.warmup, 10))
     cb = cpu_baseline_block(w, images, steps, warm)
     anchors = wl.build_anchors(w)
     per_gpu = w.batch if args.scaling == "weak" else w.batch // max(world, 1)
@@ -200,7 +207,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "images/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * images / cb["value"],
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_block(w, int(anchors.shape[0]), per_gpu, max(world, 1), {"sample_images": images}),
+        # the same keys as the GPU arm's config
+        "config": config_block(w, int(anchors.shape[0]), per_gpu, max(world, 1), {
+            "l2": "n/a (host arm)", "steps_in_flight": 1, "steps_per_graph_launch": 1,
+            "device_path": f"host: the reference's torch CPU op sequence on {images} of {w.batch} images per step, "
+                           f"{cb['cores']} torch threads (rank 0 only)"}),
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -251,19 +262,34 @@ class DeviceRunner:
                 self.pipes.append(pipe)
         # the strictly serial number uses graphs captured for a step that runs alone (full streaming grids)
         self.px_serial, self.pipes_serial = self.px, self.pipes
+        self.serial_chain = None
         if conc:
             self.px_serial = sharding.PeerExchange(batch_local * dist_world, rows, slots=self.nsets)
             self.pipes_serial = []
+            items = []
             for k, (packed, scores_d, locs_d, _) in enumerate(dev_sets):
                 ps = AnchorPipeline(w.cfg())
-                ps.capture(packed, anchors_dev, scores_d, locs_d, exchange=(self.px_serial, k))
+                ps.pass1_first = ps.pass1_first or SERIAL_CHAIN      # the chain starts with pass 1: ~2 us per step
+                if SERIAL_CHAIN:
+                    items.append((ps, packed, anchors_dev, scores_d, locs_d, {"exchange": (self.px_serial, k)}))
+                else:
+                    ps.capture(packed, anchors_dev, scores_d, locs_d, exchange=(self.px_serial, k))
                 self.pipes_serial.append(ps)
+            if SERIAL_CHAIN:
+                # all nsets steps chained in ONE graph: every step starts when the previous one has finished, without
+                # the graph-to-graph launch latency a stream exposes between single-step graphs
+                self.serial_chain = StepGroup(items, chained=True)
         torch.cuda.synchronize()
         self.streams = [torch.cuda.Stream() for _ in range(self.in_flight // self.group)]
         self.host_issue_s = 0.0
 
     def _issue(self, steps, serial):
         """-> steps actually issued (a multiple of the group size)"""
+        if (serial or self.in_flight == 1) and self.serial_chain is not None:
+            launches = -(-steps // self.nsets)
+            for _ in range(launches):
+                self.serial_chain.replay()
+            return launches * self.nsets
         if serial or self.in_flight == 1:
             for i in range(steps):
                 self.pipes_serial[i % self.nsets].replay()
@@ -506,7 +532,10 @@ def run_ours(args):
                     "path": "AnchorPipeline.stream(batches of (list of GT, pinned host scores, locs), CPU anchors) -> "
                             "(target, mask, list of host detections) per batch; H2D of batch i+1 overlaps batch i"},
             "serial": {"ms_per_step": serial_ms, "value": B * world / (serial_ms * 1e-3), "timed_steps": serial_steps,
-                       "note": "the same steps strictly one after the other on one stream (--in-flight 1)"},
+                       "note": "the same steps strictly one after the other: every step starts when the previous one has finished"
+                               + (" (the steps of all input sets chained in ONE graph: no graph-to-graph launch latency "
+                                  "between steps; SSD_SERIAL_CHAIN=0: one graph launch per step)" if SERIAL_CHAIN else
+                                  " (one graph launch per step on one stream)")},
             "host_issue_ms_per_step": getattr(runner, "host_issue_ms_per_step", None),
             "gpu_launches": launches_per_step * timed_steps,
             "launches_per_step": launches_per_step,
@@ -518,7 +547,7 @@ def run_ours(args):
         if config5 is not None:
             line["config5_strong"] = config5
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_block(w, min(args.cpu_sample_images, B), 3, 1)
+            line["cpu_baseline"] = cpu_baseline_block(w, min(args.cpu_sample_images, B), 20, 2)     # ~10 s of CPU work
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.cuda.synchronize()

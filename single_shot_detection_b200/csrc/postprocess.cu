@@ -1665,6 +1665,21 @@ image_topk_kernel(TopkArgs ta) {
 // ---------------------------------------------------------------------------------------------
 // 4. segment_nms: one CTA per (image, foreground class)
 // ---------------------------------------------------------------------------------------------
+// Overlap filter of the bit matrix: bit U of `bits` is set when the two boxes intersect with positive extent,
+// bi.z > bj.x && bj.z > bi.x && bi.w > bj.y && bj.w > bi.y (NaN fails) -- four chained FSETP and ONE predicated OR
+// (the compiler's form of `bits |= hit ? 1u << U : 0u` was MOV 0 + SEL + LOP3 per pair).
+template <int U>
+__device__ __forceinline__ void overlap_bit(uint32_t& bits, const float4& bi, const float4 bj) {
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.gt.f32 p, %1, %2;\n\t"
+        "setp.gt.and.f32 p, %3, %4, p;\n\t"
+        "setp.gt.and.f32 p, %5, %6, p;\n\t"
+        "setp.gt.and.f32 p, %7, %8, p;\n\t"
+        "@p or.b32 %0, %0, %9;\n\t}"
+        : "+r"(bits)
+        : "f"(bi.z), "f"(bj.x), "f"(bj.z), "f"(bi.x), "f"(bi.w), "f"(bj.y), "f"(bj.w), "f"(bi.y), "n"(1u << U));
+}
+
 // Returns the number of kept rows of the segment (kept_count[seg] is written by the caller).
 template <int NT>
 __device__ int nms_segment(const KernelTrace& tr, const NmsArgs& a, unsigned char* smem, uint32_t* s_hist, int* s_misc, int& s_valid, int& s_nkeep,
@@ -1920,9 +1935,23 @@ __device__ int nms_segment(const KernelTrace& tr, const NmsArgs& a, unsigned cha
         uint32_t bits = 0u;
         if (a.screen) {
             const float4 bi = i < n ? fbox[i] : make_float4(NAN, NAN, NAN, NAN);
-#pragma unroll 8
-            for (int jj = 0; jj < cols; ++jj) {
-                const float4 bj = fbox[j0 + jj];            // same address for every lane: broadcast
+            // whole groups of eight columns with compile-time bit positions (a runtime `1u << jj` costs a MOV + SHF per
+            // pair on top of the four compares), then the <= 7 columns that are left
+            int jb = 0;
+            for (; jb + 8 <= cols; jb += 8) {
+                uint32_t g8 = 0u;
+                overlap_bit<0>(g8, bi, fbox[j0 + jb + 0]);      // same address for every lane: broadcast
+                overlap_bit<1>(g8, bi, fbox[j0 + jb + 1]);
+                overlap_bit<2>(g8, bi, fbox[j0 + jb + 2]);
+                overlap_bit<3>(g8, bi, fbox[j0 + jb + 3]);
+                overlap_bit<4>(g8, bi, fbox[j0 + jb + 4]);
+                overlap_bit<5>(g8, bi, fbox[j0 + jb + 5]);
+                overlap_bit<6>(g8, bi, fbox[j0 + jb + 6]);
+                overlap_bit<7>(g8, bi, fbox[j0 + jb + 7]);
+                bits |= g8 << jb;
+            }
+            for (int jj = jb; jj < cols; ++jj) {
+                const float4 bj = fbox[j0 + jj];
                 const bool hit = bi.z > bj.x && bj.z > bi.x && bi.w > bj.y && bj.w > bi.y;
                 bits |= hit ? 1u << jj : 0u;
             }

@@ -70,6 +70,7 @@ class AnchorPipeline:
         # opt-in: the assignment branch starts behind the post-processor's first pass (see _step_device; a single
         # replayed graph gets shorter, 66 -> 59 us on the device timeline, but back-to-back replays measured slower)
         self.assign_after_pass1 = os.environ.get("SSD_ASSIGN_AFTER_PASS1", "0") != "0"
+        self.pass1_first = os.environ.get("SSD_PASS1_FIRST", "0") != "0"
         self._graph = None
         self._side = None
         self._copy = None
@@ -281,11 +282,16 @@ class AnchorPipeline:
         # (tools/graph_timeline.py); `assign_after_pass1` starts its branch behind pass 1 instead (off by default).
         late_assign = share and self.assign_after_pass1
         flight = keyed = None
-        if share and late_assign:
+        # `pass1_first`: pass 1 is CAPTURED before the assignment branch (no dependency between them): the graph then
+        # launches it first and its CTAs are resident before the assignment's arrive (tools/graph_timeline.py: the
+        # chain pass 1 -> ... -> top-k is ~5 us shorter than when the assignment wins the race for the SMs)
+        pass1_first = share and not late_assign and self.pass1_first
+        if share and (late_assign or pass1_first):
             flight = self.postprocessor.begin_padded((scores_dev, locs_dev), anchors_dev, want_loss_keys=True)
             keyed = torch.cuda.Event()
             keyed.record(main)
-            side.wait_event(keyed)
+            if late_assign:
+                side.wait_event(keyed)
         with torch.cuda.stream(side):
             if exchange is not None:
                 exchange[0].open(exchange[1])          # a new launch of the slot: its previous contents are released
@@ -294,7 +300,7 @@ class AnchorPipeline:
                 classes = target[..., CLASS_INDEX].long()                      # multibox_loss.py:49 (before the boxes change)
             else:
                 classes = None
-        if share and not late_assign:
+        if share and not late_assign and not pass1_first:
             flight = self.postprocessor.begin_padded((scores_dev, locs_dev), anchors_dev, want_loss_keys=True)
             keyed = torch.cuda.Event()
             keyed.record(main)
@@ -388,11 +394,16 @@ class StepGroup:
     than the GPU needs to run it when several steps are in flight -- the launches, not the kernels, bound the
     throughput.  Every member keeps its own buffers and workspace slot (they run concurrently)."""
 
-    def __init__(self, items, warmup: int = 2, concurrent: bool = True):
-        """``items``: [(AnchorPipeline, packed, anchors_dev, scores_dev, locs_dev, kwargs for step_device)]"""
+    def __init__(self, items, warmup: int = 2, concurrent: bool = True, chained: bool = False):
+        """``items``: [(AnchorPipeline, packed, anchors_dev, scores_dev, locs_dev, kwargs for step_device)]
+
+        ``chained``: the members run strictly ONE AFTER THE OTHER (each step starts when the previous one has finished --
+        the graph is a chain of step sub-graphs on one stream), so a replay is what ``len(items)`` replays of single-step
+        graphs on one stream are, minus the graph-to-graph launch latency the stream would expose between them."""
         from . import _native as N
         slots = [it[0].workspace_slot for it in items]
-        assert len(set(slots)) == len(slots), "members of a step group run concurrently: one workspace slot each"
+        assert chained or len(set(slots)) == len(slots), "members of a step group run concurrently: one workspace slot each"
+        concurrent = concurrent and not chained
         if concurrent:
             N.check(N.lib().ssd_b200_set_stream_ctas_per_sm(int(os.environ.get("SSD_CONCURRENT_CTAS", "1"))))
         late = [it[0].assign_after_pass1 for it in items]
@@ -412,6 +423,11 @@ class StepGroup:
             branches = [torch.cuda.Stream(priority=-1) for _ in items]
             self.outs = []
             root = torch.cuda.Stream()
+            if chained:
+                with torch.cuda.graph(self.graph, stream=torch.cuda.Stream(priority=-1)):
+                    for pipe, packed, anchors_dev, scores_dev, locs_dev, kw in items:
+                        self.outs.append(pipe.step_device(packed, anchors_dev, scores_dev, locs_dev, **kw))
+                return
             with torch.cuda.graph(self.graph, stream=root):
                 for br, (pipe, packed, anchors_dev, scores_dev, locs_dev, kw) in zip(branches, items):
                     br.wait_stream(root)

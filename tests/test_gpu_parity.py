@@ -813,6 +813,40 @@ def test_two_step_graphs_in_flight_equal_serial_steps(dev):
                 assert torch.equal(g, r), k
 
 
+@pytest.mark.parametrize("chained", [False, True])
+def test_step_group_equals_single_steps(dev, chained):
+    """pipeline.StepGroup: several steps in ONE graph -- as parallel branches (own workspace slots) or chained one
+    after the other (bench.py's serial leg, captured with pass 1 ahead of the assignment branch) -- give the outputs
+    of the same steps run alone."""
+    from single_shot_detection_b200.pipeline import AnchorPipeline, StepGroup
+    from single_shot_detection_b200.target_assigner import pack_ground_truth
+    w = wl.WORKLOADS["ssd300_voc_b8"]
+    anchors = wl.build_anchors(w).to(dev)
+    items, want = [], []
+    for k in range(3):
+        _, gt, scores, locs = wl.make_inputs(w, seed=60 + k, batch=5)
+        packed = pack_ground_truth(gt, dev)
+        packed.rows, packed.offsets = packed.rows.clone(), packed.offsets.clone()
+        scores, locs = scores.to(dev), locs.to(dev)
+        out = AnchorPipeline(w.cfg()).step_device(packed, anchors, scores, locs)
+        torch.cuda.synchronize()
+        want.append([t.clone() for t in (out.target, out.mask, out.dets, out.counts)])
+        pipe = AnchorPipeline(w.cfg(), workspace_slot=0 if chained else k)
+        pipe.pass1_first = chained
+        items.append((pipe, packed, anchors, scores, locs, {}))
+    group = StepGroup(items, chained=chained)
+    torch.cuda.synchronize()
+    for rep in range(10):
+        group.replay()
+    torch.cuda.synchronize()
+    for k, out in enumerate(group.outs):
+        for g, r in zip((out.target, out.mask, out.counts), (want[k][0], want[k][1], want[k][3])):
+            assert torch.equal(g, r), k
+        for i in range(out.dets.shape[0]):
+            n = int(out.counts[i])
+            assert torch.equal(out.dets[i, :n], want[k][2][i, :n]), k
+
+
 def test_peer_exchange_single_rank_equals_tensor_op_packing(dev):
     """sharding.PeerExchange with a world of one (the multi-GPU check is tools/exchange_check.py under torchrun):
     slots, launch counters, row flags, the wait kernel and the gathered layout; no process group needed."""
