@@ -698,20 +698,31 @@ def roofline_probe(w, dev_sets, anchors_dev, pipe, B, A, C, nsets, iters: int = 
     lib = N.lib()
 
     def timed(launch):
+        """us per launch: `iters` back-to-back launches (rotating input sets) captured into ONE CUDA graph and replayed,
+        so the host's launch rate (a ctypes call per launch costs about as much as this kernel runs at the headline
+        size) cannot leak into the number; CUDA events on the replaying stream around three replays."""
         for i in range(5):
-            launch(i % nsets)
+            launch(i % nsets, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            st = torch.cuda.current_stream().cuda_stream
+            for i in range(iters):
+                launch(i % nsets, st)
+        graph.replay()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
         e0.record()
-        for i in range(iters):
-            launch(i % nsets)
+        for _ in range(reps):
+            graph.replay()
         e1.record()
         torch.cuda.synchronize()
-        return 1e3 * e0.elapsed_time(e1) / iters
+        return 1e3 * e0.elapsed_time(e1) / (iters * reps)
 
     ws = torch.empty((max(lib.ssd_hard_negative_workspace_bytes(B, A), 256),), dtype=torch.uint8, device=dev)
 
-    def mining(k):
+    def mining(k, stream):
         N.check(lib.ssd_mining_keys(dev_sets[k][1].data_ptr(), cls[k].data_ptr(), B, A, C, keys.data_ptr(),
                                     ws.data_ptr(), ws.numel(), stream))
 
@@ -734,7 +745,7 @@ def roofline_probe(w, dev_sets, anchors_dev, pipe, B, A, C, nsets, iters: int = 
                          int(w.max_total or 0), 0.0)
     pws = ops._post_workspace(p, dev)
 
-    def pass1(k):
+    def pass1(k, stream):
         N.check(lib.ssd_postprocess_pass1(ctypes.byref(p), dev_sets[k][1].data_ptr(), keys.data_ptr() if want_keys else None,
                                           pws.data_ptr(), pws.numel(), stream))
 
@@ -747,7 +758,7 @@ def roofline_probe(w, dev_sets, anchors_dev, pipe, B, A, C, nsets, iters: int = 
             "algorithmic_bytes_per_launch": algo_p1, "us_per_launch": us, "other_streaming_kernels": other,
             "note": "the streaming kernel of the step: one read of the logits yields the row statistics, the gate "
                     "bookkeeping and the sampler's criterion (4C read + 12 written bytes per anchor); timed back to back "
-                    "on one stream, inputs rotating over sets larger than L2; `traffic` is quoted only while the kernel "
+                    "on one stream (the launches replayed from one CUDA graph), inputs rotating over sets larger than L2; `traffic` is quoted only while the kernel "
                     "sources still hash to what the committed ncu capture saw; the largest kernel of the step, "
                     "segment_nms_kernel, is ALU bound and reported under 'nms'"}
 

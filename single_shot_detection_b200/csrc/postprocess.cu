@@ -654,7 +654,7 @@ hist_gate_kernel(GateHist gh, ScoreGrid g, float* __restrict__ gate) {
 }
 
 template <int Q, int NREG, int CMIN, int CONV>
-__global__ void __launch_bounds__(kStreamThreads)
+__global__ void __launch_bounds__(kStreamThreads, 3)
 score_pass2_kernel(const float* __restrict__ scores, ScoreGrid g, const float2* __restrict__ rowstat,
                    const float* __restrict__ gate, GateHist gh, int* __restrict__ cand_count, uint2* __restrict__ cand,
                    int cand_cap) {
