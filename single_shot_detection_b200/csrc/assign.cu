@@ -78,7 +78,7 @@ __device__ __forceinline__ float4 coded_box(float4 corners, float4 prior, const 
     return make_float4(e.a, e.b, e.c, e.d);
 }
 
-__global__ void __launch_bounds__(kAssignThreads)
+__global__ void __launch_bounds__(kAssignThreads, 5)
 assign_targets_kernel(const float4* __restrict__ anchors, const float* __restrict__ gt_rows, int gt_cols,
                       const int32_t* __restrict__ gt_offsets, int A, int max_gt, float matched_thr,
                       float unmatched_thr, int force_match, float* __restrict__ target, int32_t* __restrict__ match_out,
