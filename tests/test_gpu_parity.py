@@ -433,6 +433,32 @@ def test_postprocess_overflow_fallback_is_exact(dev):
         torch.testing.assert_close(dets[0, :n].cpu(), ref[0], rtol=REL, atol=1e-6)
 
 
+@pytest.mark.parametrize("conv,c,a", [("SOFTMAX", 21, 8732), ("SOFTMAX", 7, 6500), ("SOFTMAX", 31, 6700), ("SOFTMAX", 19, 7001),
+                                      ("SIGMOID", 5, 6401), ("SIGMOID", 27, 9000), ("SOFTMAX", 21, 6399), ("SIGMOID", 20, 7000)])
+def test_postprocess_row_per_lane_shapes_vs_oracle(dev, conv, c, a):
+    """The row-per-lane shapes of the streaming kernels (C <= 8 and odd C <= 32): with >= 6400 anchors a warp step of
+    32 rows is one block of pass 1 (the block-per-step instantiation), partial last tiles included; 6399 anchors and
+    the even C take the generic block bookkeeping.  Logits -> detections against the oracle (keep lists exact through
+    the anchors, scores / boxes to REL)."""
+    from single_shot_detection_b200 import _native as N
+    from single_shot_detection_b200.ops import OPS
+    gen = torch.Generator().manual_seed(1000 + c + a)
+    b = 3
+    logits = torch.randn((b, a, c), generator=gen) + (-3.0 if conv == "SIGMOID" else 0.0)
+    cxy = torch.rand((b, a, 2), generator=gen) * 300
+    wh = torch.rand((b, a, 2), generator=gen) * 60 + 2
+    corners = torch.cat([cxy - wh / 2, cxy + wh / 2], dim=-1)
+    fg = ora.convert_scores(logits, conv)
+    # (no final top-k: among the 200 best of ~2000 kept rows two scores 1e-7 apart may swap between the host's softmax
+    # and the device's; class-major lists only depend on the order inside a class)
+    ref = ora.detections_from_scores(fg, corners, 0.01, 0.45, 100, None, canonical=True)
+    code, first = (N.CONVERT_SOFTMAX, 1) if conv == "SOFTMAX" else (N.CONVERT_SIGMOID, 0)
+    dets, counts, anchors, status = OPS.postprocess(logits.to(dev), corners.to(dev), None, code, first, N.BOXES_CORNERS,
+                                                    1.0, 1.0, 0.01, 100, 0.45, 0)
+    assert status.tolist()[1] == 0, status.tolist()          # no list overflowed: the gate path itself is what ran
+    _compare_dets([dets[i, :int(counts[i])] for i in range(b)], ref, 300)
+
+
 def test_nms_api_vs_torchvision_golden(dev):
     _, _, _, _, _, box_utils = _modules()
     z = gio.load("nms.npz")
