@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SSD_B200_ABI_VERSION 2
+#define SSD_B200_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define SSD_API __attribute__((visibility("default")))
@@ -78,6 +78,10 @@ SSD_API size_t ssd_b200_timing_report(char* buf, size_t capacity);
  * 0 = automatic (fill the shared memory: fastest for a step that runs alone); 1 leaves room for the kernels of
  * other steps when several step graphs are in flight. */
 SSD_API int ssd_b200_set_stream_ctas_per_sm(int ctas);
+/* Threads per (image, class) CTA of the NMS kernel (process-wide, read when a launch is issued or captured):
+ * 0 = default (128: best aggregate throughput with several steps in flight), or 32 / 64 / 128 / 256 (256 is
+ * ~1 us faster for a step that runs alone).  Every setting produces identical detections. */
+SSD_API int ssd_b200_set_nms_threads(int threads);
 /* Candidate selection of the post-processor: -1 = automatic (one thread-block cluster per image when the image's
  * logits fit the cluster's shared memory -- one launch instead of pass 1 / gates / pass 2), 0 = always the streaming
  * two-pass path, 1/2/4/8 = that cluster size when it fits.  Both paths produce identical detections. */

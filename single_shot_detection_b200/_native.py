@@ -79,6 +79,7 @@ _SIGNATURES = {
     "ssd_positive_mask": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "ssd_b200_launch_count": (ctypes.c_ulonglong, []),
     "ssd_b200_set_stream_ctas_per_sm": (c_int, [c_int]),
+    "ssd_b200_set_nms_threads": (c_int, [c_int]),
     "ssd_b200_set_fused_select": (c_int, [c_int]),
     "ssd_mining_keys": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ssd_hard_negative_workspace_bytes": (c_size_t, [c_int, c_int]),
@@ -159,7 +160,7 @@ def lib() -> ctypes.CDLL:
                     fn = getattr(handle, name)       # AttributeError if the symbol is not exported
                     fn.restype = res
                     fn.argtypes = args
-                if handle.ssd_b200_abi_version() != 2:
+                if handle.ssd_b200_abi_version() != 3:
                     raise ImportError("libssd_b200.so ABI version mismatch")
                 _lib = handle
     return _lib

@@ -38,6 +38,7 @@ int sm_count() {
 // runs alone), 1 = one per SM, which leaves shared memory for the NMS / selection CTAs of OTHER steps when
 // several step graphs are in flight (bench.py: 34.6 -> 32.2 us per step with four in flight, 64 -> 68 us alone).
 // Read when a launch is issued or captured.
+int g_nms_threads = 0;             // ssd_b200_set_nms_threads: 0 = default (SSD_NMS_THREADS or 128)
 static int g_stream_ctas = -1;
 int stream_ctas_override() {
     if (g_stream_ctas < 0) {
@@ -198,6 +199,13 @@ extern "C" int ssd_b200_set_fused_select(int mode) {
     SSD_REQUIRE(mode == -1 || mode == 0 || mode == 1 || mode == 2 || mode == 4 || mode == 8, SSD_ERR_INVALID_ARGUMENT,
                 "ssd_b200_set_fused_select: %d is not one of -1, 0, 1, 2, 4, 8", mode);
     ssd::g_fused_select = mode;
+    return SSD_OK;
+}
+
+extern "C" int ssd_b200_set_nms_threads(int threads) {
+    SSD_REQUIRE(threads == 0 || threads == 32 || threads == 64 || threads == 128 || threads == 256, SSD_ERR_INVALID_ARGUMENT,
+                "ssd_b200_set_nms_threads: %d is not one of 0, 32, 64, 128, 256", threads);
+    ssd::g_nms_threads = threads;
     return SSD_OK;
 }
 

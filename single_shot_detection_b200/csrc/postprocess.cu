@@ -2092,7 +2092,9 @@ extern "C" size_t ssd_postprocess_workspace_bytes(const ssd_postprocess_params* 
 }
 
 // threads per (image, class) CTA of the NMS kernel: SSD_NMS_THREADS = 32 / 64 / 128 / 256, read once
+namespace ssd { extern int g_nms_threads; }          // abi.cu (ssd_b200_set_nms_threads)
 static int nms_threads() {
+    if (g_nms_threads > 0) return g_nms_threads;
     static const int nt = [] {
         const int v = env_int("SSD_NMS_THREADS", 128);
         return (v == 32 || v == 64 || v == 256) ? v : 128;

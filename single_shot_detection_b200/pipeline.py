@@ -404,6 +404,8 @@ class StepGroup:
         slots = [it[0].workspace_slot for it in items]
         assert chained or len(set(slots)) == len(slots), "members of a step group run concurrently: one workspace slot each"
         concurrent = concurrent and not chained
+        if chained:
+            N.check(N.lib().ssd_b200_set_nms_threads(256))       # a step that runs alone: 256-thread NMS CTAs (~1 us)
         if concurrent:
             N.check(N.lib().ssd_b200_set_stream_ctas_per_sm(int(os.environ.get("SSD_CONCURRENT_CTAS", "1"))))
         late = [it[0].assign_after_pass1 for it in items]
@@ -436,6 +438,8 @@ class StepGroup:
                 for br in branches:
                     root.wait_stream(br)
         finally:
+            if chained:
+                N.check(N.lib().ssd_b200_set_nms_threads(0))
             for it, l in zip(items, late):
                 it[0].assign_after_pass1 = l
             if concurrent:

@@ -31,7 +31,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in _header_symbols():
         assert hasattr(handle, name), f"{name} is declared in ssd_b200.h but not exported"
     handle.ssd_b200_abi_version.restype = ctypes.c_int
-    assert handle.ssd_b200_abi_version() == 2
+    assert handle.ssd_b200_abi_version() == 3
     # only the declared entry points are visible (the kernels and helpers are hidden)
     import subprocess
     out = subprocess.run(["nm", "-D", "--defined-only", N.LIB_PATH], capture_output=True, text=True).stdout
