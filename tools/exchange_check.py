@@ -25,7 +25,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    batch_local, T, slots = 5, 40, 3
+    # XCHK_BATCH / XCHK_T: the shard shape (default a small one; 32 / 200 is the headline step's, used for the ncu capture)
+    batch_local, T, slots = int(os.environ.get("XCHK_BATCH", "5")), int(os.environ.get("XCHK_T", "40")), 3
     batch = batch_local * world
     px = sharding.PeerExchange(batch, T, slots=slots)
     gen = torch.Generator().manual_seed(100 + rank)

@@ -81,12 +81,21 @@ for d in sorted(rows, key=lambda x: x["n_gpus"]):
               f"{e2e:,.0f} | " + (f"{c5.get('value', 0):,.0f}, {rnd(1e3 * c5.get('ms_per_step', 0))}, {c5.get('images_per_gpu')}, {c5.get('gather_parity')}" if c5 else "-")
               + f" | {chk} |")
 mg.append("")
-mg.append("`ncu` on the exchange kernels: not possible -- Nsight Compute fails with `UnknownError` on the first kernel that touches a CUDA-IPC "
-          "mapping (`exchange_open_kernel`; it cannot save / restore peer memory), in kernel- and application-replay mode alike, and this VM's "
-          "`nvidia-smi nvlink -gt d` counters read N/A.  What the kernel moves is known exactly: every image row (T x 24 + 20 bytes padded to "
-          "16, 4 832 bytes at T = 200) is read once and stored `world` times, 16 bytes per store; at N = 8 and 32 images per GPU that is "
-          "1.08 MB per step and GPU over NVLink.  Its cost is read off the scaling column above: the step with the exchange at N = 8 is "
-          "within a few percent of the same step graph at N = 1.\n")
+mg.append("## ncu on the exchange kernels (N = 2, `tools/multi_gpu.sh 2 <tag> ncu`)\n")
+mg.append("Kernel replay fails (`==ERROR== UnknownError`, `Failed to profile \"exchange_open_kernel\"`: Nsight Compute cannot save / restore the "
+          "CUDA-IPC mappings the kernels write through); APPLICATION replay works (`--replay-mode application`, one run of "
+          "`tools/exchange_check.py` per metric group, shard shape of the headline step: 32 images per rank, T = 200).  This VM's "
+          "`nvidia-smi nvlink -gt d` counters read N/A, the `nvltx / nvlrx` counters of ncu do count:\n")
+xs = os.path.join(G, f"{tag}_ncu_exchange_n2.md")
+if os.path.exists(xs):
+    mg.append(open(xs).read().strip() + "\n")
+else:
+    mg.append("(no capture in this run)\n")
+mg.append("Algorithmic bytes: every image row (T x 24 + 20 bytes padded to 16: 4 832 at T = 200) is read once and stored `world` times with "
+          "16-byte stores, plus one 8-byte release flag per (rank, row) and one 8-byte ack per (slot, rank) from the open kernel; at N = 8 "
+          "and 32 images per GPU that is 1.08 MB per step and GPU over NVLink.  The times above are ncu's serialised, profiler-attached "
+          "launches (the pack kernel's spin on its peers' acks included); in the step graph the exchange is hidden behind the other "
+          "steps in flight -- the scaling column above is its real cost.\n")
 open(os.path.join(ROOT, "profiles", "r02_multi_gpu.md"), "w").write("\n".join(mg) + "\n")
 with open(os.path.join(ROOT, "profiles", "r02_sass_mix.md"), "w") as f:
     f.write(subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_summary.py")], capture_output=True, text=True).stdout)
