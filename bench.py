@@ -79,6 +79,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true", help="(diagnostics) skip the host-buffer leg")
     ap.add_argument("--in-flight", type=int, default=8,
                     help="steps in flight (1 = strictly one step after the other)")
+    ap.add_argument("--e2e-depth", type=int, default=2,
+                    help="batches in flight in the e2e leg (AnchorPipeline.stream depth)")
     ap.add_argument("--group", type=int, default=1,
                     help="steps per CUDA graph launch (parallel branches of one graph); in-flight / group streams")
     return ap.parse_args()
@@ -458,7 +460,8 @@ def run_ours(args):
     def e2e_run(n):
         seen = 0
         batches = (host_sets[i % nsets] for i in range(n))
-        for target, mask, dets in pipe_e.stream(batches, anchors, gather_batch=B * world if world > 1 else None):
+        for target, mask, dets in pipe_e.stream(batches, anchors, depth=args.e2e_depth,
+                                                gather_batch=B * world if world > 1 else None):
             seen += len(dets)
         assert seen == n * B * world
         torch.cuda.current_stream().synchronize()

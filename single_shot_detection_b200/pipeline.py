@@ -389,10 +389,11 @@ class AnchorPipeline:
 class StepGroup:
     """Several step graphs as the parallel branches of ONE CUDA graph.
 
-    A replay is one ``cudaGraphLaunch`` for ``len(items)`` steps: with ~10 kernel nodes and two branches per step the
-    host needs longer to launch a step graph (~25 us through ``torch.cuda.CUDAGraph.replay`` under a stream context)
-    than the GPU needs to run it when several steps are in flight -- the launches, not the kernels, bound the
-    throughput.  Every member keeps its own buffers and workspace slot (they run concurrently)."""
+    A replay is one ``cudaGraphLaunch`` for ``len(items)`` steps.  As parallel branches (the default) every member
+    keeps its own buffers and workspace slot and the members run concurrently: measured, this does NOT raise the
+    throughput of steps in flight -- the host needs ~12 us per single-step graph launch, the GPU ~28 us per step
+    (profiles/r02_tuning_log.md) -- so ``bench.py --group`` stays at 1.  ``chained=True`` is what the strictly serial leg
+    of the bench replays."""
 
     def __init__(self, items, warmup: int = 2, concurrent: bool = True, chained: bool = False):
         """``items``: [(AnchorPipeline, packed, anchors_dev, scores_dev, locs_dev, kwargs for step_device)]
@@ -405,9 +406,10 @@ class StepGroup:
         assert chained or len(set(slots)) == len(slots), "members of a step group run concurrently: one workspace slot each"
         concurrent = concurrent and not chained
         if chained:
-            N.check(N.lib().ssd_b200_set_nms_threads(256))       # a step that runs alone: 256-thread NMS CTAs (~1 us)
-        if concurrent:
-            N.check(N.lib().ssd_b200_set_stream_ctas_per_sm(int(os.environ.get("SSD_CONCURRENT_CTAS", "1"))))
+            # a step that runs alone: 256-thread NMS CTAs finish ~1 us sooner at the headline size (640 segments, about
+            # four per SM); with thousands of segments (the COCO configurations) 128 threads pack slightly better --
+            # measured after the last GPU run of the round, so the chain keeps the setting that was validated
+            N.check(N.lib().ssd_b200_set_nms_threads(256))
         late = [it[0].assign_after_pass1 for it in items]
         try:
             if concurrent:

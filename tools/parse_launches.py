@@ -1,8 +1,12 @@
 #!/usr/bin/env python
-"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: per kernel, launches and
-the duration of the LAST instance (steady state), plus the sum."""
-import collections, csv, sys
-rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 10]
+"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list as a markdown table: per kernel the number of
+launches, the median duration and the kernel's share of the summed device time."""
+import collections
+import csv
+import statistics
+import sys
+
+rows = [r for r in csv.reader(l for l in open(sys.argv[1]) if l.startswith('"')) if len(r) > 10]
 hi = next(i for i, r in enumerate(rows) if 'Kernel Name' in r)
 h = rows[hi]
 ik, iv, iu = h.index('Kernel Name'), h.index('Metric Value'), h.index('Metric Unit')
@@ -14,8 +18,10 @@ for r in rows[hi + 1:]:
         continue
     if r[iu] == 'ns':
         v /= 1e3
-    agg.setdefault(r[ik].split('(')[0][:70], []).append(v)
-tot = sum(v[-1] for v in agg.values())
-for k, v in agg.items():
-    print(f"{k:70s} n={len(v):3d} last={v[-1]:9.2f} us  {100*v[-1]/tot:5.1f}%")
-print(f"sum of last instances: {tot:.1f} us")
+    agg.setdefault(r[ik].split('(')[0].replace('void ', '').replace('ssd::', '')[:60], []).append(v)
+tot = sum(sum(v) for v in agg.values())
+print("| kernel | launches | median us | share of the summed device time |")
+print("|---|---|---|---|")
+for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+    print(f"| `{k}` | {len(v)} | {statistics.median(v):.1f} | {100 * sum(v) / tot:.1f} % |")
+print(f"\nsum over {sum(len(v) for v in agg.values())} launches: {tot / 1e3:.2f} ms")
