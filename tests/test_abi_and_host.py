@@ -165,3 +165,28 @@ def test_every_reference_sample_config_constructs_the_mirrored_classes():
         assert post.max_total == cfg["postprocess"].get("max_total"), path
         assert assigner.matched_threshold == cfg["target_assigner"]["matched_threshold"], path
         assert crit is not None
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the driver runs it before our arm, on the box's host cores): one JSON line with the
+    metric / config of our arm, `impl: reference`, the CPU baseline it timed and an `e2e` block without copies.  A tiny
+    sample here (2 images, 1 step): the plumbing, not the number."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "1",
+                          "--warmup", "1", "--cpu-sample-images", "2"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "images/sec target-assign+NMS" and line["unit"] == "images/s"
+    assert line["higher_is_better"] is True and line["n_gpus"] == 1 and line["steps"] == 1 and line["warmup"] == 1
+    assert line["value"] > 0 and line["vs_baseline"] is None and line["dtype"] == "f32"
+    assert line["config"]["workload"] == "ssd300_voc_b32" and line["config"]["anchors"] == 8732
+    for key in ("l2", "steps_in_flight", "steps_per_graph_launch", "device_path"):      # the same keys as the GPU arm
+        assert key in line["config"], key
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "2 of 32 images" in cb["sample"]
+    assert cb["one_thread"]["cores"] == 1 and set(cb["stage_ms_per_sample"]) >= {"encode_ground_truth", "sampler", "postprocess"}
+    assert line["e2e"] == {"value": line["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
