@@ -410,6 +410,8 @@ class StepGroup:
             # four per SM); with thousands of segments (the COCO configurations) 128 threads pack slightly better --
             # measured after the last GPU run of the round, so the chain keeps the setting that was validated
             N.check(N.lib().ssd_b200_set_nms_threads(256))
+        if concurrent:
+            N.check(N.lib().ssd_b200_set_stream_ctas_per_sm(int(os.environ.get("SSD_CONCURRENT_CTAS", "1"))))
         late = [it[0].assign_after_pass1 for it in items]
         try:
             if concurrent:
